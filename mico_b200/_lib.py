@@ -1,0 +1,65 @@
+"""ctypes binding of libmico_b200.so (the C-ABI in include/mico_b200.h).
+
+The library is REQUIRED: there is no CPU or PyTorch fallback.  Importing this module when the
+.so is missing raises, and every op raises if the call returns a non-zero MICO_ERR_* code.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmico_b200.so")
+
+ACT_NONE, ACT_GELU, ACT_QUICK_GELU, ACT_GELU_BWD, ACT_QUICK_GELU_BWD = 0, 1, 2, 3, 4
+
+
+class MicoError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("lda", C.c_int64), ("a_mn_major", C.c_int32),
+        ("b", C.c_void_p), ("ldb", C.c_int64), ("b_mn_major", C.c_int32),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("out", C.c_void_p), ("ldo", C.c_int64), ("out_fp32", C.c_int32),
+        ("bias", C.c_void_p),
+        ("residual", C.c_void_p), ("ldr", C.c_int64),
+        ("row_scale", C.c_void_p), ("rows_per_group", C.c_int32),
+        ("act", C.c_int32),
+        ("aux_out", C.c_void_p), ("ld_aux_out", C.c_int64),
+        ("aux_in", C.c_void_p), ("ld_aux_in", C.c_int64),
+        ("accumulate", C.c_int32),
+        ("alpha", C.c_float),
+        ("remap_gin", C.c_int32), ("remap_gout", C.c_int32), ("remap_off", C.c_int32),
+        ("residual_bcast", C.c_int32),
+    ]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise MicoError(
+            f"{LIB_PATH} not found: build it with `python -m mico_b200.build` "
+            "(mico_b200 has no CPU/PyTorch fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.mico_version.restype = C.c_int
+    lib.mico_last_error.restype = C.c_char_p
+    lib.mico_launch_count.restype = C.c_int64
+    lib.mico_reset_launch_count.restype = None
+    return lib
+
+
+lib = _load()
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib.mico_last_error().decode("utf-8", "replace")
+        raise MicoError(f"{what} failed with code {rc}: {msg}")
+
+
+def launch_count():
+    return int(lib.mico_launch_count())
+
+
+def reset_launch_count():
+    lib.mico_reset_launch_count()

@@ -1,0 +1,431 @@
+// mico_b200 -- K3: persistent warp-specialised bf16 GEMM for sm_100a.
+//
+//   out[M,N] = epilogue(alpha * A[M,K] . B[N,K]^T)      fp32 accumulation in TMEM
+//
+// Structure (one CTA per SM, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled tiles -> STAGES-deep smem ring
+//   warp 1      MMA issuer:   one elected lane issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage,
+//                             tcgen05.commit releases smem slots and publishes the accumulator
+//   warps 2..5  epilogue:     tcgen05.ld TMEM -> registers -> fused bias/GELU/DropPath/residual -> HBM
+// Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+// Either operand may be "MN-major" (the contraction index is the slow dimension in HBM); that is how
+// wgrad (dW = dY^T X) and dgrad (dX = dY W) run on the same kernel with no transposes in HBM.
+//
+// Replaces F.linear/matmul call sites listed in include/mico_b200.h (reference: eva_vit_model.py:191,
+// 197, 310, 363, 446; bert.py:196-209, 293, 357, 370, 601, 607).
+#include "common.cuh"
+#include "host_utils.h"
+
+namespace mico {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kGemmThreads = 192;
+constexpr int kAccStride = 256;   // TMEM columns between the two accumulator stages
+
+struct GemmEpi {
+    void* out;
+    int64_t ldo;
+    int out_fp32;
+    const float* bias;
+    const float* residual;
+    int64_t ldr;
+    const float* row_scale;
+    int rows_per_group;
+    int act;
+    __nv_bfloat16* aux_out;
+    int64_t ld_aux_out;
+    const __nv_bfloat16* aux_in;
+    int64_t ld_aux_in;
+    int accumulate;
+    float alpha;
+    int remap_gin, remap_gout, remap_off, residual_bcast;
+    int vec_ok;   // all pitches / bases allow 16-byte vector access
+};
+
+template <int BN, int STAGES>
+struct GemmCfg {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + alignment slack
+};
+
+template <int NC>
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const uint32_t (&acc)[NC], int row, int col0,
+                                               int M, int N) {
+    if (row >= M) return;
+    float v[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(acc[i]) * e.alpha;
+
+    int64_t orow = row;
+    int64_t rrow = row;
+    if (e.remap_gin > 0) {
+        const int g = row / e.remap_gin, r = row - g * e.remap_gin;
+        orow = (int64_t)g * e.remap_gout + r + e.remap_off;
+        rrow = e.residual_bcast ? (int64_t)(r + e.remap_off) : orow;
+    }
+    const bool full = (col0 + NC <= N) && e.vec_ok;
+    const float rs = e.row_scale ? e.row_scale[row / e.rows_per_group] : 1.0f;
+
+    if (full) {
+        if (e.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
+#pragma unroll
+            for (int i = 0; i < NC / 4; ++i) {
+                const float4 b = __ldg(b4 + i);
+                v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+        }
+        if (e.act == MICO_ACT_GELU || e.act == MICO_ACT_QUICK_GELU) {
+            if (e.aux_out) {
+                uint4* a4 = reinterpret_cast<uint4*>(e.aux_out + orow * e.ld_aux_out + col0);
+#pragma unroll
+                for (int i = 0; i < NC / 8; ++i)
+                    a4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                       pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+            }
+            if (e.act == MICO_ACT_GELU) {
+#pragma unroll
+                for (int i = 0; i < NC; ++i) v[i] = gelu_erf(v[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < NC; ++i) v[i] = quick_gelu(v[i]);
+            }
+        } else if (e.act == MICO_ACT_GELU_BWD || e.act == MICO_ACT_QUICK_GELU_BWD) {
+            const uint4* u4 = reinterpret_cast<const uint4*>(e.aux_in + orow * e.ld_aux_in + col0);
+#pragma unroll
+            for (int i = 0; i < NC / 8; ++i) {
+                const uint4 u = __ldg(u4 + i);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float lo = bf16_lo(w[j]), hi = bf16_hi(w[j]);
+                    if (e.act == MICO_ACT_GELU_BWD) {
+                        v[8 * i + 2 * j] *= gelu_erf_grad(lo);
+                        v[8 * i + 2 * j + 1] *= gelu_erf_grad(hi);
+                    } else {
+                        v[8 * i + 2 * j] *= quick_gelu_grad(lo);
+                        v[8 * i + 2 * j + 1] *= quick_gelu_grad(hi);
+                    }
+                }
+            }
+        }
+        if (e.row_scale) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) v[i] *= rs;
+        }
+        if (e.residual) {
+            const float4* r4 = reinterpret_cast<const float4*>(e.residual + rrow * e.ldr + col0);
+#pragma unroll
+            for (int i = 0; i < NC / 4; ++i) {
+                const float4 r = __ldg(r4 + i);
+                v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+            }
+        }
+        if (e.out_fp32) {
+            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + orow * e.ldo + col0);
+            if (e.accumulate) {
+#pragma unroll
+                for (int i = 0; i < NC / 4; ++i) {
+                    const float4 o = o4[i];
+                    v[4 * i + 0] += o.x; v[4 * i + 1] += o.y; v[4 * i + 2] += o.z; v[4 * i + 3] += o.w;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NC / 4; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) + orow * e.ldo + col0);
+#pragma unroll
+            for (int i = 0; i < NC / 8; ++i)
+                o4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                   pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+        }
+        return;
+    }
+    // ragged / unaligned tail: scalar path
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const int col = col0 + i;
+        if (col >= N) break;
+        float x = v[i];
+        if (e.bias) x += e.bias[col];
+        if (e.act == MICO_ACT_GELU || e.act == MICO_ACT_QUICK_GELU) {
+            if (e.aux_out) e.aux_out[orow * e.ld_aux_out + col] = __float2bfloat16(x);
+            x = (e.act == MICO_ACT_GELU) ? gelu_erf(x) : quick_gelu(x);
+        } else if (e.act == MICO_ACT_GELU_BWD) {
+            x *= gelu_erf_grad(__bfloat162float(e.aux_in[orow * e.ld_aux_in + col]));
+        } else if (e.act == MICO_ACT_QUICK_GELU_BWD) {
+            x *= quick_gelu_grad(__bfloat162float(e.aux_in[orow * e.ld_aux_in + col]));
+        }
+        x *= rs;
+        if (e.residual) x += e.residual[rrow * e.ldr + col];
+        if (e.out_fp32) {
+            float* o = reinterpret_cast<float*>(e.out) + orow * e.ldo + col;
+            if (e.accumulate) x += *o;
+            *o = x;
+        } else {
+            reinterpret_cast<__nv_bfloat16*>(e.out)[orow * e.ldo + col] = __float2bfloat16(x);
+        }
+    }
+}
+
+template <int BN, bool A_MN, bool B_MN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+                 int K, GemmEpi epi) {
+    using Cfg = GemmCfg<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int num_m = (M + BM - 1) / BM;
+    const int num_n = (N + BN - 1) / BN;
+    const int num_tiles = num_m * num_n;
+    const int num_kb = (K + BK - 1) / BK;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            tma_prefetch_desc(&tmA);
+            tma_prefetch_desc(&tmB);
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(&full_bar[s], 1);
+                mbar_init(&empty_bar[s], 1);
+            }
+            for (int a = 0; a < 2; ++a) {
+                mbar_init(&tfull_bar[a], 1);
+                mbar_init(&tempty_bar[a], 4);
+            }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc<512>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------- TMA producer
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / num_n) * BM;
+                const int n0 = (tile % num_n) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    if constexpr (!A_MN) {
+                        tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j)
+                            tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m0 + 64 * j, kb * BK);
+                    }
+                    if constexpr (!B_MN) {
+                        tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j)
+                            tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n0 + 64 * j, kb * BK);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------- MMA issuer
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BN, A_MN, B_MN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kAccStride;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t adesc = A_MN ? umma_smem_desc_sw128(sa + k * 2048, 8192, 1024)
+                                                    : umma_smem_desc_sw128(sa + k * 32, 16, 1024);
+                        const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(sb + k * 2048, 8192, 1024)
+                                                    : umma_smem_desc_sw128(sb + k * 32, 16, 1024);
+                        umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------- epilogue (warps 2..5)
+        const int q = warp & 3;   // TMEM lane quarter this warp may access
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int m0 = (tile / num_n) * BM;
+            const int n0 = (tile % num_n) * BN;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const int row = m0 + q * 32 + (int)lane_id();
+            const uint32_t t0 = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                if (n0 + c * 32 >= N) break;   // warp-uniform
+                uint32_t v[32];
+                tmem_ld_x32(t0 + c * 32, v);
+                tmem_ld_wait();
+                epilogue_chunk<32>(epi, v, row, n0 + c * 32, M, N);
+            }
+            if constexpr (BN % 32 != 0) {
+                constexpr int c0 = (BN / 32) * 32;
+                if (n0 + c0 < N) {
+                    uint32_t v[16];
+                    tmem_ld_x16(t0 + c0, v);
+                    tmem_ld_wait();
+                    epilogue_chunk<16>(epi, v, row, n0 + c0, M, N);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane_id() == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+template <int BN, bool A_MN, bool B_MN, int STAGES>
+int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN, STAGES>;
+    CUtensorMap tmA, tmB;
+    int rc;
+    if (!A_MN) {
+        const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.M};
+        const uint64_t strides[2] = {2, (uint64_t)g.lda * 2};
+        const uint32_t box[2] = {BK, BM};
+        rc = make_tmap_bf16(&tmA, g.a, 2, dims, strides, box);
+    } else {
+        const uint64_t dims[2] = {(uint64_t)g.M, (uint64_t)g.K};
+        const uint64_t strides[2] = {2, (uint64_t)g.lda * 2};
+        const uint32_t box[2] = {64, BK};
+        rc = make_tmap_bf16(&tmA, g.a, 2, dims, strides, box);
+    }
+    if (rc) return rc;
+    if (!B_MN) {
+        const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
+        const uint64_t strides[2] = {2, (uint64_t)g.ldb * 2};
+        const uint32_t box[2] = {BK, BN};
+        rc = make_tmap_bf16(&tmB, g.b, 2, dims, strides, box);
+    } else {
+        const uint64_t dims[2] = {(uint64_t)g.N, (uint64_t)g.K};
+        const uint64_t strides[2] = {2, (uint64_t)g.ldb * 2};
+        const uint32_t box[2] = {64, BK};
+        rc = make_tmap_bf16(&tmB, g.b, 2, dims, strides, box);
+    }
+    if (rc) return rc;
+
+    auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES>;
+    static bool attr_set = false;   // benign race: idempotent
+    if (!attr_set) {
+        MICO_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int tiles = ceil_div(g.M, BM) * ceil_div(g.N, BN);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, g.M, g.N, g.K, epi);
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return MICO_OK;
+}
+
+template <bool A_MN, bool B_MN>
+int dispatch_bn(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) {
+    // pick the N tile that wastes the least padded work; ties -> wider tile
+    auto padded = [&](int bn) { return (int64_t)ceil_div(g.N, bn) * bn; };
+    int best = 256;
+    int64_t best_pad = padded(256);
+    if (!B_MN && padded(176) < best_pad) { best = 176; best_pad = padded(176); }
+    if (padded(128) < best_pad) { best = 128; best_pad = padded(128); }
+    if (g.N <= 64 && padded(64) < best_pad) { best = 64; }
+    switch (best) {
+        case 256: return launch_gemm<256, A_MN, B_MN, 4>(g, epi, stream);
+        case 176: if constexpr (!B_MN) return launch_gemm<176, A_MN, B_MN, 5>(g, epi, stream);
+        case 128: return launch_gemm<128, A_MN, B_MN, 6>(g, epi, stream);
+        default:  return launch_gemm<64, A_MN, B_MN, 8>(g, epi, stream);
+    }
+}
+
+}  // namespace
+}  // namespace mico
+
+extern "C" int mico_gemm_bf16(const MicoGemmArgs* args, void* stream_) {
+    using namespace mico;
+    MICO_CHECK_ARG(args != nullptr);
+    const MicoGemmArgs& g = *args;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MICO_CHECK_ARG(g.a && g.b && g.out);
+    MICO_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0);
+    MICO_CHECK_ARG(g.lda % 8 == 0 && g.ldb % 8 == 0);
+    MICO_CHECK_ARG((reinterpret_cast<uintptr_t>(g.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.b) & 15) == 0);
+    MICO_CHECK_ARG(!(g.accumulate && !g.out_fp32));
+    MICO_CHECK_ARG(g.act >= MICO_ACT_NONE && g.act <= MICO_ACT_QUICK_GELU_BWD);
+    MICO_CHECK_ARG(!((g.act == MICO_ACT_GELU_BWD || g.act == MICO_ACT_QUICK_GELU_BWD) && !g.aux_in));
+    MICO_CHECK_ARG(!(g.row_scale && g.rows_per_group <= 0));
+    MICO_CHECK_ARG(!(g.remap_gin > 0 && g.remap_gout < g.remap_gin));
+    if (g.a_mn_major) MICO_CHECK_ARG(g.lda >= g.M); else MICO_CHECK_ARG(g.lda >= g.K);
+    if (g.b_mn_major) MICO_CHECK_ARG(g.ldb >= g.N); else MICO_CHECK_ARG(g.ldb >= g.K);
+
+    GemmEpi e;
+    e.out = g.out; e.ldo = g.ldo; e.out_fp32 = g.out_fp32;
+    e.bias = g.bias; e.residual = g.residual; e.ldr = g.ldr;
+    e.row_scale = g.row_scale; e.rows_per_group = g.rows_per_group;
+    e.act = g.act;
+    e.aux_out = reinterpret_cast<__nv_bfloat16*>(g.aux_out); e.ld_aux_out = g.ld_aux_out;
+    e.aux_in = reinterpret_cast<const __nv_bfloat16*>(g.aux_in); e.ld_aux_in = g.ld_aux_in;
+    e.accumulate = g.accumulate; e.alpha = g.alpha;
+    e.remap_gin = g.remap_gin; e.remap_gout = g.remap_gout; e.remap_off = g.remap_off;
+    e.residual_bcast = g.residual_bcast;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const int oel = g.out_fp32 ? 4 : 8;   // elements per 16 bytes
+    bool vec = al16(g.out) && (g.ldo % oel == 0);
+    if (g.bias) vec = vec && al16(g.bias);
+    if (g.residual) vec = vec && al16(g.residual) && (g.ldr % 4 == 0);
+    if (g.aux_out) vec = vec && al16(g.aux_out) && (g.ld_aux_out % 8 == 0);
+    if (g.aux_in) vec = vec && al16(g.aux_in) && (g.ld_aux_in % 8 == 0);
+    e.vec_ok = vec ? 1 : 0;
+
+    if (!g.a_mn_major && !g.b_mn_major) return dispatch_bn<false, false>(g, e, stream);
+    if (!g.a_mn_major && g.b_mn_major) return dispatch_bn<false, true>(g, e, stream);
+    if (g.a_mn_major && !g.b_mn_major) return dispatch_bn<true, false>(g, e, stream);
+    return dispatch_bn<true, true>(g, e, stream);
+}

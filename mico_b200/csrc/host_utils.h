@@ -1,0 +1,43 @@
+// mico_b200 -- host-side helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mico_b200.h"
+
+namespace mico {
+
+#define MICO_CHECK_ARG(cond)                                                             \
+    do {                                                                                 \
+        if (!(cond)) {                                                                   \
+            mico::set_last_error(__FILE__, __LINE__, "invalid argument: " #cond);        \
+            return MICO_ERR_INVALID_ARG;                                                 \
+        }                                                                                \
+    } while (0)
+
+#define MICO_CHECK_CUDA(expr)                                                            \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            mico::set_last_error(__FILE__, __LINE__, cudaGetErrorString(_e));            \
+            return MICO_ERR_CUDA;                                                        \
+        }                                                                                \
+    } while (0)
+
+void set_last_error(const char* file, int line, const char* msg);
+
+// Build a tiled bf16 tensor map with 128-byte swizzle.  dims/strides are innermost-first;
+// strides[0] is implied (2 bytes), strides[i>0] in BYTES.  Returns 0 or a MICO_ERR_* code.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box);
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+constexpr int kDefaultSMs = 148;
+int num_sms();
+
+void count_launch(int n = 1);
+
+}  // namespace mico

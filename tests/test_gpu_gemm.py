@@ -1,0 +1,141 @@
+"""GPU parity: tcgen05 GEMM (mico_gemm_bf16) vs fp32 math on the same bf16-rounded operands.
+
+Tolerance: fp32-output rel-L2 <= 2e-5 (only accumulation order differs);
+bf16-output rel-L2 <= 3e-3 = one bf16 rounding (2^-9 relative) of the fp32 result.
+"""
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).cuda()
+
+
+SHAPES = [
+    # M, N, K
+    (128, 128, 64), (128, 256, 128), (256, 176, 192), (257, 1408, 1408), (300, 4224, 1408),
+    (1000, 6144, 1408), (514, 1408, 6144), (64, 512, 768), (96, 2, 768), (130, 30522, 768), (2056, 768, 1408),
+]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_tn_fp32_out(M, N, K):
+    from mico_b200 import ops
+    a, b = _mk((M, K), 1), _mk((N, K), 2, 0.05)
+    out = ops.gemm(a, b, out_dtype=torch.float32)
+    ref = a.float() @ b.float().t()
+    torch.cuda.synchronize()
+    err = rel_l2(out, ref)
+    print(f"TN {M}x{N}x{K}: rel_l2={err:.3e} max_abs={(out - ref).abs().max().item():.3e}")
+    assert err < 2e-5
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 256), (1408, 6144, 1028), (4224, 1408, 514),
+                                   (520, 1408, 4224), (136, 768, 200)])
+def test_gemm_majors(M, N, K, a_mn, b_mn):
+    from mico_b200 import ops
+    a = _mk((K, M) if a_mn else (M, K), 3)
+    b = _mk((K, N) if b_mn else (N, K), 4, 0.05)
+    out = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32)
+    A = a.float().t() if a_mn else a.float()
+    B = b.float() if b_mn else b.float().t()
+    ref = A @ B
+    torch.cuda.synchronize()
+    err = rel_l2(out, ref)
+    print(f"a_mn={a_mn} b_mn={b_mn} {M}x{N}x{K}: rel_l2={err:.3e}")
+    assert err < 2e-5
+
+
+def test_gemm_bias_gelu_aux_bf16():
+    from mico_b200 import ops
+    M, N, K = 514, 6144, 1408
+    a, b = _mk((M, K), 5), _mk((N, K), 6, 0.03)
+    bias = torch.randn(N, device="cuda") * 0.1
+    aux = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    out = ops.gemm(a, b, bias=bias, act=ops.ACT_GELU, aux_out=aux)
+    pre = a.float() @ b.float().t() + bias
+    ref = torch.nn.functional.gelu(pre)
+    assert rel_l2(aux, pre) < 3e-3
+    assert rel_l2(out, ref) < 3e-3
+    # against the identically rounded reference the match must be ~exact
+    assert rel_l2(out, ref.to(torch.bfloat16)) < 1e-3
+
+
+def test_gemm_residual_rowscale_fp32():
+    from mico_b200 import ops
+    B_, T, N, K = 3, 257, 1408, 1408
+    M = B_ * T
+    a, b = _mk((M, K), 7), _mk((N, K), 8, 0.03)
+    bias = torch.randn(N, device="cuda") * 0.1
+    res = torch.randn(M, N, device="cuda")
+    scale = torch.tensor([1.25, 0.0, 1.0], device="cuda")
+    out = ops.gemm(a, b, bias=bias, residual=res, row_scale=scale, rows_per_group=T, out_dtype=torch.float32)
+    ref = res + (a.float() @ b.float().t() + bias) * scale.repeat_interleave(T)[:, None]
+    assert rel_l2(out, ref) < 2e-5
+    # in-place on the residual stream (out aliases residual), as the block epilogue uses it
+    x = res.clone()
+    ops.gemm(a, b, bias=bias, residual=x, row_scale=scale, rows_per_group=T, out=x)
+    assert rel_l2(x, ref) < 2e-5
+
+
+def test_gemm_gelu_bwd_and_accumulate():
+    from mico_b200 import ops
+    M, N, K = 514, 6144, 1408
+    dy, w = _mk((M, K), 9), _mk((K, N), 10, 0.03)          # w is [K rows][N] -> MN-major B
+    u = _mk((M, N), 11)
+    out = ops.gemm(dy, w, b_mn=True, act=ops.ACT_GELU_BWD, aux_in=u)
+    uf = u.float().requires_grad_(True)
+    torch.nn.functional.gelu(uf).backward(dy.float() @ w.float())
+    assert rel_l2(out, uf.grad) < 3e-3
+    # accumulate into fp32 (gradient accumulation for wgrad)
+    acc = torch.randn(M, N, device="cuda")
+    ref = acc + 0.5 * (dy.float() @ w.float())
+    ops.gemm(dy, w, b_mn=True, out=acc, accumulate=True, alpha=0.5)
+    assert rel_l2(acc, ref) < 2e-5
+
+
+def test_gemm_patch_remap():
+    from mico_b200 import ops
+    B_, P, T, N, K = 2, 256, 257, 1408, 640
+    a, b = _mk((B_ * P, K), 12), _mk((N, K), 13, 0.03)
+    bias = torch.randn(N, device="cuda") * 0.1
+    pos = torch.randn(T, N, device="cuda")
+    out = torch.zeros(B_ * T, N, device="cuda")
+    ops.gemm(a, b, bias=bias, residual=pos, out=out, remap=(P, T, 1), residual_bcast=True)
+    ref = torch.zeros(B_, T, N, device="cuda")
+    ref[:, 1:] = (a.float() @ b.float().t() + bias).view(B_, P, N) + pos[1:]
+    assert rel_l2(out, ref.view(-1, N)) < 2e-5
+    assert out.view(B_, T, N)[:, 0].abs().max().item() == 0.0
+
+
+def test_gemm_full_size_fc1_timing():
+    """ViT-g fc1 at bs 64: parity at full size through linearity (gemm(a1+a2) == gemm(a1)+gemm(a2) for
+    operands whose sum is exact in bf16) plus a coarse TFLOP/s print."""
+    from mico_b200 import ops
+    M, N, K = 16448, 6144, 1408
+    g = torch.Generator().manual_seed(0)
+    a1 = torch.randint(-8, 8, (M, K), generator=g).to(torch.bfloat16).cuda()
+    a2 = torch.randint(-8, 8, (M, K), generator=g).to(torch.bfloat16).cuda()
+    w = torch.randint(-4, 4, (N, K), generator=g).to(torch.bfloat16).cuda()
+    o1 = ops.gemm(a1, w, out_dtype=torch.float32)
+    o2 = ops.gemm(a2, w, out_dtype=torch.float32)
+    o12 = ops.gemm(a1 + a2, w, out_dtype=torch.float32)
+    assert torch.equal(o1 + o2, o12)          # small integers: exact in fp32
+    assert torch.equal(o1[:512], (a1[:512].float() @ w.float().t()))
+    out = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.gemm(a1, w, out=out)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        ops.gemm(a1, w, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"fc1 16448x6144x1408: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s")
