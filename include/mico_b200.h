@@ -75,6 +75,77 @@ typedef struct MicoGemmArgs {
 
 int mico_gemm_bf16(const MicoGemmArgs* args, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K4  Fused attention (flash-style; tcgen05 QK^T and PV, online softmax, no score matrix in HBM).
+ *     O = softmax(scale * Q K^T + mask) V          per (batch b, head h)
+ * Replaces eva_vit_model.py:340-361 (q*scale; q@k^T; softmax; @v), bert.py:233-277 (scores/sqrt(d) +
+ * additive mask; softmax; @v; self- and cross-attention), transformer.py:121-130, clip.py:185-189.
+ * Tensors are bf16 with arbitrary (16-byte aligned) strides so that the fused QKV GEMM output is read in
+ * place: element (b, i, h, d) lives at ptr + b*bs + i*rs + h*hs + d (strides in elements, multiples of 8).
+ * mask: additive fp32 (the reference's (1-m)*-10000 masks, bert.py:697-781) at mask + b*mask_bs + i*mask_qs + j
+ * (mask_qs = 0 for a per-key padding mask), or NULL.   lse: [B,H,Sq] fp32 log-sum-exp saved for backward.
+ * Backward (mico_attention_bwd) recomputes P from Q,K and lse; needs delta[b,h,i] = sum_d dO*O
+ * (mico_attention_bwd_delta) and writes dQ, dK, dV with the same stride convention.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct MicoAttnArgs {
+    const void* q; int64_t q_bs, q_rs, q_hs;
+    const void* k; int64_t k_bs, k_rs, k_hs;
+    const void* v; int64_t v_bs, v_rs, v_hs;
+    void* o;       int64_t o_bs, o_rs, o_hs;      /* forward: output; backward: forward output (input) */
+    float* lse;                                    /* [B,H,Sq] */
+    const float* mask; int64_t mask_bs, mask_qs;
+    int32_t B, H, Sq, Sk, D;
+    float scale;
+    /* backward only */
+    const void* dout; int64_t do_bs, do_rs, do_hs;
+    float* delta;                                  /* [B,H,Sq] workspace: rowsum(dO * O) */
+    void* dq; int64_t dq_bs, dq_rs, dq_hs;
+    void* dk; int64_t dk_bs, dk_rs, dk_hs;
+    void* dv; int64_t dv_bs, dv_rs, dv_hs;
+} MicoAttnArgs;
+
+int mico_attention_fwd(const MicoAttnArgs* args, void* stream);
+int mico_attention_bwd(const MicoAttnArgs* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  LayerNorm (eva_vit_model.py:375,382,542 eps 1e-6; bert.py:92,290,368,583 and mico.py:49,400-403
+ *     eps 1e-12; swin.py:212,218,329,565 eps 1e-5).  x is fp32 or bf16 [M,D]; y as bf16 and/or fp32.
+ *     Backward: dx = [dres +] LN'(dy); optional bf16 copy of dx scaled per row group (DropPath);
+ *     dgamma/dbeta reduced deterministically through `workspace` (mico_layernorm_bwd_workspace bytes).
+ * ------------------------------------------------------------------------------------------- */
+int mico_layernorm_fwd(const void* x, int x_is_bf16, int64_t ldx, const float* gamma, const float* beta,
+                       void* y_bf16, float* y_f32, int64_t ldy, float* mean, float* rstd, int M, int D,
+                       float eps, void* stream);
+size_t mico_layernorm_bwd_workspace(int M, int D);
+int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, const float* x, int64_t ldx,
+                       const float* mean, const float* rstd, const float* gamma, const float* dres,
+                       int64_t lddres, float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb,
+                       const float* row_scale, int rows_per_group, float* dgamma, float* dbeta,
+                       int accumulate_param_grads, int M, int D, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * HBM-bound helpers on the path (all vectorised 128-bit, grid sized in multiples of the SM count).
+ * ------------------------------------------------------------------------------------------- */
+/* fp32 master parameters -> bf16 GEMM operands (the reference relies on torch.autocast, pipeline.py:43) */
+int mico_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* nn.Linear bias gradient: out[n] (+)= sum_m x[m,n], x bf16 */
+size_t mico_colsum_workspace(int M, int N);
+int mico_colsum_bf16(const void* x, int64_t ldx, int M, int N, float* out, int accumulate, void* workspace,
+                     size_t ws_bytes, void* stream);
+/* d pos_embed / d cls_token: out[r] (+)= sum_b x[b*R + r] */
+int mico_batch_sum_f32(const float* x, int B, int64_t R, float* out, int accumulate, void* stream);
+/* K1 im2col for Conv2d(k=s=P) (eva_vit_model.py:440-447; swin.py:437-475): (B,C,H,W) fp32 -> bf16
+ * [B*(H/P)*(W/P), Kpad], columns (c,ky,kx) zero-padded to Kpad; chan_stride=0 replicates one channel
+ * (forward_audio_encoder's repeat(1,1,3,1,1), mico.py:139-143) */
+int mico_patchify(const float* img, int64_t img_stride, int64_t chan_stride, int B, int C, int H, int W, int P,
+                  int Kpad, void* out, void* stream);
+/* token 0 of every sample = cls_token + pos_embed[0] (eva_vit_model.py:615-619) */
+int mico_cls_pos_row(const float* cls_token, const float* pos0, float* x, int64_t sample_stride, int B, int D,
+                     void* stream);
+/* y = bf16(x * row_scale[row / rows_per_group]) */
+int mico_scale_cast_bf16(const float* x, int64_t ldx, const float* row_scale, int rows_per_group, void* y,
+                         int64_t ldy, int M, int D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

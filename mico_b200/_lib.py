@@ -63,3 +63,25 @@ def launch_count():
 
 def reset_launch_count():
     lib.mico_reset_launch_count()
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("q_bs", C.c_int64), ("q_rs", C.c_int64), ("q_hs", C.c_int64),
+        ("k", C.c_void_p), ("k_bs", C.c_int64), ("k_rs", C.c_int64), ("k_hs", C.c_int64),
+        ("v", C.c_void_p), ("v_bs", C.c_int64), ("v_rs", C.c_int64), ("v_hs", C.c_int64),
+        ("o", C.c_void_p), ("o_bs", C.c_int64), ("o_rs", C.c_int64), ("o_hs", C.c_int64),
+        ("lse", C.c_void_p),
+        ("mask", C.c_void_p), ("mask_bs", C.c_int64), ("mask_qs", C.c_int64),
+        ("B", C.c_int32), ("H", C.c_int32), ("Sq", C.c_int32), ("Sk", C.c_int32), ("D", C.c_int32),
+        ("scale", C.c_float),
+        ("dout", C.c_void_p), ("do_bs", C.c_int64), ("do_rs", C.c_int64), ("do_hs", C.c_int64),
+        ("delta", C.c_void_p),
+        ("dq", C.c_void_p), ("dq_bs", C.c_int64), ("dq_rs", C.c_int64), ("dq_hs", C.c_int64),
+        ("dk", C.c_void_p), ("dk_bs", C.c_int64), ("dk_rs", C.c_int64), ("dk_hs", C.c_int64),
+        ("dv", C.c_void_p), ("dv_bs", C.c_int64), ("dv_rs", C.c_int64), ("dv_hs", C.c_int64),
+    ]
+
+
+lib.mico_layernorm_bwd_workspace.restype = C.c_size_t
+lib.mico_colsum_workspace.restype = C.c_size_t

@@ -1,0 +1,364 @@
+// mico_b200 -- K4 forward: fused attention  O = softmax(scale * Q K^T + mask) V   (sm_100a, tcgen05).
+//
+// Replaces the naive 3-kernel attention (bmm -> softmax -> bmm, B*H*N*N scores in HBM) at
+// eva_vit_model.py:340-361, bert.py:233-277, transformer.py:121-130, clip.py (nn.MultiheadAttention).
+//
+// One persistent CTA per SM; a work item is (batch, head, 128-row query tile).  Warp roles:
+//   warps 0-3  softmax: own one query row each (TMEM lane == row); online softmax in fp32, P -> smem (bf16)
+//   warp 4     TMA producer: Q tile once, K/V tiles double-buffered (4-D tensor maps: d, head, row, batch;
+//              head_dim is zero-padded to a multiple of 16 by TMA out-of-bounds fill -- d=88 -> 96)
+//   warp 5     MMA issuer: S = Q K^T (K-major x K-major) into one of two TMEM S buffers, then
+//              O_part = P V (V read MN-major from the same row-major tile) into TMEM
+// O is accumulated in registers (one row per thread) with the usual running max / sum rescale.
+// Saves LSE = m + ln(l) per row for the backward kernels.
+#include "attn_common.cuh"
+
+namespace mico {
+namespace {
+
+struct AttnFwdParams {
+    int B, H, Sq, Sk, D;          // D = true head dim
+    float scale;                  // softmax scale (applied to Q K^T)
+    const float* mask;            // additive fp32 mask or null: mask[b*mask_bs + i*mask_qs + j]
+    int64_t mask_bs, mask_qs;
+    __nv_bfloat16* o;             // output, element (b,i,h,d) at o + b*o_bs + i*o_rs + h*o_hs + d
+    int64_t o_bs, o_rs, o_hs;
+    float* lse;                   // [B,H,Sq] or null
+};
+
+struct AttnSmem {
+    static constexpr int Q = 0;
+    static constexpr int K0 = 2 * kAtomBytes;
+    static constexpr int V0 = K0 + 2 * 2 * kAtomBytes;
+    static constexpr int P = V0 + 2 * 2 * kAtomBytes;
+    static constexpr int BARS = P + 2 * kAtomBytes;
+    static constexpr int TOTAL = BARS + 256 + 1024;
+};
+
+template <int HD_PAD>
+__global__ void __launch_bounds__(kAttThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, AttnFwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem::BARS);
+    uint64_t* q_full = bars + 0;
+    uint64_t* q_empty = bars + 1;
+    uint64_t* kv_full = bars + 2;    // [2]
+    uint64_t* kv_empty = bars + 4;   // [2]
+    uint64_t* s_full = bars + 6;     // [2]
+    uint64_t* s_empty = bars + 8;    // [2]
+    uint64_t* p_full = bars + 10;
+    uint64_t* o_full = bars + 11;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = threadIdx.x >> 5;
+    const int nqt = (p.Sq + kTile - 1) / kTile;
+    const int nkv = (p.Sk + kTile - 1) / kTile;
+    const int num_work = p.B * p.H * nqt;
+    constexpr int kAtoms = (HD_PAD + 63) / 64;          // 64-wide d atoms per tile
+    constexpr uint32_t kTileBytes = kAtoms * kAtomBytes;
+
+    if (warp == 4) {
+        if (elect_one()) {
+            tma_prefetch_desc(&tmQ);
+            tma_prefetch_desc(&tmK);
+            tma_prefetch_desc(&tmV);
+        }
+    } else if (warp == 5) {
+        if (elect_one()) {
+            mbar_init(q_full, 1);
+            mbar_init(q_empty, 1);
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&kv_full[i], 1);
+                mbar_init(&kv_empty[i], 1);
+                mbar_init(&s_full[i], 1);
+                mbar_init(&s_empty[i], 4);
+            }
+            mbar_init(p_full, 4);
+            mbar_init(o_full, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc<512>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_S = tmem_base;          // 2 x 128 columns
+    const uint32_t tmem_O = tmem_base + 256;    // HD_PAD columns
+
+    if (warp == 4) {
+        // ------------------------------------------------------------------ TMA producer
+        if (elect_one()) {
+            uint32_t wcount = 0, kvcount = 0;
+            for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
+                const int qt = w % nqt, bh = w / nqt;
+                const int h = bh % p.H, b = bh / p.H;
+                mbar_wait(q_empty, (wcount & 1) ^ 1);
+                mbar_arrive_expect_tx(q_full, kTileBytes);
+#pragma unroll
+                for (int a = 0; a < kAtoms; ++a)
+                    tma_load_4d(smem + AttnSmem::Q + a * kAtomBytes, &tmQ, q_full, a * 64, h, qt * kTile, b);
+                for (int j = 0; j < nkv; ++j, ++kvcount) {
+                    const int s = kvcount & 1;
+                    mbar_wait(&kv_empty[s], ((kvcount >> 1) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&kv_full[s], 2 * kTileBytes);
+#pragma unroll
+                    for (int a = 0; a < kAtoms; ++a) {
+                        tma_load_4d(smem + AttnSmem::K0 + s * 2 * kAtomBytes + a * kAtomBytes, &tmK, &kv_full[s], a * 64,
+                                    h, j * kTile, b);
+                        tma_load_4d(smem + AttnSmem::V0 + s * 2 * kAtomBytes + a * kAtomBytes, &tmV, &kv_full[s], a * 64,
+                                    h, j * kTile, b);
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (elect_one()) {
+            uint32_t wcount = 0, kvcount = 0, scount = 0, pcount = 0;
+            const uint32_t sQ = smem_u32(smem + AttnSmem::Q);
+            const uint32_t sP = smem_u32(smem + AttnSmem::P);
+            constexpr uint32_t idesc_pv = umma_idesc_bf16(HD_PAD, false, true);
+            for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
+                mbar_wait(q_full, wcount & 1);
+                tc_fence_after();
+                auto issue_s = [&](int j, uint32_t kvc, uint32_t sc) {
+                    const int s = kvc & 1, sb = sc & 1;
+                    mbar_wait(&kv_full[s], (kvc >> 1) & 1);
+                    mbar_wait(&s_empty[sb], ((sc >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const int valid = min(kTile, p.Sk - j * kTile);
+                    const int n = max(16, (valid + 15) & ~15);
+                    const uint32_t idesc = umma_idesc_bf16(n, false, false);
+                    const uint32_t sK = smem_u32(smem + AttnSmem::K0 + s * 2 * kAtomBytes);
+#pragma unroll
+                    for (int k = 0; k < HD_PAD / 16; ++k) {
+                        const uint32_t off = (k >> 2) * kAtomBytes + (k & 3) * 32;
+                        umma_bf16_ss(tmem_S + sb * 128, umma_smem_desc_sw128(sQ + off, 16, 1024),
+                                     umma_smem_desc_sw128(sK + off, 16, 1024), idesc, k != 0);
+                    }
+                    umma_commit(&s_full[sb]);
+                };
+                issue_s(0, kvcount, scount);
+                for (int j = 0; j < nkv; ++j) {
+                    if (j + 1 < nkv) issue_s(j + 1, kvcount + 1, scount + 1);
+                    const int s = kvcount & 1;
+                    mbar_wait(p_full, pcount & 1);
+                    tc_fence_after();
+                    const int valid = min(kTile, p.Sk - j * kTile);
+                    const int ksteps = (valid + 15) >> 4;
+                    const uint32_t sV = smem_u32(smem + AttnSmem::V0 + s * 2 * kAtomBytes);
+                    for (int k = 0; k < ksteps; ++k) {
+                        const uint32_t aoff = (k >> 2) * kAtomBytes + (k & 3) * 32;
+                        umma_bf16_ss(tmem_O, umma_smem_desc_sw128(sP + aoff, 16, 1024),
+                                     umma_smem_desc_sw128(sV + k * 2048, kAtomBytes, 1024), idesc_pv, k != 0);
+                    }
+                    umma_commit(&kv_empty[s]);
+                    umma_commit(o_full);
+                    ++kvcount; ++scount; ++pcount;
+                }
+                umma_commit(q_empty);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax warps (one row per thread)
+        const int r = threadIdx.x;                      // row within the tile == TMEM lane
+        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        const float sc2 = p.scale * kLog2e;
+        uint32_t scount = 0, ocount = 0;
+        uint8_t* sP = smem + AttnSmem::P;
+        for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+            const int qt = w % nqt, bh = w / nqt;
+            const int h = bh % p.H, b = bh / p.H;
+            const int qi = qt * kTile + r;
+            const bool row_ok = qi < p.Sq;
+            const float* mrow = p.mask ? p.mask + (int64_t)b * p.mask_bs + (int64_t)(row_ok ? qi : 0) * p.mask_qs : nullptr;
+            float m = -INFINITY, l = 0.f;
+            float oacc[HD_PAD];
+#pragma unroll
+            for (int i = 0; i < HD_PAD; ++i) oacc[i] = 0.f;
+
+            for (int j = 0; j < nkv; ++j, ++scount) {
+                const int sb = scount & 1;
+                const int valid = min(kTile, p.Sk - j * kTile);
+                const int nch = (valid + 31) >> 5;
+                const uint32_t tS = tmem_S + sb * 128 + lane_off;
+                mbar_wait(&s_full[sb], (scount >> 1) & 1);
+                tc_fence_after();
+                // pass 1: row max (log2 domain)
+                float mx = -INFINITY;
+                for (int c = 0; c < nch; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_x32(tS + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int col = c * 32 + i;
+                        float s = __uint_as_float(v[i]) * sc2;
+                        if (mrow) s += (col < valid ? mrow[j * kTile + col] : 0.f) * kLog2e;
+                        mx = fmaxf(mx, col < valid ? s : -INFINITY);
+                    }
+                }
+                const float m_new = fmaxf(m, mx);
+                const float alpha = exp2f(m - m_new);      // m = -inf on the first tile -> 0
+                // fold the previous tile's P V (its MMA finished long ago) before P smem is overwritten
+                if (j > 0) {
+                    mbar_wait(o_full, ocount & 1);
+                    ++ocount;
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < HD_PAD / 32; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_x32(tmem_O + lane_off + c * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) oacc[c * 32 + i] += __uint_as_float(v[i]);
+                    }
+                    if constexpr (HD_PAD % 32 != 0) {
+                        uint32_t v[16];
+                        tmem_ld_x16(tmem_O + lane_off + (HD_PAD / 32) * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) oacc[(HD_PAD / 32) * 32 + i] += __uint_as_float(v[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < HD_PAD; ++i) oacc[i] *= alpha;
+                // pass 2: p = exp2(s - m_new), row sum, bf16 P -> smem (K-major, 128B swizzle)
+                float sum = 0.f;
+                for (int c = 0; c < nch; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_x32(tS + c * 32, v);
+                    tmem_ld_wait();
+                    float pv[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int col = c * 32 + i;
+                        float s = __uint_as_float(v[i]) * sc2;
+                        if (mrow) s += (col < valid ? mrow[j * kTile + col] : 0.f) * kLog2e;
+                        const float e = (col < valid) ? exp2f(s - m_new) : 0.f;
+                        pv[i] = e;
+                        sum += e;
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int col = c * 32 + g * 8;     // first of 8 consecutive keys
+                        const int atom = col >> 6, chunk = (col & 63) >> 3;
+                        uint8_t* dst = sP + atom * kAtomBytes + r * 128 + ((chunk ^ (r & 7)) << 4);
+                        *reinterpret_cast<uint4*>(dst) =
+                            make_uint4(pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1]), pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3]),
+                                       pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]), pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]));
+                    }
+                }
+                l = l * alpha + sum;
+                m = m_new;
+                // S buffer drained; P visible to the async proxy (UMMA)
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane_id() == 0) {
+                    mbar_arrive(&s_empty[sb]);
+                    mbar_arrive(p_full);
+                }
+            }
+            // last tile's P V
+            mbar_wait(o_full, ocount & 1);
+            ++ocount;
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < HD_PAD / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_x32(tmem_O + lane_off + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) oacc[c * 32 + i] += __uint_as_float(v[i]);
+            }
+            if constexpr (HD_PAD % 32 != 0) {
+                uint32_t v[16];
+                tmem_ld_x16(tmem_O + lane_off + (HD_PAD / 32) * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) oacc[(HD_PAD / 32) * 32 + i] += __uint_as_float(v[i]);
+            }
+            tc_fence_before();
+            if (row_ok) {
+                const float inv = 1.0f / l;
+                __nv_bfloat16* orow = p.o + (int64_t)b * p.o_bs + (int64_t)qi * p.o_rs + (int64_t)h * p.o_hs;
+                // D % 8 == 0 and 16-byte aligned rows are checked on the host
+#pragma unroll
+                for (int g = 0; g < HD_PAD / 8; ++g) {
+                    if (g * 8 < p.D)
+                        *reinterpret_cast<uint4*>(orow + g * 8) = make_uint4(
+                            pack_bf16x2(oacc[g * 8 + 0] * inv, oacc[g * 8 + 1] * inv),
+                            pack_bf16x2(oacc[g * 8 + 2] * inv, oacc[g * 8 + 3] * inv),
+                            pack_bf16x2(oacc[g * 8 + 4] * inv, oacc[g * 8 + 5] * inv),
+                            pack_bf16x2(oacc[g * 8 + 6] * inv, oacc[g * 8 + 7] * inv));
+                }
+                if (p.lse) p.lse[((int64_t)b * p.H + h) * p.Sq + qi] = (m + log2f(l)) * 0.6931471805599453f;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace
+
+int make_attn_tmap(CUtensorMap* tm, const void* base, int D, int H, int S, int B, int64_t bs, int64_t rs, int64_t hs) {
+    const uint64_t dims[4] = {(uint64_t)D, (uint64_t)H, (uint64_t)S, (uint64_t)B};
+    const uint64_t strides[4] = {2, (uint64_t)hs * 2, (uint64_t)rs * 2, (uint64_t)bs * 2};
+    const uint32_t box[4] = {64, 1, 128, 1};
+    return make_tmap_bf16(tm, base, 4, dims, strides, box);
+}
+
+}  // namespace mico
+
+extern "C" int mico_attention_fwd(const MicoAttnArgs* a, void* stream_) {
+    using namespace mico;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MICO_CHECK_ARG(a && a->q && a->k && a->v && a->o);
+    MICO_CHECK_ARG(a->B > 0 && a->H > 0 && a->Sq > 0 && a->Sk > 0);
+    MICO_CHECK_ARG(a->D % 8 == 0 && a->D >= 16 && a->D <= 128);
+    for (const int64_t s : {a->q_bs, a->q_rs, a->q_hs, a->k_bs, a->k_rs, a->k_hs, a->v_bs, a->v_rs, a->v_hs, a->o_bs,
+                            a->o_rs, a->o_hs})
+        MICO_CHECK_ARG(s % 8 == 0);
+    for (const void* ptr : {a->q, a->k, a->v, (const void*)a->o})
+        MICO_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0);
+    CUtensorMap tq, tk, tv;
+    int rc;
+    if ((rc = make_attn_tmap(&tq, a->q, a->D, a->H, a->Sq, a->B, a->q_bs, a->q_rs, a->q_hs))) return rc;
+    if ((rc = make_attn_tmap(&tk, a->k, a->D, a->H, a->Sk, a->B, a->k_bs, a->k_rs, a->k_hs))) return rc;
+    if ((rc = make_attn_tmap(&tv, a->v, a->D, a->H, a->Sk, a->B, a->v_bs, a->v_rs, a->v_hs))) return rc;
+    AttnFwdParams p;
+    p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk; p.D = a->D;
+    p.scale = a->scale;
+    p.mask = a->mask; p.mask_bs = a->mask_bs; p.mask_qs = a->mask_qs;
+    p.o = reinterpret_cast<__nv_bfloat16*>(a->o); p.o_bs = a->o_bs; p.o_rs = a->o_rs; p.o_hs = a->o_hs;
+    p.lse = a->lse;
+    const int work = a->B * a->H * ceil_div(a->Sq, kTile);
+    const int grid = work < num_sms() ? work : num_sms();
+    const int hd_pad = (a->D + 15) & ~15;
+    auto launch = [&](auto kern) -> int {
+        MICO_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
+        kern<<<grid, kAttThreads, AttnSmem::TOTAL, stream>>>(tq, tk, tv, p);
+        MICO_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+        return MICO_OK;
+    };
+    switch (hd_pad) {
+        case 32: return launch(attn_fwd_kernel<32>);
+        case 64: return launch(attn_fwd_kernel<64>);
+        case 96: return launch(attn_fwd_kernel<96>);
+        case 128: return launch(attn_fwd_kernel<128>);
+        default:
+            set_last_error(__FILE__, __LINE__, "head_dim must pad to 32, 64, 96 or 128");
+            return MICO_ERR_UNSUPPORTED;
+    }
+}

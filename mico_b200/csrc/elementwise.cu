@@ -1,0 +1,242 @@
+// mico_b200 -- HBM-bound helper kernels of the ViT/BERT path (coalesced 128-bit accesses).
+//
+//   mico_cast_f32_to_bf16   fp32 master weights -> bf16 GEMM operands (once per optimizer step)
+//   mico_colsum_bf16        bias gradients: out[n] = sum_m x[m,n]            (nn.Linear bias backward)
+//   mico_batch_sum_f32      d pos_embed / d cls_token: out[r] = sum_b x[b,r] (eva_vit_model.py:615-619 backward)
+//   mico_patchify           K1 im2col: (B,C,H,W) fp32 -> bf16 [B*gh*gw, Kpad]   (eva_vit_model.py:440-447)
+//   mico_cls_pos_row        token 0 = cls_token + pos_embed[0]                  (eva_vit_model.py:615-619)
+//   mico_scale_cast_bf16    bf16(x * row_scale[row/rpg])  (gradient entering a DropPath'd residual branch)
+#include "common.cuh"
+#include "host_utils.h"
+
+namespace mico {
+namespace {
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+    const int64_t nvec = n >> 3;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        const float4 a = reinterpret_cast<const float4*>(src)[2 * i];
+        const float4 b = reinterpret_cast<const float4*>(src)[2 * i + 1];
+        reinterpret_cast<uint4*>(dst)[i] = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w),
+                                                      pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+    }
+    // tail
+    for (int64_t i = (nvec << 3) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = __float2bfloat16(src[i]);
+}
+
+// grid: (ceil(N/256), splits); block 256 = 8 warps; lane owns 8 consecutive columns.
+constexpr int kColsumCols = 256;
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int M, int N, float* __restrict__ partials) {
+    __shared__ float red[8][kColsumCols];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col = blockIdx.x * kColsumCols + lane * 8;
+    const int rows_per_split = (M + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * rows_per_split;
+    const int r1 = min(M, r0 + rows_per_split);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (col + 8 <= N) {
+        for (int r = r0 + warp; r < r1; r += 8) {
+            const uint4 u = *reinterpret_cast<const uint4*>(x + (int64_t)r * ldx + col);
+            acc[0] += bf16_lo(u.x); acc[1] += bf16_hi(u.x); acc[2] += bf16_lo(u.y); acc[3] += bf16_hi(u.y);
+            acc[4] += bf16_lo(u.z); acc[5] += bf16_hi(u.z); acc[6] += bf16_lo(u.w); acc[7] += bf16_hi(u.w);
+        }
+    } else {
+        for (int r = r0 + warp; r < r1; r += 8)
+            for (int j = 0; j < 8; ++j)
+                if (col + j < N) acc[j] += __bfloat162float(x[(int64_t)r * ldx + col + j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+    __syncthreads();
+    const int c = blockIdx.x * kColsumCols + threadIdx.x;
+    if (c < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        partials[(size_t)blockIdx.y * N + c] = s;
+    }
+}
+
+__global__ void colsum_finalize_kernel(const float* __restrict__ partials, int splits, int N, float* __restrict__ out,
+                                       int accumulate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    float s = 0.f;
+    for (int i = 0; i < splits; ++i) s += partials[(size_t)i * N + c];
+    out[c] = accumulate ? out[c] + s : s;
+}
+
+// out[r] (+)= sum_b x[b*R + r]; R % 4 == 0
+__global__ void batch_sum_f32_kernel(const float* __restrict__ x, int B, int64_t R, float* __restrict__ out,
+                                     int accumulate) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= R) return;
+    float4 s = make_float4(0, 0, 0, 0);
+    for (int b = 0; b < B; ++b) {
+        const float4 v = *reinterpret_cast<const float4*>(x + (int64_t)b * R + i);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    float4* o = reinterpret_cast<float4*>(out + i);
+    if (accumulate) { const float4 p = *o; s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w; }
+    *o = s;
+}
+
+// One block per (image, patch-row): stage C x P x W pixels through smem, emit gw patch rows of Kpad bf16.
+// Column order within a patch row is (c, ky, kx) == Conv2d weight.view(out, C*P*P).
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float* __restrict__ img, int64_t img_stride, int64_t chan_stride, int C, int H, int W, int P,
+                int Kpad, __nv_bfloat16* __restrict__ out) {
+    extern __shared__ float ps[];   // [C*P][W]
+    const int gw = W / P, gh = H / P;
+    const int b = blockIdx.x / gh, py = blockIdx.x % gh;
+    const float* src = img + (int64_t)b * img_stride;
+    const int rows = C * P;
+    for (int idx = threadIdx.x; idx < rows * W; idx += blockDim.x) {
+        const int rr = idx / W, xx = idx - rr * W;
+        const int c = rr / P, ky = rr - c * P;
+        ps[idx] = src[(int64_t)c * chan_stride + (int64_t)(py * P + ky) * W + xx];
+    }
+    __syncthreads();
+    const int K = C * P * P;
+    __nv_bfloat16* dst = out + ((int64_t)(b * gh + py) * gw) * Kpad;
+    for (int idx = threadIdx.x; idx < gw * (Kpad / 2); idx += blockDim.x) {
+        const int px = idx / (Kpad / 2);
+        const int k = (idx - px * (Kpad / 2)) * 2;
+        float v0 = 0.f, v1 = 0.f;
+        if (k < K) {
+            const int rr = k / P, kx = k - rr * P;
+            v0 = ps[rr * W + px * P + kx];
+        }
+        if (k + 1 < K) {
+            const int rr = (k + 1) / P, kx = (k + 1) - rr * P;
+            v1 = ps[rr * W + px * P + kx];
+        }
+        *reinterpret_cast<uint32_t*>(dst + (int64_t)px * Kpad + k) = pack_bf16x2(v0, v1);
+    }
+}
+
+__global__ void cls_pos_row_kernel(const float* __restrict__ cls, const float* __restrict__ pos0, float* __restrict__ x,
+                                   int64_t sample_stride, int B, int D) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * D) return;
+    const int b = i / D, d = i - b * D;
+    x[(int64_t)b * sample_stride + d] = cls[d] + pos0[d];
+}
+
+__global__ void scale_cast_bf16_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ row_scale,
+                                       int rows_per_group, __nv_bfloat16* __restrict__ y, int64_t ldy, int M, int D) {
+    const int nvec = D >> 2;
+    const int64_t total = (int64_t)M * nvec;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(i / nvec), c = (int)(i - (int64_t)row * nvec) * 4;
+        const float s = row_scale ? row_scale[row / rows_per_group] : 1.0f;
+        const float4 v = *reinterpret_cast<const float4*>(x + (int64_t)row * ldx + c);
+        *reinterpret_cast<uint2*>(y + (int64_t)row * ldy + c) =
+            make_uint2(pack_bf16x2(v.x * s, v.y * s), pack_bf16x2(v.z * s, v.w * s));
+    }
+}
+
+int colsum_splits(int M, int N) {
+    const int colblocks = ceil_div(N, kColsumCols);
+    int s = ceil_div(num_sms() * 4, colblocks);
+    const int maxs = ceil_div(M, 64);
+    if (s > maxs) s = maxs;
+    return s < 1 ? 1 : s;
+}
+
+}  // namespace
+}  // namespace mico
+
+extern "C" int mico_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream_) {
+    using namespace mico;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MICO_CHECK_ARG(src && dst && n > 0);
+    MICO_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    int64_t want = (n / 8 + 255) / 256;
+    const int grid = (int)(want < 1 ? 1 : (want > num_sms() * 16 ? num_sms() * 16 : want));
+    cast_f32_bf16_kernel<<<grid, 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return MICO_OK;
+}
+
+extern "C" size_t mico_colsum_workspace(int M, int N) { return (size_t)mico::colsum_splits(M, N) * N * sizeof(float); }
+
+extern "C" int mico_colsum_bf16(const void* x, int64_t ldx, int M, int N, float* out, int accumulate, void* workspace,
+                                size_t ws_bytes, void* stream_) {
+    using namespace mico;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MICO_CHECK_ARG(x && out && workspace && M > 0 && N > 0);
+    MICO_CHECK_ARG(ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    const int splits = colsum_splits(M, N);
+    MICO_CHECK_ARG(ws_bytes >= (size_t)splits * N * sizeof(float));
+    dim3 grid(ceil_div(N, kColsumCols), splits);
+    colsum_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, N,
+                                                 reinterpret_cast<float*>(workspace));
+    MICO_CHECK_CUDA(cudaGetLastError());
+    colsum_finalize_kernel<<<ceil_div(N, 256), 256, 0, stream>>>(reinterpret_cast<const float*>(workspace), splits, N,
+                                                                out, accumulate);
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch(2);
+    return MICO_OK;
+}
+
+extern "C" int mico_batch_sum_f32(const float* x, int B, int64_t R, float* out, int accumulate, void* stream_) {
+    using namespace mico;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MICO_CHECK_ARG(x && out && B > 0 && R > 0 && R % 4 == 0);
+    batch_sum_f32_kernel<<<(int)((R / 4 + 255) / 256), 256, 0, stream>>>(x, B, R, out, accumulate);
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return MICO_OK;
+}
+
+extern "C" int mico_patchify(const float* img, int64_t img_stride, int64_t chan_stride, int B, int C, int H, int W,
+                             int P, int Kpad, void* out, void* stream_) {
+    using namespace mico;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MICO_CHECK_ARG(img && out && B > 0 && C > 0 && P > 0 && H % P == 0 && W % P == 0);
+    MICO_CHECK_ARG(Kpad >= C * P * P && Kpad % 8 == 0);
+    const size_t smem = (size_t)C * P * W * sizeof(float);
+    MICO_CHECK_ARG(smem <= 200 * 1024);
+    static bool attr = false;
+    if (smem > 48 * 1024 && !attr) {
+        MICO_CHECK_CUDA(cudaFuncSetAttribute(patchify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    patchify_kernel<<<B * (H / P), 256, smem, stream>>>(img, img_stride, chan_stride, C, H, W, P, Kpad,
+                                                        reinterpret_cast<__nv_bfloat16*>(out));
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return MICO_OK;
+}
+
+extern "C" int mico_cls_pos_row(const float* cls_token, const float* pos0, float* x, int64_t sample_stride, int B, int D,
+                                void* stream_) {
+    using namespace mico;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MICO_CHECK_ARG(cls_token && pos0 && x && B > 0 && D > 0);
+    cls_pos_row_kernel<<<ceil_div(B * D, 256), 256, 0, stream>>>(cls_token, pos0, x, sample_stride, B, D);
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return MICO_OK;
+}
+
+extern "C" int mico_scale_cast_bf16(const float* x, int64_t ldx, const float* row_scale, int rows_per_group, void* y,
+                                    int64_t ldy, int M, int D, void* stream_) {
+    using namespace mico;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MICO_CHECK_ARG(x && y && M > 0 && D > 0 && D % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0);
+    MICO_CHECK_ARG(!(row_scale && rows_per_group <= 0));
+    const int64_t total = (int64_t)M * (D / 4);
+    int64_t want = (total + 255) / 256;
+    const int grid = (int)(want > num_sms() * 16 ? num_sms() * 16 : want);
+    scale_cast_bf16_kernel<<<grid, 256, 0, stream>>>(x, ldx, row_scale, rows_per_group,
+                                                     reinterpret_cast<__nv_bfloat16*>(y), ldy, M, D);
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return MICO_OK;
+}

@@ -1,0 +1,239 @@
+// mico_b200 -- K2: LayerNorm forward / backward (HBM-bound; one warp per row, 128-bit accesses).
+//
+// Replaces torch LayerNorm at eva_vit_model.py:375,382,542 (eps 1e-6), bert.py:92,290,368,583 and
+// mico.py:49,400-403 (eps 1e-12), swin.py:212,218,329,565 (eps 1e-5).
+//
+// forward : y = (x - mean) * rstd * gamma + beta, statistics in fp32, two-pass (mean, then centred
+//           variance) with the row held in registers; writes bf16 (next GEMM operand) and/or fp32.
+// backward: dx = [dres +] rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy * gamma
+//           optionally also emits bf16(dx * row_scale[row / rows_per_group]) -- the operand of the
+//           upstream linear's dgrad/wgrad (DropPath scale folded in);
+//           dgamma/dbeta: per-warp shared-memory accumulators -> per-block partials in a caller
+//           workspace -> deterministic finalize kernel (no atomics).
+#include "common.cuh"
+#include "host_utils.h"
+
+namespace mico {
+namespace {
+
+constexpr int kLnWarps = 4;
+constexpr int kLnThreads = kLnWarps * 32;
+constexpr int kMaxVec = 12;   // float4 per lane kept in registers: D <= 12*32*4 = 1536
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(kLnThreads)
+ln_fwd_kernel(const TIn* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
+              const float* __restrict__ beta, __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32,
+              int64_t ldy, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int D, float eps) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nvec = D >> 2;
+    for (int row = blockIdx.x * kLnWarps + warp; row < M; row += gridDim.x * kLnWarps) {
+        const TIn* xr = x + (int64_t)row * ldx;
+        float4 v[kMaxVec];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMaxVec; ++j) {
+            const int i = lane + 32 * j;
+            if (i < nvec) {
+                v[j] = ld4(xr + 4 * i);
+                s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+            }
+        }
+        const float mean = warp_sum(s) / (float)D;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMaxVec; ++j) {
+            const int i = lane + 32 * j;
+            if (i < nvec) {
+                const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+                q += (a * a + b * b) + (c * c + d * d);
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+        if (lane == 0) {
+            if (mean_out) mean_out[row] = mean;
+            if (rstd_out) rstd_out[row] = rstd;
+        }
+#pragma unroll
+        for (int j = 0; j < kMaxVec; ++j) {
+            const int i = lane + 32 * j;
+            if (i < nvec) {
+                const float4 g = ld4(gamma + 4 * i), b = ld4(beta + 4 * i);
+                float4 o;
+                o.x = (v[j].x - mean) * rstd * g.x + b.x;
+                o.y = (v[j].y - mean) * rstd * g.y + b.y;
+                o.z = (v[j].z - mean) * rstd * g.z + b.z;
+                o.w = (v[j].w - mean) * rstd * g.w + b.w;
+                if (y_bf16) st4(y_bf16 + (int64_t)row * ldy + 4 * i, o);
+                if (y_f32) st4(y_f32 + (int64_t)row * ldy + 4 * i, o);
+            }
+        }
+    }
+}
+
+// dynamic smem: [kLnWarps][2][D] floats (dgamma, dbeta per warp)
+template <typename TDy>
+__global__ void __launch_bounds__(kLnThreads)
+ln_bwd_kernel(const TDy* __restrict__ dy, int64_t lddy, const float* __restrict__ x, int64_t ldx,
+              const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+              const float* __restrict__ dres, int64_t lddres, float* __restrict__ dx, int64_t lddx,
+              __nv_bfloat16* __restrict__ dx_bf16, int64_t lddxb, const float* __restrict__ row_scale,
+              int rows_per_group, float* __restrict__ partials, int M, int D) {
+    extern __shared__ float ln_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nvec = D >> 2;
+    float* sg = ln_smem + (size_t)warp * 2 * D;
+    float* sb = sg + D;
+    for (int i = lane; i < 2 * D; i += 32) sg[i] = 0.f;
+    __syncwarp();
+    for (int row = blockIdx.x * kLnWarps + warp; row < M; row += gridDim.x * kLnWarps) {
+        const float mu = mean[row], rs = rstd[row];
+        const TDy* dyr = dy + (int64_t)row * lddy;
+        const float* xr = x + (int64_t)row * ldx;
+        float4 g[kMaxVec], xh[kMaxVec];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMaxVec; ++j) {
+            const int i = lane + 32 * j;
+            if (i < nvec) {
+                const float4 d = ld4(dyr + 4 * i);
+                const float4 xv = ld4(xr + 4 * i);
+                const float4 gm = ld4(gamma + 4 * i);
+                xh[j] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+                // parameter gradients: this lane always owns the same columns -> race-free smem RMW
+                float4 ag = ld4(sg + 4 * i), ab = ld4(sb + 4 * i);
+                ag.x += d.x * xh[j].x; ag.y += d.y * xh[j].y; ag.z += d.z * xh[j].z; ag.w += d.w * xh[j].w;
+                ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+                st4(sg + 4 * i, ag);
+                st4(sb + 4 * i, ab);
+                g[j] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+                s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+                s2 += (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
+            }
+        }
+        const float m1 = warp_sum(s1) / (float)D;
+        const float m2 = warp_sum(s2) / (float)D;
+        const float sc = row_scale ? row_scale[row / rows_per_group] : 1.0f;
+#pragma unroll
+        for (int j = 0; j < kMaxVec; ++j) {
+            const int i = lane + 32 * j;
+            if (i < nvec) {
+                float4 o;
+                o.x = rs * (g[j].x - m1 - xh[j].x * m2);
+                o.y = rs * (g[j].y - m1 - xh[j].y * m2);
+                o.z = rs * (g[j].z - m1 - xh[j].z * m2);
+                o.w = rs * (g[j].w - m1 - xh[j].w * m2);
+                if (dres) {
+                    const float4 r = ld4(dres + (int64_t)row * lddres + 4 * i);
+                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                }
+                if (dx) st4(dx + (int64_t)row * lddx + 4 * i, o);
+                if (dx_bf16)
+                    st4(dx_bf16 + (int64_t)row * lddxb + 4 * i, make_float4(o.x * sc, o.y * sc, o.z * sc, o.w * sc));
+            }
+        }
+    }
+    __syncthreads();
+    // block partial = sum over warps -> partials[block][2][D]
+    float* out = partials + (size_t)blockIdx.x * 2 * D;
+    for (int i = threadIdx.x; i < 2 * D; i += kLnThreads) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLnWarps; ++w) a += ln_smem[(size_t)w * 2 * D + i];
+        out[i] = a;
+    }
+}
+
+__global__ void ln_bwd_finalize_kernel(const float* __restrict__ partials, int nblocks, int D,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over 2*D
+    if (i >= 2 * D) return;
+    float a = 0.f;
+    for (int b = 0; b < nblocks; ++b) a += partials[(size_t)b * 2 * D + i];
+    float* dst = (i < D) ? (dgamma + i) : (dbeta + (i - D));
+    *dst = accumulate ? (*dst + a) : a;
+}
+
+int ln_bwd_grid(int M) {
+    const int want = ceil_div(M, kLnWarps);
+    const int cap = num_sms() * 4;
+    return want < cap ? want : cap;
+}
+
+}  // namespace
+}  // namespace mico
+
+extern "C" int mico_layernorm_fwd(const void* x, int x_is_bf16, int64_t ldx, const float* gamma, const float* beta,
+                                  void* y_bf16, float* y_f32, int64_t ldy, float* mean, float* rstd, int M, int D,
+                                  float eps, void* stream_) {
+    using namespace mico;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MICO_CHECK_ARG(x && gamma && beta && (y_bf16 || y_f32));
+    MICO_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= kMaxVec * 128);
+    MICO_CHECK_ARG(ldx % 4 == 0 && ldy % 4 == 0);
+    const int want = ceil_div(M, kLnWarps);
+    const int grid = want < num_sms() * 16 ? want : num_sms() * 16;
+    if (x_is_bf16)
+        ln_fwd_kernel<__nv_bfloat16><<<grid, kLnThreads, 0, stream>>>(
+            reinterpret_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32,
+            ldy, mean, rstd, M, D, eps);
+    else
+        ln_fwd_kernel<float><<<grid, kLnThreads, 0, stream>>>(reinterpret_cast<const float*>(x), ldx, gamma, beta,
+                                                              reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, ldy,
+                                                              mean, rstd, M, D, eps);
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return MICO_OK;
+}
+
+extern "C" size_t mico_layernorm_bwd_workspace(int M, int D) {
+    return (size_t)mico::ln_bwd_grid(M) * 2 * (size_t)D * sizeof(float);
+}
+
+extern "C" int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, const float* x, int64_t ldx,
+                                  const float* mean, const float* rstd, const float* gamma, const float* dres,
+                                  int64_t lddres, float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb,
+                                  const float* row_scale, int rows_per_group, float* dgamma, float* dbeta,
+                                  int accumulate_param_grads, int M, int D, void* workspace, size_t ws_bytes,
+                                  void* stream_) {
+    using namespace mico;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MICO_CHECK_ARG(dy && x && mean && rstd && gamma && dgamma && dbeta && workspace);
+    MICO_CHECK_ARG(dx || dx_bf16);
+    MICO_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= kMaxVec * 128);
+    MICO_CHECK_ARG(lddy % 4 == 0 && ldx % 4 == 0 && lddx % 4 == 0 && lddxb % 4 == 0 && lddres % 4 == 0);
+    MICO_CHECK_ARG(!(row_scale && rows_per_group <= 0));
+    MICO_CHECK_ARG(ws_bytes >= mico_layernorm_bwd_workspace(M, D));
+    const int grid = ln_bwd_grid(M);
+    const size_t smem = (size_t)kLnWarps * 2 * D * sizeof(float);
+    float* partials = reinterpret_cast<float*>(workspace);
+    if (dy_is_bf16) {
+        auto k = ln_bwd_kernel<__nv_bfloat16>;
+        if (smem > 48 * 1024) MICO_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kLnThreads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, x, ldx, mean, rstd, gamma,
+                                              dres, lddres, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), lddxb,
+                                              row_scale, rows_per_group, partials, M, D);
+    } else {
+        auto k = ln_bwd_kernel<float>;
+        if (smem > 48 * 1024) MICO_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kLnThreads, smem, stream>>>(reinterpret_cast<const float*>(dy), lddy, x, ldx, mean, rstd, gamma, dres,
+                                              lddres, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), lddxb,
+                                              row_scale, rows_per_group, partials, M, D);
+    }
+    MICO_CHECK_CUDA(cudaGetLastError());
+    ln_bwd_finalize_kernel<<<ceil_div(2 * D, 256), 256, 0, stream>>>(partials, grid, D, dgamma, dbeta,
+                                                                    accumulate_param_grads);
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch(2);
+    return MICO_OK;
+}

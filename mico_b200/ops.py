@@ -88,3 +88,181 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, r
         g.residual_bcast = int(residual_bcast)
     check(lib.mico_gemm_bf16(C.byref(g), _stream()), "mico_gemm_bf16")
     return out
+
+
+# ----------------------------------------------------------------------------- attention
+def _bhsd_strides(t):
+    """t: 4-D view indexed [b, s, h, d] (any strides, d contiguous) -> (ptr, bs, rs, hs)."""
+    if t.dim() != 4 or t.stride(3) != 1:
+        raise MicoError("attention operands must be 4-D [B,S,H,D] views with contiguous D")
+    return t.data_ptr(), t.stride(0), t.stride(1), t.stride(2)
+
+
+def _attn_args(q, k, v, o, lse, mask, scale):
+    a = _lib.AttnArgs()
+    B, Sq, H, D = q.shape
+    Sk = k.shape[1]
+    for name, t in (("q", q), ("k", k), ("v", v), ("o", o)):
+        _req(t, BF16, name)
+    a.q, a.q_bs, a.q_rs, a.q_hs = _bhsd_strides(q)
+    a.k, a.k_bs, a.k_rs, a.k_hs = _bhsd_strides(k)
+    a.v, a.v_bs, a.v_rs, a.v_hs = _bhsd_strides(v)
+    a.o, a.o_bs, a.o_rs, a.o_hs = _bhsd_strides(o)
+    if lse is not None:
+        _req(lse, F32, "lse")
+        a.lse = lse.data_ptr()
+    if mask is not None:
+        _req(mask, F32, "mask")
+        if mask.dim() == 2:      # [B, Sk] key padding mask
+            a.mask, a.mask_bs, a.mask_qs = mask.data_ptr(), mask.stride(0), 0
+        elif mask.dim() == 3:    # [B, Sq, Sk]
+            a.mask, a.mask_bs, a.mask_qs = mask.data_ptr(), mask.stride(0), mask.stride(1)
+        else:
+            raise MicoError("mask must be [B,Sk] or [B,Sq,Sk] additive fp32")
+    a.B, a.H, a.Sq, a.Sk, a.D = B, H, Sq, Sk, D
+    a.scale = float(scale)
+    return a
+
+
+def attention_fwd(q, k, v, scale, mask=None, out=None, need_lse=True):
+    """q,k,v: bf16 views [B,S,H,D] (e.g. slices of a fused qkv buffer). Returns (o [B,Sq,H,D], lse [B,H,Sq])."""
+    B, Sq, H, D = q.shape
+    if out is None:
+        out = torch.empty((B, Sq, H, D), device=q.device, dtype=BF16)
+    lse = torch.empty((B, H, Sq), device=q.device, dtype=F32) if need_lse else None
+    a = _attn_args(q, k, v, out, lse, mask, scale)
+    check(lib.mico_attention_fwd(C.byref(a), _stream()), "mico_attention_fwd")
+    return out, lse
+
+
+def attention_bwd(q, k, v, o, lse, dout, scale, mask=None, dq=None, dk=None, dv=None):
+    B, Sq, H, D = q.shape
+    Sk = k.shape[1]
+    dq = torch.empty((B, Sq, H, D), device=q.device, dtype=BF16) if dq is None else dq
+    dk = torch.empty((B, Sk, H, D), device=q.device, dtype=BF16) if dk is None else dk
+    dv = torch.empty((B, Sk, H, D), device=q.device, dtype=BF16) if dv is None else dv
+    delta = torch.empty((B, H, Sq), device=q.device, dtype=F32)
+    a = _attn_args(q, k, v, o, lse, mask, scale)
+    _req(dout, BF16, "dout")
+    a.dout, a.do_bs, a.do_rs, a.do_hs = _bhsd_strides(dout)
+    a.delta = delta.data_ptr()
+    a.dq, a.dq_bs, a.dq_rs, a.dq_hs = _bhsd_strides(dq)
+    a.dk, a.dk_bs, a.dk_rs, a.dk_hs = _bhsd_strides(dk)
+    a.dv, a.dv_bs, a.dv_rs, a.dv_hs = _bhsd_strides(dv)
+    check(lib.mico_attention_bwd(C.byref(a), _stream()), "mico_attention_bwd")
+    return dq, dk, dv
+
+
+# ----------------------------------------------------------------------------- layernorm
+_ws_cache = {}
+
+
+def workspace(nbytes, device):
+    """Grow-only scratch buffer per device (stream-ordered reuse on the current stream)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), device=device, dtype=torch.uint8)
+        _ws_cache[key] = buf
+    return buf
+
+
+def layernorm_fwd(x, gamma, beta, eps, out_bf16=True, out_f32=False, save_stats=True):
+    """x: [M,D] fp32 or bf16.  Returns (y_bf16|None, y_f32|None, mean|None, rstd|None)."""
+    M, D = x.shape
+    if x.dtype not in (F32, BF16):
+        raise MicoError("layernorm: x must be fp32 or bf16")
+    _req(gamma, F32, "gamma")
+    _req(beta, F32, "beta")
+    yb = torch.empty((M, D), device=x.device, dtype=BF16) if out_bf16 else None
+    yf = torch.empty((M, D), device=x.device, dtype=F32) if out_f32 else None
+    mean = torch.empty(M, device=x.device, dtype=F32) if save_stats else None
+    rstd = torch.empty(M, device=x.device, dtype=F32) if save_stats else None
+    check(lib.mico_layernorm_fwd(_ptr(x), int(x.dtype == BF16), C.c_int64(x.stride(0)), _ptr(gamma), _ptr(beta),
+                                 _ptr(yb), _ptr(yf), C.c_int64(D), _ptr(mean), _ptr(rstd), M, D, C.c_float(eps),
+                                 _stream()), "mico_layernorm_fwd")
+    return yb, yf, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, dres=None, want_f32=True, want_bf16=False,
+                  row_scale=None, rows_per_group=0, accumulate=False):
+    """Returns (dx_f32|None, dx_bf16|None); writes dgamma/dbeta (fp32 [D])."""
+    M, D = x.shape
+    _req(x, F32, "x")
+    dx = torch.empty((M, D), device=x.device, dtype=F32) if want_f32 else None
+    dxb = torch.empty((M, D), device=x.device, dtype=BF16) if want_bf16 else None
+    nws = lib.mico_layernorm_bwd_workspace(M, D)
+    ws = workspace(nws, x.device)
+    check(lib.mico_layernorm_bwd(_ptr(dy), int(dy.dtype == BF16), C.c_int64(dy.stride(0)), _ptr(x), C.c_int64(x.stride(0)),
+                                 _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres),
+                                 C.c_int64(dres.stride(0) if dres is not None else 0), _ptr(dx), C.c_int64(D), _ptr(dxb),
+                                 C.c_int64(D), _ptr(row_scale), int(rows_per_group), _ptr(dgamma), _ptr(dbeta),
+                                 int(accumulate), M, D, _ptr(ws), C.c_size_t(ws.numel()), _stream()),
+          "mico_layernorm_bwd")
+    return dx, dxb
+
+
+# ----------------------------------------------------------------------------- helpers
+def cast_bf16(src, dst=None):
+    _req(src, F32, "src")
+    if not src.is_contiguous():
+        raise MicoError("cast_bf16: src must be contiguous")
+    if dst is None:
+        dst = torch.empty(src.shape, device=src.device, dtype=BF16)
+    check(lib.mico_cast_f32_to_bf16(_ptr(src), _ptr(dst), C.c_int64(src.numel()), _stream()), "mico_cast_f32_to_bf16")
+    return dst
+
+
+def colsum(x, out=None, accumulate=False):
+    _req(x, BF16, "x")
+    M, N = x.shape
+    if out is None:
+        out = torch.empty(N, device=x.device, dtype=F32)
+    ws = workspace(lib.mico_colsum_workspace(M, N), x.device)
+    check(lib.mico_colsum_bf16(_ptr(x), C.c_int64(x.stride(0)), M, N, _ptr(out), int(accumulate), _ptr(ws),
+                               C.c_size_t(ws.numel()), _stream()), "mico_colsum_bf16")
+    return out
+
+
+def batch_sum(x, B, out=None, accumulate=False):
+    """x: fp32 contiguous, viewed as [B, R] -> out[R]."""
+    _req(x, F32, "x")
+    R = x.numel() // B
+    if out is None:
+        out = torch.empty(R, device=x.device, dtype=F32)
+    check(lib.mico_batch_sum_f32(_ptr(x), B, C.c_int64(R), _ptr(out), int(accumulate), _stream()), "mico_batch_sum_f32")
+    return out
+
+
+def patchify(img, P, Kpad, replicate_channel=False, out=None):
+    """img: fp32 [B,C,H,W] contiguous (or [B,H,W] with replicate_channel -> 3 identical channels)."""
+    _req(img, F32, "img")
+    if replicate_channel:
+        B, H, W = img.shape
+        Cc, img_stride, chan_stride = 3, img.stride(0), 0
+    else:
+        B, Cc, H, W = img.shape
+        img_stride, chan_stride = img.stride(0), img.stride(1)
+    if img.stride(-1) != 1 or img.stride(-2) != W:
+        raise MicoError("patchify: image rows must be contiguous")
+    rows = B * (H // P) * (W // P)
+    if out is None:
+        out = torch.empty((rows, Kpad), device=img.device, dtype=BF16)
+    check(lib.mico_patchify(_ptr(img), C.c_int64(img_stride), C.c_int64(chan_stride), B, Cc, H, W, P, Kpad, _ptr(out),
+                            _stream()), "mico_patchify")
+    return out
+
+
+def cls_pos_row(cls_token, pos0, x, B, T, D):
+    """x: fp32 [B*T, D]; writes rows b*T with cls_token + pos0."""
+    check(lib.mico_cls_pos_row(_ptr(cls_token), _ptr(pos0), _ptr(x), C.c_int64(T * D), B, D, _stream()), "mico_cls_pos_row")
+
+
+def scale_cast_bf16(x, row_scale=None, rows_per_group=0, out=None):
+    _req(x, F32, "x")
+    M, D = x.shape
+    if out is None:
+        out = torch.empty((M, D), device=x.device, dtype=BF16)
+    check(lib.mico_scale_cast_bf16(_ptr(x), C.c_int64(x.stride(0)), _ptr(row_scale), int(rows_per_group), _ptr(out),
+                                   C.c_int64(out.stride(0)), M, D, _stream()), "mico_scale_cast_bf16")
+    return out

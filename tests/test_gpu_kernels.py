@@ -1,0 +1,131 @@
+"""GPU parity for the non-GEMM kernels: attention fwd, LayerNorm fwd/bwd, helpers.
+References are plain PyTorch fp32 ops on the same (bf16-rounded) inputs.
+Tolerances: bf16 outputs 4e-3 rel-L2 (one bf16 rounding of P and of the result), fp32 outputs 1e-5."""
+import math
+
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _randn(shape, seed, scale=1.0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).cuda()
+
+
+def _attn_ref(q, k, v, scale, mask=None):
+    # q,k,v: [B,S,H,D] fp32
+    s = torch.einsum("bihd,bjhd->bhij", q, k) * scale
+    if mask is not None:
+        s = s + (mask[:, None, None, :] if mask.dim() == 2 else mask[:, None])
+    p = s.softmax(-1)
+    o = torch.einsum("bhij,bjhd->bihd", p, v)
+    return o, torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("B,H,S,D", [(2, 2, 257, 88), (1, 3, 128, 64), (2, 4, 49, 32), (1, 2, 300, 128),
+                                     (3, 16, 257, 88)])
+def test_attention_fwd_fused_qkv(B, H, S, D):
+    from mico_b200 import ops
+    qkv = _randn((B, S, 3, H, D), 1, 1.0, torch.bfloat16)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    scale = D ** -0.5
+    o, lse = ops.attention_fwd(q, k, v, scale)
+    ro, rl = _attn_ref(q.float(), k.float(), v.float(), scale)
+    torch.cuda.synchronize()
+    print(f"attn fwd B{B} H{H} S{S} D{D}: o rel={rel_l2(o, ro):.3e} lse rel={rel_l2(lse, rl):.3e}")
+    assert rel_l2(o, ro) < 4e-3
+    assert rel_l2(lse, rl) < 1e-5
+
+
+@pytest.mark.parametrize("Sq,Sk,three_d", [(128, 257, False), (40, 40, True), (70, 2056, False), (128, 128, True)])
+def test_attention_fwd_bert_masks(Sq, Sk, three_d):
+    """BERT: separate q / k / v projections, additive -10000 masks (bert.py:260, 697-781)."""
+    from mico_b200 import ops
+    B, H, D = 3, 12, 64
+    q = _randn((B, Sq, H, D), 2, 1.0, torch.bfloat16)
+    k = _randn((B, Sk, H, D), 3, 1.0, torch.bfloat16)
+    v = _randn((B, Sk, H, D), 4, 1.0, torch.bfloat16)
+    g = torch.Generator().manual_seed(5)
+    lens = torch.randint(max(1, Sk // 2), Sk + 1, (B,), generator=g)
+    keep = (torch.arange(Sk)[None, :] < lens[:, None]).float()
+    if three_d:
+        keep = torch.tril(keep[:, None, :].expand(B, Sq, Sk))
+    mask = ((1.0 - keep) * -10000.0).cuda()
+    scale = 1.0 / math.sqrt(D)
+    o, lse = ops.attention_fwd(q, k, v, scale, mask=mask)
+    ro, rl = _attn_ref(q.float(), k.float(), v.float(), scale, mask)
+    assert rel_l2(o, ro) < 4e-3
+    assert rel_l2(lse, rl) < 1e-5
+
+
+@pytest.mark.parametrize("M,D,eps", [(514, 1408, 1e-6), (384, 768, 1e-12), (100, 176, 1e-6), (49 * 4, 128, 1e-5)])
+def test_layernorm_fwd_bwd(M, D, eps):
+    from mico_b200 import ops
+    x = _randn((M, D), 1) * 3 + 0.5
+    gamma = 1 + _randn((D,), 2, 0.1)
+    beta = _randn((D,), 3, 0.1)
+    yb, yf, mean, rstd = ops.layernorm_fwd(x, gamma, beta, eps, out_bf16=True, out_f32=True)
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (D,), gr, br, eps)
+    assert rel_l2(yf, ref) < 1e-5
+    assert rel_l2(yb, ref) < 3e-3
+    assert rel_l2(mean, x.mean(-1)) < 1e-5
+    dy = _randn((M, D), 4)
+    dres = _randn((M, D), 5)
+    ref.backward(dy)
+    dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+    T = 7 if M % 7 == 0 else 1
+    rs = torch.rand(M // T, device="cuda") + 0.5
+    dx, dxb = ops.layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=dres, want_f32=True, want_bf16=True,
+                                row_scale=rs, rows_per_group=T)
+    assert rel_l2(dx, xr.grad + dres) < 1e-5
+    assert rel_l2(dxb, (xr.grad + dres) * rs.repeat_interleave(T)[:, None]) < 3e-3
+    assert rel_l2(dgamma, gr.grad) < 1e-5
+    assert rel_l2(dbeta, br.grad) < 1e-5
+    # bf16 dy + accumulate
+    dyb = dy.to(torch.bfloat16)
+    dg2, db2 = dgamma.clone(), dbeta.clone()
+    ops.layernorm_bwd(dyb, x, mean, rstd, gamma, dg2, db2, accumulate=True)
+    xr2 = x.clone().requires_grad_(True)
+    g2 = gamma.clone().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr2, (D,), g2, beta, eps).backward(dyb.float())
+    assert rel_l2(dg2, dgamma + g2.grad) < 1e-5
+
+
+def test_helpers():
+    from mico_b200 import ops
+    x = _randn((1000, 1408), 1)
+    assert torch.equal(ops.cast_bf16(x), x.to(torch.bfloat16))
+    odd = _randn((12345,), 2)
+    assert torch.equal(ops.cast_bf16(odd), odd.to(torch.bfloat16))
+    xb = _randn((16448, 6144), 3, 1.0, torch.bfloat16)
+    assert rel_l2(ops.colsum(xb), xb.float().sum(0)) < 1e-5
+    xb2 = _randn((77, 4224), 4, 1.0, torch.bfloat16)
+    acc = torch.ones(4224, device="cuda")
+    assert rel_l2(ops.colsum(xb2, out=acc, accumulate=True), 1 + xb2.float().sum(0)) < 1e-5
+    f = _randn((5, 257, 1408), 5)
+    assert rel_l2(ops.batch_sum(f, 5), f.sum(0).flatten()) < 1e-6
+    s = torch.rand(5, device="cuda")
+    y = ops.scale_cast_bf16(f.view(-1, 1408), s, 257)
+    assert torch.equal(y, (f * s[:, None, None]).view(-1, 1408).to(torch.bfloat16))
+
+
+def test_patchify_matches_conv():
+    from mico_b200 import ops
+    B, P, W_ = 3, 14, 176
+    img = _randn((B, 3, 224, 224), 1)
+    cols = ops.patchify(img, P, 640)
+    assert cols.shape == (B * 256, 640)
+    assert cols[:, 588:].abs().max().item() == 0
+    ref = torch.nn.functional.unfold(img, P, stride=P).transpose(1, 2).reshape(B * 256, 588)
+    assert torch.equal(cols[:, :588], ref.to(torch.bfloat16))
+    # audio: one channel replicated three times (mico.py:139-143)
+    spec = _randn((B, 224, 224), 3)
+    c2 = ops.patchify(spec, P, 640, replicate_channel=True)
+    ref2 = torch.nn.functional.unfold(spec[:, None].repeat(1, 3, 1, 1), P, stride=P).transpose(1, 2).reshape(B * 256, 588)
+    assert torch.equal(c2[:, :588], ref2.to(torch.bfloat16))
