@@ -129,3 +129,62 @@ def test_patchify_matches_conv():
     c2 = ops.patchify(spec, P, 640, replicate_channel=True)
     ref2 = torch.nn.functional.unfold(spec[:, None].repeat(1, 3, 1, 1), P, stride=P).transpose(1, 2).reshape(B * 256, 588)
     assert torch.equal(c2[:, :588], ref2.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk,D,masked", [(2, 2, 257, 257, 88, False), (1, 3, 128, 128, 64, False),
+                                                (2, 12, 40, 257, 64, True), (2, 4, 49, 49, 32, False),
+                                                (1, 2, 300, 200, 128, True), (3, 16, 257, 257, 88, False),
+                                                (2, 12, 128, 128, 64, "3d")])
+def test_attention_bwd(B, H, Sq, Sk, D, masked):
+    """dQ/dK/dV vs autograd of the fp32 reference on the same bf16 inputs.
+    Tolerance 1e-2 rel-L2: P, dS and the outputs are each rounded to bf16 once (3 x 2^-9 in quadrature ~ 4e-3)."""
+    from mico_b200 import ops
+    q = _randn((B, Sq, H, D), 1, 1.0, torch.bfloat16)
+    k = _randn((B, Sk, H, D), 2, 1.0, torch.bfloat16)
+    v = _randn((B, Sk, H, D), 3, 1.0, torch.bfloat16)
+    do = _randn((B, Sq, H, D), 4, 1.0, torch.bfloat16)
+    mask = None
+    if masked:
+        g = torch.Generator().manual_seed(5)
+        lens = torch.randint(max(1, Sk // 2), Sk + 1, (B,), generator=g)
+        keep = (torch.arange(Sk)[None, :] < lens[:, None]).float()
+        if masked == "3d":
+            keep = torch.tril(keep[:, None, :].expand(B, Sq, Sk))
+        mask = ((1.0 - keep) * -10000.0).cuda()
+    scale = D ** -0.5
+    o, lse = ops.attention_fwd(q, k, v, scale, mask=mask)
+    dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, do, scale, mask=mask)
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    ro, _ = _attn_ref(qf, kf, vf, scale, mask)
+    ro.backward(do.float())
+    torch.cuda.synchronize()
+    errs = [rel_l2(dq, qf.grad), rel_l2(dk, kf.grad), rel_l2(dv, vf.grad)]
+    print(f"attn bwd B{B} H{H} Sq{Sq} Sk{Sk} D{D} mask={masked}: dq {errs[0]:.3e} dk {errs[1]:.3e} dv {errs[2]:.3e}")
+    assert max(errs) < 1e-2
+
+
+def test_attention_timing_vitg():
+    """ViT-g shape at bs 64 (B*H = 1024 problems of 257 x 88): coarse timing print, fwd and bwd."""
+    from mico_b200 import ops
+    B, H, S, D = 64, 16, 257, 88
+    qkv = _randn((B, S, 3, H, D), 1, 1.0, torch.bfloat16)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    do = _randn((B, S, H, D), 2, 1.0, torch.bfloat16)
+    dqkv = torch.empty_like(qkv)
+    scale = D ** -0.5
+    o, lse = ops.attention_fwd(q, k, v, scale)
+    for _ in range(2):
+        ops.attention_fwd(q, k, v, scale, out=o)
+        ops.attention_bwd(q, k, v, o, lse, do, scale, dq=dqkv[:, :, 0], dk=dqkv[:, :, 1], dv=dqkv[:, :, 2])
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    for _ in range(10):
+        ops.attention_fwd(q, k, v, scale, out=o)
+    ev[1].record()
+    for _ in range(10):
+        ops.attention_bwd(q, k, v, o, lse, do, scale, dq=dqkv[:, :, 0], dk=dqkv[:, :, 1], dv=dqkv[:, :, 2])
+    ev[2].record()
+    torch.cuda.synchronize()
+    fl = 4.0 * B * H * S * S * D
+    tf, tb = ev[0].elapsed_time(ev[1]) / 10, ev[1].elapsed_time(ev[2]) / 10
+    print(f"attention ViT-g bs64: fwd {tf:.3f} ms ({fl / tf / 1e9:.0f} TFLOP/s)  bwd {tb:.3f} ms ({2.5 * fl / tb / 1e9:.0f} TFLOP/s)")
