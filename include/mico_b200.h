@@ -128,7 +128,10 @@ int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, const float
  * ------------------------------------------------------------------------------------------- */
 /* fp32 master parameters -> bf16 GEMM operands (the reference relies on torch.autocast, pipeline.py:43) */
 int mico_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
-/* nn.Linear bias gradient: out[n] (+)= sum_m x[m,n], x bf16 */
+/* same for a [rows, cols] matrix into a wider bf16 pitch ldd, zero-filling columns cols..ldd-1
+ * (patch-embed weight (1408, 3*14*14=588) -> K padded to a 16-byte multiple, eva_vit_model.py:440) */
+int mico_cast_f32_to_bf16_2d(const float* src, int64_t lds, int rows, int cols, void* dst, int64_t ldd, void* stream);
+/* nn.Linear bias gradient: out[n] = sum_m x[m,n] (accumulate 0), out += sum (1), out -= sum (2); x bf16 */
 size_t mico_colsum_workspace(int M, int N);
 int mico_colsum_bf16(const void* x, int64_t ldx, int M, int N, float* out, int accumulate, void* workspace,
                      size_t ws_bytes, void* stream);
@@ -136,9 +139,11 @@ int mico_colsum_bf16(const void* x, int64_t ldx, int M, int N, float* out, int a
 int mico_batch_sum_f32(const float* x, int B, int64_t R, float* out, int accumulate, void* stream);
 /* K1 im2col for Conv2d(k=s=P) (eva_vit_model.py:440-447; swin.py:437-475): (B,C,H,W) fp32 -> bf16
  * [B*(H/P)*(W/P), Kpad], columns (c,ky,kx) zero-padded to Kpad; chan_stride=0 replicates one channel
- * (forward_audio_encoder's repeat(1,1,3,1,1), mico.py:139-143) */
+ * (forward_audio_encoder's repeat(1,1,3,1,1), mico.py:139-143).  tokens_per_img > 0 lays image b's patches at
+ * rows b*tokens_per_img + token_off ... and zero-fills the other rows of that image (token_off = 1 leaves the
+ * cls slot of eva_vit_model.py:615-616 as a zero row so the token matrix is one dense [B*257, Kpad] operand). */
 int mico_patchify(const float* img, int64_t img_stride, int64_t chan_stride, int B, int C, int H, int W, int P,
-                  int Kpad, void* out, void* stream);
+                  int Kpad, int tokens_per_img, int token_off, void* out, void* stream);
 /* token 0 of every sample = cls_token + pos_embed[0] (eva_vit_model.py:615-619) */
 int mico_cls_pos_row(const float* cls_token, const float* pos0, float* x, int64_t sample_stride, int B, int D,
                      void* stream);

@@ -26,6 +26,17 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
         dst[i] = __float2bfloat16(src[i]);
 }
 
+// rows x cols fp32 (pitch lds) -> bf16 (pitch ldd >= cols); columns cols..ldd-1 are zero-filled.
+__global__ void cast_f32_bf16_2d_kernel(const float* __restrict__ src, int64_t lds, int rows, int cols,
+                                        __nv_bfloat16* __restrict__ dst, int64_t ldd) {
+    const int64_t total = (int64_t)rows * ldd;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / ldd;
+        const int c = (int)(i - r * ldd);
+        dst[i] = __float2bfloat16(c < cols ? src[r * lds + c] : 0.0f);
+    }
+}
+
 // grid: (ceil(N/256), splits); block 256 = 8 warps; lane owns 8 consecutive columns.
 constexpr int kColsumCols = 256;
 __global__ void __launch_bounds__(256)
@@ -66,7 +77,7 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ partials, int s
     if (c >= N) return;
     float s = 0.f;
     for (int i = 0; i < splits; ++i) s += partials[(size_t)i * N + c];
-    out[c] = accumulate ? out[c] + s : s;
+    out[c] = accumulate == 1 ? out[c] + s : (accumulate == 2 ? out[c] - s : s);
 }
 
 // out[r] (+)= sum_b x[b*R + r]; R % 4 == 0
@@ -88,7 +99,7 @@ __global__ void batch_sum_f32_kernel(const float* __restrict__ x, int B, int64_t
 // Column order within a patch row is (c, ky, kx) == Conv2d weight.view(out, C*P*P).
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ img, int64_t img_stride, int64_t chan_stride, int C, int H, int W, int P,
-                int Kpad, __nv_bfloat16* __restrict__ out) {
+                int Kpad, int tokens_per_img, int token_off, __nv_bfloat16* __restrict__ out) {
     extern __shared__ float ps[];   // [C*P][W]
     const int gw = W / P, gh = H / P;
     const int b = blockIdx.x / gh, py = blockIdx.x % gh;
@@ -101,7 +112,15 @@ patchify_kernel(const float* __restrict__ img, int64_t img_stride, int64_t chan_
     }
     __syncthreads();
     const int K = C * P * P;
-    __nv_bfloat16* dst = out + ((int64_t)(b * gh + py) * gw) * Kpad;
+    __nv_bfloat16* dst = out + ((int64_t)b * tokens_per_img + token_off + (int64_t)py * gw) * Kpad;
+    if (py == 0) {   // leading rows of this image (the cls slot) and any trailing slack are zero
+        __nv_bfloat16* lead = out + (int64_t)b * tokens_per_img * Kpad;
+        for (int idx = threadIdx.x; idx < token_off * (Kpad / 2); idx += blockDim.x)
+            reinterpret_cast<uint32_t*>(lead)[idx] = 0u;
+        __nv_bfloat16* trail = lead + (int64_t)(token_off + gh * gw) * Kpad;
+        for (int idx = threadIdx.x; idx < (tokens_per_img - token_off - gh * gw) * (Kpad / 2); idx += blockDim.x)
+            reinterpret_cast<uint32_t*>(trail)[idx] = 0u;
+    }
     for (int idx = threadIdx.x; idx < gw * (Kpad / 2); idx += blockDim.x) {
         const int px = idx / (Kpad / 2);
         const int k = (idx - px * (Kpad / 2)) * 2;
@@ -163,6 +182,20 @@ extern "C" int mico_cast_f32_to_bf16(const float* src, void* dst, int64_t n, voi
     return MICO_OK;
 }
 
+extern "C" int mico_cast_f32_to_bf16_2d(const float* src, int64_t lds, int rows, int cols, void* dst, int64_t ldd,
+                                        void* stream_) {
+    using namespace mico;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MICO_CHECK_ARG(src && dst && rows > 0 && cols > 0 && lds >= cols && ldd >= cols);
+    const int64_t total = (int64_t)rows * ldd;
+    int64_t want = (total + 255) / 256;
+    const int grid = (int)(want > num_sms() * 16 ? num_sms() * 16 : want);
+    cast_f32_bf16_2d_kernel<<<grid, 256, 0, stream>>>(src, lds, rows, cols, reinterpret_cast<__nv_bfloat16*>(dst), ldd);
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return MICO_OK;
+}
+
 extern "C" size_t mico_colsum_workspace(int M, int N) { return (size_t)mico::colsum_splits(M, N) * N * sizeof(float); }
 
 extern "C" int mico_colsum_bf16(const void* x, int64_t ldx, int M, int N, float* out, int accumulate, void* workspace,
@@ -195,11 +228,13 @@ extern "C" int mico_batch_sum_f32(const float* x, int B, int64_t R, float* out, 
 }
 
 extern "C" int mico_patchify(const float* img, int64_t img_stride, int64_t chan_stride, int B, int C, int H, int W,
-                             int P, int Kpad, void* out, void* stream_) {
+                             int P, int Kpad, int tokens_per_img, int token_off, void* out, void* stream_) {
     using namespace mico;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     MICO_CHECK_ARG(img && out && B > 0 && C > 0 && P > 0 && H % P == 0 && W % P == 0);
     MICO_CHECK_ARG(Kpad >= C * P * P && Kpad % 8 == 0);
+    if (tokens_per_img <= 0) { tokens_per_img = (H / P) * (W / P); token_off = 0; }
+    MICO_CHECK_ARG(token_off >= 0 && tokens_per_img >= token_off + (H / P) * (W / P));
     const size_t smem = (size_t)C * P * W * sizeof(float);
     MICO_CHECK_ARG(smem <= 200 * 1024);
     static bool attr = false;
@@ -207,8 +242,8 @@ extern "C" int mico_patchify(const float* img, int64_t img_stride, int64_t chan_
         MICO_CHECK_CUDA(cudaFuncSetAttribute(patchify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
     }
-    patchify_kernel<<<B * (H / P), 256, smem, stream>>>(img, img_stride, chan_stride, C, H, W, P, Kpad,
-                                                        reinterpret_cast<__nv_bfloat16*>(out));
+    patchify_kernel<<<B * (H / P), 256, smem, stream>>>(img, img_stride, chan_stride, C, H, W, P, Kpad, tokens_per_img,
+                                                        token_off, reinterpret_cast<__nv_bfloat16*>(out));
     MICO_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return MICO_OK;

@@ -213,7 +213,18 @@ def cast_bf16(src, dst=None):
     return dst
 
 
+def cast_bf16_2d(src, ldd):
+    """fp32 [rows, cols] (row pitch src.stride(0)) -> bf16 [rows, ldd], zero-filled past cols."""
+    _req(src, F32, "src")
+    rows, cols = src.shape
+    dst = torch.empty((rows, ldd), device=src.device, dtype=BF16)
+    check(lib.mico_cast_f32_to_bf16_2d(_ptr(src), C.c_int64(src.stride(0)), rows, cols, _ptr(dst), C.c_int64(ldd),
+                                       _stream()), "mico_cast_f32_to_bf16_2d")
+    return dst
+
+
 def colsum(x, out=None, accumulate=False):
+    """out[n] = sum_m x[m,n]; accumulate: False/0 overwrite, True/1 add, 2 subtract."""
     _req(x, BF16, "x")
     M, N = x.shape
     if out is None:
@@ -234,8 +245,9 @@ def batch_sum(x, B, out=None, accumulate=False):
     return out
 
 
-def patchify(img, P, Kpad, replicate_channel=False, out=None):
-    """img: fp32 [B,C,H,W] contiguous (or [B,H,W] with replicate_channel -> 3 identical channels)."""
+def patchify(img, P, Kpad, replicate_channel=False, out=None, tokens_per_img=0, token_off=0):
+    """img: fp32 [B,C,H,W] contiguous (or [B,H,W] with replicate_channel -> 3 identical channels).
+    tokens_per_img > 0: image b's patches land at rows b*tokens_per_img + token_off.., other rows zeroed."""
     _req(img, F32, "img")
     if replicate_channel:
         B, H, W = img.shape
@@ -245,11 +257,11 @@ def patchify(img, P, Kpad, replicate_channel=False, out=None):
         img_stride, chan_stride = img.stride(0), img.stride(1)
     if img.stride(-1) != 1 or img.stride(-2) != W:
         raise MicoError("patchify: image rows must be contiguous")
-    rows = B * (H // P) * (W // P)
+    rows = B * (tokens_per_img if tokens_per_img > 0 else (H // P) * (W // P))
     if out is None:
         out = torch.empty((rows, Kpad), device=img.device, dtype=BF16)
-    check(lib.mico_patchify(_ptr(img), C.c_int64(img_stride), C.c_int64(chan_stride), B, Cc, H, W, P, Kpad, _ptr(out),
-                            _stream()), "mico_patchify")
+    check(lib.mico_patchify(_ptr(img), C.c_int64(img_stride), C.c_int64(chan_stride), B, Cc, H, W, P, Kpad,
+                            int(tokens_per_img), int(token_off), _ptr(out), _stream()), "mico_patchify")
     return out
 
 

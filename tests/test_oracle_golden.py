@@ -1,0 +1,40 @@
+"""CPU: the oracle restatement (oracle/eva_vit.py) against fixtures produced by the UNMODIFIED reference
+(oracle/make_golden.py ran model/evaclip/eva_vit_model.py on CPU in the build container).
+fp32 vs fp32 on the same weights/inputs: tolerance 1e-5 rel-L2 (summation order only)."""
+import os
+
+import torch
+
+from conftest import rel_l2
+from oracle import eva_vit as O
+
+
+def _load(golden_dir):
+    return torch.load(os.path.join(golden_dir, "eva_vit_tiny.pt"), weights_only=False)
+
+
+def test_vit_eval_forward_matches_reference(golden_dir):
+    g = _load(golden_dir)
+    y = O.forward_features(g["state_dict"], g["x"], g["cfg"])
+    assert y.shape == g["y_eval"].shape == (2, 257, 176)
+    assert rel_l2(y, g["y_eval"]) < 1e-5
+
+
+def test_vit_train_forward_backward_matches_reference(golden_dir):
+    g = _load(golden_dir)
+    p = {k: v.clone().requires_grad_(True) for k, v in g["state_dict"].items()}
+    y = O.forward_features(p, g["x"], g["cfg"], dp_scales=g["dp_scales"])
+    assert rel_l2(y, g["y_train"]) < 1e-5
+    loss = y.float().pow(2).mean()
+    assert abs(loss.item() - g["loss"].item()) <= 1e-5 * abs(g["loss"].item())
+    loss.backward()
+    for k, ref in g["grads"].items():
+        if k.startswith("head."):
+            continue   # the classifier head is not on the return_all_features path (mico.py:120)
+        assert p[k].grad is not None, k
+        assert rel_l2(p[k].grad, ref) < 2e-5, k
+
+
+def test_drop_path_rates_match_linspace():
+    assert O.drop_path_rates(40)[0] == 0.0
+    assert abs(O.drop_path_rates(40)[-1] - 0.4) < 1e-7
