@@ -36,6 +36,19 @@ const char* mico_last_error(void);
 /* number of kernels this library has launched since load / since the last reset (bench "gpu_launches") */
 int64_t mico_launch_count(void);
 void mico_reset_launch_count(void);
+/* Device timing per kernel family for bench.py's roofline: while enabled, every entry point brackets its launches
+ * with a cudaEvent pair on the launching stream.  mico_profile_collect synchronises the device and returns, per
+ * family (MICO_PROF_*), the summed milliseconds, the summed algorithmic work (FLOPs for GEMM/attention, bytes for
+ * the HBM-bound families) and the number of calls.  mico_profile_enable(0/1) also clears the records. */
+#define MICO_PROF_GEMM 0
+#define MICO_PROF_ATTN_FWD 1
+#define MICO_PROF_ATTN_BWD 2
+#define MICO_PROF_LN_FWD 3
+#define MICO_PROF_LN_BWD 4
+#define MICO_PROF_OTHER 5
+#define MICO_PROF_KINDS 6
+int mico_profile_enable(int on);
+int mico_profile_collect(double* ms, double* work, int64_t* count, int nkinds);
 
 /* ---------------------------------------------------------------------------------------------
  * K3  Linear layers and every other dense contraction on the path (tcgen05 + TMA + TMEM).
@@ -147,6 +160,11 @@ int mico_patchify(const float* img, int64_t img_stride, int64_t chan_stride, int
 /* token 0 of every sample = cls_token + pos_embed[0] (eva_vit_model.py:615-619) */
 int mico_cls_pos_row(const float* cls_token, const float* pos0, float* x, int64_t sample_stride, int B, int D,
                      void* stream);
+/* K12 DropPath (eva_vit_model.py:121-138, rates linspace(0, 0.4, depth) :533): all per-sample multipliers of a tower
+ * in one launch, out[l][j][b] = Bernoulli(1 - drop_prob[l]) / (1 - drop_prob[l]) for branch j in {attn, mlp};
+ * counter-based Philox so a (seed, offset) pair reproduces the masks.  drop_prob: device fp32 [L]. */
+int mico_drop_path_scales(const float* drop_prob, int L, int B, uint64_t seed, uint64_t offset, float* out,
+                          void* stream);
 /* y = bf16(x * row_scale[row / rows_per_group]) */
 int mico_scale_cast_bf16(const float* x, int64_t ldx, const float* row_scale, int rows_per_group, void* y,
                          int64_t ldy, int M, int D, void* stream);

@@ -1,6 +1,7 @@
 // mico_b200 -- library-wide host utilities behind the C-ABI (error slot, TMA descriptor encode, counters).
 #include <atomic>
 #include <mutex>
+#include <vector>
 #include <string.h>
 
 #include "host_utils.h"
@@ -15,6 +16,36 @@ void set_last_error(const char* file, int line, const char* msg) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ------------------------------------------------------------------ per-family event timing
+struct ProfRec { cudaEvent_t e0, e1; int kind; double work; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;        // records of the current session
+static std::vector<cudaEvent_t> g_ev_pool; // recycled events
+static std::atomic<bool> g_prof_on{false};
+
+static cudaEvent_t prof_event() {
+    if (!g_ev_pool.empty()) { cudaEvent_t e = g_ev_pool.back(); g_ev_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+ProfScope::ProfScope(int kind, double work, cudaStream_t s) : slot(-1), stream(s) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r;
+    r.e0 = prof_event(); r.e1 = prof_event(); r.kind = kind; r.work = work;
+    if (!r.e0 || !r.e1) return;
+    cudaEventRecord(r.e0, s);
+    g_prof.push_back(r);
+    slot = (int)g_prof.size() - 1;
+}
+ProfScope::~ProfScope() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].e1, stream);
+}
 
 int num_sms() {
     static int n = [] {
@@ -79,3 +110,26 @@ extern "C" int mico_version(void) { return 100; }
 extern "C" const char* mico_last_error(void) { return mico::g_err; }
 extern "C" int64_t mico_launch_count(void) { return mico::g_launches.load(); }
 extern "C" void mico_reset_launch_count(void) { mico::g_launches.store(0); }
+
+extern "C" int mico_profile_enable(int on) {
+    using namespace mico;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof) { g_ev_pool.push_back(r.e0); g_ev_pool.push_back(r.e1); }
+    g_prof.clear();
+    g_prof_on.store(on != 0);
+    return MICO_OK;
+}
+
+extern "C" int mico_profile_collect(double* ms, double* work, int64_t* count, int nkinds) {
+    using namespace mico;
+    MICO_CHECK_ARG(ms && work && count && nkinds >= kProfKinds);
+    MICO_CHECK_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int i = 0; i < nkinds; ++i) { ms[i] = 0.0; work[i] = 0.0; count[i] = 0; }
+    for (auto& r : g_prof) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) continue;
+        ms[r.kind] += t; work[r.kind] += r.work; count[r.kind] += 1;
+    }
+    return MICO_OK;
+}

@@ -476,6 +476,7 @@ extern "C" int mico_attention_bwd(const MicoAttnArgs* a, void* stream_) {
                             (const void*)a->dv})
         MICO_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0);
 
+    ProfScope prof(kProfAttnBwd, 10.0 * a->B * a->H * (double)a->Sq * a->Sk * a->D, stream);
     {
         const int64_t n = (int64_t)a->B * a->Sq * a->H;
         attn_delta_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(

@@ -331,6 +331,7 @@ extern "C" int mico_attention_fwd(const MicoAttnArgs* a, void* stream_) {
         MICO_CHECK_ARG(s % 8 == 0);
     for (const void* ptr : {a->q, a->k, a->v, (const void*)a->o})
         MICO_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0);
+    ProfScope prof(kProfAttnFwd, 4.0 * a->B * a->H * (double)a->Sq * a->Sk * a->D, stream);
     CUtensorMap tq, tk, tv;
     int rc;
     if ((rc = make_attn_tmap(&tq, a->q, a->D, a->H, a->Sq, a->B, a->q_bs, a->q_rs, a->q_hs))) return rc;

@@ -6,6 +6,8 @@
 //   mico_patchify           K1 im2col: (B,C,H,W) fp32 -> bf16 [B*gh*gw, Kpad]   (eva_vit_model.py:440-447)
 //   mico_cls_pos_row        token 0 = cls_token + pos_embed[0]                  (eva_vit_model.py:615-619)
 //   mico_scale_cast_bf16    bf16(x * row_scale[row/rpg])  (gradient entering a DropPath'd residual branch)
+#include <curand_kernel.h>
+
 #include "common.cuh"
 #include "host_utils.h"
 
@@ -158,6 +160,24 @@ __global__ void scale_cast_bf16_kernel(const float* __restrict__ x, int64_t ldx,
     }
 }
 
+// DropPath multipliers for a whole tower in one launch: out[l][j][b] = Bernoulli(1-p_l) / (1-p_l)
+// (eva_vit_model.py:121-138, scale_by_keep=True); Philox counter = flat index, so results depend only on (seed, offset).
+__global__ void drop_path_scales_kernel(const float* __restrict__ drop_prob, int L, int B, uint64_t seed, uint64_t offset,
+                                        float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L * 2 * B) return;
+    const float p = drop_prob[i / (2 * B)];
+    float v = 1.0f;
+    if (p > 0.0f) {
+        curandStatePhilox4_32_10_t st;
+        curand_init(seed, (uint64_t)i, offset, &st);
+        const float keep = 1.0f - p;
+        const float u = curand_uniform(&st);   // (0, 1]
+        v = (u <= keep) ? (keep > 0.0f ? 1.0f / keep : 1.0f) : 0.0f;
+    }
+    out[i] = v;
+}
+
 int colsum_splits(int M, int N) {
     const int colblocks = ceil_div(N, kColsumCols);
     int s = ceil_div(num_sms() * 4, colblocks);
@@ -172,6 +192,7 @@ int colsum_splits(int M, int N) {
 extern "C" int mico_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream_) {
     using namespace mico;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    ProfScope prof(kProfOther, 6.0 * (double)n, stream);
     MICO_CHECK_ARG(src && dst && n > 0);
     MICO_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0);
     int64_t want = (n / 8 + 255) / 256;
@@ -186,6 +207,7 @@ extern "C" int mico_cast_f32_to_bf16_2d(const float* src, int64_t lds, int rows,
                                         void* stream_) {
     using namespace mico;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    ProfScope prof(kProfOther, 6.0 * (double)rows * cols, stream);
     MICO_CHECK_ARG(src && dst && rows > 0 && cols > 0 && lds >= cols && ldd >= cols);
     const int64_t total = (int64_t)rows * ldd;
     int64_t want = (total + 255) / 256;
@@ -202,6 +224,7 @@ extern "C" int mico_colsum_bf16(const void* x, int64_t ldx, int M, int N, float*
                                 size_t ws_bytes, void* stream_) {
     using namespace mico;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    ProfScope prof(kProfOther, 2.0 * (double)M * N, stream);
     MICO_CHECK_ARG(x && out && workspace && M > 0 && N > 0);
     MICO_CHECK_ARG(ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0);
     const int splits = colsum_splits(M, N);
@@ -220,6 +243,7 @@ extern "C" int mico_colsum_bf16(const void* x, int64_t ldx, int M, int N, float*
 extern "C" int mico_batch_sum_f32(const float* x, int B, int64_t R, float* out, int accumulate, void* stream_) {
     using namespace mico;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    ProfScope prof(kProfOther, 4.0 * (double)B * R, stream);
     MICO_CHECK_ARG(x && out && B > 0 && R > 0 && R % 4 == 0);
     batch_sum_f32_kernel<<<(int)((R / 4 + 255) / 256), 256, 0, stream>>>(x, B, R, out, accumulate);
     MICO_CHECK_CUDA(cudaGetLastError());
@@ -231,6 +255,7 @@ extern "C" int mico_patchify(const float* img, int64_t img_stride, int64_t chan_
                              int P, int Kpad, int tokens_per_img, int token_off, void* out, void* stream_) {
     using namespace mico;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    ProfScope prof(kProfOther, (double)B * C * H * W * 4.0 + (double)B * (H / P) * (W / P) * Kpad * 2.0, stream);
     MICO_CHECK_ARG(img && out && B > 0 && C > 0 && P > 0 && H % P == 0 && W % P == 0);
     MICO_CHECK_ARG(Kpad >= C * P * P && Kpad % 8 == 0);
     if (tokens_per_img <= 0) { tokens_per_img = (H / P) * (W / P); token_off = 0; }
@@ -253,6 +278,7 @@ extern "C" int mico_cls_pos_row(const float* cls_token, const float* pos0, float
                                 void* stream_) {
     using namespace mico;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    ProfScope prof(kProfOther, 4.0 * (double)B * D, stream);
     MICO_CHECK_ARG(cls_token && pos0 && x && B > 0 && D > 0);
     cls_pos_row_kernel<<<ceil_div(B * D, 256), 256, 0, stream>>>(cls_token, pos0, x, sample_stride, B, D);
     MICO_CHECK_CUDA(cudaGetLastError());
@@ -264,6 +290,7 @@ extern "C" int mico_scale_cast_bf16(const float* x, int64_t ldx, const float* ro
                                     int64_t ldy, int M, int D, void* stream_) {
     using namespace mico;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    ProfScope prof(kProfOther, 6.0 * (double)M * D, stream);
     MICO_CHECK_ARG(x && y && M > 0 && D > 0 && D % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0);
     MICO_CHECK_ARG(!(row_scale && rows_per_group <= 0));
     const int64_t total = (int64_t)M * (D / 4);
@@ -271,6 +298,18 @@ extern "C" int mico_scale_cast_bf16(const float* x, int64_t ldx, const float* ro
     const int grid = (int)(want > num_sms() * 16 ? num_sms() * 16 : want);
     scale_cast_bf16_kernel<<<grid, 256, 0, stream>>>(x, ldx, row_scale, rows_per_group,
                                                      reinterpret_cast<__nv_bfloat16*>(y), ldy, M, D);
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return MICO_OK;
+}
+
+extern "C" int mico_drop_path_scales(const float* drop_prob, int L, int B, uint64_t seed, uint64_t offset, float* out,
+                                     void* stream_) {
+    using namespace mico;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    ProfScope prof(kProfOther, 4.0 * (double)L * 2 * B, stream);
+    MICO_CHECK_ARG(drop_prob && out && L > 0 && B > 0);
+    drop_path_scales_kernel<<<ceil_div(L * 2 * B, 256), 256, 0, stream>>>(drop_prob, L, B, seed, offset, out);
     MICO_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return MICO_OK;

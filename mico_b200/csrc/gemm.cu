@@ -423,6 +423,7 @@ extern "C" int mico_gemm_bf16(const MicoGemmArgs* args, void* stream_) {
     if (g.aux_out) vec = vec && al16(g.aux_out) && (g.ld_aux_out % 8 == 0);
     if (g.aux_in) vec = vec && al16(g.aux_in) && (g.ld_aux_in % 8 == 0);
     e.vec_ok = vec ? 1 : 0;
+    ProfScope prof(kProfGemm, 2.0 * g.M * (double)g.N * g.K, stream);
 
     if (!g.a_mn_major && !g.b_mn_major) return dispatch_bn<false, false>(g, e, stream);
     if (!g.a_mn_major && g.b_mn_major) return dispatch_bn<false, true>(g, e, stream);

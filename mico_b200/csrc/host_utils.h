@@ -40,4 +40,14 @@ int num_sms();
 
 void count_launch(int n = 1);
 
+// Per-kernel-family device timing (mico_profile_* in the C-ABI): when enabled, every entry point brackets its
+// launches with a cudaEvent pair on the launching stream; mico_profile_collect() reads them back.
+enum ProfKind { kProfGemm = 0, kProfAttnFwd, kProfAttnBwd, kProfLnFwd, kProfLnBwd, kProfOther, kProfKinds };
+struct ProfScope {
+    int slot;
+    cudaStream_t stream;
+    ProfScope(int kind, double work, cudaStream_t s);
+    ~ProfScope();
+};
+
 }  // namespace mico

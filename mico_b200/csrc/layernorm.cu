@@ -183,6 +183,7 @@ extern "C" int mico_layernorm_fwd(const void* x, int x_is_bf16, int64_t ldx, con
     MICO_CHECK_ARG(ldx % 4 == 0 && ldy % 4 == 0);
     const int want = ceil_div(M, kLnWarps);
     const int grid = want < num_sms() * 16 ? want : num_sms() * 16;
+    ProfScope prof(kProfLnFwd, (double)M * D * ((x_is_bf16 ? 2 : 4) + (y_bf16 ? 2 : 0) + (y_f32 ? 4 : 0)), stream);
     if (x_is_bf16)
         ln_fwd_kernel<__nv_bfloat16><<<grid, kLnThreads, 0, stream>>>(
             reinterpret_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32,
@@ -216,6 +217,8 @@ extern "C" int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, 
     MICO_CHECK_ARG(ws_bytes >= mico_layernorm_bwd_workspace(M, D));
     const int grid = ln_bwd_grid(M);
     const size_t smem = (size_t)kLnWarps * 2 * D * sizeof(float);
+    ProfScope prof(kProfLnBwd, (double)M * D * ((dy_is_bf16 ? 2 : 4) + 4 + (dres ? 4 : 0) + (dx ? 4 : 0) + (dx_bf16 ? 2 : 0)),
+                   stream);
     float* partials = reinterpret_cast<float*>(workspace);
     if (dy_is_bf16) {
         auto k = ln_bwd_kernel<__nv_bfloat16>;

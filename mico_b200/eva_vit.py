@@ -234,6 +234,11 @@ class EVAVisionTransformer(nn.Module):
         k = in_chans * patch_size * patch_size
         self._kpad = (k + 63) // 64 * 64
         self._injected_dp = None
+        # "philox": all DropPath multipliers from one counter-based launch; "torch": the reference's own
+        # bernoulli_ calls in the reference's order (bit-identical masks to a reference run with the same seed)
+        self.drop_path_rng = "philox"
+        self._dp_rates = None
+        self._dp_calls = 0
 
     # ------------------------------------------------------------------ reference-compatible helpers
     def get_num_layers(self):
@@ -263,6 +268,11 @@ class EVAVisionTransformer(nn.Module):
                     blk.mlp.fc1.weight, blk.mlp.fc1.bias, blk.mlp.fc2.weight, blk.mlp.fc2.bias]
         return top
 
+    def invalidate_weight_cache(self):
+        """Drop the bf16 operand copies (an optimizer step that bypasses tensor versioning, or a benchmark
+        that wants the per-step cast of changed weights inside the timed region)."""
+        self._bf16 = _Bf16Cache()
+
     def inject_drop_path_scales(self, scales):
         """Parity hook: use these (depth, 2, B) DropPath multipliers (mask / keep_prob) for the next
         training-mode forward instead of drawing them."""
@@ -277,6 +287,11 @@ class EVAVisionTransformer(nn.Module):
             return dp.to(device=device, dtype=F32).contiguous()
         if not self.training or all(b.drop_prob == 0.0 for b in self.blocks):
             return None
+        if self.drop_path_rng == "philox":   # one launch for the whole tower (K12)
+            if self._dp_rates is None or self._dp_rates.device != device:
+                self._dp_rates = torch.tensor([b.drop_prob for b in self.blocks], device=device, dtype=F32)
+            self._dp_calls += 1
+            return ops.drop_path_scales(self._dp_rates, B, torch.initial_seed() & (2 ** 63 - 1), self._dp_calls)
         dp = torch.ones(len(self.blocks), 2, B, device=device, dtype=F32)
         for i, blk in enumerate(self.blocks):
             if blk.drop_prob > 0.0:
@@ -345,9 +360,17 @@ class EVAVisionTransformer(nn.Module):
         c = self._bf16
         scale = d ** -0.5
         grads = [None] * len(params)
+        # one flat fp32 gradient buffer in parameter order (block i's gradients are contiguous: a data-parallel
+        # caller can reduce them bucket by bucket while earlier blocks are still in backward)
+        sizes = [(p.numel() + 3) // 4 * 4 for p in params]
+        flat = torch.empty(sum(sizes), device=dev, dtype=F32)
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + n)
+        self._last_flat_grad = (flat, offs)
 
         def pgrad(idx):
-            g = torch.empty_like(params[idx], dtype=F32)
+            g = flat[offs[idx]:offs[idx] + params[idx].numel()].view(params[idx].shape)
             grads[idx] = g
             return g
 
@@ -391,8 +414,8 @@ class EVAVisionTransformer(nn.Module):
                               dq=g5[:, :, 0], dk=g5[:, :, 1], dv=g5[:, :, 2])
             del do, o, lse, qkv
             ops.gemm(dqkv, h, a_mn=True, b_mn=True, out=pgrad(base + _QKVW))
-            dbqkv = ops.colsum(dqkv)
-            grads[base + _QB], grads[base + _VB] = dbqkv[:D], dbqkv[2 * D:]
+            ops.colsum(dqkv[:, :D], out=pgrad(base + _QB))         # k has no bias (eva_vit_model.py:307)
+            ops.colsum(dqkv[:, 2 * D:], out=pgrad(base + _VB))
             dh = ops.gemm(dqkv, c.get(params[base + _QKVW], ("qkv", i)), b_mn=True)
             del dqkv, h
             dx, dxb = ops.layernorm_bwd(dh, xr, mean1, rstd1, p[_N1W], pgrad(base + _N1W), pgrad(base + _N1B),
@@ -400,16 +423,12 @@ class EVAVisionTransformer(nn.Module):
             del dh, dx1, xr
         # ---- patch embedding / cls / pos (eva_vit_model.py:613-619); pixels get no gradient
         cols = saved.pop("cols")
-        gw = torch.empty((D, self._kpad), device=dev, dtype=F32)
-        ops.gemm(dxb, cols, a_mn=True, b_mn=True, out=gw)          # cls rows of `cols` are zero
         k = params[_PEW][0].numel()
-        grads[_PEW] = gw[:, :k].reshape(params[_PEW].shape)
-        gb = ops.colsum(dxb)                                       # all rows ...
+        ops.gemm(dxb, cols[:, :k], a_mn=True, b_mn=True, out=pgrad(_PEW).view(D, k))   # cls rows of `cols` are zero
+        gb = ops.colsum(dxb, out=pgrad(_PEB))                      # all rows ...
         ops.colsum(dxb.view(B, T * D)[:, :D], out=gb, accumulate=2)   # ... minus the cls rows
-        grads[_PEB] = gb
-        gpos = ops.batch_sum(dx, B)
-        grads[_POS] = gpos.view(1, T, D)
-        grads[_CLS] = gpos[:D].reshape(1, 1, D).clone()
+        gpos = ops.batch_sum(dx, B, out=pgrad(_POS).view(-1))
+        pgrad(_CLS).view(-1).copy_(gpos[:D])
         return grads
 
     # ------------------------------------------------------------------ public forward

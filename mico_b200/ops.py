@@ -278,3 +278,29 @@ def scale_cast_bf16(x, row_scale=None, rows_per_group=0, out=None):
     check(lib.mico_scale_cast_bf16(_ptr(x), C.c_int64(x.stride(0)), _ptr(row_scale), int(rows_per_group), _ptr(out),
                                    C.c_int64(out.stride(0)), M, D, _stream()), "mico_scale_cast_bf16")
     return out
+
+
+def drop_path_scales(drop_prob, B, seed, offset=0):
+    """drop_prob: fp32 device [L] -> fp32 [L, 2, B] DropPath multipliers (mask / keep_prob)."""
+    _req(drop_prob, F32, "drop_prob")
+    L = drop_prob.numel()
+    out = torch.empty((L, 2, B), device=drop_prob.device, dtype=F32)
+    check(lib.mico_drop_path_scales(_ptr(drop_prob), L, B, C.c_uint64(seed), C.c_uint64(offset), _ptr(out), _stream()),
+          "mico_drop_path_scales")
+    return out
+
+
+# ----------------------------------------------------------------------------- per-family device timing
+PROF_KINDS = ("gemm", "attention_fwd", "attention_bwd", "layernorm_fwd", "layernorm_bwd", "other")
+
+
+def profile_enable(on=True):
+    check(lib.mico_profile_enable(int(bool(on))), "mico_profile_enable")
+
+
+def profile_collect():
+    """-> {family: dict(ms=, work=, calls=)}; synchronises the device."""
+    n = len(PROF_KINDS)
+    ms, work, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_int64 * n)()
+    check(lib.mico_profile_collect(ms, work, cnt, n), "mico_profile_collect")
+    return {k: dict(ms=ms[i], work=work[i], calls=int(cnt[i])) for i, k in enumerate(PROF_KINDS)}
