@@ -97,6 +97,7 @@ int mico_gemm_bf16(const MicoGemmArgs* args, void* stream);
  * place: element (b, i, h, d) lives at ptr + b*bs + i*rs + h*hs + d (strides in elements, multiples of 8).
  * mask: additive fp32 (the reference's (1-m)*-10000 masks, bert.py:697-781) at mask + b*mask_bs + i*mask_qs + j
  * (mask_qs = 0 for a per-key padding mask), or NULL.   lse: [B,H,Sq] fp32 log-sum-exp saved for backward.
+ * head_dim D: multiple of 8, <= 128 forward, <= 96 backward (ViT-g 88, BERT/CLIP 64, Swin 32).
  * Backward (mico_attention_bwd) recomputes P from Q,K and lse; needs delta[b,h,i] = sum_d dO*O
  * (mico_attention_bwd_delta) and writes dQ, dK, dV with the same stride convention.
  * ------------------------------------------------------------------------------------------- */

@@ -4,14 +4,17 @@
 // from Q, K and the saved log-sum-exp, and delta_i = sum_d dO_id O_id:
 //     dV = P^T dO          dP = dO V^T          dS = scale * P o (dP - delta)
 //     dQ = dS K            dK = dS^T Q
-// Three launches:
+// Launches:
 //   attn_delta_kernel   delta[b,h,i]                                     (HBM-bound row reduction)
-//   attn_dq_kernel      CTA per (b,h,q-tile), loops over KV tiles:  S, dP -> dS (smem) -> dQ += dS K
-//   attn_dkv_kernel     CTA per (b,h,kv-tile), loops over Q tiles:  S^T, dP^T -> P^T, dS^T (smem)
+//   attn_dq_kernel      CTA per (b,h,q-tile), loops over KV tiles:  S, dP -> dS (TMEM) -> dQ += dS K
+//   attn_dkv_kernel     CTA per (b,h,kv-tile), loops over Q tiles:  S^T, dP^T -> P^T, dS^T (TMEM)
 //                                                                  -> dV += P^T dO, dK += dS^T Q
+//   attention_tail_bwd  (attention_tail.cu) the <= 8 remainder rows of the owned side, SIMT
 // Both MMA kernels recompute S (7 GEMMs instead of 5) so that no atomics are needed and the result is
-// deterministic.  The dS / P^T tiles written to shared memory serve as K-major A operands; K, Q and dO tiles
-// are read K-major for the score GEMMs and MN-major (same bytes) for the gradient GEMMs.
+// deterministic.  The dS / P^T / dS^T operands never leave tensor memory: the softmax warps write them back as
+// packed bf16 (tcgen05.st) and the gradient MMAs read them as the TMEM A operand; K, Q and dO tiles are read
+// K-major for the score GEMMs and MN-major (same bytes) for the gradient GEMMs.  Streamed tiles hold 128 rows,
+// the last one up to 144 (S = 257 -> 128 + 129); 8 softmax warps (two per TMEM lane quarter) split the columns.
 #include "attn_common.cuh"
 
 namespace mico {
@@ -51,20 +54,22 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int64_t o
 }
 
 // ------------------------------------------------------------------------------------------------ dQ
+// TMEM columns: S [0,160)  dP [160,320)  dS as bf16 A operand [320,392)  dQ accumulator [400,400+HD_PAD)
 struct DqSmem {
-    static constexpr int Q = 0;
+    static constexpr int Q = 0;                                   // 2 atoms x 128 rows
     static constexpr int DO = 2 * kAtomBytes;
-    static constexpr int K0 = 4 * kAtomBytes;               // 2 stages x 2 atoms
-    static constexpr int V0 = 8 * kAtomBytes;
-    static constexpr int DS = 12 * kAtomBytes;
-    static constexpr int BARS = 14 * kAtomBytes;
+    static constexpr int K0 = 4 * kAtomBytes;                     // 2 stages x 2 atoms x 144 rows
+    static constexpr int V0 = K0 + 4 * kAtomBytesN;
+    static constexpr int BARS = V0 + 4 * kAtomBytesN;
     static constexpr int TOTAL = BARS + 256 + 1024;
 };
+constexpr uint32_t kDqS = 0, kDqDP = 160, kDqDS = 320, kDqAcc = 400;
 
 template <int HD_PAD>
-__global__ void __launch_bounds__(kAttThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, AttnBwdParams p) {
+               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+               const __grid_constant__ CUtensorMap tmKx, const __grid_constant__ CUtensorMap tmVx, AttnBwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DqSmem::BARS);
@@ -74,28 +79,30 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     uint64_t* kv_empty = bars + 4;   // [2]
     uint64_t* sdp_full = bars + 6;   // S and dP in TMEM
     uint64_t* sdp_empty = bars + 7;  // softmax finished reading them
-    uint64_t* ds_full = bars + 8;    // dS tile in smem
+    uint64_t* ds_full = bars + 8;    // dS operand in TMEM
     uint64_t* ds_empty = bars + 9;   // dQ MMA finished reading it
     uint64_t* dq_full = bars + 10;   // dQ accumulator final
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int warp = threadIdx.x >> 5;
-    const int nqt = (p.Sq + kTile - 1) / kTile;
-    const int nkv = (p.Sk + kTile - 1) / kTile;
+    const int nqt = m_tiles(p.Sq);
+    const NTiling kt = n_tiling(p.Sk);
+    const int nkv = kt.n;
     const int num_work = p.B * p.H * nqt;
     constexpr int kAtoms = (HD_PAD + 63) / 64;
     constexpr uint32_t kTileBytes = kAtoms * kAtomBytes;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (elect_one()) {
             tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+            tma_prefetch_desc(&tmKx); tma_prefetch_desc(&tmVx);
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         if (elect_one()) {
             mbar_init(q_full, 1); mbar_init(q_empty, 1);
             for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-            mbar_init(sdp_full, 1); mbar_init(sdp_empty, 4);
-            mbar_init(ds_full, 4); mbar_init(ds_empty, 1);
+            mbar_init(sdp_full, 1); mbar_init(sdp_empty, 8);
+            mbar_init(ds_full, 8); mbar_init(ds_empty, 1);
             mbar_init(dq_full, 1);
             fence_mbar_init();
         }
@@ -106,9 +113,10 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_dQ = tmem_base + 256;
+    const uint32_t tmem_S = tmem_base + kDqS, tmem_dP = tmem_base + kDqDP, tmem_dS = tmem_base + kDqDS,
+                   tmem_dQ = tmem_base + kDqAcc;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (elect_one()) {
             uint32_t wcount = 0, kvcount = 0;
             for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
@@ -124,20 +132,17 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 for (int j = 0; j < nkv; ++j, ++kvcount) {
                     const int s = kvcount & 1;
                     mbar_wait(&kv_empty[s], ((kvcount >> 1) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&kv_full[s], 2 * kTileBytes);
-#pragma unroll
-                    for (int a = 0; a < kAtoms; ++a) {
-                        tma_load_4d(smem + DqSmem::K0 + (s * 2 + a) * kAtomBytes, &tmK, &kv_full[s], a * 64, h, j * kTile, b);
-                        tma_load_4d(smem + DqSmem::V0 + (s * 2 + a) * kAtomBytes, &tmV, &kv_full[s], a * 64, h, j * kTile, b);
-                    }
+                    const bool ext = n_valid(kt, j) > kTile;
+                    mbar_arrive_expect_tx(&kv_full[s], 2 * n_tile_bytes(kAtoms, ext));
+                    load_n_tile<kAtoms>(smem + DqSmem::K0 + s * 2 * kAtomBytesN, &tmK, &tmKx, &kv_full[s], h, j * kTile, b, ext);
+                    load_n_tile<kAtoms>(smem + DqSmem::V0 + s * 2 * kAtomBytesN, &tmV, &tmVx, &kv_full[s], h, j * kTile, b, ext);
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         if (elect_one()) {
             uint32_t wcount = 0, kvcount = 0, tcount = 0;   // tcount: kv tiles processed (sdp / ds barrier phases)
             const uint32_t sQ = smem_u32(smem + DqSmem::Q), sDO = smem_u32(smem + DqSmem::DO);
-            const uint32_t sDS = smem_u32(smem + DqSmem::DS);
             constexpr uint32_t idesc_dq = umma_idesc_bf16(HD_PAD, false, true);
             for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
                 mbar_wait(q_full, wcount & 1);
@@ -147,22 +152,18 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     mbar_wait(&kv_full[s], (kvc >> 1) & 1);
                     mbar_wait(sdp_empty, (tc & 1) ^ 1);
                     tc_fence_after();
-                    const int valid = min(kTile, p.Sk - j * kTile);
+                    const int valid = n_valid(kt, j);
                     const uint32_t idesc = umma_idesc_bf16(max(16, (valid + 15) & ~15), false, false);
-                    const uint32_t sK = smem_u32(smem + DqSmem::K0 + s * 2 * kAtomBytes);
-                    const uint32_t sV = smem_u32(smem + DqSmem::V0 + s * 2 * kAtomBytes);
+                    const uint32_t sK = smem_u32(smem + DqSmem::K0 + s * 2 * kAtomBytesN);
+                    const uint32_t sV = smem_u32(smem + DqSmem::V0 + s * 2 * kAtomBytesN);
 #pragma unroll
-                    for (int k = 0; k < HD_PAD / 16; ++k) {
-                        const uint32_t off = (k >> 2) * kAtomBytes + (k & 3) * 32;
-                        umma_bf16_ss(tmem_S, umma_smem_desc_sw128(sQ + off, 16, 1024),
-                                     umma_smem_desc_sw128(sK + off, 16, 1024), idesc, k != 0);
-                    }
+                    for (int k = 0; k < HD_PAD / 16; ++k)
+                        umma_bf16_ss(tmem_S, umma_smem_desc_sw128(sQ + (k >> 2) * kAtomBytes + (k & 3) * 32, 16, 1024),
+                                     umma_smem_desc_sw128(sK + (k >> 2) * kAtomBytesN + (k & 3) * 32, 16, 1024), idesc, k != 0);
 #pragma unroll
-                    for (int k = 0; k < HD_PAD / 16; ++k) {
-                        const uint32_t off = (k >> 2) * kAtomBytes + (k & 3) * 32;
-                        umma_bf16_ss(tmem_dP, umma_smem_desc_sw128(sDO + off, 16, 1024),
-                                     umma_smem_desc_sw128(sV + off, 16, 1024), idesc, k != 0);
-                    }
+                    for (int k = 0; k < HD_PAD / 16; ++k)
+                        umma_bf16_ss(tmem_dP, umma_smem_desc_sw128(sDO + (k >> 2) * kAtomBytes + (k & 3) * 32, 16, 1024),
+                                     umma_smem_desc_sw128(sV + (k >> 2) * kAtomBytesN + (k & 3) * 32, 16, 1024), idesc, k != 0);
                     umma_commit(sdp_full);
                 };
                 issue_scores(0, kvcount, tcount);
@@ -171,14 +172,12 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     const int s = kvcount & 1;
                     mbar_wait(ds_full, tcount & 1);
                     tc_fence_after();
-                    const int valid = min(kTile, p.Sk - j * kTile);
+                    const int valid = n_valid(kt, j);
                     const int ksteps = (valid + 15) >> 4;
-                    const uint32_t sK = smem_u32(smem + DqSmem::K0 + s * 2 * kAtomBytes);
-                    for (int k = 0; k < ksteps; ++k) {
-                        const uint32_t aoff = (k >> 2) * kAtomBytes + (k & 3) * 32;
-                        umma_bf16_ss(tmem_dQ, umma_smem_desc_sw128(sDS + aoff, 16, 1024),
-                                     umma_smem_desc_sw128(sK + k * 2048, kAtomBytes, 1024), idesc_dq, (j | k) != 0);
-                    }
+                    const uint32_t sK = smem_u32(smem + DqSmem::K0 + s * 2 * kAtomBytesN);
+                    for (int k = 0; k < ksteps; ++k)    // dQ += dS(TMEM, 16 keys = 8 columns per step) . K(MN-major)
+                        umma_bf16_ts(tmem_dQ, tmem_dS + k * 8, umma_smem_desc_sw128(sK + k * 2048, kAtomBytesN, 1024),
+                                     idesc_dq, (j | k) != 0);
                     umma_commit(&kv_empty[s]);
                     umma_commit(ds_empty);
                     ++kvcount; ++tcount;
@@ -188,117 +187,132 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
         }
     } else {
-        const int r = threadIdx.x;
-        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        // softmax warps 0..7: TMEM lane quarter = warp & 3; the two warps of a quarter alternate 32-key chunks
+        const int r = threadIdx.x & 127;
+        const int half = warp >> 2;
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
         const float sc2 = p.scale * kLog2e;
         uint32_t tcount = 0, wcount = 0;
-        uint8_t* sDS = smem + DqSmem::DS;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
             const int qt = w % nqt, bh = w / nqt;
             const int h = bh % p.H, b = bh / p.H;
             const int qi = qt * kTile + r;
             const bool row_ok = qi < p.Sq;
             const int64_t stat = ((int64_t)b * p.H + h) * p.Sq + (row_ok ? qi : 0);
-            const float lse2 = row_ok ? p.lse[stat] * kLog2e : 0.f;
-            const float dlt = row_ok ? p.delta[stat] : 0.f;
+            // rows past Sq get lse = +huge -> p = 0 -> dS = 0 with no per-element predicate
+            const float nlse2 = row_ok ? -p.lse[stat] * kLog2e : -1e30f;
+            const float ndlt = row_ok ? -p.delta[stat] * p.scale : 0.f;     // dS = p * (dP*scale - delta*scale)
             const float* mrow = p.mask ? p.mask + (int64_t)b * p.mask_bs + (int64_t)(row_ok ? qi : 0) * p.mask_qs : nullptr;
             for (int j = 0; j < nkv; ++j, ++tcount) {
-                const int valid = min(kTile, p.Sk - j * kTile);
+                const int valid = n_valid(kt, j);
                 const int nch = (valid + 31) >> 5;
                 mbar_wait(sdp_full, tcount & 1);
                 tc_fence_after();
-                mbar_wait(ds_empty, (tcount & 1) ^ 1);   // previous dQ MMA no longer reads the dS tile
-                for (int c = 0; c < nch; ++c) {
+                mbar_wait(ds_empty, (tcount & 1) ^ 1);   // previous dQ MMA no longer reads the dS operand
+                tc_fence_after();
+                for (int c = half; c < nch; c += 2) {
                     uint32_t sv[32], dv[32];
                     tmem_ld_x32(tmem_S + lane_off + c * 32, sv);
                     tmem_ld_x32(tmem_dP + lane_off + c * 32, dv);
                     tmem_ld_wait();
                     float ds[32];
+                    const int lim = valid - c * 32;
+                    if (!mrow && lim >= 32) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int col = c * 32 + i;
-                        float s = __uint_as_float(sv[i]) * sc2 - lse2;
-                        if (mrow) s += (col < valid ? mrow[j * kTile + col] : 0.f) * kLog2e;
-                        const float pr = exp2f(s);
-                        ds[i] = (col < valid && row_ok) ? pr * (__uint_as_float(dv[i]) - dlt) * p.scale : 0.f;
+                        for (int i = 0; i < 32; ++i)
+                            ds[i] = ex2_fast(fmaf(__uint_as_float(sv[i]), sc2, nlse2)) * fmaf(__uint_as_float(dv[i]), p.scale, ndlt);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float s = fmaf(__uint_as_float(sv[i]), sc2, nlse2);
+                            if (mrow && i < lim) s = fmaf(mrow[j * kTile + c * 32 + i], kLog2e, s);
+                            ds[i] = i < lim ? ex2_fast(s) * fmaf(__uint_as_float(dv[i]), p.scale, ndlt) : 0.f;
+                        }
                     }
-                    store_tile_chunk32(sDS, r, c * 32, ds);
+                    tmem_store_bf16x32(tmem_dS + lane_off + c * 16, ds);
                 }
+                tmem_st_wait();
                 tc_fence_before();
-                fence_proxy_async_smem();
                 __syncwarp();
                 if (lane_id() == 0) {
                     mbar_arrive(sdp_empty);
                     mbar_arrive(ds_full);
                 }
             }
-            mbar_wait(dq_full, wcount & 1);
-            tc_fence_after();
-            float acc[HD_PAD];
-            tmem_load_row<HD_PAD, false>(tmem_dQ + lane_off, acc);
-            tc_fence_before();
-            if (row_ok)
-                store_row_bf16<HD_PAD>(p.dq + (int64_t)b * p.dq_bs + (int64_t)qi * p.dq_rs + (int64_t)h * p.dq_hs, acc, p.D, 1.0f);
+            if (half == 0) {
+                mbar_wait(dq_full, wcount & 1);
+                tc_fence_after();
+                float acc[HD_PAD];
+                tmem_load_row<HD_PAD, false>(tmem_dQ + lane_off, acc);
+                tc_fence_before();
+                if (row_ok)
+                    store_row_bf16<HD_PAD>(p.dq + (int64_t)b * p.dq_bs + (int64_t)qi * p.dq_rs + (int64_t)h * p.dq_hs, acc, p.D, 1.0f);
+                // the next work item's first dQ MMA is ordered after these loads: it waits for ds_full, on which
+                // this warp arrives only later in program order
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == 9) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ dK, dV
+// TMEM columns: S^T [0,144)  dP^T [144,288)  dV [288,288+HD_PAD)  dK [384,384+HD_PAD).  P^T and dS^T (bf16 A operands)
+// overwrite the S^T / dP^T columns in place: the two warps of a lane quarter own disjoint column ranges
+// [0,hA) and [hA,n16) of the tile and write their packed output at the start of their own range, behind their reads.
 struct DkvSmem {
-    static constexpr int K = 0;
+    static constexpr int K = 0;                                   // 2 atoms x 128 rows
     static constexpr int V = 2 * kAtomBytes;
-    static constexpr int Q = 4 * kAtomBytes;
-    static constexpr int DO = 6 * kAtomBytes;
-    static constexpr int PT = 8 * kAtomBytes;
-    static constexpr int DST = 10 * kAtomBytes;
-    static constexpr int STATS = 12 * kAtomBytes;             // lse2[128], delta[128]
-    static constexpr int BARS = STATS + 1024;
+    static constexpr int Q0 = 4 * kAtomBytes;                     // 2 stages x 2 atoms x 144 rows
+    static constexpr int DO0 = Q0 + 4 * kAtomBytesN;
+    static constexpr int STATS = DO0 + 4 * kAtomBytesN;           // 2 stages x (-lse*log2e [256], -delta*scale [256])
+    static constexpr int BARS = STATS + 4 * 1024;
     static constexpr int TOTAL = BARS + 256 + 1024;
 };
+constexpr uint32_t kKvST = 0, kKvDPT = 144, kKvDV = 288, kKvDK = 384;
+
+__device__ __forceinline__ int split_a(int n16) { return ((n16 / 16 + 1) / 2) * 16; }   // columns owned by half 0
 
 template <int HD_PAD>
-__global__ void __launch_bounds__(kAttThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                const __grid_constant__ CUtensorMap tmQx, const __grid_constant__ CUtensorMap tmDOx, AttnBwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DkvSmem::BARS);
     uint64_t* kv_full = bars + 0;
     uint64_t* kv_empty = bars + 1;
-    uint64_t* qdo_full = bars + 2;
-    uint64_t* qdo_empty = bars + 3;
-    uint64_t* st_full = bars + 4;
-    uint64_t* st_empty = bars + 5;
-    uint64_t* pds_full = bars + 6;
-    uint64_t* pds_empty = bars + 7;
-    uint64_t* acc_full = bars + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-    float* s_lse2 = reinterpret_cast<float*>(smem + DkvSmem::STATS);
-    float* s_delta = s_lse2 + kTile;
+    uint64_t* qdo_full = bars + 2;    // [2]
+    uint64_t* qdo_empty = bars + 4;   // [2]
+    uint64_t* st_full = bars + 6;     // S^T, dP^T in TMEM
+    uint64_t* pds_full = bars + 7;    // P^T, dS^T operands in TMEM
+    uint64_t* acc_full = bars + 9;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int warp = threadIdx.x >> 5;
-    const int nqt = (p.Sq + kTile - 1) / kTile;
-    const int nkv = (p.Sk + kTile - 1) / kTile;
-    const int num_work = p.B * p.H * nkv;
+    const int nkt = m_tiles(p.Sk);
+    const NTiling qtl = n_tiling(p.Sq);
+    const int nqt = qtl.n;
+    const int num_work = p.B * p.H * nkt;
     constexpr int kAtoms = (HD_PAD + 63) / 64;
     constexpr uint32_t kTileBytes = kAtoms * kAtomBytes;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (elect_one()) {
             tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+            tma_prefetch_desc(&tmQx); tma_prefetch_desc(&tmDOx);
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         if (elect_one()) {
             mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
-            mbar_init(qdo_full, 1); mbar_init(qdo_empty, 1);
-            mbar_init(st_full, 1); mbar_init(st_empty, 4);
-            mbar_init(pds_full, 4); mbar_init(pds_empty, 1);
+            for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+            mbar_init(st_full, 1);
+            mbar_init(pds_full, 8);
             mbar_init(acc_full, 1);
             fence_mbar_init();
         }
@@ -309,13 +323,14 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_ST = tmem_base, tmem_dPT = tmem_base + 128, tmem_dV = tmem_base + 256, tmem_dK = tmem_base + 384;
+    const uint32_t tmem_ST = tmem_base + kKvST, tmem_dPT = tmem_base + kKvDPT, tmem_dV = tmem_base + kKvDV,
+                   tmem_dK = tmem_base + kKvDK;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (elect_one()) {
             uint32_t wcount = 0, qcount = 0;
             for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
-                const int jt = w % nkv, bh = w / nkv;
+                const int jt = w % nkt, bh = w / nkt;
                 const int h = bh % p.H, b = bh / p.H;
                 mbar_wait(kv_empty, (wcount & 1) ^ 1);
                 mbar_arrive_expect_tx(kv_full, 2 * kTileBytes);
@@ -325,135 +340,169 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     tma_load_4d(smem + DkvSmem::V + a * kAtomBytes, &tmV, kv_full, a * 64, h, jt * kTile, b);
                 }
                 for (int i = 0; i < nqt; ++i, ++qcount) {
-                    mbar_wait(qdo_empty, (qcount & 1) ^ 1);
-                    mbar_arrive_expect_tx(qdo_full, 2 * kTileBytes);
-#pragma unroll
-                    for (int a = 0; a < kAtoms; ++a) {
-                        tma_load_4d(smem + DkvSmem::Q + a * kAtomBytes, &tmQ, qdo_full, a * 64, h, i * kTile, b);
-                        tma_load_4d(smem + DkvSmem::DO + a * kAtomBytes, &tmDO, qdo_full, a * 64, h, i * kTile, b);
-                    }
+                    const int s = qcount & 1;
+                    mbar_wait(&qdo_empty[s], ((qcount >> 1) & 1) ^ 1);
+                    const bool ext = n_valid(qtl, i) > kTile;
+                    mbar_arrive_expect_tx(&qdo_full[s], 2 * n_tile_bytes(kAtoms, ext));
+                    load_n_tile<kAtoms>(smem + DkvSmem::Q0 + s * 2 * kAtomBytesN, &tmQ, &tmQx, &qdo_full[s], h, i * kTile, b, ext);
+                    load_n_tile<kAtoms>(smem + DkvSmem::DO0 + s * 2 * kAtomBytesN, &tmDO, &tmDOx, &qdo_full[s], h, i * kTile, b, ext);
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         if (elect_one()) {
             uint32_t wcount = 0, qcount = 0;
             const uint32_t sK = smem_u32(smem + DkvSmem::K), sV = smem_u32(smem + DkvSmem::V);
-            const uint32_t sQ = smem_u32(smem + DkvSmem::Q), sDO = smem_u32(smem + DkvSmem::DO);
-            const uint32_t sPT = smem_u32(smem + DkvSmem::PT), sDST = smem_u32(smem + DkvSmem::DST);
             constexpr uint32_t idesc_g = umma_idesc_bf16(HD_PAD, false, true);
             for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
                 mbar_wait(kv_full, wcount & 1);
                 tc_fence_after();
                 for (int i = 0; i < nqt; ++i, ++qcount) {
-                    mbar_wait(qdo_full, qcount & 1);
-                    mbar_wait(st_empty, (qcount & 1) ^ 1);
+                    const int s = qcount & 1;
+                    const uint32_t sQ = smem_u32(smem + DkvSmem::Q0 + s * 2 * kAtomBytesN);
+                    const uint32_t sDO = smem_u32(smem + DkvSmem::DO0 + s * 2 * kAtomBytesN);
+                    mbar_wait(&qdo_full[s], (qcount >> 1) & 1);
                     tc_fence_after();
-                    const int validq = min(kTile, p.Sq - i * kTile);
-                    const uint32_t idesc = umma_idesc_bf16(max(16, (validq + 15) & ~15), false, false);
+                    // S^T / dP^T columns are free: the previous tile's gradient MMAs (which read P^T / dS^T from
+                    // them) were issued by this thread earlier and tcgen05.mma executes in issue order.
+                    const int validq = n_valid(qtl, i);
+                    const int n16 = max(16, (validq + 15) & ~15);
+                    const uint32_t idesc = umma_idesc_bf16(n16, false, false);
 #pragma unroll
-                    for (int k = 0; k < HD_PAD / 16; ++k) {
-                        const uint32_t off = (k >> 2) * kAtomBytes + (k & 3) * 32;
-                        umma_bf16_ss(tmem_ST, umma_smem_desc_sw128(sK + off, 16, 1024),
-                                     umma_smem_desc_sw128(sQ + off, 16, 1024), idesc, k != 0);
-                    }
+                    for (int k = 0; k < HD_PAD / 16; ++k)
+                        umma_bf16_ss(tmem_ST, umma_smem_desc_sw128(sK + (k >> 2) * kAtomBytes + (k & 3) * 32, 16, 1024),
+                                     umma_smem_desc_sw128(sQ + (k >> 2) * kAtomBytesN + (k & 3) * 32, 16, 1024), idesc, k != 0);
 #pragma unroll
-                    for (int k = 0; k < HD_PAD / 16; ++k) {
-                        const uint32_t off = (k >> 2) * kAtomBytes + (k & 3) * 32;
-                        umma_bf16_ss(tmem_dPT, umma_smem_desc_sw128(sV + off, 16, 1024),
-                                     umma_smem_desc_sw128(sDO + off, 16, 1024), idesc, k != 0);
-                    }
+                    for (int k = 0; k < HD_PAD / 16; ++k)
+                        umma_bf16_ss(tmem_dPT, umma_smem_desc_sw128(sV + (k >> 2) * kAtomBytes + (k & 3) * 32, 16, 1024),
+                                     umma_smem_desc_sw128(sDO + (k >> 2) * kAtomBytesN + (k & 3) * 32, 16, 1024), idesc, k != 0);
                     umma_commit(st_full);
                     mbar_wait(pds_full, qcount & 1);
                     tc_fence_after();
-                    const int ksteps = (validq + 15) >> 4;
+                    const int ksteps = n16 >> 4;
+                    const int hA = split_a(n16);
                     for (int k = 0; k < ksteps; ++k) {
-                        const uint32_t aoff = (k >> 2) * kAtomBytes + (k & 3) * 32;
-                        umma_bf16_ss(tmem_dV, umma_smem_desc_sw128(sPT + aoff, 16, 1024),
-                                     umma_smem_desc_sw128(sDO + k * 2048, kAtomBytes, 1024), idesc_g, (i | k) != 0);
+                        const int q0 = k * 16;
+                        const uint32_t acol = q0 < hA ? q0 / 2 : hA + (q0 - hA) / 2;
+                        umma_bf16_ts(tmem_dV, tmem_ST + acol, umma_smem_desc_sw128(sDO + k * 2048, kAtomBytesN, 1024),
+                                     idesc_g, (i | k) != 0);
                     }
                     for (int k = 0; k < ksteps; ++k) {
-                        const uint32_t aoff = (k >> 2) * kAtomBytes + (k & 3) * 32;
-                        umma_bf16_ss(tmem_dK, umma_smem_desc_sw128(sDST + aoff, 16, 1024),
-                                     umma_smem_desc_sw128(sQ + k * 2048, kAtomBytes, 1024), idesc_g, (i | k) != 0);
+                        const int q0 = k * 16;
+                        const uint32_t acol = q0 < hA ? q0 / 2 : hA + (q0 - hA) / 2;
+                        umma_bf16_ts(tmem_dK, tmem_dPT + acol, umma_smem_desc_sw128(sQ + k * 2048, kAtomBytesN, 1024),
+                                     idesc_g, (i | k) != 0);
                     }
-                    umma_commit(qdo_empty);
-                    umma_commit(pds_empty);
+                    umma_commit(&qdo_empty[s]);
                 }
                 umma_commit(acc_full);
                 umma_commit(kv_empty);
             }
         }
     } else {
-        const int r = threadIdx.x;                    // key row within the tile
-        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        const int r = threadIdx.x & 127;              // key row within the tile
+        const int half = warp >> 2;
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
         const float sc2 = p.scale * kLog2e;
         uint32_t qcount = 0, wcount = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
-            const int jt = w % nkv, bh = w / nkv;
+            const int jt = w % nkt, bh = w / nkt;
             const int h = bh % p.H, b = bh / p.H;
             const int kj = jt * kTile + r;
             const bool key_ok = kj < p.Sk;
             const int64_t stat0 = ((int64_t)b * p.H + h) * p.Sq;
             for (int i = 0; i < nqt; ++i, ++qcount) {
-                const int validq = min(kTile, p.Sq - i * kTile);
-                const int nch = (validq + 31) >> 5;
-                // stage this q tile's lse / delta (previous tile's readers are past their last use: they have
-                // all arrived on pds_full, and we only get here after waiting st_full of this tile)
-                softmax_group_sync();
-                s_lse2[r] = (r < validq) ? p.lse[stat0 + i * kTile + r] * kLog2e : 0.f;
-                s_delta[r] = (r < validq) ? p.delta[stat0 + i * kTile + r] : 0.f;
-                softmax_group_sync();
+                const int validq = n_valid(qtl, i);
+                const int n16 = max(16, (validq + 15) & ~15);
+                const int hA = split_a(n16);
+                // stage this q tile's lse / delta in the stats buffer of parity qcount & 1: its previous readers
+                // (tile qcount - 2) all passed the 256-thread barrier of tile qcount - 1 after their last read
+                float* s_nlse2 = reinterpret_cast<float*>(smem + DkvSmem::STATS + (qcount & 1) * 2048);
+                float* s_ndlt = s_nlse2 + 256;
+                if (threadIdx.x < 160) {
+                    // queries past the tile's valid count get lse = +huge -> p = 0, dS = 0 with no per-element predicate
+                    const int t = threadIdx.x;
+                    s_nlse2[t] = (t < validq) ? -p.lse[stat0 + i * kTile + t] * kLog2e : -1e30f;
+                    s_ndlt[t] = (t < validq) ? -p.delta[stat0 + i * kTile + t] * p.scale : 0.f;
+                }
+                softmax_group_sync256();
                 mbar_wait(st_full, qcount & 1);
                 tc_fence_after();
-                mbar_wait(pds_empty, (qcount & 1) ^ 1);
-                for (int c = 0; c < nch; ++c) {
+                const int c_begin = half == 0 ? 0 : hA, c_end = half == 0 ? hA : n16;
+                const bool masked = p.mask != nullptr;
+                for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                     uint32_t sv[32], dv[32];
-                    tmem_ld_x32(tmem_ST + lane_off + c * 32, sv);
-                    tmem_ld_x32(tmem_dPT + lane_off + c * 32, dv);
-                    tmem_ld_wait();
                     float pt[32], dst[32];
+                    const bool full = c_end - c0 >= 32;
+                    if (full) {
+                        tmem_ld_x32(tmem_ST + lane_off + c0, sv);
+                        tmem_ld_x32(tmem_dPT + lane_off + c0, dv);
+                    } else {   // 16-column remainder of this half
+                        uint32_t a16[16], b16[16];
+                        tmem_ld_x16(tmem_ST + lane_off + c0, a16);
+                        tmem_ld_x16(tmem_dPT + lane_off + c0, b16);
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        const int col = c * 32 + q;                 // query within the tile
-                        float s = __uint_as_float(sv[q]) * sc2 - s_lse2[col];
-                        if (p.mask && key_ok && col < validq)
-                            s += p.mask[(int64_t)b * p.mask_bs + (int64_t)(i * kTile + col) * p.mask_qs + kj] * kLog2e;
-                        const bool ok = key_ok && col < validq;
-                        const float pr = ok ? exp2f(s) : 0.f;
-                        pt[q] = pr;
-                        dst[q] = ok ? pr * (__uint_as_float(dv[q]) - s_delta[col]) * p.scale : 0.f;
+                        for (int q = 0; q < 16; ++q) { sv[q] = a16[q]; dv[q] = b16[q]; sv[16 + q] = 0; dv[16 + q] = 0; }
                     }
-                    store_tile_chunk32(smem + DkvSmem::PT, r, c * 32, pt);
-                    store_tile_chunk32(smem + DkvSmem::DST, r, c * 32, dst);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q4 = 0; q4 < 8; ++q4) {
+                        const float4 l4 = *reinterpret_cast<const float4*>(s_nlse2 + c0 + q4 * 4);   // c0 + 32 <= 160
+                        const float4 d4 = *reinterpret_cast<const float4*>(s_ndlt + c0 + q4 * 4);
+                        const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int q = q4 * 4 + e;
+                            float s = fmaf(__uint_as_float(sv[q]), sc2, ls[e]);
+                            if (masked && key_ok && c0 + q < validq)
+                                s = fmaf(p.mask[(int64_t)b * p.mask_bs + (int64_t)(i * kTile + c0 + q) * p.mask_qs + kj], kLog2e, s);
+                            pt[q] = ex2_fast(s);
+                            dst[q] = pt[q] * fmaf(__uint_as_float(dv[q]), p.scale, dl[e]);
+                        }
+                    }
+                    // packed bf16 output: 16 (or 8) columns at the start of this half's own range, behind its reads
+                    const uint32_t ocol = c_begin + (c0 - c_begin) / 2;
+                    if (full) {
+                        tmem_store_bf16x32(tmem_ST + lane_off + ocol, pt);
+                        tmem_store_bf16x32(tmem_dPT + lane_off + ocol, dst);
+                    } else {
+                        uint32_t w0[8], w1[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            w0[q] = pack_bf16x2(pt[2 * q], pt[2 * q + 1]);
+                            w1[q] = pack_bf16x2(dst[2 * q], dst[2 * q + 1]);
+                        }
+                        tmem_st_x8(tmem_ST + lane_off + ocol, w0);
+                        tmem_st_x8(tmem_dPT + lane_off + ocol, w1);
+                    }
                 }
+                tmem_st_wait();
                 tc_fence_before();
-                fence_proxy_async_smem();
                 __syncwarp();
-                if (lane_id() == 0) {
-                    mbar_arrive(st_empty);
-                    mbar_arrive(pds_full);
-                }
+                if (lane_id() == 0) mbar_arrive(pds_full);
             }
             mbar_wait(acc_full, wcount & 1);
             tc_fence_after();
             {
                 float acc[HD_PAD];
-                tmem_load_row<HD_PAD, false>(tmem_dV + lane_off, acc);
-                if (key_ok)
-                    store_row_bf16<HD_PAD>(p.dv + (int64_t)b * p.dv_bs + (int64_t)kj * p.dv_rs + (int64_t)h * p.dv_hs, acc, p.D, 1.0f);
-                tmem_load_row<HD_PAD, false>(tmem_dK + lane_off, acc);
-                if (key_ok)
-                    store_row_bf16<HD_PAD>(p.dk + (int64_t)b * p.dk_bs + (int64_t)kj * p.dk_rs + (int64_t)h * p.dk_hs, acc, p.D, 1.0f);
+                if (half == 0) {
+                    tmem_load_row<HD_PAD, false>(tmem_dV + lane_off, acc);
+                    if (key_ok)
+                        store_row_bf16<HD_PAD>(p.dv + (int64_t)b * p.dv_bs + (int64_t)kj * p.dv_rs + (int64_t)h * p.dv_hs, acc, p.D, 1.0f);
+                } else {
+                    tmem_load_row<HD_PAD, false>(tmem_dK + lane_off, acc);
+                    if (key_ok)
+                        store_row_bf16<HD_PAD>(p.dk + (int64_t)b * p.dk_bs + (int64_t)kj * p.dk_rs + (int64_t)h * p.dk_hs, acc, p.D, 1.0f);
+                }
             }
             tc_fence_before();
-            // the next work item's first MMAs overwrite dV/dK: they are ordered after our reads through
-            // st_empty (arrived only after these loads in program order on the next tile).
+            // the next work item's first gradient MMAs overwrite dV/dK: they wait for pds_full, on which every
+            // softmax warp arrives only after these loads in program order.
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == 9) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
@@ -484,12 +533,16 @@ extern "C" int mico_attention_bwd(const MicoAttnArgs* a, void* stream_) {
             reinterpret_cast<const __nv_bfloat16*>(a->dout), a->do_bs, a->do_rs, a->do_hs, a->delta, a->B, a->H, a->Sq, a->D);
         MICO_CHECK_CUDA(cudaGetLastError());
     }
-    CUtensorMap tq, tk, tv, tdo;
+    CUtensorMap tq, tk, tv, tdo, tqx, tkx, tvx, tdox;
     int rc;
     if ((rc = make_attn_tmap(&tq, a->q, a->D, a->H, a->Sq, a->B, a->q_bs, a->q_rs, a->q_hs))) return rc;
     if ((rc = make_attn_tmap(&tk, a->k, a->D, a->H, a->Sk, a->B, a->k_bs, a->k_rs, a->k_hs))) return rc;
     if ((rc = make_attn_tmap(&tv, a->v, a->D, a->H, a->Sk, a->B, a->v_bs, a->v_rs, a->v_hs))) return rc;
     if ((rc = make_attn_tmap(&tdo, a->dout, a->D, a->H, a->Sq, a->B, a->do_bs, a->do_rs, a->do_hs))) return rc;
+    if ((rc = make_attn_tmap(&tqx, a->q, a->D, a->H, a->Sq, a->B, a->q_bs, a->q_rs, a->q_hs, kExtRows))) return rc;
+    if ((rc = make_attn_tmap(&tkx, a->k, a->D, a->H, a->Sk, a->B, a->k_bs, a->k_rs, a->k_hs, kExtRows))) return rc;
+    if ((rc = make_attn_tmap(&tvx, a->v, a->D, a->H, a->Sk, a->B, a->v_bs, a->v_rs, a->v_hs, kExtRows))) return rc;
+    if ((rc = make_attn_tmap(&tdox, a->dout, a->D, a->H, a->Sq, a->B, a->do_bs, a->do_rs, a->do_hs, kExtRows))) return rc;
     AttnBwdParams p;
     p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk; p.D = a->D; p.scale = a->scale;
     p.mask = a->mask; p.mask_bs = a->mask_bs; p.mask_qs = a->mask_qs;
@@ -498,25 +551,27 @@ extern "C" int mico_attention_bwd(const MicoAttnArgs* a, void* stream_) {
     p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk); p.dk_bs = a->dk_bs; p.dk_rs = a->dk_rs; p.dk_hs = a->dk_hs;
     p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv); p.dv_bs = a->dv_bs; p.dv_rs = a->dv_rs; p.dv_hs = a->dv_hs;
     const int hd_pad = (a->D + 15) & ~15;
-    const int work_q = a->B * a->H * ceil_div(a->Sq, kTile);
-    const int work_k = a->B * a->H * ceil_div(a->Sk, kTile);
+    const int work_q = a->B * a->H * m_tiles(a->Sq);
+    const int work_k = a->B * a->H * m_tiles(a->Sk);
     auto launch = [&](auto kq, auto kkv) -> int {
         MICO_CHECK_CUDA(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::TOTAL));
         MICO_CHECK_CUDA(cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem::TOTAL));
-        kq<<<work_q < num_sms() ? work_q : num_sms(), kAttThreads, DqSmem::TOTAL, stream>>>(tq, tk, tv, tdo, p);
+        kq<<<work_q < num_sms() ? work_q : num_sms(), kBwdThreads, DqSmem::TOTAL, stream>>>(tq, tk, tv, tdo, tkx, tvx, p);
         MICO_CHECK_CUDA(cudaGetLastError());
-        kkv<<<work_k < num_sms() ? work_k : num_sms(), kAttThreads, DkvSmem::TOTAL, stream>>>(tq, tk, tv, tdo, p);
+        kkv<<<work_k < num_sms() ? work_k : num_sms(), kBwdThreads, DkvSmem::TOTAL, stream>>>(tq, tk, tv, tdo, tqx, tdox, p);
         MICO_CHECK_CUDA(cudaGetLastError());
         count_launch(3);
+        if (m_tail_rows(a->Sq) || m_tail_rows(a->Sk)) return attention_tail_bwd(a, stream);
         return MICO_OK;
     };
     switch (hd_pad) {
         case 32: return launch(attn_dq_kernel<32>, attn_dkv_kernel<32>);
         case 64: return launch(attn_dq_kernel<64>, attn_dkv_kernel<64>);
         case 96: return launch(attn_dq_kernel<96>, attn_dkv_kernel<96>);
-        case 128: return launch(attn_dq_kernel<128>, attn_dkv_kernel<128>);
         default:
-            set_last_error(__FILE__, __LINE__, "head_dim must pad to 32, 64, 96 or 128");
+            // head_dim 128 would need 2 x 144 + 2 x 128 TMEM columns in attn_dkv_kernel; no tower on the MiCo path
+            // has it (ViT-g 88, BERT / CLIP 64, Swin 32)
+            set_last_error(__FILE__, __LINE__, "attention backward: head_dim must pad to 32, 64 or 96");
             return MICO_ERR_UNSUPPORTED;
     }
 }

@@ -3,7 +3,10 @@
 // Replaces the naive 3-kernel attention (bmm -> softmax -> bmm, B*H*N*N scores in HBM) at
 // eva_vit_model.py:340-361, bert.py:233-277, transformer.py:121-130, clip.py (nn.MultiheadAttention).
 //
-// One persistent CTA per SM; a work item is (batch, head, 128-row query tile).  Warp roles:
+// One persistent CTA per SM; a work item is (batch, head, 128-row query tile).  Keys are streamed in tiles of
+// 128 rows, the last of which absorbs a remainder of <= 16 keys (N = 144 MMA), and a query remainder of <= 8
+// rows is computed by the SIMT tail kernel (attention_tail.cu): for the ViT's 257 tokens that is 2 x 2 tile
+// pairs per (batch, head) instead of 3 x 3 mostly-empty ones.  Warp roles:
 //   warps 0-3  softmax: own one query row each (TMEM lane == row); online softmax in fp32, P -> smem (bf16)
 //   warp 4     TMA producer: Q tile once, K/V tiles double-buffered (4-D tensor maps: d, head, row, batch;
 //              head_dim is zero-padded to a multiple of 16 by TMA out-of-bounds fill -- d=88 -> 96)
@@ -27,18 +30,20 @@ struct AttnFwdParams {
 };
 
 struct AttnSmem {
-    static constexpr int Q = 0;
-    static constexpr int K0 = 2 * kAtomBytes;
-    static constexpr int V0 = K0 + 2 * 2 * kAtomBytes;
-    static constexpr int P = V0 + 2 * 2 * kAtomBytes;
-    static constexpr int BARS = P + 2 * kAtomBytes;
+    static constexpr int Q = 0;                                  // 2 atoms x 128 rows
+    static constexpr int K0 = 2 * kAtomBytes;                    // 2 stages x 2 atoms x 144 rows
+    static constexpr int V0 = K0 + 2 * 2 * kAtomBytesN;
+    static constexpr int P = V0 + 2 * 2 * kAtomBytesN;           // 128 x 144 bf16 = 3 atoms
+    static constexpr int BARS = P + 3 * kAtomBytes;
     static constexpr int TOTAL = BARS + 256 + 1024;
 };
+constexpr int kSStride = 160;   // TMEM columns between the two S buffers (a 144-wide tile is read in 5 x 32 columns)
 
 template <int HD_PAD>
 __global__ void __launch_bounds__(kAttThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, AttnFwdParams p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKx,
+                const __grid_constant__ CUtensorMap tmVx, AttnFwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem::BARS);
@@ -53,8 +58,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int warp = threadIdx.x >> 5;
-    const int nqt = (p.Sq + kTile - 1) / kTile;
-    const int nkv = (p.Sk + kTile - 1) / kTile;
+    const int nqt = m_tiles(p.Sq);
+    const NTiling kt = n_tiling(p.Sk);
+    const int nkv = kt.n;
     const int num_work = p.B * p.H * nqt;
     constexpr int kAtoms = (HD_PAD + 63) / 64;          // 64-wide d atoms per tile
     constexpr uint32_t kTileBytes = kAtoms * kAtomBytes;
@@ -64,6 +70,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tma_prefetch_desc(&tmQ);
             tma_prefetch_desc(&tmK);
             tma_prefetch_desc(&tmV);
+            tma_prefetch_desc(&tmKx);
+            tma_prefetch_desc(&tmVx);
         }
     } else if (warp == 5) {
         if (elect_one()) {
@@ -86,8 +94,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base;          // 2 x 128 columns
-    const uint32_t tmem_O = tmem_base + 256;    // HD_PAD columns
+    const uint32_t tmem_S = tmem_base;                    // 2 x kSStride columns
+    const uint32_t tmem_O = tmem_base + 2 * kSStride;     // HD_PAD columns
 
     if (warp == 4) {
         // ------------------------------------------------------------------ TMA producer
@@ -104,14 +112,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 for (int j = 0; j < nkv; ++j, ++kvcount) {
                     const int s = kvcount & 1;
                     mbar_wait(&kv_empty[s], ((kvcount >> 1) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&kv_full[s], 2 * kTileBytes);
-#pragma unroll
-                    for (int a = 0; a < kAtoms; ++a) {
-                        tma_load_4d(smem + AttnSmem::K0 + s * 2 * kAtomBytes + a * kAtomBytes, &tmK, &kv_full[s], a * 64,
-                                    h, j * kTile, b);
-                        tma_load_4d(smem + AttnSmem::V0 + s * 2 * kAtomBytes + a * kAtomBytes, &tmV, &kv_full[s], a * 64,
-                                    h, j * kTile, b);
-                    }
+                    const bool ext = n_valid(kt, j) > kTile;
+                    mbar_arrive_expect_tx(&kv_full[s], 2 * n_tile_bytes(kAtoms, ext));
+                    load_n_tile<kAtoms>(smem + AttnSmem::K0 + s * 2 * kAtomBytesN, &tmK, &tmKx, &kv_full[s], h, j * kTile, b, ext);
+                    load_n_tile<kAtoms>(smem + AttnSmem::V0 + s * 2 * kAtomBytesN, &tmV, &tmVx, &kv_full[s], h, j * kTile, b, ext);
                 }
             }
         }
@@ -130,15 +134,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     mbar_wait(&kv_full[s], (kvc >> 1) & 1);
                     mbar_wait(&s_empty[sb], ((sc >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    const int valid = min(kTile, p.Sk - j * kTile);
+                    const int valid = n_valid(kt, j);
                     const int n = max(16, (valid + 15) & ~15);
                     const uint32_t idesc = umma_idesc_bf16(n, false, false);
-                    const uint32_t sK = smem_u32(smem + AttnSmem::K0 + s * 2 * kAtomBytes);
+                    const uint32_t sK = smem_u32(smem + AttnSmem::K0 + s * 2 * kAtomBytesN);
 #pragma unroll
                     for (int k = 0; k < HD_PAD / 16; ++k) {
-                        const uint32_t off = (k >> 2) * kAtomBytes + (k & 3) * 32;
-                        umma_bf16_ss(tmem_S + sb * 128, umma_smem_desc_sw128(sQ + off, 16, 1024),
-                                     umma_smem_desc_sw128(sK + off, 16, 1024), idesc, k != 0);
+                        umma_bf16_ss(tmem_S + sb * kSStride,
+                                     umma_smem_desc_sw128(sQ + (k >> 2) * kAtomBytes + (k & 3) * 32, 16, 1024),
+                                     umma_smem_desc_sw128(sK + (k >> 2) * kAtomBytesN + (k & 3) * 32, 16, 1024), idesc,
+                                     k != 0);
                     }
                     umma_commit(&s_full[sb]);
                 };
@@ -148,13 +153,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     const int s = kvcount & 1;
                     mbar_wait(p_full, pcount & 1);
                     tc_fence_after();
-                    const int valid = min(kTile, p.Sk - j * kTile);
+                    const int valid = n_valid(kt, j);
                     const int ksteps = (valid + 15) >> 4;
-                    const uint32_t sV = smem_u32(smem + AttnSmem::V0 + s * 2 * kAtomBytes);
+                    const uint32_t sV = smem_u32(smem + AttnSmem::V0 + s * 2 * kAtomBytesN);
                     for (int k = 0; k < ksteps; ++k) {
                         const uint32_t aoff = (k >> 2) * kAtomBytes + (k & 3) * 32;
                         umma_bf16_ss(tmem_O, umma_smem_desc_sw128(sP + aoff, 16, 1024),
-                                     umma_smem_desc_sw128(sV + k * 2048, kAtomBytes, 1024), idesc_pv, k != 0);
+                                     umma_smem_desc_sw128(sV + k * 2048, kAtomBytesN, 1024), idesc_pv, k != 0);
                     }
                     umma_commit(&kv_empty[s]);
                     umma_commit(o_full);
@@ -183,27 +188,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
             for (int j = 0; j < nkv; ++j, ++scount) {
                 const int sb = scount & 1;
-                const int valid = min(kTile, p.Sk - j * kTile);
+                const int valid = n_valid(kt, j);
                 const int nch = (valid + 31) >> 5;
-                const uint32_t tS = tmem_S + sb * 128 + lane_off;
+                const uint32_t tS = tmem_S + sb * kSStride + lane_off;
                 mbar_wait(&s_full[sb], (scount >> 1) & 1);
                 tc_fence_after();
-                // pass 1: row max (log2 domain)
+                // pass 1: row max (log2 domain).  scale > 0, so without a mask the max is taken on the raw scores.
                 float mx = -INFINITY;
                 for (int c = 0; c < nch; ++c) {
                     uint32_t v[32];
                     tmem_ld_x32(tS + c * 32, v);
                     tmem_ld_wait();
+                    const int lim = valid - c * 32;
+                    if (!mrow && lim >= 32) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int col = c * 32 + i;
-                        float s = __uint_as_float(v[i]) * sc2;
-                        if (mrow) s += (col < valid ? mrow[j * kTile + col] : 0.f) * kLog2e;
-                        mx = fmaxf(mx, col < valid ? s : -INFINITY);
+                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    } else if (!mrow) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, i < lim ? __uint_as_float(v[i]) : -INFINITY);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float s = i < lim ? fmaf(__uint_as_float(v[i]), sc2, mrow[j * kTile + c * 32 + i] * kLog2e)
+                                                    : -INFINITY;
+                            mx = fmaxf(mx, s);
+                        }
                     }
                 }
+                if (!mrow) mx *= sc2;
                 const float m_new = fmaxf(m, mx);
-                const float alpha = exp2f(m - m_new);      // m = -inf on the first tile -> 0
+                const float alpha = ex2_fast(m - m_new);   // m = -inf on the first tile -> 0
                 // fold the previous tile's P V (its MMA finished long ago) before P smem is overwritten
                 if (j > 0) {
                     mbar_wait(o_full, ocount & 1);
@@ -234,14 +248,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     tmem_ld_x32(tS + c * 32, v);
                     tmem_ld_wait();
                     float pv[32];
+                    const int lim = valid - c * 32;
+                    if (!mrow && lim >= 32) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int col = c * 32 + i;
-                        float s = __uint_as_float(v[i]) * sc2;
-                        if (mrow) s += (col < valid ? mrow[j * kTile + col] : 0.f) * kLog2e;
-                        const float e = (col < valid) ? exp2f(s - m_new) : 0.f;
-                        pv[i] = e;
-                        sum += e;
+                        for (int i = 0; i < 32; ++i) {
+                            pv[i] = ex2_fast(fmaf(__uint_as_float(v[i]), sc2, -m_new));
+                            sum += pv[i];
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float s = fmaf(__uint_as_float(v[i]), sc2, -m_new);
+                            if (mrow && i < lim) s = fmaf(mrow[j * kTile + c * 32 + i], kLog2e, s);
+                            pv[i] = i < lim ? ex2_fast(s) : 0.f;
+                            sum += pv[i];
+                        }
                     }
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -311,10 +332,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 }  // namespace
 
-int make_attn_tmap(CUtensorMap* tm, const void* base, int D, int H, int S, int B, int64_t bs, int64_t rs, int64_t hs) {
+int make_attn_tmap(CUtensorMap* tm, const void* base, int D, int H, int S, int B, int64_t bs, int64_t rs, int64_t hs,
+                   int box_rows) {
     const uint64_t dims[4] = {(uint64_t)D, (uint64_t)H, (uint64_t)S, (uint64_t)B};
     const uint64_t strides[4] = {2, (uint64_t)hs * 2, (uint64_t)rs * 2, (uint64_t)bs * 2};
-    const uint32_t box[4] = {64, 1, 128, 1};
+    const uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
     return make_tmap_bf16(tm, base, 4, dims, strides, box);
 }
 
@@ -325,6 +347,7 @@ extern "C" int mico_attention_fwd(const MicoAttnArgs* a, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     MICO_CHECK_ARG(a && a->q && a->k && a->v && a->o);
     MICO_CHECK_ARG(a->B > 0 && a->H > 0 && a->Sq > 0 && a->Sk > 0);
+    MICO_CHECK_ARG(a->scale > 0.0f);   // the row max is taken on unscaled scores
     MICO_CHECK_ARG(a->D % 8 == 0 && a->D >= 16 && a->D <= 128);
     for (const int64_t s : {a->q_bs, a->q_rs, a->q_hs, a->k_bs, a->k_rs, a->k_hs, a->v_bs, a->v_rs, a->v_hs, a->o_bs,
                             a->o_rs, a->o_hs})
@@ -332,25 +355,28 @@ extern "C" int mico_attention_fwd(const MicoAttnArgs* a, void* stream_) {
     for (const void* ptr : {a->q, a->k, a->v, (const void*)a->o})
         MICO_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0);
     ProfScope prof(kProfAttnFwd, 4.0 * a->B * a->H * (double)a->Sq * a->Sk * a->D, stream);
-    CUtensorMap tq, tk, tv;
+    CUtensorMap tq, tk, tv, tkx, tvx;
     int rc;
     if ((rc = make_attn_tmap(&tq, a->q, a->D, a->H, a->Sq, a->B, a->q_bs, a->q_rs, a->q_hs))) return rc;
     if ((rc = make_attn_tmap(&tk, a->k, a->D, a->H, a->Sk, a->B, a->k_bs, a->k_rs, a->k_hs))) return rc;
     if ((rc = make_attn_tmap(&tv, a->v, a->D, a->H, a->Sk, a->B, a->v_bs, a->v_rs, a->v_hs))) return rc;
+    if ((rc = make_attn_tmap(&tkx, a->k, a->D, a->H, a->Sk, a->B, a->k_bs, a->k_rs, a->k_hs, kExtRows))) return rc;
+    if ((rc = make_attn_tmap(&tvx, a->v, a->D, a->H, a->Sk, a->B, a->v_bs, a->v_rs, a->v_hs, kExtRows))) return rc;
     AttnFwdParams p;
     p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk; p.D = a->D;
     p.scale = a->scale;
     p.mask = a->mask; p.mask_bs = a->mask_bs; p.mask_qs = a->mask_qs;
     p.o = reinterpret_cast<__nv_bfloat16*>(a->o); p.o_bs = a->o_bs; p.o_rs = a->o_rs; p.o_hs = a->o_hs;
     p.lse = a->lse;
-    const int work = a->B * a->H * ceil_div(a->Sq, kTile);
+    const int work = a->B * a->H * m_tiles(a->Sq);
     const int grid = work < num_sms() ? work : num_sms();
     const int hd_pad = (a->D + 15) & ~15;
     auto launch = [&](auto kern) -> int {
         MICO_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
-        kern<<<grid, kAttThreads, AttnSmem::TOTAL, stream>>>(tq, tk, tv, p);
+        kern<<<grid, kAttThreads, AttnSmem::TOTAL, stream>>>(tq, tk, tv, tkx, tvx, p);
         MICO_CHECK_CUDA(cudaGetLastError());
         count_launch();
+        if (m_tail_rows(a->Sq)) return attention_tail_fwd(a, stream);
         return MICO_OK;
     };
     switch (hd_pad) {

@@ -183,6 +183,11 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------ small math helpers
@@ -193,16 +198,45 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (nn.GELU default, eva_vit_model.py:173; ACT2FN["gelu"], bert.py:354) and its derivative.
+// erfc(|z|) = poly5(t) * exp(-z^2), t = 1/(1 + p|z|)  (Abramowitz & Stegun 7.1.26, |abs err| <= 1.5e-7): two MUFU
+// ops (ex2, rcp) + a 5-term Horner chain instead of erff()'s branchy ~40 instructions -- the GEMM epilogue
+// applies this to 128x256 accumulators per tile and has to stay under the tile's MMA time.  Evaluating the
+// complementary function keeps the x << 0 tail free of cancellation.  With z = x/sqrt(2), exp(-z^2) is also
+// the Gaussian of the derivative, so gelu'(x) = Phi(x) + x*phi(x) costs the same two MUFU ops.
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& gauss) {
+    const float az = fabsf(x) * 0.70710678118654752f;
+    const float e = __expf(-az * az);                       // exp(-x^2/2)
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float half_erfc = 0.5f * p * t * e;               // 0.5 * erfc(|z|)
+    cdf = x < 0.0f ? half_erfc : 1.0f - half_erfc;
+    gauss = e;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+    float cdf, g;
+    gelu_parts(x, cdf, g);
+    return x * cdf;
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-    const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-    return cdf + x * pdf;
+    float cdf, g;
+    gelu_parts(x, cdf, g);
+    return fmaf(x * 0.3989422804014327f, g, cdf);
 }
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 __device__ __forceinline__ float quick_gelu_grad(float x) {
     const float s = 1.0f / (1.0f + __expf(-1.702f * x));
     return s * (1.0f + 1.702f * x * (1.0f - s));
+}
+
+// 2^x on the MUFU unit, one instruction (no range fix-ups: callers pass x <= ~0 or accept +inf saturation)
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

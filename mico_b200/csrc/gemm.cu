@@ -2,11 +2,13 @@
 //
 //   out[M,N] = epilogue(alpha * A[M,K] . B[N,K]^T)      fp32 accumulation in TMEM
 //
-// Structure (one CTA per SM, 192 threads):
+// Structure (one CTA per SM, 320 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled tiles -> STAGES-deep smem ring
 //   warp 1      MMA issuer:   one elected lane issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage,
 //                             tcgen05.commit releases smem slots and publishes the accumulator
-//   warps 2..5  epilogue:     tcgen05.ld TMEM -> registers -> fused bias/GELU/DropPath/residual -> HBM
+//   warps 2..9  epilogue:     tcgen05.ld TMEM -> registers -> fused bias/GELU/DropPath/residual -> HBM
+//                             (two warps per TMEM lane quarter, alternating 32-column chunks: two resident
+//                             epilogue warps per scheduler hide the global-load / MUFU latency of the fused math)
 // Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 // Either operand may be "MN-major" (the contraction index is the slow dimension in HBM); that is how
 // wgrad (dW = dY^T X) and dgrad (dX = dY W) run on the same kernel with no transposes in HBM.
@@ -22,7 +24,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;
 constexpr int kAccStride = 256;   // TMEM columns between the two accumulator stages
 
 struct GemmEpi {
@@ -206,7 +208,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             for (int a = 0; a < 2; ++a) {
                 mbar_init(&tfull_bar[a], 1);
-                mbar_init(&tempty_bar[a], 4);
+                mbar_init(&tempty_bar[a], 8);
             }
             fence_mbar_init();
         }
@@ -282,8 +284,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else {
-        // ------------------------------------------------------------- epilogue (warps 2..5)
-        const int q = warp & 3;   // TMEM lane quarter this warp may access
+        // ------------------------------------------------------------- epilogue (warps 2..9)
+        const int q = warp & 3;            // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;  // which of the two warps of that quarter: owns chunks c with (c & 1) == half
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -295,7 +298,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int row = m0 + q * 32 + (int)lane_id();
             const uint32_t t0 = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = half; c < BN / 32; c += 2) {
                 if (n0 + c * 32 >= N) break;   // warp-uniform
                 uint32_t v[32];
                 tmem_ld_x32(t0 + c * 32, v);
@@ -304,7 +307,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             if constexpr (BN % 32 != 0) {
                 constexpr int c0 = (BN / 32) * 32;
-                if (n0 + c0 < N) {
+                if (half == ((BN / 32) & 1) && n0 + c0 < N) {
                     uint32_t v[16];
                     tmem_ld_x16(t0 + c0, v);
                     tmem_ld_wait();

@@ -27,7 +27,8 @@ def _attn_ref(q, k, v, scale, mask=None):
 
 
 @pytest.mark.parametrize("B,H,S,D", [(2, 2, 257, 88), (1, 3, 128, 64), (2, 4, 49, 32), (1, 2, 300, 128),
-                                     (3, 16, 257, 88)])
+                                     (3, 16, 257, 88), (1, 2, 136, 64), (2, 2, 264, 88), (1, 1, 513, 32),
+                                     (1, 2, 144, 88), (1, 2, 145, 64)])
 def test_attention_fwd_fused_qkv(B, H, S, D):
     from mico_b200 import ops
     qkv = _randn((B, S, 3, H, D), 1, 1.0, torch.bfloat16)
@@ -133,8 +134,10 @@ def test_patchify_matches_conv():
 
 @pytest.mark.parametrize("B,H,Sq,Sk,D,masked", [(2, 2, 257, 257, 88, False), (1, 3, 128, 128, 64, False),
                                                 (2, 12, 40, 257, 64, True), (2, 4, 49, 49, 32, False),
-                                                (1, 2, 300, 200, 128, True), (3, 16, 257, 257, 88, False),
-                                                (2, 12, 128, 128, 64, "3d")])
+                                                (1, 2, 300, 200, 96, True), (3, 16, 257, 257, 88, False),
+                                                (2, 12, 128, 128, 64, "3d"), (1, 2, 264, 136, 64, True),
+                                                (2, 1, 129, 129, 32, "3d"), (1, 3, 144, 385, 88, False),
+                                                (1, 2, 16, 2056, 64, True)])
 def test_attention_bwd(B, H, Sq, Sk, D, masked):
     """dQ/dK/dV vs autograd of the fp32 reference on the same bf16 inputs.
     Tolerance 1e-2 rel-L2: P, dS and the outputs are each rounded to bf16 once (3 x 2^-9 in quadrature ~ 4e-3)."""
