@@ -53,33 +53,60 @@ struct GemmCfg {
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + alignment slack
+    static constexpr int BIAS_BYTES = 2 * 256 * 4;   // bias slice of the tile, one copy per accumulator stage
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;   // + alignment slack
+};
+
+// Global operands of one epilogue chunk, requested BEFORE the TMEM load is waited for so that their latency
+// overlaps it (ncu round 1: the epilogue warps sat in long-scoreboard stalls on exactly these loads).
+// Holds the fp32 residual (8 x 16 B) or, when there is no residual, the bf16 pre-activation of *_BWD (4 x 16 B).
+struct EpiOperands {
+    uint4 pre[8];
+    float rs;
+    int64_t orow, rrow;
+    bool full;
 };
 
 template <int NC>
-__device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const uint32_t (&acc)[NC], int row, int col0,
-                                               int M, int N) {
+__device__ __forceinline__ void epilogue_prefetch(const GemmEpi& e, EpiOperands& o, int row, int col0, int M, int N) {
+    o.orow = row;
+    o.rrow = row;
+    if (e.remap_gin > 0) {
+        const int g = row / e.remap_gin, r = row - g * e.remap_gin;
+        o.orow = (int64_t)g * e.remap_gout + r + e.remap_off;
+        o.rrow = e.residual_bcast ? (int64_t)(r + e.remap_off) : o.orow;
+    }
+    o.full = (col0 + NC <= N) && e.vec_ok;
+    o.rs = 1.0f;
+    if (row >= M) return;
+    if (e.row_scale) o.rs = __ldg(e.row_scale + row / e.rows_per_group);
+    if (!o.full) return;
+    if (e.residual) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(e.residual + o.rrow * e.ldr + col0);
+#pragma unroll
+        for (int i = 0; i < NC / 4; ++i) o.pre[i] = __ldg(r4 + i);
+    } else if (e.act == MICO_ACT_GELU_BWD || e.act == MICO_ACT_QUICK_GELU_BWD) {
+        const uint4* u4 = reinterpret_cast<const uint4*>(e.aux_in + o.orow * e.ld_aux_in + col0);
+#pragma unroll
+        for (int i = 0; i < NC / 8; ++i) o.pre[i] = __ldg(u4 + i);
+    }
+}
+
+template <int NC>
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const EpiOperands& o, const float* sbias,
+                                               const uint32_t (&acc)[NC], int row, int col0, int M, int N) {
     if (row >= M) return;
     float v[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(acc[i]) * e.alpha;
+    const int64_t orow = o.orow, rrow = o.rrow;
+    const float rs = o.rs;
 
-    int64_t orow = row;
-    int64_t rrow = row;
-    if (e.remap_gin > 0) {
-        const int g = row / e.remap_gin, r = row - g * e.remap_gin;
-        orow = (int64_t)g * e.remap_gout + r + e.remap_off;
-        rrow = e.residual_bcast ? (int64_t)(r + e.remap_off) : orow;
-    }
-    const bool full = (col0 + NC <= N) && e.vec_ok;
-    const float rs = e.row_scale ? e.row_scale[row / e.rows_per_group] : 1.0f;
-
-    if (full) {
+    if (o.full) {
         if (e.bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
 #pragma unroll
             for (int i = 0; i < NC / 4; ++i) {
-                const float4 b = __ldg(b4 + i);
+                const float4 b = *reinterpret_cast<const float4*>(sbias + 4 * i);
                 v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
             }
         }
@@ -102,7 +129,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const uint32_t 
             const uint4* u4 = reinterpret_cast<const uint4*>(e.aux_in + orow * e.ld_aux_in + col0);
 #pragma unroll
             for (int i = 0; i < NC / 8; ++i) {
-                const uint4 u = __ldg(u4 + i);
+                const uint4 u = e.residual ? __ldg(u4 + i) : o.pre[i];
                 const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -122,11 +149,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const uint32_t 
             for (int i = 0; i < NC; ++i) v[i] *= rs;
         }
         if (e.residual) {
-            const float4* r4 = reinterpret_cast<const float4*>(e.residual + rrow * e.ldr + col0);
 #pragma unroll
             for (int i = 0; i < NC / 4; ++i) {
-                const float4 r = __ldg(r4 + i);
-                v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+                const uint4 r = o.pre[i];
+                v[4 * i + 0] += __uint_as_float(r.x); v[4 * i + 1] += __uint_as_float(r.y);
+                v[4 * i + 2] += __uint_as_float(r.z); v[4 * i + 3] += __uint_as_float(r.w);
             }
         }
         if (e.out_fp32) {
@@ -134,8 +161,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const uint32_t 
             if (e.accumulate) {
 #pragma unroll
                 for (int i = 0; i < NC / 4; ++i) {
-                    const float4 o = o4[i];
-                    v[4 * i + 0] += o.x; v[4 * i + 1] += o.y; v[4 * i + 2] += o.z; v[4 * i + 3] += o.w;
+                    const float4 p = o4[i];
+                    v[4 * i + 0] += p.x; v[4 * i + 1] += p.y; v[4 * i + 2] += p.z; v[4 * i + 3] += p.w;
                 }
             }
 #pragma unroll
@@ -155,7 +182,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const uint32_t 
         const int col = col0 + i;
         if (col >= N) break;
         float x = v[i];
-        if (e.bias) x += e.bias[col];
+        if (e.bias) x += sbias[i];
         if (e.act == MICO_ACT_GELU || e.act == MICO_ACT_QUICK_GELU) {
             if (e.aux_out) e.aux_out[orow * e.ld_aux_out + col] = __float2bfloat16(x);
             x = (e.act == MICO_ACT_GELU) ? gelu_erf(x) : quick_gelu(x);
@@ -167,9 +194,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const uint32_t 
         x *= rs;
         if (e.residual) x += e.residual[rrow * e.ldr + col];
         if (e.out_fp32) {
-            float* o = reinterpret_cast<float*>(e.out) + orow * e.ldo + col;
-            if (e.accumulate) x += *o;
-            *o = x;
+            float* po = reinterpret_cast<float*>(e.out) + orow * e.ldo + col;
+            if (e.accumulate) x += *po;
+            *po = x;
         } else {
             reinterpret_cast<__nv_bfloat16*>(e.out)[orow * e.ldo + col] = __float2bfloat16(x);
         }
@@ -188,6 +215,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* sbias_all = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
 
     const int warp = threadIdx.x >> 5;
     const int num_m = (M + BM - 1) / BM;
@@ -293,25 +321,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t acc_phase = (it >> 1) & 1;
             const int m0 = (tile / num_n) * BM;
             const int n0 = (tile % num_n) * BN;
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
+            // bias slice of this tile -> smem (one coalesced load per tile instead of 8 x 16 B per thread and chunk).
+            // Stage `acc` of the buffer was last read two tiles ago; every epilogue thread has passed the named
+            // barrier of the previous tile since then.
+            float* sbias = sbias_all + acc * 256;
+            if (epi.bias) {
+                const int t = threadIdx.x - 64;
+                if (t < BN) sbias[t] = (n0 + t < N) ? __ldg(epi.bias + n0 + t) : 0.f;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             const int row = m0 + q * 32 + (int)lane_id();
             const uint32_t t0 = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
+            bool waited = false;
 #pragma unroll 1
             for (int c = half; c < BN / 32; c += 2) {
                 if (n0 + c * 32 >= N) break;   // warp-uniform
+                EpiOperands ops;
+                epilogue_prefetch<32>(epi, ops, row, n0 + c * 32, M, N);
+                if (!waited) { mbar_wait(&tfull_bar[acc], acc_phase); tc_fence_after(); waited = true; }
                 uint32_t v[32];
                 tmem_ld_x32(t0 + c * 32, v);
                 tmem_ld_wait();
-                epilogue_chunk<32>(epi, v, row, n0 + c * 32, M, N);
+                epilogue_chunk<32>(epi, ops, sbias + c * 32, v, row, n0 + c * 32, M, N);
             }
+            if (!waited) { mbar_wait(&tfull_bar[acc], acc_phase); tc_fence_after(); }
             if constexpr (BN % 32 != 0) {
                 constexpr int c0 = (BN / 32) * 32;
                 if (half == ((BN / 32) & 1) && n0 + c0 < N) {
+                    EpiOperands ops;
+                    epilogue_prefetch<16>(epi, ops, row, n0 + c0, M, N);
                     uint32_t v[16];
                     tmem_ld_x16(t0 + c0, v);
                     tmem_ld_wait();
-                    epilogue_chunk<16>(epi, v, row, n0 + c0, M, N);
+                    epilogue_chunk<16>(epi, ops, sbias + c0, v, row, n0 + c0, M, N);
                 }
             }
             tc_fence_before();

@@ -81,9 +81,12 @@ ln_fwd_kernel(const TIn* __restrict__ x, int64_t ldx, const float* __restrict__ 
     }
 }
 
-// dynamic smem: [kLnWarps][2][D] floats (dgamma, dbeta per warp)
+// Each lane owns the same columns of every row it visits, so the dgamma / dbeta partial sums live in registers
+// for the whole kernel; all global loads of a row are issued before the first use (the kernel is latency-bound
+// otherwise: ncu round 1 showed 90 % long-scoreboard stalls at 15 % occupancy with shared-memory accumulators).
+// dynamic smem: [kLnWarps][2][D] floats, used once at the end for the cross-warp reduction.
 template <typename TDy>
-__global__ void __launch_bounds__(kLnThreads)
+__global__ void __launch_bounds__(kLnThreads, 2)
 ln_bwd_kernel(const TDy* __restrict__ dy, int64_t lddy, const float* __restrict__ x, int64_t ldx,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
               const float* __restrict__ dres, int64_t lddres, float* __restrict__ dx, int64_t lddx,
@@ -92,59 +95,73 @@ ln_bwd_kernel(const TDy* __restrict__ dy, int64_t lddy, const float* __restrict_
     extern __shared__ float ln_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nvec = D >> 2;
-    float* sg = ln_smem + (size_t)warp * 2 * D;
-    float* sb = sg + D;
-    for (int i = lane; i < 2 * D; i += 32) sg[i] = 0.f;
-    __syncwarp();
+    float4 ag[kMaxVec], ab[kMaxVec];
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) { ag[j] = make_float4(0, 0, 0, 0); ab[j] = make_float4(0, 0, 0, 0); }
     for (int row = blockIdx.x * kLnWarps + warp; row < M; row += gridDim.x * kLnWarps) {
-        const float mu = mean[row], rs = rstd[row];
         const TDy* dyr = dy + (int64_t)row * lddy;
         const float* xr = x + (int64_t)row * ldx;
-        float4 g[kMaxVec], xh[kMaxVec];
+        float4 d[kMaxVec], xh[kMaxVec];
+#pragma unroll
+        for (int j = 0; j < kMaxVec; ++j) {     // issue every load of the row first
+            const int i = lane + 32 * j;
+            if (i < nvec) {
+                d[j] = ld4(dyr + 4 * i);
+                xh[j] = ld4(xr + 4 * i);
+            }
+        }
+        const float mu = mean[row], rs = rstd[row];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int j = 0; j < kMaxVec; ++j) {
             const int i = lane + 32 * j;
             if (i < nvec) {
-                const float4 d = ld4(dyr + 4 * i);
-                const float4 xv = ld4(xr + 4 * i);
                 const float4 gm = ld4(gamma + 4 * i);
-                xh[j] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-                // parameter gradients: this lane always owns the same columns -> race-free smem RMW
-                float4 ag = ld4(sg + 4 * i), ab = ld4(sb + 4 * i);
-                ag.x += d.x * xh[j].x; ag.y += d.y * xh[j].y; ag.z += d.z * xh[j].z; ag.w += d.w * xh[j].w;
-                ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
-                st4(sg + 4 * i, ag);
-                st4(sb + 4 * i, ab);
-                g[j] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
-                s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
-                s2 += (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
+                xh[j] = make_float4((xh[j].x - mu) * rs, (xh[j].y - mu) * rs, (xh[j].z - mu) * rs, (xh[j].w - mu) * rs);
+                ag[j].x += d[j].x * xh[j].x; ag[j].y += d[j].y * xh[j].y; ag[j].z += d[j].z * xh[j].z; ag[j].w += d[j].w * xh[j].w;
+                ab[j].x += d[j].x; ab[j].y += d[j].y; ab[j].z += d[j].z; ab[j].w += d[j].w;
+                d[j] = make_float4(d[j].x * gm.x, d[j].y * gm.y, d[j].z * gm.z, d[j].w * gm.w);   // g = dy * gamma
+                s1 += (d[j].x + d[j].y) + (d[j].z + d[j].w);
+                s2 += (d[j].x * xh[j].x + d[j].y * xh[j].y) + (d[j].z * xh[j].z + d[j].w * xh[j].w);
             }
         }
         const float m1 = warp_sum(s1) / (float)D;
         const float m2 = warp_sum(s2) / (float)D;
         const float sc = row_scale ? row_scale[row / rows_per_group] : 1.0f;
 #pragma unroll
-        for (int j = 0; j < kMaxVec; ++j) {
-            const int i = lane + 32 * j;
-            if (i < nvec) {
-                float4 o;
-                o.x = rs * (g[j].x - m1 - xh[j].x * m2);
-                o.y = rs * (g[j].y - m1 - xh[j].y * m2);
-                o.z = rs * (g[j].z - m1 - xh[j].z * m2);
-                o.w = rs * (g[j].w - m1 - xh[j].w * m2);
-                if (dres) {
-                    const float4 r = ld4(dres + (int64_t)row * lddres + 4 * i);
-                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        for (int jb = 0; jb < kMaxVec; jb += 4) {      // residual loads in batches of four, then finish four vectors
+            float4 r[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int i = lane + 32 * (jb + t);
+                r[t] = (dres && i < nvec) ? ld4(dres + (int64_t)row * lddres + 4 * i) : make_float4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int j = jb + t;
+                const int i = lane + 32 * j;
+                if (i < nvec) {
+                    float4 o;
+                    o.x = rs * (d[j].x - m1 - xh[j].x * m2) + r[t].x;
+                    o.y = rs * (d[j].y - m1 - xh[j].y * m2) + r[t].y;
+                    o.z = rs * (d[j].z - m1 - xh[j].z * m2) + r[t].z;
+                    o.w = rs * (d[j].w - m1 - xh[j].w * m2) + r[t].w;
+                    if (dx) st4(dx + (int64_t)row * lddx + 4 * i, o);
+                    if (dx_bf16)
+                        st4(dx_bf16 + (int64_t)row * lddxb + 4 * i, make_float4(o.x * sc, o.y * sc, o.z * sc, o.w * sc));
                 }
-                if (dx) st4(dx + (int64_t)row * lddx + 4 * i, o);
-                if (dx_bf16)
-                    st4(dx_bf16 + (int64_t)row * lddxb + 4 * i, make_float4(o.x * sc, o.y * sc, o.z * sc, o.w * sc));
             }
         }
     }
+    // cross-warp reduction of the register partials -> partials[block][2][D]
+    float* sg = ln_smem + (size_t)warp * 2 * D;
+    float* sb = sg + D;
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+        const int i = lane + 32 * j;
+        if (i < nvec) { st4(sg + 4 * i, ag[j]); st4(sb + 4 * i, ab[j]); }
+    }
     __syncthreads();
-    // block partial = sum over warps -> partials[block][2][D]
     float* out = partials + (size_t)blockIdx.x * 2 * D;
     for (int i = threadIdx.x; i < 2 * D; i += kLnThreads) {
         float a = 0.f;
@@ -154,19 +171,30 @@ ln_bwd_kernel(const TDy* __restrict__ dy, int64_t lddy, const float* __restrict_
     }
 }
 
-__global__ void ln_bwd_finalize_kernel(const float* __restrict__ partials, int nblocks, int D,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over 2*D
-    if (i >= 2 * D) return;
+// partials[nblocks][2*D] -> dgamma, dbeta.  Block = 32 columns x 32 row-slices; coalesced 128-byte reads.
+__global__ void __launch_bounds__(1024)
+ln_bwd_finalize_kernel(const float* __restrict__ partials, int nblocks, int D, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta, int accumulate) {
+    __shared__ float red[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + tx;   // over 2*D
     float a = 0.f;
-    for (int b = 0; b < nblocks; ++b) a += partials[(size_t)b * 2 * D + i];
-    float* dst = (i < D) ? (dgamma + i) : (dbeta + (i - D));
-    *dst = accumulate ? (*dst + a) : a;
+    if (i < 2 * D)
+        for (int b = ty; b < nblocks; b += 32) a += partials[(size_t)b * 2 * D + i];
+    red[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && i < 2 * D) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) t += red[k][tx];
+        float* dst = (i < D) ? (dgamma + i) : (dbeta + (i - D));
+        *dst = accumulate ? (*dst + t) : t;
+    }
 }
 
 int ln_bwd_grid(int M) {
     const int want = ceil_div(M, kLnWarps);
-    const int cap = num_sms() * 4;
+    const int cap = num_sms() * 2;   // two resident blocks per SM (register-limited): exactly one wave
     return want < cap ? want : cap;
 }
 
@@ -234,7 +262,7 @@ extern "C" int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, 
                                               row_scale, rows_per_group, partials, M, D);
     }
     MICO_CHECK_CUDA(cudaGetLastError());
-    ln_bwd_finalize_kernel<<<ceil_div(2 * D, 256), 256, 0, stream>>>(partials, grid, D, dgamma, dbeta,
+    ln_bwd_finalize_kernel<<<ceil_div(2 * D, 32), 1024, 0, stream>>>(partials, grid, D, dgamma, dbeta,
                                                                     accumulate_param_grads);
     MICO_CHECK_CUDA(cudaGetLastError());
     count_launch(2);

@@ -1,0 +1,38 @@
+"""Launch each hot kernel a few times on the ViT-g bs=64 shapes (target for `ncu --set full -k regex:...`)."""
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from mico_b200 import ops
+from mico_b200.ops import ACT_GELU, ACT_GELU_BWD, BF16, F32
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+M, D, F = 64 * 257, 1408, 6144
+dev = "cuda"
+r = lambda *s: (torch.randn(*s, device=dev) * 0.05).to(BF16)
+reps = 3
+if which in ("all", "gemm"):
+    x, w1, w2, a, dy = r(M, D), r(F, D), r(D, F), r(M, F), r(M, D)
+    pre = r(M, F)
+    bias = torch.randn(F, device=dev)
+    for _ in range(reps):
+        ops.gemm(x, w1, bias=bias, act=ACT_GELU, aux_out=pre)            # fc1 fwd
+        ops.gemm(dy, w2, b_mn=True, act=ACT_GELU_BWD, aux_in=pre)        # fc2 dgrad
+        ops.gemm(dy, a, a_mn=True, b_mn=True, out_dtype=F32)             # fc2 wgrad
+        ops.gemm(a, w2, out_dtype=F32, residual=torch.zeros(M, D, device=dev))  # fc2 fwd
+if which in ("all", "ln"):
+    xf = torch.randn(M, D, device=dev)
+    g, b = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+    dg, db = torch.empty_like(g), torch.empty_like(b)
+    for _ in range(reps):
+        yb, _, mean, rstd = ops.layernorm_fwd(xf, g, b, 1e-6)
+        ops.layernorm_bwd(yb, xf, mean, rstd, g, dg, db, dres=xf, want_bf16=True)
+if which in ("all", "attn"):
+    B, H, S, d = 64, 16, 257, 88
+    qkv = r(B, S, 3, H, d)
+    do = r(B, S, H, d)
+    dq = torch.empty_like(qkv)
+    for _ in range(reps):
+        o, lse = ops.attention_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], d ** -0.5)
+        ops.attention_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], o, lse, do, d ** -0.5, dq=dq[:, :, 0], dk=dq[:, :, 1], dv=dq[:, :, 2])
+torch.cuda.synchronize()
