@@ -124,14 +124,16 @@ int mico_attention_bwd(const MicoAttnArgs* args, void* stream);
 /* ---------------------------------------------------------------------------------------------
  * K2  LayerNorm (eva_vit_model.py:375,382,542 eps 1e-6; bert.py:92,290,368,583 and mico.py:49,400-403
  *     eps 1e-12; swin.py:212,218,329,565 eps 1e-5).  x is fp32 or bf16 [M,D]; y as bf16 and/or fp32.
- *     Backward: dx = [dres +] LN'(dy); optional bf16 copy of dx scaled per row group (DropPath);
+ *     Backward: dx = [dres +] LN'(dy [+ dy2]); dy2 = optional second (bf16) upstream gradient, for a LayerNorm
+ *     output that feeds both the next GEMM and the next residual add (post-LN BERT, bert.py:286-297); optional bf16 copy of dx scaled per row group (DropPath);
  *     dgamma/dbeta reduced deterministically through `workspace` (mico_layernorm_bwd_workspace bytes).
  * ------------------------------------------------------------------------------------------- */
 int mico_layernorm_fwd(const void* x, int x_is_bf16, int64_t ldx, const float* gamma, const float* beta,
                        void* y_bf16, float* y_f32, int64_t ldy, float* mean, float* rstd, int M, int D,
                        float eps, void* stream);
 size_t mico_layernorm_bwd_workspace(int M, int D);
-int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, const float* x, int64_t ldx,
+int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, const void* dy2_bf16, int64_t lddy2,
+                       const float* x, int64_t ldx,
                        const float* mean, const float* rstd, const float* gamma, const float* dres,
                        int64_t lddres, float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb,
                        const float* row_scale, int rows_per_group, float* dgamma, float* dbeta,
@@ -169,6 +171,39 @@ int mico_drop_path_scales(const float* drop_prob, int L, int B, uint64_t seed, u
 /* y = bf16(x * row_scale[row / rows_per_group]) */
 int mico_scale_cast_bf16(const float* x, int64_t ldx, const float* row_scale, int rows_per_group, void* y,
                          int64_t ldy, int M, int D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Text head and losses (fp32 SIMT kernels; small or HBM-bound).
+ * ------------------------------------------------------------------------------------------- */
+/* K6 BertEmbeddings (bert.py:139-146): out[m] = word[ids[m]] + type[type_ids[m] or 0] + pos[pos_ids[m] or (m % S) + pos_offset];
+ * the LayerNorm that follows is mico_layernorm_fwd.  Backward into the word table: dtable[ids[m]] += dx[m] (atomics). */
+int mico_embedding_gather(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, int pos_offset,
+                          const float* word, const float* pos, const float* type, float* out, int M, int S, int D, int V,
+                          int P, int T, void* stream);
+int mico_embedding_scatter_add(const float* dx, const int64_t* ids, float* dtable, int M, int D, int V, void* stream);
+/* K7/K8 F.cross_entropy(logits[M,V], labels, ignore_index, label_smoothing), mean over non-ignored rows
+ * (bert.py:1088-1090; vast.py:412-415 with label_smoothing 0.1; vast.py:456).  loss_and_count[0] = loss,
+ * [1] = number of contributing rows.  Backward writes dlogits = grad[0] * dloss/dlogits as bf16 or fp32. */
+int mico_cross_entropy_fwd(const void* logits, int logits_bf16, int64_t ld, const int64_t* labels, int64_t ignore_index,
+                           float label_smoothing, float* row_loss, float* lse, float* loss_and_count, int M, int V,
+                           void* stream);
+int mico_cross_entropy_bwd(const void* logits, int logits_bf16, int64_t ld, const int64_t* labels, int64_t ignore_index,
+                           float label_smoothing, const float* lse, const float* grad, const float* loss_and_count,
+                           void* dlogits, int dlogits_bf16, int64_t ldd, int M, int V, void* stream);
+/* F.normalize(x, dim=-1) (vast.py:225): y = x / max(||x||, eps); norm[m] saved for the backward */
+int mico_l2norm_fwd(const float* x, float* y, float* norm, int M, int D, float eps, void* stream);
+int mico_l2norm_bwd(const float* y, const float* dy, const float* norm, float* dx, int M, int D, void* stream);
+/* Small fp32 GEMM with arbitrary operand strides: C[m,n] (+)= s * sum_k A(m,k) B(n,k) + bias[n],
+ * A(m,k) = a[m*a_sm + k*a_sk], B(n,k) = b[n*b_sn + k*b_sk], s = alpha * (alpha_dev ? (alpha_recip ? 1/ *alpha_dev : *alpha_dev) : 1).
+ * K8 contrastive logits sim = f . f_all^T / contra_temp (vast.py:405-408, temperature read on the device) and the
+ * fp32 heads (Contra_head mico.py:36-41, contra_head_va/id/vs/vas :386-394, Match_head :44-52). */
+int mico_sgemm_strided(const float* a, int64_t a_sm, int64_t a_sk, const float* b, int64_t b_sn, int64_t b_sk, float* c,
+                       int64_t ldc, const float* bias, int M, int N, int K, float alpha, const float* alpha_dev,
+                       int alpha_recip, int accumulate, void* stream);
+/* exact-erf GELU on a small fp32 tensor (Match_head, mico.py:44-52): out = gelu(x), or out = dy * gelu'(x) when dy != NULL */
+int mico_gelu_f32(const float* x, const float* dy, float* out, int64_t n, void* stream);
+/* out[0] (+)= alpha * <a, b>  (d contra_temp) */
+int mico_dot_f32(const float* a, const float* b, int64_t n, float alpha, float* out, int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

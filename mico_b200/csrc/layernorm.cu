@@ -87,7 +87,8 @@ ln_fwd_kernel(const TIn* __restrict__ x, int64_t ldx, const float* __restrict__ 
 // dynamic smem: [kLnWarps][2][D] floats, used once at the end for the cross-warp reduction.
 template <typename TDy>
 __global__ void __launch_bounds__(kLnThreads, 2)
-ln_bwd_kernel(const TDy* __restrict__ dy, int64_t lddy, const float* __restrict__ x, int64_t ldx,
+ln_bwd_kernel(const TDy* __restrict__ dy, int64_t lddy, const __nv_bfloat16* __restrict__ dy2, int64_t lddy2,
+              const float* __restrict__ x, int64_t ldx,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
               const float* __restrict__ dres, int64_t lddres, float* __restrict__ dx, int64_t lddx,
               __nv_bfloat16* __restrict__ dx_bf16, int64_t lddxb, const float* __restrict__ row_scale,
@@ -108,6 +109,17 @@ ln_bwd_kernel(const TDy* __restrict__ dy, int64_t lddy, const float* __restrict_
             if (i < nvec) {
                 d[j] = ld4(dyr + 4 * i);
                 xh[j] = ld4(xr + 4 * i);
+            }
+        }
+        if (dy2) {   // second consumer of the LayerNorm output (post-LN BERT: next GEMM's dgrad + next residual)
+            const __nv_bfloat16* d2r = dy2 + (int64_t)row * lddy2;
+#pragma unroll
+            for (int j = 0; j < kMaxVec; ++j) {
+                const int i = lane + 32 * j;
+                if (i < nvec) {
+                    const float4 e = ld4(d2r + 4 * i);
+                    d[j].x += e.x; d[j].y += e.y; d[j].z += e.z; d[j].w += e.w;
+                }
             }
         }
         const float mu = mean[row], rs = rstd[row];
@@ -229,7 +241,8 @@ extern "C" size_t mico_layernorm_bwd_workspace(int M, int D) {
     return (size_t)mico::ln_bwd_grid(M) * 2 * (size_t)D * sizeof(float);
 }
 
-extern "C" int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, const float* x, int64_t ldx,
+extern "C" int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, const void* dy2_bf16, int64_t lddy2,
+                                  const float* x, int64_t ldx,
                                   const float* mean, const float* rstd, const float* gamma, const float* dres,
                                   int64_t lddres, float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb,
                                   const float* row_scale, int rows_per_group, float* dgamma, float* dbeta,
@@ -240,7 +253,8 @@ extern "C" int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, 
     MICO_CHECK_ARG(dy && x && mean && rstd && gamma && dgamma && dbeta && workspace);
     MICO_CHECK_ARG(dx || dx_bf16);
     MICO_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= kMaxVec * 128);
-    MICO_CHECK_ARG(lddy % 4 == 0 && ldx % 4 == 0 && lddx % 4 == 0 && lddxb % 4 == 0 && lddres % 4 == 0);
+    MICO_CHECK_ARG(lddy % 4 == 0 && ldx % 4 == 0 && lddx % 4 == 0 && lddxb % 4 == 0 && lddres % 4 == 0 && lddy2 % 4 == 0);
+    const __nv_bfloat16* dy2 = reinterpret_cast<const __nv_bfloat16*>(dy2_bf16);
     MICO_CHECK_ARG(!(row_scale && rows_per_group <= 0));
     MICO_CHECK_ARG(ws_bytes >= mico_layernorm_bwd_workspace(M, D));
     const int grid = ln_bwd_grid(M);
@@ -251,13 +265,13 @@ extern "C" int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, 
     if (dy_is_bf16) {
         auto k = ln_bwd_kernel<__nv_bfloat16>;
         if (smem > 48 * 1024) MICO_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kLnThreads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, x, ldx, mean, rstd, gamma,
+        k<<<grid, kLnThreads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy2, lddy2, x, ldx, mean, rstd, gamma,
                                               dres, lddres, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), lddxb,
                                               row_scale, rows_per_group, partials, M, D);
     } else {
         auto k = ln_bwd_kernel<float>;
         if (smem > 48 * 1024) MICO_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kLnThreads, smem, stream>>>(reinterpret_cast<const float*>(dy), lddy, x, ldx, mean, rstd, gamma, dres,
+        k<<<grid, kLnThreads, smem, stream>>>(reinterpret_cast<const float*>(dy), lddy, dy2, lddy2, x, ldx, mean, rstd, gamma, dres,
                                               lddres, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), lddxb,
                                               row_scale, rows_per_group, partials, M, D);
     }

@@ -185,7 +185,7 @@ def layernorm_fwd(x, gamma, beta, eps, out_bf16=True, out_f32=False, save_stats=
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, dres=None, want_f32=True, want_bf16=False,
-                  row_scale=None, rows_per_group=0, accumulate=False):
+                  row_scale=None, rows_per_group=0, accumulate=False, dy2=None):
     """Returns (dx_f32|None, dx_bf16|None); writes dgamma/dbeta (fp32 [D])."""
     M, D = x.shape
     _req(x, F32, "x")
@@ -193,7 +193,10 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, dres=None, want_f3
     dxb = torch.empty((M, D), device=x.device, dtype=BF16) if want_bf16 else None
     nws = lib.mico_layernorm_bwd_workspace(M, D)
     ws = workspace(nws, x.device)
-    check(lib.mico_layernorm_bwd(_ptr(dy), int(dy.dtype == BF16), C.c_int64(dy.stride(0)), _ptr(x), C.c_int64(x.stride(0)),
+    if dy2 is not None:
+        _req(dy2, BF16, "dy2")
+    check(lib.mico_layernorm_bwd(_ptr(dy), int(dy.dtype == BF16), C.c_int64(dy.stride(0)), _ptr(dy2),
+                                 C.c_int64(dy2.stride(0) if dy2 is not None else 0), _ptr(x), C.c_int64(x.stride(0)),
                                  _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres),
                                  C.c_int64(dres.stride(0) if dres is not None else 0), _ptr(dx), C.c_int64(D), _ptr(dxb),
                                  C.c_int64(D), _ptr(row_scale), int(rows_per_group), _ptr(dgamma), _ptr(dbeta),
@@ -304,3 +307,109 @@ def profile_collect():
     ms, work, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_int64 * n)()
     check(lib.mico_profile_collect(ms, work, cnt, n), "mico_profile_collect")
     return {k: dict(ms=ms[i], work=work[i], calls=int(cnt[i])) for i, k in enumerate(PROF_KINDS)}
+
+
+# ----------------------------------------------------------------------------- text head / loss kernels
+I64 = torch.int64
+
+
+def embedding_gather(ids, word, pos, typ, S, type_ids=None, pos_ids=None, pos_offset=0):
+    """ids: int64 [M] -> fp32 [M, D] = word[ids] + type[type_ids|0] + pos[pos_ids | m % S + pos_offset]."""
+    _req(ids, I64, "ids")
+    M, D = ids.numel(), word.shape[1]
+    out = torch.empty((M, D), device=ids.device, dtype=F32)
+    check(lib.mico_embedding_gather(_ptr(ids), _ptr(type_ids), _ptr(pos_ids), int(pos_offset), _ptr(word), _ptr(pos),
+                                    _ptr(typ), _ptr(out), M, int(S), D, word.shape[0], pos.shape[0], typ.shape[0], _stream()),
+          "mico_embedding_gather")
+    return out
+
+
+def embedding_scatter_add(dx, ids, dtable):
+    _req(dx, F32, "dx")
+    check(lib.mico_embedding_scatter_add(_ptr(dx), _ptr(ids), _ptr(dtable), dx.shape[0], dx.shape[1], dtable.shape[0],
+                                         _stream()), "mico_embedding_scatter_add")
+
+
+def cross_entropy_fwd(logits, labels, ignore_index=-100, label_smoothing=0.0):
+    """-> (stats [2] = (loss, n_valid), lse [M])"""
+    M, V = logits.shape
+    _req(labels, I64, "labels")
+    row_loss = torch.empty(M, device=logits.device, dtype=F32)
+    lse = torch.empty(M, device=logits.device, dtype=F32)
+    stats = torch.empty(2, device=logits.device, dtype=F32)
+    check(lib.mico_cross_entropy_fwd(_ptr(logits), int(logits.dtype == BF16), C.c_int64(logits.stride(0)), _ptr(labels),
+                                     C.c_int64(ignore_index), C.c_float(label_smoothing), _ptr(row_loss), _ptr(lse),
+                                     _ptr(stats), M, V, _stream()), "mico_cross_entropy_fwd")
+    return stats, lse
+
+
+def cross_entropy_bwd(logits, labels, lse, grad, stats, ignore_index=-100, label_smoothing=0.0, out_dtype=F32):
+    M, V = logits.shape
+    ldd = (V + 7) // 8 * 8
+    buf = torch.empty((M, ldd), device=logits.device, dtype=out_dtype)
+    d = buf[:, :V]
+    check(lib.mico_cross_entropy_bwd(_ptr(logits), int(logits.dtype == BF16), C.c_int64(logits.stride(0)), _ptr(labels),
+                                     C.c_int64(ignore_index), C.c_float(label_smoothing), _ptr(lse), _ptr(grad), _ptr(stats),
+                                     _ptr(d), int(out_dtype == BF16), C.c_int64(ldd), M, V, _stream()),
+          "mico_cross_entropy_bwd")
+    return d
+
+
+def l2norm_fwd(x, eps=1e-12):
+    _req(x, F32, "x")
+    M, D = x.shape
+    y = torch.empty_like(x)
+    norm = torch.empty(M, device=x.device, dtype=F32)
+    check(lib.mico_l2norm_fwd(_ptr(x), _ptr(y), _ptr(norm), M, D, C.c_float(eps), _stream()), "mico_l2norm_fwd")
+    return y, norm
+
+
+def l2norm_bwd(y, dy, norm):
+    M, D = y.shape
+    dx = torch.empty_like(y)
+    check(lib.mico_l2norm_bwd(_ptr(y), _ptr(dy), _ptr(norm), _ptr(dx), M, D, _stream()), "mico_l2norm_bwd")
+    return dx
+
+
+def sgemm(a, b, *, a_t=False, b_t=False, bias=None, alpha=1.0, alpha_dev=None, alpha_recip=False, out=None,
+          accumulate=False):
+    """fp32: out[M,N] (+)= s * A . B^T + bias.  a: [M,K] ([K,M] if a_t), b: [N,K] ([K,N] if b_t); any 2-D strides."""
+    _req2 = lambda t, n: (_ for _ in ()).throw(MicoError(f"{n}: fp32 CUDA 2-D tensor expected")) \
+        if (not t.is_cuda or t.dtype != F32 or t.dim() != 2) else None
+    _req2(a, "a")
+    _req2(b, "b")
+    if a_t:
+        K, M = a.shape
+        a_sm, a_sk = a.stride(1), a.stride(0)
+    else:
+        M, K = a.shape
+        a_sm, a_sk = a.stride(0), a.stride(1)
+    if b_t:
+        Kb, N = b.shape
+        b_sn, b_sk = b.stride(1), b.stride(0)
+    else:
+        N, Kb = b.shape
+        b_sn, b_sk = b.stride(0), b.stride(1)
+    if K != Kb:
+        raise MicoError(f"sgemm: contraction mismatch {K} vs {Kb}")
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=F32)
+    check(lib.mico_sgemm_strided(_ptr(a), C.c_int64(a_sm), C.c_int64(a_sk), _ptr(b), C.c_int64(b_sn), C.c_int64(b_sk),
+                                 _ptr(out), C.c_int64(out.stride(0)), _ptr(bias), M, N, K, C.c_float(alpha), _ptr(alpha_dev),
+                                 int(alpha_recip), int(accumulate), _stream()), "mico_sgemm_strided")
+    return out
+
+
+def dot(a, b, alpha=1.0, out=None, accumulate=False):
+    if out is None:
+        out = torch.empty((), device=a.device, dtype=F32)
+    check(lib.mico_dot_f32(_ptr(a), _ptr(b), C.c_int64(a.numel()), C.c_float(alpha), _ptr(out), int(accumulate), _stream()),
+          "mico_dot_f32")
+    return out
+
+
+def gelu_f32(x, dy=None):
+    _req(x, F32, "x")
+    out = torch.empty_like(x)
+    check(lib.mico_gelu_f32(_ptr(x), _ptr(dy), _ptr(out), C.c_int64(x.numel()), _stream()), "mico_gelu_f32")
+    return out

@@ -78,7 +78,50 @@ def gen_vit():
                                   dp_scales=dp, grads=grads))
 
 
-GENERATORS = {"vit": gen_vit}
+def gen_bert():
+    """Reference BertForMaskedLM (model/bert.py:1021) at hidden 128 = 2 heads x 64, 2 layers, FFN 256, vocab 1000,
+    is_decoder + add_cross_attention, dropout 0 (so train-mode gradients are deterministic):
+      (a) text-only, 2-D padding mask            -> last_hidden_state        (vast.py:150-156 'caption_output')
+      (b) cross-attention to 37 encoder tokens, 3-D causal mask, labels -> loss, logits, every gradient (vast.py:493-507)"""
+    from transformers.models.bert.configuration_bert import BertConfig
+    from model.bert import BertForMaskedLM
+    cfg = BertConfig(vocab_size=1000, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
+                     hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, max_position_embeddings=64,
+                     is_decoder=True, add_cross_attention=True, layer_norm_eps=1e-12, pad_token_id=0)
+    torch.manual_seed(0)
+    m = BertForMaskedLM(cfg)
+    _randomize(m, 3)
+    # transformers 4.31 ties decoder.weight to the word embeddings; 5.x does not (SURVEY.md 8c) -> tie explicitly
+    m.cls.predictions.decoder.weight = m.bert.embeddings.word_embeddings.weight
+    g = torch.Generator().manual_seed(99)
+    b, S, Sk = 3, 24, 37
+    ids = torch.randint(1, 1000, (b, S), generator=g)
+    lens = torch.tensor([24, 17, 9])
+    att = (torch.arange(S)[None] < lens[:, None]).long()
+    ids = ids * att
+    m.eval()
+    with torch.no_grad():
+        text_only = m.bert(input_ids=ids, attention_mask=att).last_hidden_state
+    enc = torch.randn(b, Sk, 128, generator=g, requires_grad=True)
+    att3 = att.unsqueeze(1).expand(-1, S, -1).clone()
+    att3[:, :S, :S] = torch.tril(att3[:, :S, :S])
+    labels = torch.full((b, S), -100, dtype=torch.long)
+    pick = torch.rand(b, S, generator=g) < 0.5
+    labels[pick & (att > 0)] = ids[pick & (att > 0)]
+    m.train()
+    out = m(input_ids=ids, attention_mask=att3, encoder_hidden_states=enc, labels=labels)
+    out.loss.backward()
+    grads = {k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None}
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    _save("bert_tiny.pt", dict(cfg=dict(vocab_size=1000, hidden_size=128, num_hidden_layers=2, num_attention_heads=2,
+                                        intermediate_size=256, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                                        max_position_embeddings=64, layer_norm_eps=1e-12, pad_token_id=0),
+                               state_dict=sd, ids=ids, att=att, att3=att3, enc=enc.detach(), labels=labels,
+                               text_only=text_only, loss=out.loss.detach(), logits=out.logits.detach(),
+                               sequence_output=out.sequence_output.detach(), grads=grads, d_enc=enc.grad.clone()))
+
+
+GENERATORS = {"vit": gen_vit, "bert": gen_bert}
 
 
 def main():

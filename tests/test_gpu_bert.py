@@ -1,0 +1,107 @@
+"""GPU parity of the BERT text/fusion encoder (mico_b200.bert) against the golden fixture produced by the unmodified
+reference (tests/golden/bert_tiny.pt: hidden 128 = 2 heads x 64, 2 layers, cross-attention, tied decoder) and against
+the CPU oracle at bert-base width.  Tolerances as in test_gpu_vit.py: features 5e-3, gradients 2e-2 rel-L2, loss 1e-3."""
+import os
+
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+FEAT_TOL, GRAD_TOL, LOSS_TOL = 5e-3, 2e-2, 1e-3
+
+
+def _model(cfgd):
+    from mico_b200.bert import BertConfig, BertForMaskedLM
+    return BertForMaskedLM(BertConfig(**cfgd))
+
+
+def test_golden_text_only(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "bert_tiny.pt"), weights_only=False)
+    m = _model(g["cfg"])
+    m.load_state_dict(g["state_dict"], strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        h = m.bert(input_ids=g["ids"].cuda(), attention_mask=g["att"].cuda()).last_hidden_state
+    e = rel_l2(h.cpu(), g["text_only"])
+    print(f"bert text-only rel-L2 {e:.3e}")
+    assert e < FEAT_TOL
+
+
+def test_golden_caption_loss_and_grads(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "bert_tiny.pt"), weights_only=False)
+    m = _model(g["cfg"])
+    m.load_state_dict(g["state_dict"], strict=True)
+    m = m.cuda().train()          # dropout probabilities are 0 in this fixture
+    enc = g["enc"].cuda().requires_grad_(True)
+    out = m(input_ids=g["ids"].cuda(), attention_mask=g["att3"].cuda(), encoder_hidden_states=enc, labels=g["labels"].cuda())
+    assert rel_l2(out.sequence_output.detach().cpu(), g["sequence_output"]) < FEAT_TOL
+    assert rel_l2(out.logits.detach().cpu(), g["logits"]) < FEAT_TOL
+    assert abs(out.loss.item() - g["loss"].item()) <= LOSS_TOL * abs(g["loss"].item())
+    out.loss.backward()
+    assert rel_l2(enc.grad.cpu(), g["d_enc"]) < GRAD_TOL
+    worst = ("", 0.0)
+    for k, p in m.named_parameters():
+        ref = g["grads"].get(k)
+        if ref is None:
+            continue
+        if k.endswith("self.key.bias"):
+            # softmax is invariant to a per-row constant q.b_k, so this gradient is exactly 0 in exact arithmetic:
+            # both sides hold only rounding noise -- compare it with the query-bias gradient's scale instead
+            qn = g["grads"][k.replace("key.bias", "query.bias")].norm().item()
+            assert p.grad.norm().item() < 2e-2 * qn, (k, p.grad.norm().item(), qn)
+            continue
+        e = rel_l2(p.grad.cpu(), ref)
+        worst = max(worst, (k, e), key=lambda t: t[1])
+        assert e < GRAD_TOL, (k, e)
+    print(f"bert caption: loss {out.loss.item():.5f} vs {g['loss'].item():.5f}; worst grad {worst[0]} {worst[1]:.3e}")
+
+
+def test_training_with_dropout_refuses():
+    from mico_b200.bert import BertConfig, BertForMaskedLM
+    m = BertForMaskedLM(BertConfig(vocab_size=100, hidden_size=64, num_hidden_layers=1, num_attention_heads=1,
+                                   intermediate_size=128, max_position_embeddings=16)).cuda().train()
+    with pytest.raises(NotImplementedError):
+        m(input_ids=torch.ones(1, 8, dtype=torch.long, device="cuda"))
+
+
+def test_bert_base_width_vs_oracle():
+    """bert-base layer shapes (768, 12 heads x 64, FFN 3072, vocab 30522), 2 layers, S=40, S_k=257, 2-D masks both sides."""
+    from oracle import bert as OB
+    cfgd = dict(num_hidden_layers=2, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    torch.manual_seed(5)
+    m = _model(cfgd)
+    with torch.no_grad():
+        for n, p in sorted(m.named_parameters()):
+            if p.dim() == 1:
+                p.add_(0.02 * torch.randn(p.shape))
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.cuda().train()
+    g = torch.Generator().manual_seed(3)
+    b, S, Sk = 2, 40, 257
+    ids = torch.randint(1, 30522, (b, S), generator=g)
+    att = (torch.arange(S)[None] < torch.tensor([40, 23])[:, None]).long()
+    ids = ids * att
+    enc = torch.randn(b, Sk, 768, generator=g)
+    enc_att = (torch.arange(Sk)[None] < torch.tensor([257, 200])[:, None]).long()
+    labels = torch.where((torch.rand(b, S, generator=g) < 0.6) & (att > 0), ids, torch.full_like(ids, -100))
+    encg = enc.cuda().requires_grad_(True)
+    out = m(input_ids=ids.cuda(), attention_mask=att.cuda(), encoder_hidden_states=encg, encoder_attention_mask=enc_att.cuda(),
+            labels=labels.cuda())
+    out.loss.backward()
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    p["cls.predictions.decoder.weight"] = p["bert.embeddings.word_embeddings.weight"]
+    encr = enc.clone().requires_grad_(True)
+    loss, logits, seq = OB.masked_lm(p, ids, att, encr, enc_att, labels, layers=2, heads=12)
+    loss.backward()
+    print(f"bert-base x2: seq {rel_l2(out.sequence_output.detach().cpu(), seq):.3e} logits "
+          f"{rel_l2(out.logits.detach().cpu(), logits):.3e} loss {out.loss.item():.5f} vs {loss.item():.5f}")
+    assert rel_l2(out.sequence_output.detach().cpu(), seq) < FEAT_TOL
+    assert rel_l2(out.logits.detach().cpu(), logits) < FEAT_TOL
+    assert abs(out.loss.item() - loss.item()) <= LOSS_TOL * abs(loss.item())
+    assert rel_l2(encg.grad.cpu(), encr.grad) < GRAD_TOL
+    for k, v in m.named_parameters():
+        if v.grad is None or k.endswith("self.key.bias"):    # key-bias gradient is identically zero (see above)
+            continue
+        assert rel_l2(v.grad.cpu(), p[k].grad) < GRAD_TOL, k

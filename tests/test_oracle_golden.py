@@ -38,3 +38,34 @@ def test_vit_train_forward_backward_matches_reference(golden_dir):
 def test_drop_path_rates_match_linspace():
     assert O.drop_path_rates(40)[0] == 0.0
     assert abs(O.drop_path_rates(40)[-1] - 0.4) < 1e-7
+
+
+# ---------------------------------------------------------------------------------------------- BERT
+def _load_bert(golden_dir):
+    return torch.load(os.path.join(golden_dir, "bert_tiny.pt"), weights_only=False)
+
+
+def test_bert_text_only_matches_reference(golden_dir):
+    from oracle import bert as OB
+    g = _load_bert(golden_dir)
+    h = OB.bert_model(g["state_dict"], g["ids"], g["att"], layers=2, heads=2)
+    assert rel_l2(h, g["text_only"]) < 1e-5
+
+
+def test_bert_cross_attention_caption_loss_and_grads_match_reference(golden_dir):
+    from oracle import bert as OB
+    g = _load_bert(golden_dir)
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in g["state_dict"].items()}
+    # tied decoder / word embeddings (transformers 4.31 behaviour): one leaf under both names
+    p["cls.predictions.decoder.weight"] = p["bert.embeddings.word_embeddings.weight"]
+    enc = g["enc"].clone().requires_grad_(True)
+    loss, logits, seq = OB.masked_lm(p, g["ids"], g["att3"], enc, None, g["labels"], layers=2, heads=2)
+    assert rel_l2(seq, g["sequence_output"]) < 1e-5
+    assert rel_l2(logits, g["logits"]) < 1e-5
+    assert abs(loss.item() - g["loss"].item()) < 1e-5 * abs(g["loss"].item())
+    loss.backward()
+    assert rel_l2(enc.grad, g["d_enc"]) < 2e-5
+    for k, ref in g["grads"].items():
+        if k == "cls.predictions.decoder.weight":
+            continue
+        assert rel_l2(p[k].grad, ref) < 5e-5, k
