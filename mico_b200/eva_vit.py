@@ -213,7 +213,7 @@ class EVAVisionTransformer(nn.Module):
         num_patches = self.patch_embed.num_patches
         self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
         self.pos_embed = nn.Parameter(torch.zeros(1, num_patches + 1, embed_dim))
-        dpr = [v.item() for v in torch.linspace(0, drop_path_rate, depth)]   # eva_vit_model.py:533
+        dpr = [v.item() for v in torch.linspace(0, drop_path_rate, depth, device="cpu")]   # eva_vit_model.py:533
         self.blocks = nn.ModuleList([Block(embed_dim, num_heads, mlp_ratio, qkv_bias, dpr[i], eps)
                                      for i in range(depth)])
         self.norm = LayerNorm(embed_dim, eps)
@@ -314,7 +314,9 @@ class EVAVisionTransformer(nn.Module):
         dev = x.device
         c = self._bf16
         # K1 patch embedding: im2col -> GEMM with bias + broadcast pos_embed in the epilogue; row 0 = cls + pos[0]
-        cols = ops.patchify(x, P, self._kpad, tokens_per_img=T, token_off=1)
+        # a 3-D input (B,H,W) is one channel replicated three times (forward_audio_encoder, mico.py:139-143): the
+        # im2col kernel reads the same plane for every channel instead of materialising repeat(1,1,3,1,1)
+        cols = ops.patchify(x, P, self._kpad, tokens_per_img=T, token_off=1, replicate_channel=(x.dim() == 3))
         w_pe = c.get(params[_PEW], "pe", pad_to=self._kpad)
         pos = params[_POS].detach().reshape(T, D)
         xr = ops.gemm(cols, w_pe, out_dtype=F32, bias=params[_PEB].detach(), residual=pos, remap=(T, T, 0),
@@ -433,9 +435,11 @@ class EVAVisionTransformer(nn.Module):
 
     # ------------------------------------------------------------------ public forward
     def forward_features(self, x, return_all_features=False):
-        if x.dim() != 4:
-            raise MicoError("EVAVisionTransformer expects (B, C, H, W) pixels")
-        B, C, Himg, Wimg = x.shape
+        if x.dim() == 4 and x.stride(1) == 0 and x.shape[1] == 3:
+            x = x[:, 0]                  # expanded single channel -> replicate inside the im2col kernel
+        if x.dim() not in (3, 4):
+            raise MicoError("EVAVisionTransformer expects (B, C, H, W) pixels (or (B, H, W) for one replicated channel)")
+        B, Himg, Wimg = x.shape[0], x.shape[-2], x.shape[-1]
         assert Himg == self.patch_embed.img_size[0] and Wimg == self.patch_embed.img_size[1], \
             f"Input image size ({Himg}*{Wimg}) doesn't match model ({self.patch_embed.img_size[0]}*{self.patch_embed.img_size[1]})."
         if not x.is_cuda:

@@ -121,7 +121,85 @@ def gen_bert():
                                sequence_output=out.sequence_output.detach(), grads=grads, d_enc=enc.grad.clone()))
 
 
-GENERATORS = {"vit": gen_vit, "bert": gen_bert}
+def gen_mico_parts():
+    """Reference MiCo pieces that run standalone at small sizes (the full class hard-wires the 1.2 B-parameter towers):
+    Contra_head / Match_head (model/mico.py:36-52), and the unbound MMGeneralModule methods pool_vision_for_contra,
+    get_multimodal_forward_input_{vision,audio} (model/mico.py:157-227) driven through a stub `self` that carries the
+    same attributes the real module has; plus the reference collectives' single-process semantics."""
+    import torch.nn as nn
+    from model import mico as RM
+    torch.manual_seed(0)
+    vd, md, cd = 176, 128, 64
+    ch, mh = RM.Contra_head(vd, cd), RM.Match_head(md)
+    _randomize(ch, 1)
+    _randomize(mh, 2)
+
+    class Stub(RM.MMGeneralModule):
+        pass
+
+    st = Stub()
+    st.config = ref_shims.default_model_cfg(pool_video=False)
+    st.multimodal_dim = md
+    st.hidden_trans_vision_multimodal = nn.Sequential(nn.Linear(vd, md), RM.LayerNorm(md, eps=1e-12))
+    st.hidden_trans_audio_multimodal = nn.Sequential(nn.Linear(vd, md), RM.LayerNorm(md, eps=1e-12))
+    st.vision_frame_embedding = nn.Parameter(0.02 * torch.randn(1, 8, md))
+    st.audio_frame_embedding = nn.Parameter(0.02 * torch.randn(1, 3, md))
+    st.vision_type_embeddings = nn.Parameter(0.02 * torch.randn(1, 1, md))
+    st.audio_type_embeddings = nn.Parameter(0.02 * torch.randn(1, 1, md))
+    _randomize(st, 3)
+    g = torch.Generator().manual_seed(5)
+    feat8 = torch.randn(2, 8, 9, vd, generator=g)     # 8-frame video
+    feat2 = torch.randn(2, 2, 9, vd, generator=g)     # 2 frames -> nearest-interpolated frame table
+    aud3 = torch.randn(2, 3, 9, vd, generator=g)
+    with torch.no_grad():
+        out = dict(
+            pooled=st.pool_vision_for_contra(feat8), contra=ch(st.pool_vision_for_contra(feat8)),
+            match=mh(torch.randn(6, md, generator=torch.Generator().manual_seed(6))),
+            fuse_v8=st.get_multimodal_forward_input_vision(feat8), fuse_v2=st.get_multimodal_forward_input_vision(feat2),
+            fuse_a3=st.get_multimodal_forward_input_audio(aud3))
+        st.config.pool_video = True
+        out["fuse_v8_pool"] = st.get_multimodal_forward_input_vision(feat8)
+    sd = {"contra_head_v." + k: v.detach().clone() for k, v in ch.state_dict().items()}
+    sd.update({"itm_head." + k: v.detach().clone() for k, v in mh.state_dict().items()})
+    sd.update({k: v.detach().clone() for k, v in st.state_dict().items()})
+    _save("mico_parts_tiny.pt", dict(state_dict=sd, feat8=feat8, feat2=feat2, aud3=aud3,
+                                     match_in=torch.randn(6, md, generator=torch.Generator().manual_seed(6)), **out))
+
+
+def _dist_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ref_shims.REF_ROOT, "data"))
+    from utils.distributed import all_gather_with_grad, concat_all_gather   # the reference's own collectives
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    x = torch.randn(3, 5, generator=g, requires_grad=True)
+    ids = torch.randint(0, 50, (3, 4), generator=g)
+    gathered = all_gather_with_grad(x)
+    ids_all = concat_all_gather(ids)
+    w = torch.arange(1, gathered.numel() + 1, dtype=torch.float32).view_as(gathered) * (rank + 1)
+    (gathered * w).sum().backward()
+    q.put((rank, x.detach(), ids, gathered.detach(), ids_all, x.grad.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def gen_dist():
+    """data/utils/distributed.py:12-66 run UNMODIFIED on 2 gloo ranks: all_gather_with_grad (forward all-gather, backward
+    all-reduce(SUM) + own slice) and concat_all_gather."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dist_worker, args=(r, 2, 29613, q)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p_ in procs:
+        p_.join()
+    _save("dist_gather_2rank.pt", dict(x=[r[1] for r in res], ids=[r[2] for r in res], gathered=[r[3] for r in res],
+                                       ids_all=[r[4] for r in res], x_grad=[r[5] for r in res]))
+
+
+GENERATORS = {"vit": gen_vit, "bert": gen_bert, "mico_parts": gen_mico_parts, "dist": gen_dist}
 
 
 def main():

@@ -1,0 +1,121 @@
+"""Oracle: MiCo heads, pooling, fusion inputs and the retrieval / caption training step, fp32 CPU.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Restates
+  * Contra_head / Match_head                               model/mico.py:36-52
+  * pool_{vision,audio,depth,text}_for_contra               model/mico.py:157-185
+  * get_multimodal_forward_input_{vision,audio,depth}       model/mico.py:187-241 (Linear+LN(1e-12), + frame emb, + type emb)
+  * forward_{vision,audio}_encoder                          model/mico.py:115-148 (frames folded into the batch; audio = 3x channel repeat)
+  * batch_get features                                      data/model/vast.py:209-272 (feat_* = normalize(head(pool(.))))
+  * ITC loss                                                data/model/vast.py:394-417
+  * ITM loss                                                data/model/vast.py:419-457 (negatives passed in explicitly)
+  * caption loss                                            data/model/vast.py:493-510
+  * concat_all_gather / all_gather_with_grad                data/utils/distributed.py:12-66 (world given as lists of per-rank tensors)
+over the reference's own state_dict key names.  The multi-rank step is simulated in ONE process by evaluating every rank's
+tensors and concatenating them (all_gather) -- autograd through the concatenation reproduces GatherLayer's backward
+(all-reduce(SUM) of the stacked gradients, own slice) when the per-rank losses are SUMMED, which is what a DDP-less loop
+computes (pipeline.py:93-99 sums gradients without dividing).
+"""
+import torch
+import torch.nn.functional as F
+
+from . import bert as OB
+from . import eva_vit as OV
+
+
+def contra_head(p, name, x):
+    return F.linear(x, p[name + ".linear.weight"])
+
+
+def match_head(p, x, name="itm_head"):
+    h = F.gelu(F.linear(x, p[name + ".linear1.weight"], p[name + ".linear1.bias"]))
+    h = F.layer_norm(h, (h.shape[-1],), p[name + ".layernorm.weight"], p[name + ".layernorm.bias"], 1e-12)
+    return F.linear(h, p[name + ".linear2.weight"], p[name + ".linear2.bias"])
+
+
+def vision_encoder(p, pixels, vit_cfg, dp_scales=None):
+    b, n = pixels.shape[:2]
+    y = OV.forward_features(p, pixels.reshape(b * n, *pixels.shape[2:]), vit_cfg, prefix="vision_encoder.visual.",
+                            dp_scales=dp_scales)
+    return y.reshape(b, n, *y.shape[-2:])
+
+
+def audio_encoder(p, spec, vit_cfg):
+    return vision_encoder(p, spec.unsqueeze(2).repeat(1, 1, 3, 1, 1), vit_cfg)
+
+
+def pool_tower(feature):
+    return feature[:, :, 0].mean(dim=1)
+
+
+def fusion_input(p, out, kind, pool_video=False):
+    """kind in {vision, audio, depth}"""
+    b, n, x, c = out.shape
+    if pool_video:
+        out = torch.cat([out[:, :, 0:1], out[:, :, 1:].mean(2, keepdim=True)], dim=2)
+    t = f"hidden_trans_{kind}_multimodal."
+    out = F.linear(out, p[t + "0.weight"], p[t + "0.bias"])
+    out = F.layer_norm(out, (out.shape[-1],), p[t + "1.weight"], p[t + "1.bias"], 1e-12)
+    fe = p[f"{kind}_frame_embedding"]
+    if n != fe.shape[1]:
+        fe = F.interpolate(fe.permute(0, 2, 1), n, mode="nearest").permute(0, 2, 1)
+    out = out + fe.unsqueeze(-2)
+    out = out.reshape(b, -1, out.shape[-1])
+    return out + p[f"{kind}_type_embeddings"]
+
+
+def text_feature(p, ids, att, layers, heads):
+    h = OB.bert_model(p, ids, att, prefix="multimodal_encoder.bert.", layers=layers, heads=heads)
+    return F.normalize(contra_head(p, "contra_head_t", h[:, 0]), dim=-1)
+
+
+def itc_loss(feat_c, feat_t, feat_c_all, feat_t_all, temp, rank):
+    bs = feat_t.shape[0]
+    sim_c2t = feat_c @ feat_t_all.t() / temp
+    sim_t2c = feat_t @ feat_c_all.t() / temp
+    tgt = torch.arange(rank * bs, rank * bs + bs)
+    loss = (F.cross_entropy(sim_c2t, tgt, label_smoothing=0.1) + F.cross_entropy(sim_t2c, tgt, label_smoothing=0.1)) / 2
+    return loss, sim_c2t, sim_t2c
+
+
+def itm_loss(p, cond, cond_all, ids, att, ids_all, att_all, neg_c, neg_t, itm_ratio, layers, heads):
+    bs = cond.shape[0]
+    ids_1 = torch.cat((ids, ids, ids_all[neg_t]), 0)
+    att_1 = torch.cat((att, att, att_all[neg_t]), 0)
+    cond_3 = torch.cat((cond, cond_all[neg_c], cond), 0)
+    out = OB.bert_model(p, ids_1, att_1, cond_3, None, prefix="multimodal_encoder.bert.", layers=layers, heads=heads)
+    logits = match_head(p, out[:, 0])
+    truth = torch.zeros(bs * 3, dtype=torch.long)
+    truth[:bs] = 1
+    return itm_ratio * F.cross_entropy(logits, truth)
+
+
+def caption_loss(p, cond, ids_masked, att, labels, layers, heads):
+    S = att.shape[1]
+    att3 = torch.tril(att.unsqueeze(1).expand(-1, S, -1).clone())
+    loss, _, _ = OB.masked_lm(p, ids_masked, att3, cond, None, labels, layers=layers, heads=heads, prefix="multimodal_encoder.")
+    return loss
+
+
+def retrieval_caption_step(p, ranks, vit_cfg, layers, heads, itm_ratio=0.1, task="ret%tv_cap%tv"):
+    """One 'ret%tv[_cap%tv]' step for every rank of a simulated world.  `ranks` is a list of per-rank dicts with
+    pixels (b,n,3,H,W), ids, att, neg_c, neg_t [, cap_ids, cap_labels].  Returns per-rank dicts of losses."""
+    feats_t = [text_feature(p, r["ids"], r["att"], layers, heads) for r in ranks]
+    vis = [vision_encoder(p, r["pixels"], vit_cfg) for r in ranks]
+    feats_v = [F.normalize(contra_head(p, "contra_head_v", pool_tower(v)), dim=-1) for v in vis]
+    conds = [fusion_input(p, v, "vision") for v in vis]
+    ft_all = torch.cat(feats_t).detach()          # concat_all_gather: no gradient (distributed.py:53-66)
+    fv_all = torch.cat(feats_v).detach()
+    ids_all = torch.cat([r["ids"] for r in ranks])
+    att_all = torch.cat([r["att"] for r in ranks])
+    cond_all = torch.cat(conds)                    # all_gather_with_grad
+    out = []
+    for k, r in enumerate(ranks):
+        d = {}
+        l_itc, _, _ = itc_loss(feats_v[k], feats_t[k], fv_all, ft_all, p["contra_temp"], k)
+        d["loss_itc"] = l_itc
+        d["loss_itm"] = itm_loss(p, conds[k], cond_all, r["ids"], r["att"], ids_all, att_all, r["neg_c"], r["neg_t"],
+                                 itm_ratio, layers, heads)
+        if "cap" in task:
+            d["loss_cap"] = caption_loss(p, conds[k], r["cap_ids"], r["att"], r["cap_labels"], layers, heads)
+        out.append(d)
+    return out

@@ -1,0 +1,147 @@
+"""GPU parity of the MiCo training step (mico_b200.mico.MiCo.forward: ITC + ITM + caption losses)
+against the CPU oracle (oracle/mico.py, which restates data/model/vast.py:383-512 over the pinned tower oracles), on a
+small configuration: EVA tower width 176 (2 heads x 88), 2 blocks, 257 tokens; BERT hidden 128, 2 layers, cross-attention;
+2 frames per sample.  Hard negatives and MLM masks are injected so both sides see the same discrete choices.
+Tolerances: losses 1e-3 relative (BASELINE.json), gradients 3e-2 rel-L2 (bf16 operands through two towers)."""
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def make_cfg():
+    from mico_b200.mico import _AttrDict
+    return _AttrDict(vision_encoder_type="evaclip01_giant", vision_resolution=224, checkpointing=False, contra_dim=64,
+                     max_vision_sample_num=2, max_audio_sample_num=3, max_depth_sample_num=1, beam_size=3, itm_ratio=0.1,
+                     max_omni_caption_len=70, max_caption_len=24, max_subtitle_len=70, frame_embedding_type="adaptive",
+                     pool_video=False,
+                     vision_tower_kwargs=dict(embed_dim=176, depth=2, num_heads=2, mlp_ratio=2.0, drop_path_rate=0.0,
+                                              num_classes=8),
+                     bert_config=dict(vocab_size=1000, hidden_size=128, num_hidden_layers=2, num_attention_heads=2,
+                                      intermediate_size=256, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                                      max_position_embeddings=64))
+
+
+def make_rank_batch(rank, b=4, n=2, S=24):
+    g = torch.Generator().manual_seed(1234 + rank)
+    pixels = torch.randn(b, n, 3, 224, 224, generator=g)
+    lens = torch.randint(6, S + 1, (b,), generator=g)
+    att = (torch.arange(S)[None] < lens[:, None]).long()
+    ids = torch.randint(5, 1000, (b, S), generator=g) * att
+    ids[:, 0] = 101
+    pick = (torch.rand(b, S, generator=g) < 0.6) & (att > 0)
+    pick[:, 0] = False
+    pick[:, 1] = True
+    cap_labels = torch.where(pick, ids, torch.full_like(ids, -100))
+    cap_ids = torch.where(pick, torch.full_like(ids, 103), ids)
+    return dict(pixels=pixels, ids=ids, att=att, cap_ids=cap_ids, cap_labels=cap_labels)
+
+
+def oracle_params(model):
+    p = {k: (v.detach().cpu().clone().requires_grad_(True) if v.is_floating_point() else v.detach().cpu())
+         for k, v in model.state_dict().items()}
+    p["multimodal_encoder.cls.predictions.decoder.weight"] = p["multimodal_encoder.bert.embeddings.word_embeddings.weight"]
+    p["multimodal_encoder.cls.predictions.decoder.bias"] = p["multimodal_encoder.cls.predictions.bias"]
+    return p
+
+
+def test_retrieval_and_caption_step_single_rank():
+    from mico_b200.mico import MiCo, _AttrDict
+    from oracle import eva_vit as OV
+    from oracle import mico as OM
+    torch.manual_seed(0)
+    cfg = make_cfg()
+    model = MiCo.from_pretrained(cfg, {})
+    with torch.no_grad():       # non-trivial biases / affines so every term is exercised
+        gen = torch.Generator().manual_seed(9)
+        for _, prm in sorted(model.named_parameters()):
+            if prm.dim() <= 1 and prm.numel() > 1:
+                prm.add_(0.02 * torch.randn(prm.shape, generator=gen))
+    p = oracle_params(model)
+    model = model.cuda().train()
+    r = make_rank_batch(0)
+    b = r["ids"].shape[0]
+    g = torch.Generator().manual_seed(77)
+    neg_c = (torch.arange(b) + torch.randint(1, b, (b,), generator=g)) % b
+    neg_t = (torch.arange(b) + torch.randint(1, b, (b,), generator=g)) % b
+    batch = dict(vision_pixels=r["pixels"].cuda(),
+                 caption_tokens=_AttrDict(input_ids=r["ids"].cuda(), attention_mask=r["att"].cuda()),
+                 cap_input_ids=r["cap_ids"].cuda(), cap_labels=r["cap_labels"].cuda())
+    batch["itm_neg_cond_tv"], batch["itm_neg_text_tv"] = neg_c, neg_t
+    out = model(batch, "ret%tv_cap%tv", compute_loss=True)
+    assert set(out) == {"loss_itc", "loss_itm", "loss_cap"}
+    sum(out.values()).backward()
+
+    vit_cfg = OV.vit_cfg(width=176, depth=2, heads=2, mlp=352)
+    ref = OM.retrieval_caption_step(p, [dict(r, neg_c=neg_c, neg_t=neg_t)], vit_cfg, layers=2, heads=2, itm_ratio=0.1)[0]
+    sum(ref.values()).backward()
+    for k in out:
+        print(f"{k}: {out[k].item():.6f} vs oracle {ref[k].item():.6f}")
+        assert abs(out[k].item() - ref[k].item()) <= 1e-3 * abs(ref[k].item()), k
+    errs = []
+    for k, v in model.named_parameters():
+        if v.grad is None or k.endswith("self.key.bias") or k.endswith("decoder.weight"):
+            continue
+        rg = p[k].grad
+        assert rg is not None, k
+        if rg.norm().item() < 1e-7:
+            continue
+        errs.append((rel_l2(v.grad.cpu(), rg), k))
+    errs.sort(reverse=True)
+    print("worst gradient errors:", [(f"{e:.3e}", k) for e, k in errs[:6]], "median", f"{errs[len(errs) // 2][0]:.3e}")
+    # The ITC logits are features / 0.07: a 2^-9 bf16 rounding of a tower feature moves a logit by ~0.03, i.e. the
+    # softmax weights (and through them every ITC gradient) by a few per cent -- the reference's own fp16 autocast has
+    # the same sensitivity.  Bulk of the parameters 3e-2, none above 1e-1.
+    assert errs[0][0] < 1e-1, errs[0]
+    assert errs[len(errs) // 2][0] < 3e-2
+    assert len(errs) > 60
+    # parameters the step does not touch get no gradient on either side
+    assert model.contra_head_a.linear.weight.grad is None and p["contra_head_a.linear.weight"].grad is None
+
+
+def test_inference_demo_call_sequence():
+    """inference_demo.py:132-158 minus tokenizer / generate: vision features, text features, t2v similarity, ITM score."""
+    from mico_b200.mico import MiCo
+    from oracle import eva_vit as OV
+    from oracle import mico as OM
+    from oracle import bert as OB
+    import torch.nn.functional as F
+    torch.manual_seed(1)
+    model = MiCo.from_pretrained(make_cfg(), {})
+    p = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    model = model.cuda().eval()
+    r = make_rank_batch(3, b=2, n=1)
+    with torch.no_grad():
+        vo = model.forward_vision_encoder(r["pixels"].cuda())
+        feat_v = F.normalize(model.contra_head_v(model.pool_vision_for_contra(vo)), dim=-1)
+        to = model.forward_multimodal_encoder(r["ids"].cuda(), r["att"].cuda()).sequence_output
+        feat_t = F.normalize(model.contra_head_t(model.pool_text_for_contra(to)), dim=-1)
+        sim = feat_t @ feat_v.t()
+        cond = model.get_multimodal_forward_input_vision(vo)
+        fused = model.forward_multimodal_encoder(r["ids"].cuda(), r["att"].cuda(), cond).sequence_output
+        itm = F.softmax(model.itm_head(fused[:, 0]), dim=1)[:, 1]
+    vit_cfg = OV.vit_cfg(width=176, depth=2, heads=2, mlp=352)
+    rv = OM.vision_encoder(p, r["pixels"], vit_cfg)
+    rfv = F.normalize(OM.contra_head(p, "contra_head_v", OM.pool_tower(rv)), dim=-1)
+    rft = OM.text_feature(p, r["ids"], r["att"], 2, 2)
+    rcond = OM.fusion_input(p, rv, "vision")
+    rfused = OB.bert_model(p, r["ids"], r["att"], rcond, None, prefix="multimodal_encoder.bert.", layers=2, heads=2)
+    ritm = F.softmax(OM.match_head(p, rfused[:, 0]), dim=1)[:, 1]
+    assert vo.shape == (2, 1, 257, 176)
+    assert rel_l2(vo.cpu(), rv) < 5e-3
+    assert (sim.cpu() - rft @ rfv.t()).abs().max().item() < 5e-3
+    assert (itm.cpu() - ritm).abs().max().item() < 5e-3
+
+
+def test_audio_path_replicates_channel():
+    from mico_b200.mico import MiCo
+    torch.manual_seed(2)
+    model = MiCo.from_pretrained(make_cfg(), {}).cuda().eval()
+    spec = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(4)).cuda()
+    with torch.no_grad():
+        a = model.forward_audio_encoder(spec)
+        v = model.forward_vision_encoder(spec.unsqueeze(2).repeat(1, 1, 3, 1, 1))
+    assert a.shape == (2, 3, 257, 176)
+    assert torch.equal(a, v)

@@ -69,3 +69,18 @@ def test_bert_cross_attention_caption_loss_and_grads_match_reference(golden_dir)
         if k == "cls.predictions.decoder.weight":
             continue
         assert rel_l2(p[k].grad, ref) < 5e-5, k
+
+
+# ---------------------------------------------------------------------------------------------- MiCo heads / fusion inputs
+def test_mico_parts_match_reference(golden_dir):
+    from oracle import mico as OM
+    g = torch.load(os.path.join(golden_dir, "mico_parts_tiny.pt"), weights_only=False)
+    p = g["state_dict"]
+    pooled = OM.pool_tower(g["feat8"])
+    assert rel_l2(pooled, g["pooled"]) < 1e-6
+    assert rel_l2(OM.contra_head(p, "contra_head_v", pooled), g["contra"]) < 1e-5
+    assert rel_l2(OM.match_head(p, g["match_in"]), g["match"]) < 1e-5
+    assert rel_l2(OM.fusion_input(p, g["feat8"], "vision"), g["fuse_v8"]) < 1e-5
+    assert rel_l2(OM.fusion_input(p, g["feat2"], "vision"), g["fuse_v2"]) < 1e-5      # frame table nearest-resized 8 -> 2
+    assert rel_l2(OM.fusion_input(p, g["aud3"], "audio"), g["fuse_a3"]) < 1e-5
+    assert rel_l2(OM.fusion_input(p, g["feat8"], "vision", pool_video=True), g["fuse_v8_pool"]) < 1e-5
