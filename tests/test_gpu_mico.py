@@ -145,3 +145,18 @@ def test_audio_path_replicates_channel():
         v = model.forward_vision_encoder(spec.unsqueeze(2).repeat(1, 1, 3, 1, 1))
     assert a.shape == (2, 3, 257, 176)
     assert torch.equal(a, v)
+
+
+def test_two_gpu_retrieval_step_under_torchrun():
+    """ITC / ITM with real NCCL gathers on 2 GPUs (skipped on a 1-GPU box): tests/dist_mico_step.py under torchrun."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29711", os.path.join(here, "dist_mico_step.py")],
+                       capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "DIST_MICO_STEP PASS" in r.stdout
