@@ -204,15 +204,26 @@ __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v 
 // applies this to 128x256 accumulators per tile and has to stay under the tile's MMA time.  Evaluating the
 // complementary function keeps the x << 0 tail free of cancellation.  With z = x/sqrt(2), exp(-z^2) is also
 // the Gaussian of the derivative, so gelu'(x) = Phi(x) + x*phi(x) costs the same two MUFU ops.
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_raw(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// 15 instructions per element: raw MUFU ex2 / rcp (arguments are always in range: exponent <= 0, denominator >= 1),
+// constants folded (exp(-x^2/2) = 2^(x^2 * -log2(e)/2); the 0.5 of 0.5*erfc is folded into the polynomial).
 __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& gauss) {
-    const float az = fabsf(x) * 0.70710678118654752f;
-    const float e = __expf(-az * az);                       // exp(-x^2/2)
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float half_erfc = 0.5f * p * t * e;               // 0.5 * erfc(|z|)
+    const float e = ex2_raw(x * x * -0.72134752044448170368f);                     // exp(-x^2/2)
+    const float t = rcp_fast(fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.0f));
+    float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+    p = fmaf(p, t, 0.5f * 1.421413741f);
+    p = fmaf(p, t, 0.5f * -0.284496736f);
+    p = fmaf(p, t, 0.5f * 0.254829592f);
+    const float half_erfc = p * t * e;                                              // 0.5 * erfc(|x|/sqrt 2)
     cdf = x < 0.0f ? half_erfc : 1.0f - half_erfc;
     gauss = e;
 }

@@ -54,7 +54,8 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
     static constexpr int BIAS_BYTES = 2 * 256 * 4;   // bias slice of the tile, one copy per accumulator stage
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;   // + alignment slack
+    static constexpr int STAGING_BYTES = 8 * 2048;   // one [32 x 64 B] transpose tile per epilogue warp
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + STAGING_BYTES + 1024;   // + alignment slack
 };
 
 // Global operands of one epilogue chunk, requested BEFORE the TMEM load is waited for so that their latency
@@ -203,6 +204,168 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const EpiOperan
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Coalesced epilogue I/O.  A TMEM lane is an output ROW, so a thread naturally owns 32 consecutive columns of one
+// row and a warp-wide 16-byte access touches 32 different rows = 32 cache lines: the L1/LSU serialises them (one
+// line per cycle), which made every epilogue with extra operands LSU-bound (ncu round 1: fc1+GELU 49 % and
+// fc2-dgrad+GELU' 44 % tensor-active vs 83 % for a plain store).  Each epilogue warp therefore owns a 2 KB staging
+// tile [32 rows x 64 B] in shared memory (16-byte groups XOR-swizzled by (row >> 1) & 3: conflict-free both ways)
+// and moves 64-byte row segments with the mapping  lane l <-> (row 8i + l/4, group l%4), i = 0..3:
+// 8 rows x 64 contiguous bytes per instruction instead of 32 rows x 16 bytes.
+__device__ __forceinline__ uint4* stage_at(uint8_t* st, int row, int g) {
+    return reinterpret_cast<uint4*>(st + row * 64 + ((g ^ ((row >> 1) & 3)) << 4));
+}
+__device__ __forceinline__ int64_t map_out_row(const GemmEpi& e, int row) {
+    if (e.remap_gin <= 0) return row;
+    const int g = row / e.remap_gin, r = row - g * e.remap_gin;
+    return (int64_t)g * e.remap_gout + r + e.remap_off;
+}
+__device__ __forceinline__ int64_t map_res_row(const GemmEpi& e, int row) {
+    if (e.remap_gin <= 0) return row;
+    const int g = row / e.remap_gin, r = row - g * e.remap_gin;
+    return e.residual_bcast ? (int64_t)(r + e.remap_off) : (int64_t)g * e.remap_gout + r + e.remap_off;
+}
+// own row (4 x 16 B in `own`) -> staging -> global rows base + maprow(row)*pitch_bytes + byte_off
+template <bool kResRows>
+__device__ __forceinline__ void staged_store(const GemmEpi& e, uint8_t* st, const uint4 (&own)[4], uint8_t* base,
+                                             int64_t pitch_bytes, int64_t byte_off, int row0, int M) {
+    const int l = (int)lane_id();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) *stage_at(st, l, g) = own[g];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int rr = 8 * i + (l >> 2), g = l & 3, row = row0 + rr;
+        const uint4 v = *stage_at(st, rr, g);
+        if (row < M) {
+            const int64_t mr = kResRows ? map_res_row(e, row) : map_out_row(e, row);
+            *reinterpret_cast<uint4*>(base + mr * pitch_bytes + byte_off + g * 16) = v;
+        }
+    }
+    __syncwarp();
+}
+// coalesced registers (pre[i] <-> row 8i + l/4, group l%4) -> staging -> own row
+__device__ __forceinline__ void staged_to_own(uint8_t* st, const uint4* pre, uint4 (&own)[4]) {
+    const int l = (int)lane_id();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *stage_at(st, 8 * i + (l >> 2), l & 3) = pre[i];
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) own[g] = *stage_at(st, l, g);
+    __syncwarp();
+}
+template <bool kResRows>
+__device__ __forceinline__ void coalesced_load(const GemmEpi& e, uint4* pre, const uint8_t* base, int64_t pitch_bytes,
+                                               int64_t byte_off, int row0, int M) {
+    const int l = (int)lane_id();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = row0 + 8 * i + (l >> 2);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (row < M) {
+            const int64_t mr = kResRows ? map_res_row(e, row) : map_out_row(e, row);
+            v = __ldg(reinterpret_cast<const uint4*>(base + mr * pitch_bytes + byte_off + (l & 3) * 16));
+        }
+        pre[i] = v;
+    }
+}
+
+// operands of a full 32-column chunk, requested before the accumulator wait (warp-cooperative, coalesced)
+__device__ __forceinline__ void staged_prefetch(const GemmEpi& e, uint4 (&pre)[8], int row0, int col0, int M) {
+    if (e.residual) {
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(e.residual);
+        coalesced_load<true>(e, pre, b, e.ldr * 4, (int64_t)col0 * 4, row0, M);
+        coalesced_load<true>(e, pre + 4, b, e.ldr * 4, (int64_t)col0 * 4 + 64, row0, M);
+    } else if (e.act == MICO_ACT_GELU_BWD || e.act == MICO_ACT_QUICK_GELU_BWD) {
+        coalesced_load<false>(e, pre, reinterpret_cast<const uint8_t*>(e.aux_in), e.ld_aux_in * 2, (int64_t)col0 * 2, row0, M);
+    }
+}
+
+// full 32-column chunk, all 32 lanes participate (rows >= M are predicated off at the global accesses)
+__device__ __forceinline__ void epilogue_chunk32_staged(const GemmEpi& e, uint8_t* st, const uint4 (&pre)[8],
+                                                        const float* sbias, const uint32_t (&acc)[32], int row0, int col0,
+                                                        int M) {
+    const int row = row0 + (int)lane_id();
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * e.alpha;
+    if (e.bias) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 b = *reinterpret_cast<const float4*>(sbias + 4 * i);
+            v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+        }
+    }
+    uint4 own[4];
+    if (e.act == MICO_ACT_GELU || e.act == MICO_ACT_QUICK_GELU) {
+        if (e.aux_out) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                own[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                    pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+            staged_store<false>(e, st, own, reinterpret_cast<uint8_t*>(e.aux_out), e.ld_aux_out * 2, (int64_t)col0 * 2, row0, M);
+        }
+        if (e.act == MICO_ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = quick_gelu(v[i]);
+        }
+    } else if (e.act == MICO_ACT_GELU_BWD || e.act == MICO_ACT_QUICK_GELU_BWD) {
+        if (e.residual) {   // rare combination: the pre-activation was not prefetched
+            uint4 tmp[4];
+            coalesced_load<false>(e, tmp, reinterpret_cast<const uint8_t*>(e.aux_in), e.ld_aux_in * 2, (int64_t)col0 * 2, row0, M);
+            staged_to_own(st, tmp, own);
+        } else {
+            staged_to_own(st, pre, own);
+        }
+        const bool erf_gelu = e.act == MICO_ACT_GELU_BWD;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t w[4] = {own[i].x, own[i].y, own[i].z, own[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float lo = bf16_lo(w[j]), hi = bf16_hi(w[j]);
+                v[8 * i + 2 * j] *= erf_gelu ? gelu_erf_grad(lo) : quick_gelu_grad(lo);
+                v[8 * i + 2 * j + 1] *= erf_gelu ? gelu_erf_grad(hi) : quick_gelu_grad(hi);
+            }
+        }
+    }
+    if (e.row_scale) {
+        const float rs = row < M ? __ldg(e.row_scale + row / e.rows_per_group) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= rs;
+    }
+    if (e.residual) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            staged_to_own(st, pre + 4 * h, own);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                v[16 * h + 4 * i + 0] += __uint_as_float(own[i].x); v[16 * h + 4 * i + 1] += __uint_as_float(own[i].y);
+                v[16 * h + 4 * i + 2] += __uint_as_float(own[i].z); v[16 * h + 4 * i + 3] += __uint_as_float(own[i].w);
+            }
+        }
+    }
+    if (e.out_fp32) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                own[i] = make_uint4(__float_as_uint(v[16 * h + 4 * i]), __float_as_uint(v[16 * h + 4 * i + 1]),
+                                    __float_as_uint(v[16 * h + 4 * i + 2]), __float_as_uint(v[16 * h + 4 * i + 3]));
+            staged_store<false>(e, st, own, reinterpret_cast<uint8_t*>(e.out), e.ldo * 4, (int64_t)col0 * 4 + 64 * h, row0, M);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            own[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+        staged_store<false>(e, st, own, reinterpret_cast<uint8_t*>(e.out), e.ldo * 2, (int64_t)col0 * 2, row0, M);
+    }
+}
+
 template <int BN, bool A_MN, bool B_MN, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
@@ -216,6 +379,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     float* sbias_all = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
+    uint8_t* staging_all = smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + Cfg::BIAS_BYTES;
 
     const int warp = threadIdx.x >> 5;
     const int num_m = (M + BM - 1) / BM;
@@ -333,9 +497,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int row = m0 + q * 32 + (int)lane_id();
             const uint32_t t0 = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
             bool waited = false;
+            uint8_t* st = staging_all + (warp - 2) * 2048;
+            const int row0 = m0 + q * 32;
+            // the staged (coalesced) path needs 16-byte-aligned pitches and no read-modify-write of the output
+            const bool staged_ok = epi.vec_ok && !epi.accumulate;
 #pragma unroll 1
             for (int c = half; c < BN / 32; c += 2) {
                 if (n0 + c * 32 >= N) break;   // warp-uniform
+                if (staged_ok && n0 + c * 32 + 32 <= N) {
+                    uint4 pre[8];
+                    staged_prefetch(epi, pre, row0, n0 + c * 32, M);
+                    if (!waited) { mbar_wait(&tfull_bar[acc], acc_phase); tc_fence_after(); waited = true; }
+                    uint32_t v[32];
+                    tmem_ld_x32(t0 + c * 32, v);
+                    tmem_ld_wait();
+                    epilogue_chunk32_staged(epi, st, pre, sbias + c * 32, v, row0, n0 + c * 32, M);
+                    continue;
+                }
                 EpiOperands ops;
                 epilogue_prefetch<32>(epi, ops, row, n0 + c * 32, M, N);
                 if (!waited) { mbar_wait(&tfull_bar[acc], acc_phase); tc_fence_after(); waited = true; }

@@ -237,6 +237,10 @@ class EVAVisionTransformer(nn.Module):
         # "philox": all DropPath multipliers from one counter-based launch; "torch": the reference's own
         # bernoulli_ calls in the reference's order (bit-identical masks to a reference run with the same seed)
         self.drop_path_rng = "philox"
+        # data-parallel hook: called during backward with each finished, contiguous slice of the flat fp32 gradient
+        # buffer (one per block, last block first; then the tower-level parameters) so that a caller can overlap the
+        # gradient reduction (data/utils/pipeline.py:93-99) with the rest of the backward pass
+        self.grad_bucket_hook = None
         self._dp_rates = None
         self._dp_calls = 0
 
@@ -423,6 +427,8 @@ class EVAVisionTransformer(nn.Module):
             dx, dxb = ops.layernorm_bwd(dh, xr, mean1, rstd1, p[_N1W], pgrad(base + _N1W), pgrad(base + _N1B),
                                         dres=dx1, want_bf16=True, row_scale=branch_scale(i - 1, 1), rows_per_group=T)
             del dh, dx1, xr
+            if self.grad_bucket_hook is not None:      # block i's gradients are final and contiguous: reduce them now
+                self.grad_bucket_hook(flat[offs[base]:offs[base + _NBLK]])
         # ---- patch embedding / cls / pos (eva_vit_model.py:613-619); pixels get no gradient
         cols = saved.pop("cols")
         k = params[_PEW][0].numel()
@@ -431,6 +437,8 @@ class EVAVisionTransformer(nn.Module):
         ops.colsum(dxb.view(B, T * D)[:, :D], out=gb, accumulate=2)   # ... minus the cls rows
         gpos = ops.batch_sum(dx, B, out=pgrad(_POS).view(-1))
         pgrad(_CLS).view(-1).copy_(gpos[:D])
+        if self.grad_bucket_hook is not None:
+            self.grad_bucket_hook(flat[:offs[_NTOP]])
         return grads
 
     # ------------------------------------------------------------------ public forward

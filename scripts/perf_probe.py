@@ -46,6 +46,9 @@ def main():
         ("proj fwd  [M,1408]x[1408,1408] +res", 2.0 * M * D * D, lambda: ops.gemm(x, w_p, out=out_d32, bias=bias_d, residual=res)),
         ("fc1 fwd   [M,1408]x[6144,1408] gelu", 2.0 * M * D * F, lambda: ops.gemm(x, w1, out=out_f, bias=bias_f, act=ACT_GELU, aux_out=pre)),
         ("fc1 fwd plain (no epilogue)", 2.0 * M * D * F, lambda: ops.gemm(x, w1, out=out_f)),
+        ("fc1 fwd bias only", 2.0 * M * D * F, lambda: ops.gemm(x, w1, out=out_f, bias=bias_f)),
+        ("fc1 fwd gelu, no pre-activation store", 2.0 * M * D * F, lambda: ops.gemm(x, w1, out=out_f, bias=bias_f, act=ACT_GELU)),
+        ("fc2 dgrad plain (no gelu')", 2.0 * M * D * F, lambda: ops.gemm(dy, w2, b_mn=True, out=out_f)),
         ("fc2 fwd   [M,6144]x[1408,6144] +res", 2.0 * M * D * F, lambda: ops.gemm(a, w2, out=out_d32, bias=bias_d, residual=res)),
         ("fc2 dgrad [M,1408]x[1408,6144]mn gelu'", 2.0 * M * D * F, lambda: ops.gemm(dy, w2, b_mn=True, out=out_f, act=ACT_GELU_BWD, aux_in=pre)),
         ("fc1 dgrad [M,6144]x[6144,1408]mn", 2.0 * M * D * F, lambda: ops.gemm(a, w1, b_mn=True, out=out_d)),
