@@ -116,6 +116,11 @@ typedef struct MicoAttnArgs {
     void* dq; int64_t dq_bs, dq_rs, dq_hs;
     void* dk; int64_t dk_bs, dk_rs, dk_hs;
     void* dv; int64_t dv_bs, dv_rs, dv_hs;
+    /* additive bias that also depends on the head, shared by groups of batch entries -- Swin's relative position bias
+     * + shifted-window mask (swin.py:135-147): the mask element is at
+     *   mask + (mask_bmod ? b % mask_bmod : b) * mask_bs + h * mask_hs + i * mask_qs + j
+     * (batch entry = window; mask_bmod = windows per image; 0 / 0 reproduces the per-batch mask above) */
+    int64_t mask_hs; int32_t mask_bmod;
 } MicoAttnArgs;
 
 int mico_attention_fwd(const MicoAttnArgs* args, void* stream);

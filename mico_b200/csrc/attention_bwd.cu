@@ -24,7 +24,8 @@ struct AttnBwdParams {
     int B, H, Sq, Sk, D;
     float scale;
     const float* mask;
-    int64_t mask_bs, mask_qs;
+    int64_t mask_bs, mask_qs, mask_hs;
+    int mask_bmod;
     const float* lse;     // [B,H,Sq]
     const float* delta;   // [B,H,Sq]
     __nv_bfloat16* dq; int64_t dq_bs, dq_rs, dq_hs;
@@ -202,7 +203,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             // rows past Sq get lse = +huge -> p = 0 -> dS = 0 with no per-element predicate
             const float nlse2 = row_ok ? -p.lse[stat] * kLog2e : -1e30f;
             const float ndlt = row_ok ? -p.delta[stat] * p.scale : 0.f;     // dS = p * (dP*scale - delta*scale)
-            const float* mrow = p.mask ? p.mask + (int64_t)b * p.mask_bs + (int64_t)(row_ok ? qi : 0) * p.mask_qs : nullptr;
+            const float* mrow = p.mask ? (p.mask + (int64_t)(p.mask_bmod ? b % p.mask_bmod : b) * p.mask_bs + (int64_t)h * p.mask_hs) + (int64_t)(row_ok ? qi : 0) * p.mask_qs : nullptr;
             for (int j = 0; j < nkv; ++j, ++tcount) {
                 const int valid = n_valid(kt, j);
                 const int nch = (valid + 31) >> 5;
@@ -455,7 +456,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                             const int q = q4 * 4 + e;
                             float s = fmaf(__uint_as_float(sv[q]), sc2, ls[e]);
                             if (masked && key_ok && c0 + q < validq)
-                                s = fmaf(p.mask[(int64_t)b * p.mask_bs + (int64_t)(i * kTile + c0 + q) * p.mask_qs + kj], kLog2e, s);
+                                s = fmaf((p.mask + (int64_t)(p.mask_bmod ? b % p.mask_bmod : b) * p.mask_bs + (int64_t)h * p.mask_hs)[(int64_t)(i * kTile + c0 + q) * p.mask_qs + kj], kLog2e, s);
                             pt[q] = ex2_fast(s);
                             dst[q] = pt[q] * fmaf(__uint_as_float(dv[q]), p.scale, dl[e]);
                         }
@@ -545,7 +546,7 @@ extern "C" int mico_attention_bwd(const MicoAttnArgs* a, void* stream_) {
     if ((rc = make_attn_tmap(&tdox, a->dout, a->D, a->H, a->Sq, a->B, a->do_bs, a->do_rs, a->do_hs, kExtRows))) return rc;
     AttnBwdParams p;
     p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk; p.D = a->D; p.scale = a->scale;
-    p.mask = a->mask; p.mask_bs = a->mask_bs; p.mask_qs = a->mask_qs;
+    p.mask = a->mask; p.mask_bs = a->mask_bs; p.mask_qs = a->mask_qs; p.mask_hs = a->mask_hs; p.mask_bmod = a->mask_bmod;
     p.lse = a->lse; p.delta = a->delta;
     p.dq = reinterpret_cast<__nv_bfloat16*>(a->dq); p.dq_bs = a->dq_bs; p.dq_rs = a->dq_rs; p.dq_hs = a->dq_hs;
     p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk); p.dk_bs = a->dk_bs; p.dk_rs = a->dk_rs; p.dk_hs = a->dk_hs;

@@ -23,7 +23,8 @@ struct AttnFwdParams {
     int B, H, Sq, Sk, D;          // D = true head dim
     float scale;                  // softmax scale (applied to Q K^T)
     const float* mask;            // additive fp32 mask or null: mask[b*mask_bs + i*mask_qs + j]
-    int64_t mask_bs, mask_qs;
+    int64_t mask_bs, mask_qs, mask_hs;
+    int mask_bmod;
     __nv_bfloat16* o;             // output, element (b,i,h,d) at o + b*o_bs + i*o_rs + h*o_hs + d
     int64_t o_bs, o_rs, o_hs;
     float* lse;                   // [B,H,Sq] or null
@@ -180,7 +181,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const int h = bh % p.H, b = bh / p.H;
             const int qi = qt * kTile + r;
             const bool row_ok = qi < p.Sq;
-            const float* mrow = p.mask ? p.mask + (int64_t)b * p.mask_bs + (int64_t)(row_ok ? qi : 0) * p.mask_qs : nullptr;
+            const float* mrow = p.mask ? (p.mask + (int64_t)(p.mask_bmod ? b % p.mask_bmod : b) * p.mask_bs + (int64_t)h * p.mask_hs) + (int64_t)(row_ok ? qi : 0) * p.mask_qs : nullptr;
             float m = -INFINITY, l = 0.f;
             float oacc[HD_PAD];
 #pragma unroll
@@ -365,7 +366,7 @@ extern "C" int mico_attention_fwd(const MicoAttnArgs* a, void* stream_) {
     AttnFwdParams p;
     p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk; p.D = a->D;
     p.scale = a->scale;
-    p.mask = a->mask; p.mask_bs = a->mask_bs; p.mask_qs = a->mask_qs;
+    p.mask = a->mask; p.mask_bs = a->mask_bs; p.mask_qs = a->mask_qs; p.mask_hs = a->mask_hs; p.mask_bmod = a->mask_bmod;
     p.o = reinterpret_cast<__nv_bfloat16*>(a->o); p.o_bs = a->o_bs; p.o_rs = a->o_rs; p.o_hs = a->o_hs;
     p.lse = a->lse;
     const int work = a->B * a->H * m_tiles(a->Sq);

@@ -18,7 +18,7 @@ struct TailParams {
     int64_t q_bs, q_rs, q_hs, k_bs, k_rs, k_hs, v_bs, v_rs, v_hs, o_bs, o_rs, o_hs, do_bs, do_rs, do_hs;
     __nv_bfloat16 *out0, *out1;     // fwd: o ; dq: dq ; dkv: dk, dv
     int64_t o0_bs, o0_rs, o0_hs, o1_bs, o1_rs, o1_hs;
-    const float* mask; int64_t mask_bs, mask_qs;
+    const float* mask; int64_t mask_bs, mask_qs, mask_hs; int mask_bmod;
     float* lse; const float* delta;
     int B, H, Sq, Sk, D, row0, rows;
     float scale;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kTailThreads) attn_tail_q_kernel(TailParams p)
     __syncthreads();
     const __nv_bfloat16* K = p.k + b * p.k_bs + h * p.k_hs;
     const __nv_bfloat16* V = p.v + b * p.v_bs + h * p.v_hs;
-    const float* mrow = p.mask ? p.mask + (int64_t)b * p.mask_bs + (int64_t)i * p.mask_qs : nullptr;
+    const float* mrow = p.mask ? (p.mask + (int64_t)(p.mask_bmod ? b % p.mask_bmod : b) * p.mask_bs + (int64_t)h * p.mask_hs) + (int64_t)i * p.mask_qs : nullptr;
     const int64_t stat = ((int64_t)b * p.H + h) * p.Sq + i;
     if (MODE == 0) {
         float mx = -INFINITY;
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kTailThreads) attn_tail_kv_kernel(TailParams p
     const int64_t stat0 = ((int64_t)b * p.H + h) * p.Sq;
     for (int i = threadIdx.x; i < p.Sq; i += kTailThreads) {
         float s = p.scale * row_dot(Q + (int64_t)i * p.q_rs, kv, p.D);
-        if (p.mask) s += p.mask[(int64_t)b * p.mask_bs + (int64_t)i * p.mask_qs + j];
+        if (p.mask) s += (p.mask + (int64_t)(p.mask_bmod ? b % p.mask_bmod : b) * p.mask_bs + (int64_t)h * p.mask_hs)[(int64_t)i * p.mask_qs + j];
         const float pr = __expf(s - p.lse[stat0 + i]);
         const float dp = row_dot(DO + (int64_t)i * p.do_rs, vv, p.D);
         pa[i] = pr;
@@ -186,7 +186,7 @@ TailParams base_params(const MicoAttnArgs* a) {
     p.v = reinterpret_cast<const __nv_bfloat16*>(a->v); p.v_bs = a->v_bs; p.v_rs = a->v_rs; p.v_hs = a->v_hs;
     p.o = reinterpret_cast<const __nv_bfloat16*>(a->o); p.o_bs = a->o_bs; p.o_rs = a->o_rs; p.o_hs = a->o_hs;
     p.d_o = reinterpret_cast<const __nv_bfloat16*>(a->dout); p.do_bs = a->do_bs; p.do_rs = a->do_rs; p.do_hs = a->do_hs;
-    p.mask = a->mask; p.mask_bs = a->mask_bs; p.mask_qs = a->mask_qs;
+    p.mask = a->mask; p.mask_bs = a->mask_bs; p.mask_qs = a->mask_qs; p.mask_hs = a->mask_hs; p.mask_bmod = a->mask_bmod;
     p.lse = a->lse; p.delta = a->delta;
     p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk; p.D = a->D; p.scale = a->scale;
     return p;

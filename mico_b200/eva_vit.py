@@ -26,7 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .ops import ACT_GELU, ACT_GELU_BWD, BF16, F32, MicoError
+from .ops import ACT_GELU, ACT_GELU_BWD, ACT_QUICK_GELU, ACT_QUICK_GELU_BWD, BF16, F32, MicoError
 
 _BLOCK_KEYS = ("norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.q_bias", "attn.v_bias", "attn.proj.weight",
                "attn.proj.bias", "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight",
@@ -34,8 +34,8 @@ _BLOCK_KEYS = ("norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.q_bias", "
 _N1W, _N1B, _QKVW, _QB, _VB, _PW, _PB, _N2W, _N2B, _F1W, _F1B, _F2W, _F2B = range(13)
 _NBLK = len(_BLOCK_KEYS)
 # tower-level parameters come first in the flat list
-_CLS, _POS, _PEW, _PEB, _NW, _NB = range(6)
-_NTOP = 6
+_CLS, _POS, _PEW, _PEB, _NW, _NB, _LPW, _LPB = range(8)   # _LPW/_LPB: ln_pre of the OpenAI-CLIP tower (clip.py:245)
+_NTOP = 8
 
 
 def trunc_normal_(t, std=0.02):
@@ -234,6 +234,10 @@ class EVAVisionTransformer(nn.Module):
         k = in_chans * patch_size * patch_size
         self._kpad = (k + 63) // 64 * 64
         self._injected_dp = None
+        # launch-sequence variant (the OpenAI-CLIP tower in clip_vit.py flips these)
+        self._act, self._act_bwd = ACT_GELU, ACT_GELU_BWD
+        self._full_qkv_bias = False      # EVA: cat(q_bias, 0, v_bias); CLIP: in_proj_bias [3D]
+        self._ln_pre = False
         # "philox": all DropPath multipliers from one counter-based launch; "torch": the reference's own
         # bernoulli_ calls in the reference's order (bit-identical masks to a reference run with the same seed)
         self.drop_path_rng = "philox"
@@ -265,7 +269,7 @@ class EVAVisionTransformer(nn.Module):
     # ------------------------------------------------------------------ parameters in launch order
     def _flat_params(self):
         top = [self.cls_token, self.pos_embed, self.patch_embed.proj.weight, self.patch_embed.proj.bias,
-               self.norm.weight, self.norm.bias]
+               self.norm.weight, self.norm.bias, None, None]
         for blk in self.blocks:
             top += [blk.norm1.weight, blk.norm1.bias, blk.attn.qkv.weight, blk.attn.q_bias, blk.attn.v_bias,
                     blk.attn.proj.weight, blk.attn.proj.bias, blk.norm2.weight, blk.norm2.bias,
@@ -323,16 +327,25 @@ class EVAVisionTransformer(nn.Module):
         cols = ops.patchify(x, P, self._kpad, tokens_per_img=T, token_off=1, replicate_channel=(x.dim() == 3))
         w_pe = c.get(params[_PEW], "pe", pad_to=self._kpad)
         pos = params[_POS].detach().reshape(T, D)
-        xr = ops.gemm(cols, w_pe, out_dtype=F32, bias=params[_PEB].detach(), residual=pos, remap=(T, T, 0),
-                      residual_bcast=True)
-        ops.cls_pos_row(params[_CLS].detach(), pos, xr, B, T, D)
+        pe_bias = params[_PEB].detach() if params[_PEB].numel() else None      # clip.py:239 conv1 has no bias
+        xr = ops.gemm(cols, w_pe, out_dtype=F32, bias=pe_bias, residual=pos, remap=(T, T, 0), residual_bcast=True)
+        ops.cls_pos_row(params[_CLS].detach().reshape(-1), pos, xr, B, T, D)
         saved = {"cols": cols, "B": B, "blocks": []} if keep else None
+        if self._ln_pre:     # clip.py:283: x = ln_pre(x) becomes the residual stream
+            x0 = xr
+            _, xr, m0, r0 = ops.layernorm_fwd(x0, params[_LPW].detach(), params[_LPB].detach(), self.eps, out_bf16=False,
+                                              out_f32=True, save_stats=keep)
+            if keep:
+                saved["ln_pre"] = (x0, m0, r0)
         scale = d ** -0.5
         for i in range(len(self.blocks)):
             p = params[_NTOP + i * _NBLK:_NTOP + (i + 1) * _NBLK]
             p = [t.detach() for t in p]
             h, _, mean1, rstd1 = ops.layernorm_fwd(xr, p[_N1W], p[_N1B], self.eps, save_stats=keep)
-            qkv_bias = c.qkv_bias(params[_NTOP + i * _NBLK + _QB], params[_NTOP + i * _NBLK + _VB], ("qkvb", i))
+            if self._full_qkv_bias:
+                qkv_bias = params[_NTOP + i * _NBLK + _QB].detach()
+            else:
+                qkv_bias = c.qkv_bias(params[_NTOP + i * _NBLK + _QB], params[_NTOP + i * _NBLK + _VB], ("qkvb", i))
             qkv = ops.gemm(h, c.get(params[_NTOP + i * _NBLK + _QKVW], ("qkv", i)), bias=qkv_bias)
             qkv5 = qkv.view(B, T, 3, H, d)
             o, lse = ops.attention_fwd(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], scale, need_lse=keep)
@@ -343,7 +356,7 @@ class EVAVisionTransformer(nn.Module):
             h2, _, mean2, rstd2 = ops.layernorm_fwd(x1, p[_N2W], p[_N2B], self.eps, save_stats=keep)
             w1 = c.get(params[_NTOP + i * _NBLK + _F1W], ("fc1", i))
             pre = torch.empty((M, w1.shape[0]), device=dev, dtype=BF16) if keep else None
-            a = ops.gemm(h2, w1, bias=p[_F1B], act=ACT_GELU, aux_out=pre)
+            a = ops.gemm(h2, w1, bias=p[_F1B], act=self._act, aux_out=pre)
             x2 = ops.gemm(a, c.get(params[_NTOP + i * _NBLK + _F2W], ("fc2", i)), out_dtype=F32, bias=p[_F2B],
                           residual=x1, row_scale=s_mlp, rows_per_group=T)
             if keep:
@@ -400,7 +413,7 @@ class EVAVisionTransformer(nn.Module):
             # ---- MLP branch: x2 = x1 + s * (a W2^T + b2)
             ops.gemm(dxb, a, a_mn=True, b_mn=True, out=pgrad(base + _F2W))           # dW2 = dY^T a
             ops.colsum(dxb, out=pgrad(base + _F2B))
-            dpre = ops.gemm(dxb, c.get(params[base + _F2W], ("fc2", i)), b_mn=True, act=ACT_GELU_BWD, aux_in=pre)
+            dpre = ops.gemm(dxb, c.get(params[base + _F2W], ("fc2", i)), b_mn=True, act=self._act_bwd, aux_in=pre)
             del a, pre
             ops.gemm(dpre, h2, a_mn=True, b_mn=True, out=pgrad(base + _F1W))         # dW1
             ops.colsum(dpre, out=pgrad(base + _F1B))
@@ -420,8 +433,11 @@ class EVAVisionTransformer(nn.Module):
                               dq=g5[:, :, 0], dk=g5[:, :, 1], dv=g5[:, :, 2])
             del do, o, lse, qkv
             ops.gemm(dqkv, h, a_mn=True, b_mn=True, out=pgrad(base + _QKVW))
-            ops.colsum(dqkv[:, :D], out=pgrad(base + _QB))         # k has no bias (eva_vit_model.py:307)
-            ops.colsum(dqkv[:, 2 * D:], out=pgrad(base + _VB))
+            if self._full_qkv_bias:
+                ops.colsum(dqkv, out=pgrad(base + _QB))
+            else:
+                ops.colsum(dqkv[:, :D], out=pgrad(base + _QB))         # k has no bias (eva_vit_model.py:307)
+                ops.colsum(dqkv[:, 2 * D:], out=pgrad(base + _VB))
             dh = ops.gemm(dqkv, c.get(params[base + _QKVW], ("qkv", i)), b_mn=True)
             del dqkv, h
             dx, dxb = ops.layernorm_bwd(dh, xr, mean1, rstd1, p[_N1W], pgrad(base + _N1W), pgrad(base + _N1B),
@@ -431,10 +447,14 @@ class EVAVisionTransformer(nn.Module):
                 self.grad_bucket_hook(flat[offs[base]:offs[base + _NBLK]])
         # ---- patch embedding / cls / pos (eva_vit_model.py:613-619); pixels get no gradient
         cols = saved.pop("cols")
+        if self._ln_pre:
+            x0, m0, r0 = saved.pop("ln_pre")
+            dx, dxb = ops.layernorm_bwd(dx, x0, m0, r0, params[_LPW].detach(), pgrad(_LPW), pgrad(_LPB), want_bf16=True)
         k = params[_PEW][0].numel()
         ops.gemm(dxb, cols[:, :k], a_mn=True, b_mn=True, out=pgrad(_PEW).view(D, k))   # cls rows of `cols` are zero
-        gb = ops.colsum(dxb, out=pgrad(_PEB))                      # all rows ...
-        ops.colsum(dxb.view(B, T * D)[:, :D], out=gb, accumulate=2)   # ... minus the cls rows
+        if params[_PEB].numel():
+            gb = ops.colsum(dxb, out=pgrad(_PEB))                      # all rows ...
+            ops.colsum(dxb.view(B, T * D)[:, :D], out=gb, accumulate=2)   # ... minus the cls rows
         gpos = ops.batch_sum(dx, B, out=pgrad(_POS).view(-1))
         pgrad(_CLS).view(-1).copy_(gpos[:D])
         if self.grad_bucket_hook is not None:
@@ -457,7 +477,8 @@ class EVAVisionTransformer(nn.Module):
             x = x.float()
         dp = self._draw_drop_path(B, x.device)
         flat = self._flat_params()
-        keep = torch.is_grad_enabled() and any(p.requires_grad for p in flat)   # save activations for backward?
+        keep = torch.is_grad_enabled() and any(p.requires_grad for p in flat if p is not None)   # keep activations?
+        flat = [p if p is not None else x.new_empty(0) for p in flat]    # slots a variant does not have
         y = _TowerFn.apply(self, keep, x, dp, *flat)
         if not return_all_features:
             return y[:, 0]      # fc_norm is None when use_mean_pooling=False (eva_vit_model.py:643-648)

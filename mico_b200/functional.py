@@ -19,7 +19,7 @@ class _LinearTC(torch.autograd.Function):
     """y = act(x W^T + b) on the tcgen05 GEMM (bf16 operands, fp32 accumulate).  x: [..., K] fp32 or bf16."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act, out_dtype):
+    def forward(ctx, x, weight, bias, act, out_dtype, residual=None):
         shp = x.shape
         x2 = _flat2d(x)
         xb = x2 if x2.dtype == BF16 else ops.scale_cast_bf16(x2.contiguous())
@@ -29,9 +29,15 @@ class _LinearTC(torch.autograd.Function):
         pre = None
         if act == ACT_GELU:
             pre = torch.empty((xb.shape[0], weight.shape[0]), device=x.device, dtype=BF16)
-        y = ops.gemm(xb, wb, bias=None if bias is None else bias.detach(), act=act, aux_out=pre, out_dtype=out_dtype)
+        res2 = None
+        if residual is not None:      # fused residual add (fp32) in the GEMM epilogue
+            res2 = _flat2d(residual).contiguous().float()
+            out_dtype = F32
+        y = ops.gemm(xb, wb, bias=None if bias is None else bias.detach(), act=act, aux_out=pre, out_dtype=out_dtype,
+                     residual=res2)
         ctx.save_for_backward(xb, wb, pre)
         ctx.meta = (shp, x.dtype, bias is not None, act)
+        ctx.has_res = residual is not None
         return y.view(*shp[:-1], weight.shape[0])
 
     @staticmethod
@@ -49,11 +55,11 @@ class _LinearTC(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = ops.gemm(dyb, wb, b_mn=True, out_dtype=F32 if xdtype == F32 else BF16).view(shp)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, (dy if ctx.has_res else None)
 
 
-def linear_tc(x, weight, bias=None, out_dtype=F32):
-    return _LinearTC.apply(x, weight, bias, ACT_NONE, out_dtype)
+def linear_tc(x, weight, bias=None, out_dtype=F32, residual=None):
+    return _LinearTC.apply(x, weight, bias, ACT_NONE, out_dtype, residual)
 
 
 class _LinearF32(torch.autograd.Function):
@@ -211,3 +217,68 @@ class _ContrastiveLogits(torch.autograd.Function):
 
 def contrastive_logits(a, b_all, temp):
     return _ContrastiveLogits.apply(a, b_all, temp)
+
+
+class _Attention(torch.autograd.Function):
+    """o = softmax(scale * q k^T + mask) v on the fused tcgen05 kernels; q,k,v: bf16 [B,S,H,D] views (any strides)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, scale, mask):
+        o, lse = ops.attention_fwd(q, k, v, scale, mask=mask, need_lse=True)
+        ctx.save_for_backward(q, k, v, o, lse, mask if mask is not None else torch.empty(0))
+        ctx.scale, ctx.has_mask = scale, mask is not None
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o, lse, mask = ctx.saved_tensors
+        do = do.contiguous() if do.dtype == BF16 else do.to(BF16).contiguous()
+        dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, do, ctx.scale, mask=mask if ctx.has_mask else None)
+        return dq, dk, dv, None, None
+
+
+def attention(q, k, v, scale, mask=None):
+    return _Attention.apply(q, k, v, scale, mask)
+
+
+class _LinearGeluTC(torch.autograd.Function):
+    """y = act(x W^T + b) with the activation fused in the GEMM epilogue; backward applies act' in an fp32 helper."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        shp = x.shape
+        x2 = _flat2d(x)
+        xb = x2 if x2.dtype == BF16 else ops.scale_cast_bf16(x2.contiguous())
+        if not xb.is_contiguous():
+            xb = xb.contiguous()
+        wb = ops.cast_bf16(weight.detach().contiguous())
+        pre = torch.empty((xb.shape[0], weight.shape[0]), device=x.device, dtype=BF16)
+        y = ops.gemm(xb, wb, bias=None if bias is None else bias.detach(), act=act, aux_out=pre)
+        ctx.save_for_backward(xb, wb, pre)
+        ctx.meta = (shp, x.dtype, bias is not None, act)
+        return y.view(*shp[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, wb, pre = ctx.saved_tensors
+        shp, xdtype, has_bias, act = ctx.meta
+        dyb = _flat2d(dy)
+        if dyb.dtype != BF16:
+            dyb = dyb.to(BF16)
+        dyb = dyb.contiguous()
+        # dpre = dy * act'(pre) = (dy . I) with the *_BWD epilogue: an identity GEMM would waste FLOPs, so use the
+        # elementwise fp32 helper for erf-GELU (QuickGELU only occurs inside the CLIP tower's own launch sequence)
+        if act != ACT_GELU:
+            raise MicoError("linear_act: only exact-erf GELU is available outside the towers")
+        dpre = ops.scale_cast_bf16(ops.gelu_f32(pre.float(), dyb.float()))
+        dw = ops.gemm(dpre, xb, a_mn=True, b_mn=True, out_dtype=F32)
+        db = ops.colsum(dpre) if has_bias else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm(dpre, wb, b_mn=True, out_dtype=F32 if xdtype == F32 else BF16).view(shp)
+        return dx, dw, db, None
+
+
+def linear_gelu(x, weight, bias=None):
+    """bf16 GELU(x W^T + b) on the tensor-core GEMM (returns bf16)."""
+    return _LinearGeluTC.apply(x, weight, bias, ACT_GELU)

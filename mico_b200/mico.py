@@ -31,6 +31,12 @@ _EVA_CFG = {
 }
 
 
+_CLIP_CFG = {
+    "clip_vit_base_16": dict(patch_size=16, width=768, layers=12, heads=12, output_dim=512),
+    "clip_vit_large_14_336px": dict(patch_size=14, width=1024, layers=24, heads=16, output_dim=768),
+}
+
+
 class _AttrDict(dict):
     """attribute access over a dict (stands in for easydict.EasyDict, which the reference wraps batches/configs in)"""
 
@@ -233,8 +239,16 @@ class MiCo(nn.Module):
             tower = EVAVisionTransformer(img_size=self.config.vision_resolution, qkv_bias=True, use_mean_pooling=False,
                                          grad_checkpointing=bool(self.config.checkpointing), **kw)
             self.vision_encoder = _VisionEncoder(tower)
+        elif t in _CLIP_CFG:      # OpenAI CLIP towers (mico.py:354-371; reference needs JIT weights at a hard-coded path)
+            from .clip_vit import VisionTransformer
+            kw = dict(_CLIP_CFG[t])
+            kw.update(getattr(self.config, "vision_tower_kwargs", None) or {})
+            self.vision_dim = kw["width"]
+            kw["input_resolution"] = self.config.vision_resolution
+            self.vision_encoder = _VisionEncoder(VisionTransformer(checkpointing=bool(self.config.checkpointing), **kw))
         else:
-            raise NotImplementedError(f"vision_encoder_type {t!r}: only the EVA01-g tower is built (DESIGN.md)")
+            raise NotImplementedError(f"vision_encoder_type {t!r}: EVA01-g and the OpenAI CLIP ViTs are built; EVA02 "
+                                      "(RoPE / SwiGLU) and Swin towers are not (DESIGN.md)")
 
     def construct_multimodal_encoder(self):
         bert_kw = dict(getattr(self.config, "bert_config", None) or {})

@@ -117,8 +117,13 @@ def _attn_args(q, k, v, o, lse, mask, scale):
             a.mask, a.mask_bs, a.mask_qs = mask.data_ptr(), mask.stride(0), 0
         elif mask.dim() == 3:    # [B, Sq, Sk]
             a.mask, a.mask_bs, a.mask_qs = mask.data_ptr(), mask.stride(0), mask.stride(1)
+        elif mask.dim() == 4:    # [G, H, Sq, Sk]: per-head bias shared by batch entries b % G (Swin windows)
+            if mask.shape[1] != H or B % mask.shape[0]:
+                raise MicoError("4-D mask must be [G,H,Sq,Sk] with B % G == 0")
+            a.mask, a.mask_bs, a.mask_hs, a.mask_qs = mask.data_ptr(), mask.stride(0), mask.stride(1), mask.stride(2)
+            a.mask_bmod = mask.shape[0]
         else:
-            raise MicoError("mask must be [B,Sk] or [B,Sq,Sk] additive fp32")
+            raise MicoError("mask must be [B,Sk], [B,Sq,Sk] or [G,H,Sq,Sk] additive fp32")
     a.B, a.H, a.Sq, a.Sk, a.D = B, H, Sq, Sk, D
     a.scale = float(scale)
     return a

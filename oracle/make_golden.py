@@ -166,6 +166,49 @@ def gen_mico_parts():
                                      match_in=torch.randn(6, md, generator=torch.Generator().manual_seed(6)), **out))
 
 
+def gen_transformer():
+    """Reference model/transformer.py TransformerEncoder, pre-norm and post-norm, hidden 128 = 2 heads x 64, FFN 256,
+    2 layers, dropout 0, additive padding mask (b,1,1,S); forward + gradients of sum(y^2)."""
+    from model.transformer import TransformerEncoder
+    out = {}
+    for mode in ("prenorm", "postnorm"):
+        cfg = ref_shims._AttrDict(hidden_size=128, num_attention_heads=2, intermediate_size=256, num_hidden_layers=2,
+                                  hidden_dropout=0.0, attention_dropout=0.0, checkpointing=False)
+        torch.manual_seed(0)
+        m = TransformerEncoder(cfg, mode)
+        _randomize(m, 4)
+        g = torch.Generator().manual_seed(8)
+        x = torch.randn(3, 40, 128, generator=g, requires_grad=True)
+        lens = torch.tensor([40, 31, 12])
+        mask = ((torch.arange(40)[None] >= lens[:, None]).float() * -10000.0)[:, None, None, :]
+        m.train()
+        y, _ = m(x, mask)
+        y.pow(2).sum().backward()
+        out[mode] = dict(state_dict={k: v.detach().clone() for k, v in m.state_dict().items()}, x=x.detach().clone(),
+                         mask=mask, y=y.detach().clone(), dx=x.grad.clone(),
+                         grads={k: v.grad.clone() for k, v in m.named_parameters()})
+    _save("transformer_tiny.pt", out)
+
+
+def gen_clip():
+    """Reference OpenAI-CLIP VisionTransformer (model/clip/clip.py:228) at width 128 = 2 heads x 64, 2 layers, patch 16,
+    224x224 -> 197 tokens: forward (all features) and gradients of mean(y^2)."""
+    from model.clip.clip import VisionTransformer
+    torch.manual_seed(0)
+    m = VisionTransformer(input_resolution=224, patch_size=16, width=128, layers=2, heads=2, output_dim=32)
+    _randomize(m, 6)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 3, 224, 224, generator=g)
+    m.train()
+    y = m(x, return_all_features=True)
+    y.pow(2).mean().backward()
+    with torch.no_grad():
+        pooled = m(x)
+    _save("clip_vit_tiny.pt", dict(state_dict={k: v.detach().clone() for k, v in m.state_dict().items()}, x=x,
+                                   y=y.detach().clone(), pooled=pooled,
+                                   grads={k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None}))
+
+
 def _dist_worker(rank, world, port, q):
     import torch.distributed as dist
     sys.path.insert(0, os.path.join(ref_shims.REF_ROOT, "data"))
@@ -199,7 +242,8 @@ def gen_dist():
                                        ids_all=[r[4] for r in res], x_grad=[r[5] for r in res]))
 
 
-GENERATORS = {"vit": gen_vit, "bert": gen_bert, "mico_parts": gen_mico_parts, "dist": gen_dist}
+GENERATORS = {"vit": gen_vit, "bert": gen_bert, "mico_parts": gen_mico_parts, "dist": gen_dist,
+              "transformer": gen_transformer, "clip": gen_clip}
 
 
 def main():
