@@ -210,6 +210,15 @@ int mico_gelu_f32(const float* x, const float* dy, float* out, int64_t n, void* 
 /* out[0] (+)= alpha * <a, b>  (d contra_temp) */
 int mico_dot_f32(const float* a, const float* b, int64_t n, float alpha, float* out, int accumulate, void* stream);
 
+/* K11 Kaldi-compatible log-mel filterbank (model/audioprocessor.py:38-46: waveform * 2^15 -> torchaudio
+ * compliance.kaldi.fbank(num_mel_bins, 16 kHz, frame_length 25 ms, frame_shift 10 ms; defaults: snip_edges, DC removal,
+ * pre-emphasis 0.97, povey window, 512-point power spectrum, mel 20 Hz..Nyquist, log) and the normalisation
+ * (x - norm_sub) * norm_mul of :47-48).  wave: fp32 [n_clips][clip_stride]; window: fp32 [frame_len]; mel: fp32
+ * [num_mel][257]; out: fp32 [n_clips][n_frames][num_mel], n_frames = 1 + (n_samples - frame_len) / frame_shift. */
+int mico_fbank(const float* wave, int64_t clip_stride, int n_clips, int n_samples, int frame_len, int frame_shift,
+               const float* window, const float* mel, int num_mel, float in_scale, float preemph, float log_floor,
+               float norm_sub, float norm_mul, float* out, int64_t out_clip_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

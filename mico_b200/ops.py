@@ -418,3 +418,25 @@ def gelu_f32(x, dy=None):
     out = torch.empty_like(x)
     check(lib.mico_gelu_f32(_ptr(x), _ptr(dy), _ptr(out), C.c_int64(x.numel()), _stream()), "mico_gelu_f32")
     return out
+
+
+def fbank(wave, window, mel, frame_shift=160, in_scale=32768.0, preemph=0.97, log_floor=1.1920928955078125e-07,
+          norm_sub=0.0, norm_mul=1.0):
+    """wave: fp32 [n_clips, n_samples] -> fp32 [n_clips, n_frames, num_mel] log-mel (Kaldi fbank semantics)."""
+    _req(wave, F32, "wave")
+    _req(window, F32, "window")
+    _req(mel, F32, "mel")
+    n_clips, n_samples = wave.shape
+    frame_len = window.numel()
+    if n_samples < frame_len:
+        raise MicoError("fbank: clip shorter than one frame")
+    n_frames = 1 + (n_samples - frame_len) // frame_shift
+    num_mel = mel.shape[0]
+    if mel.shape[1] != 257 or not mel.is_contiguous():
+        raise MicoError("fbank: mel bank must be contiguous [num_mel, 257]")
+    out = torch.empty((n_clips, n_frames, num_mel), device=wave.device, dtype=F32)
+    check(lib.mico_fbank(_ptr(wave), C.c_int64(wave.stride(0)), n_clips, n_samples, frame_len, int(frame_shift), _ptr(window),
+                         _ptr(mel), num_mel, C.c_float(in_scale), C.c_float(preemph), C.c_float(log_floor),
+                         C.c_float(norm_sub), C.c_float(norm_mul), _ptr(out), C.c_int64(n_frames * num_mel), _stream()),
+          "mico_fbank")
+    return out

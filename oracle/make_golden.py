@@ -209,6 +209,22 @@ def gen_clip():
                                    grads={k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None}))
 
 
+def gen_fbank():
+    """torchaudio.compliance.kaldi.fbank exactly as model/audioprocessor.py:39-40 calls it (the reference's own
+    AudioProcessor needs torchaudio.load, which needs torchcodec here -- SURVEY.md 8c -- so the call is made directly on a
+    synthetic 16 kHz waveform), for 224 and 64 mel bins."""
+    import torchaudio
+    g = torch.Generator().manual_seed(4242)
+    wave = 0.1 * torch.randn(1, 16000 * 3 + 123, generator=g)        # 3 s clip, ragged tail
+    t = torch.arange(wave.shape[1]) / 16000.0
+    wave = wave + 0.3 * torch.sin(2 * 3.14159265 * 440.0 * t) + 0.05                # tone + DC offset
+    out = {"wave": wave, "torchaudio": torchaudio.__version__}
+    for bins in (224, 64):
+        out[f"fbank_{bins}"] = torchaudio.compliance.kaldi.fbank(wave * 2 ** 15, num_mel_bins=bins, sample_frequency=16000,
+                                                                 frame_length=25, frame_shift=10)
+    _save("fbank.pt", out)
+
+
 def _dist_worker(rank, world, port, q):
     import torch.distributed as dist
     sys.path.insert(0, os.path.join(ref_shims.REF_ROOT, "data"))
@@ -243,7 +259,7 @@ def gen_dist():
 
 
 GENERATORS = {"vit": gen_vit, "bert": gen_bert, "mico_parts": gen_mico_parts, "dist": gen_dist,
-              "transformer": gen_transformer, "clip": gen_clip}
+              "transformer": gen_transformer, "clip": gen_clip, "fbank": gen_fbank}
 
 
 def main():

@@ -84,3 +84,15 @@ def test_mico_parts_match_reference(golden_dir):
     assert rel_l2(OM.fusion_input(p, g["feat2"], "vision"), g["fuse_v2"]) < 1e-5      # frame table nearest-resized 8 -> 2
     assert rel_l2(OM.fusion_input(p, g["aud3"], "audio"), g["fuse_a3"]) < 1e-5
     assert rel_l2(OM.fusion_input(p, g["feat8"], "vision", pool_video=True), g["fuse_v8_pool"]) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------- Kaldi fbank
+def test_fbank_oracle_matches_torchaudio(golden_dir):
+    from oracle import fbank as OF
+    g = torch.load(os.path.join(golden_dir, "fbank.pt"), weights_only=False)
+    for bins in (224, 64):
+        fb = OF.kaldi_fbank(g["wave"] * 2 ** 15, bins)
+        assert fb.shape == g[f"fbank_{bins}"].shape == (299, bins)
+        assert (fb - g[f"fbank_{bins}"]).abs().max().item() < 2e-4      # log-mel values are O(10)
+    out = OF.audio_processor(g["wave"], 224, 224, 3)
+    assert out.shape == (3, 224, 224)
