@@ -125,6 +125,10 @@ typedef struct MicoAttnArgs {
 
 int mico_attention_fwd(const MicoAttnArgs* args, void* stream);
 int mico_attention_bwd(const MicoAttnArgs* args, void* stream);
+/* gradient of a learnable additive bias (Swin relative position bias, swin.py:135-139): dmask (same layout as mask, zeroed
+ * by the caller) += P o (dO V^T - delta), summed over the batch entries that share a mask slice.  Call after
+ * mico_attention_bwd with the same arguments (it needs lse and delta).  Small windows only. */
+int mico_attention_dmask(const MicoAttnArgs* args, float* dmask, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K2  LayerNorm (eva_vit_model.py:375,382,542 eps 1e-6; bert.py:92,290,368,583 and mico.py:49,400-403

@@ -179,6 +179,48 @@ __global__ void __launch_bounds__(kTailThreads) attn_tail_kv_kernel(TailParams p
     weighted_rows(DO, p.do_rs, p.Sq, pa, p.D, 1.0f, p.out1 + b * p.o1_bs + (int64_t)j * p.o1_rs + h * p.o1_hs, red);
 }
 
+// Gradient of an additive attention bias that is a PARAMETER (Swin's relative position bias, swin.py:135-139):
+//   d mask[g,h,i,j] += p_ij * (dO_i . v_j - delta_i)      summed over the batch entries b with b % G == g.
+// One block per (b, h); K and V of the (small) window are staged in shared memory as fp32, threads own (i, j) pairs.
+__global__ void __launch_bounds__(256) attn_dmask_kernel(TailParams p, float* __restrict__ dmask) {
+    extern __shared__ float sm[];
+    float* ks = sm;                              // [Sk][D]
+    float* vs = ks + (size_t)p.Sk * p.D;         // [Sk][D]
+    float* qs = vs + (size_t)p.Sk * p.D;         // [Sq][D]
+    float* gs = qs + (size_t)p.Sq * p.D;         // [Sq][D]  dO
+    const int h = blockIdx.x % p.H, b = blockIdx.x / p.H;
+    const __nv_bfloat16* K = p.k + b * p.k_bs + h * p.k_hs;
+    const __nv_bfloat16* V = p.v + b * p.v_bs + h * p.v_hs;
+    const __nv_bfloat16* Q = p.q + b * p.q_bs + h * p.q_hs;
+    const __nv_bfloat16* DO = p.d_o + b * p.do_bs + h * p.do_hs;
+    for (int idx = threadIdx.x; idx < p.Sk * p.D; idx += blockDim.x) {
+        const int j = idx / p.D, d = idx - j * p.D;
+        ks[idx] = __bfloat162float(K[(int64_t)j * p.k_rs + d]);
+        vs[idx] = __bfloat162float(V[(int64_t)j * p.v_rs + d]);
+    }
+    for (int idx = threadIdx.x; idx < p.Sq * p.D; idx += blockDim.x) {
+        const int i = idx / p.D, d = idx - i * p.D;
+        qs[idx] = __bfloat162float(Q[(int64_t)i * p.q_rs + d]);
+        gs[idx] = __bfloat162float(DO[(int64_t)i * p.do_rs + d]);
+    }
+    __syncthreads();
+    const int g = p.mask_bmod ? b % p.mask_bmod : b;
+    const float* mbase = p.mask + (int64_t)g * p.mask_bs + (int64_t)h * p.mask_hs;
+    float* dbase = dmask + (int64_t)g * p.mask_bs + (int64_t)h * p.mask_hs;
+    const int64_t stat0 = ((int64_t)b * p.H + h) * p.Sq;
+    for (int idx = threadIdx.x; idx < p.Sq * p.Sk; idx += blockDim.x) {
+        const int i = idx / p.Sk, j = idx - i * p.Sk;
+        float s = 0.f, dp = 0.f;
+        for (int d = 0; d < p.D; ++d) {
+            s += qs[i * p.D + d] * ks[j * p.D + d];
+            dp += gs[i * p.D + d] * vs[j * p.D + d];
+        }
+        s = s * p.scale + mbase[(int64_t)i * p.mask_qs + j];
+        const float pr = __expf(s - p.lse[stat0 + i]);
+        atomicAdd(dbase + (int64_t)i * p.mask_qs + j, pr * (dp - p.delta[stat0 + i]));
+    }
+}
+
 TailParams base_params(const MicoAttnArgs* a) {
     TailParams p{};
     p.q = reinterpret_cast<const __nv_bfloat16*>(a->q); p.q_bs = a->q_bs; p.q_rs = a->q_rs; p.q_hs = a->q_hs;
@@ -237,3 +279,22 @@ int attention_tail_bwd(const MicoAttnArgs* a, cudaStream_t stream) {
 }
 
 }  // namespace mico
+
+extern "C" int mico_attention_dmask(const MicoAttnArgs* a, float* dmask, void* stream_) {
+    using namespace mico;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MICO_CHECK_ARG(a && dmask && a->mask && a->q && a->k && a->v && a->dout && a->lse && a->delta);
+    TailParams p = base_params(a);
+    const size_t smem = (size_t)2 * (a->Sk + a->Sq) * a->D * sizeof(float);
+    if (smem > 200 * 1024) {
+        set_last_error(__FILE__, __LINE__, "attention bias gradient: window too large for the SIMT kernel (Sq+Sk)*D*8 > 200 KB");
+        return MICO_ERR_UNSUPPORTED;
+    }
+    if (smem > 48 * 1024)
+        MICO_CHECK_CUDA(cudaFuncSetAttribute(attn_dmask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope prof(kProfAttnBwd, 4.0 * a->B * a->H * (double)a->Sq * a->Sk * a->D, stream);
+    attn_dmask_kernel<<<a->B * a->H, 256, smem, stream>>>(p, dmask);
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return MICO_OK;
+}

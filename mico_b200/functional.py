@@ -104,15 +104,16 @@ def linear(x, weight, bias=None):
 
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, eps):
+    def forward(ctx, x, weight, bias, eps, out_dtype=F32):
         shp = x.shape
         x2 = _flat2d(x).contiguous()
         if x2.dtype != F32:
             x2 = x2.float()
-        _, y, mean, rstd = ops.layernorm_fwd(x2, weight.detach(), bias.detach(), eps, out_bf16=False, out_f32=True)
+        yb, y, mean, rstd = ops.layernorm_fwd(x2, weight.detach(), bias.detach(), eps, out_bf16=out_dtype == BF16,
+                                              out_f32=out_dtype == F32)
         ctx.save_for_backward(x2, mean, rstd, weight)
         ctx.shp = shp
-        return y.view(shp)
+        return (yb if out_dtype == BF16 else y).view(shp)
 
     @staticmethod
     def backward(ctx, dy):
@@ -122,11 +123,12 @@ class _LayerNorm(torch.autograd.Function):
             dy2 = dy2.float()
         dg, db = torch.empty_like(weight), torch.empty_like(weight)
         dx, _ = ops.layernorm_bwd(dy2, x2, mean, rstd, weight.detach(), dg, db)
-        return dx.view(ctx.shp), dg, db, None
+        return dx.view(ctx.shp), dg, db, None, None
 
 
-def layer_norm(x, weight, bias, eps):
-    return _LayerNorm.apply(x, weight, bias, eps)
+def layer_norm(x, weight, bias, eps, out_dtype=F32):
+    """LayerNorm over the last dim of an fp32 tensor; out_dtype=bf16 emits the next GEMM's operand directly."""
+    return _LayerNorm.apply(x, weight, bias, eps, out_dtype)
 
 
 class _GeluF32(torch.autograd.Function):
@@ -233,8 +235,9 @@ class _Attention(torch.autograd.Function):
     def backward(ctx, do):
         q, k, v, o, lse, mask = ctx.saved_tensors
         do = do.contiguous() if do.dtype == BF16 else do.to(BF16).contiguous()
-        dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, do, ctx.scale, mask=mask if ctx.has_mask else None)
-        return dq, dk, dv, None, None
+        dmask = torch.zeros_like(mask) if (ctx.has_mask and ctx.needs_input_grad[4]) else None
+        dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, do, ctx.scale, mask=mask if ctx.has_mask else None, dmask=dmask)
+        return dq, dk, dv, None, dmask
 
 
 def attention(q, k, v, scale, mask=None):

@@ -246,9 +246,16 @@ class MiCo(nn.Module):
             self.vision_dim = kw["width"]
             kw["input_resolution"] = self.config.vision_resolution
             self.vision_encoder = _VisionEncoder(VisionTransformer(checkpointing=bool(self.config.checkpointing), **kw))
+        elif t.startswith("swin"):     # mico.py:86 calls an undefined load_swin_model(); general_module.py:230-241 builds Swin-B 22k
+            from .swin import SwinTransformer
+            kw = dict(embed_dim=128, depths=[2, 2, 18, 2], num_heads=[4, 8, 16, 32], window_size=7, drop_path_rate=0.2,
+                      num_classes=0)
+            kw.update(getattr(self.config, "vision_tower_kwargs", None) or {})
+            self.vision_encoder = SwinTransformer(img_size=self.config.vision_resolution, **kw)
+            self.vision_dim = self.vision_encoder.num_features
         else:
-            raise NotImplementedError(f"vision_encoder_type {t!r}: EVA01-g and the OpenAI CLIP ViTs are built; EVA02 "
-                                      "(RoPE / SwiGLU) and Swin towers are not (DESIGN.md)")
+            raise NotImplementedError(f"vision_encoder_type {t!r}: EVA01-g, the OpenAI CLIP ViTs and Swin are built; EVA02 "
+                                      "(RoPE / SwiGLU) and VideoSwin towers are not (DESIGN.md)")
 
     def construct_multimodal_encoder(self):
         bert_kw = dict(getattr(self.config, "bert_config", None) or {})
@@ -260,7 +267,8 @@ class MiCo(nn.Module):
     def from_pretrained(cls, opts, state_dict, *inputs, **kwargs):
         model = cls(opts, *inputs, **kwargs)
         missing_keys, unexpected_keys = model.load_state_dict(state_dict, strict=False)
-        del model.vision_encoder.text
+        if hasattr(model.vision_encoder, "text"):
+            del model.vision_encoder.text
         if state_dict != {}:
             print(f"Unexpected keys {unexpected_keys}")
             print(f"missing_keys  {missing_keys}")
@@ -269,11 +277,16 @@ class MiCo(nn.Module):
     # ------------------------------------------------------------------ encoders (mico.py:115-155)
     def forward_vision_encoder(self, vision_pixels):
         b, n, _, h, w = vision_pixels.shape
-        out = self.vision_encoder.visual(vision_pixels.reshape(b * n, 3, h, w), return_all_features=True)
+        if self.config.vision_encoder_type.startswith("swin"):          # mico.py:125-127
+            out = self.vision_encoder(vision_pixels.reshape(b * n, 3, h, w))
+        else:
+            out = self.vision_encoder.visual(vision_pixels.reshape(b * n, 3, h, w), return_all_features=True)
         return out.reshape(b, -1, *out.shape[-2:])
 
     def forward_audio_encoder(self, audio_spectrograms):
         # reference: unsqueeze(2).repeat(1,1,3,1,1) then the vision tower (mico.py:139-143)
+        if self.config.vision_encoder_type.startswith("swin"):
+            return self.forward_vision_encoder(audio_spectrograms.unsqueeze(2).repeat(1, 1, 3, 1, 1))
         b, n, h, w = audio_spectrograms.shape
         out = self.vision_encoder.visual(audio_spectrograms.reshape(b * n, h, w), return_all_features=True)
         return out.reshape(b, -1, *out.shape[-2:])
@@ -288,6 +301,8 @@ class MiCo(nn.Module):
 
     # ------------------------------------------------------------------ pooling (mico.py:157-185)
     def pool_vision_for_contra(self, feature):
+        if self.config.vision_encoder_type.startswith("swin"):          # mico.py:161-162: token mean, then frame mean
+            return feature.mean(dim=2).mean(dim=1)
         return feature[:, :, 0].mean(dim=1)
 
     pool_audio_for_contra = pool_vision_for_contra

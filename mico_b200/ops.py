@@ -140,7 +140,8 @@ def attention_fwd(q, k, v, scale, mask=None, out=None, need_lse=True):
     return out, lse
 
 
-def attention_bwd(q, k, v, o, lse, dout, scale, mask=None, dq=None, dk=None, dv=None):
+def attention_bwd(q, k, v, o, lse, dout, scale, mask=None, dq=None, dk=None, dv=None, dmask=None):
+    """dmask: optional zero-initialised fp32 tensor shaped like mask; receives the gradient of the additive bias."""
     B, Sq, H, D = q.shape
     Sk = k.shape[1]
     dq = torch.empty((B, Sq, H, D), device=q.device, dtype=BF16) if dq is None else dq
@@ -155,6 +156,11 @@ def attention_bwd(q, k, v, o, lse, dout, scale, mask=None, dq=None, dk=None, dv=
     a.dk, a.dk_bs, a.dk_rs, a.dk_hs = _bhsd_strides(dk)
     a.dv, a.dv_bs, a.dv_rs, a.dv_hs = _bhsd_strides(dv)
     check(lib.mico_attention_bwd(C.byref(a), _stream()), "mico_attention_bwd")
+    if dmask is not None:
+        _req(dmask, F32, "dmask")
+        if mask is None or dmask.shape != mask.shape or dmask.stride() != mask.stride():
+            raise MicoError("dmask must have the layout of mask")
+        check(lib.mico_attention_dmask(C.byref(a), _ptr(dmask), _stream()), "mico_attention_dmask")
     return dq, dk, dv
 
 

@@ -225,6 +225,29 @@ def gen_fbank():
     _save("fbank.pt", out)
 
 
+def gen_swin():
+    """Reference SwinTransformer (model/swin.py:485) at embed_dim 32, depths [2,2], heads [1,2] (head_dim 32 like Swin-B),
+    window 7, 56x56 input with patch 4 -> 14x14 tokens -> shifted windows -> patch merge -> 7x7: forward_features and
+    gradients of mean(y^2), drop_path 0."""
+    from model.swin import SwinTransformer
+    torch.manual_seed(0)
+    m = SwinTransformer(img_size=56, patch_size=4, in_chans=3, num_classes=0, embed_dim=32, depths=[2, 2], num_heads=[1, 2],
+                        window_size=7, mlp_ratio=4., drop_path_rate=0.0)
+    _randomize(m, 8)
+    with torch.no_grad():
+        for n_, prm in m.named_parameters():
+            if "relative_position_bias_table" in n_:
+                prm.add_(0.5 * torch.randn(prm.shape, generator=torch.Generator().manual_seed(9)))
+    g = torch.Generator().manual_seed(33)
+    x = torch.randn(3, 3, 56, 56, generator=g)
+    m.train()
+    y = m.forward_features(x)
+    y.pow(2).mean().backward()
+    _save("swin_tiny.pt", dict(state_dict={k: v.detach().clone() for k, v in m.state_dict().items()}, x=x,
+                               y=y.detach().clone(),
+                               grads={k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None}))
+
+
 def _dist_worker(rank, world, port, q):
     import torch.distributed as dist
     sys.path.insert(0, os.path.join(ref_shims.REF_ROOT, "data"))
@@ -259,7 +282,7 @@ def gen_dist():
 
 
 GENERATORS = {"vit": gen_vit, "bert": gen_bert, "mico_parts": gen_mico_parts, "dist": gen_dist,
-              "transformer": gen_transformer, "clip": gen_clip, "fbank": gen_fbank}
+              "transformer": gen_transformer, "clip": gen_clip, "fbank": gen_fbank, "swin": gen_swin}
 
 
 def main():
