@@ -45,11 +45,19 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int64_t o
     const uint4* po = reinterpret_cast<const uint4*>(o + b * o_bs + i * o_rs + h * o_hs);
     const uint4* pd = reinterpret_cast<const uint4*>(d_o + b * do_bs + i * do_rs + h * do_hs);
     float acc = 0.f;
-    for (int c = 0; c < D / 8; ++c) {
-        const uint4 a = po[c], g = pd[c];
-        acc += bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
-               bf16_hi(a.y) * bf16_hi(g.y) + bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) +
-               bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
+    for (int c0 = 0; c0 < D / 8; c0 += 4) {       // eight 16-byte loads in flight per thread
+        uint4 a[4], g[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const bool ok = c0 + t < D / 8;
+            a[t] = ok ? po[c0 + t] : make_uint4(0, 0, 0, 0);
+            g[t] = ok ? pd[c0 + t] : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            acc += bf16_lo(a[t].x) * bf16_lo(g[t].x) + bf16_hi(a[t].x) * bf16_hi(g[t].x) + bf16_lo(a[t].y) * bf16_lo(g[t].y) +
+                   bf16_hi(a[t].y) * bf16_hi(g[t].y) + bf16_lo(a[t].z) * bf16_lo(g[t].z) + bf16_hi(a[t].z) * bf16_hi(g[t].z) +
+                   bf16_lo(a[t].w) * bf16_lo(g[t].w) + bf16_hi(a[t].w) * bf16_hi(g[t].w);
     }
     delta[((int64_t)b * H + h) * S + i] = acc;
 }

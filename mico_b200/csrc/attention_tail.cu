@@ -31,16 +31,20 @@ __device__ __forceinline__ float dot8(const uint4& u, const float* vec) {
     return bf16_lo(u.x) * vec[0] + bf16_hi(u.x) * vec[1] + bf16_lo(u.y) * vec[2] + bf16_hi(u.y) * vec[3] +
            bf16_lo(u.z) * vec[4] + bf16_hi(u.z) * vec[5] + bf16_lo(u.w) * vec[6] + bf16_hi(u.w) * vec[7];
 }
+// All (up to 16) 16-byte chunks of the row are requested before the first use: the tail kernels are pure
+// latency chains of L2 hits, so the number of dependent round trips -- not bandwidth -- sets their run time.
 __device__ __forceinline__ float row_dot(const __nv_bfloat16* row, const float* vec, int D) {
+    const int nch = D >> 3;
+    uint4 u[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+        u[c] = c < nch ? *reinterpret_cast<const uint4*>(row + 8 * c) : make_uint4(0, 0, 0, 0);
     float acc0 = 0.f, acc1 = 0.f;
-    int c = 0;
-    for (; c + 32 <= D; c += 32) {   // four 16-byte loads in flight
-        const uint4 u0 = *reinterpret_cast<const uint4*>(row + c), u1 = *reinterpret_cast<const uint4*>(row + c + 8);
-        const uint4 u2 = *reinterpret_cast<const uint4*>(row + c + 16), u3 = *reinterpret_cast<const uint4*>(row + c + 24);
-        acc0 += dot8(u0, vec + c) + dot8(u2, vec + c + 16);
-        acc1 += dot8(u1, vec + c + 8) + dot8(u3, vec + c + 24);
+#pragma unroll
+    for (int c = 0; c < 16; c += 2) {
+        if (c < nch) acc0 += dot8(u[c], vec + 8 * c);
+        if (c + 1 < nch) acc1 += dot8(u[c + 1], vec + 8 * c + 8);
     }
-    for (; c < D; c += 8) acc0 += dot8(*reinterpret_cast<const uint4*>(row + c), vec + c);
     return acc0 + acc1;
 }
 
@@ -65,12 +69,12 @@ __device__ __forceinline__ void weighted_rows(const __nv_bfloat16* M, int64_t rs
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (c < D) {
         int j = g;
-        for (; j + 24 < n; j += 32) {
-            uint4 u[4];
+        for (; j + 56 < n; j += 64) {
+            uint4 u[8];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) u[t] = *reinterpret_cast<const uint4*>(M + (int64_t)(j + 8 * t) * rs + c);
+            for (int t = 0; t < 8; ++t) u[t] = *reinterpret_cast<const uint4*>(M + (int64_t)(j + 8 * t) * rs + c);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
+            for (int t = 0; t < 8; ++t) {
                 const float x = w[j + 8 * t];
                 acc[0] += x * bf16_lo(u[t].x); acc[1] += x * bf16_hi(u[t].x); acc[2] += x * bf16_lo(u[t].y); acc[3] += x * bf16_hi(u[t].y);
                 acc[4] += x * bf16_lo(u[t].z); acc[5] += x * bf16_hi(u[t].z); acc[6] += x * bf16_lo(u[t].w); acc[7] += x * bf16_hi(u[t].w);

@@ -312,6 +312,36 @@ class EVAVisionTransformer(nn.Module):
         return dp
 
     # ------------------------------------------------------------------ forward / backward launch sequences
+    def _block_forward(self, xr, i, params, dp, B, T, keep):
+        """One pre-norm block (eva_vit_model.py:409-424) as a launch sequence; returns (x_out, tensors kept for backward)."""
+        D, H = self.embed_dim, self.num_heads
+        d = D // H
+        M = B * T
+        c = self._bf16
+        scale = d ** -0.5
+        base = _NTOP + i * _NBLK
+        p = [t.detach() for t in params[base:base + _NBLK]]
+        h, _, mean1, rstd1 = ops.layernorm_fwd(xr, p[_N1W], p[_N1B], self.eps, save_stats=keep)
+        if self._full_qkv_bias:
+            qkv_bias = params[base + _QB].detach()
+        else:
+            qkv_bias = c.qkv_bias(params[base + _QB], params[base + _VB], ("qkvb", i))
+        qkv = ops.gemm(h, c.get(params[base + _QKVW], ("qkv", i)), bias=qkv_bias)
+        qkv5 = qkv.view(B, T, 3, H, d)
+        o, lse = ops.attention_fwd(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], scale, need_lse=keep)
+        s_attn = dp[i, 0] if dp is not None else None
+        s_mlp = dp[i, 1] if dp is not None else None
+        x1 = ops.gemm(o.view(M, D), c.get(params[base + _PW], ("proj", i)), out_dtype=F32, bias=p[_PB], residual=xr,
+                      row_scale=s_attn, rows_per_group=T)
+        h2, _, mean2, rstd2 = ops.layernorm_fwd(x1, p[_N2W], p[_N2B], self.eps, save_stats=keep)
+        w1 = c.get(params[base + _F1W], ("fc1", i))
+        pre = torch.empty((M, w1.shape[0]), device=xr.device, dtype=BF16) if keep else None
+        a = ops.gemm(h2, w1, bias=p[_F1B], act=self._act, aux_out=pre)
+        x2 = ops.gemm(a, c.get(params[base + _F2W], ("fc2", i)), out_dtype=F32, bias=p[_F2B], residual=x1,
+                      row_scale=s_mlp, rows_per_group=T)
+        rec = (xr, mean1, rstd1, h, qkv, o, lse, x1, mean2, rstd2, h2, pre, a) if keep else None
+        return x2, rec
+
     def _launch_forward(self, x, dp, params, keep):
         P = self.patch_embed.patch_size[0]
         D, H = self.embed_dim, self.num_heads
@@ -337,30 +367,11 @@ class EVAVisionTransformer(nn.Module):
                                               out_f32=True, save_stats=keep)
             if keep:
                 saved["ln_pre"] = (x0, m0, r0)
-        scale = d ** -0.5
+        ckpt = keep and self.grad_checkpointing      # eva_vit_model.py:635-637: keep only each block's input
         for i in range(len(self.blocks)):
-            p = params[_NTOP + i * _NBLK:_NTOP + (i + 1) * _NBLK]
-            p = [t.detach() for t in p]
-            h, _, mean1, rstd1 = ops.layernorm_fwd(xr, p[_N1W], p[_N1B], self.eps, save_stats=keep)
-            if self._full_qkv_bias:
-                qkv_bias = params[_NTOP + i * _NBLK + _QB].detach()
-            else:
-                qkv_bias = c.qkv_bias(params[_NTOP + i * _NBLK + _QB], params[_NTOP + i * _NBLK + _VB], ("qkvb", i))
-            qkv = ops.gemm(h, c.get(params[_NTOP + i * _NBLK + _QKVW], ("qkv", i)), bias=qkv_bias)
-            qkv5 = qkv.view(B, T, 3, H, d)
-            o, lse = ops.attention_fwd(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], scale, need_lse=keep)
-            s_attn = dp[i, 0] if dp is not None else None
-            s_mlp = dp[i, 1] if dp is not None else None
-            x1 = ops.gemm(o.view(M, D), c.get(params[_NTOP + i * _NBLK + _PW], ("proj", i)), out_dtype=F32,
-                          bias=p[_PB], residual=xr, row_scale=s_attn, rows_per_group=T)
-            h2, _, mean2, rstd2 = ops.layernorm_fwd(x1, p[_N2W], p[_N2B], self.eps, save_stats=keep)
-            w1 = c.get(params[_NTOP + i * _NBLK + _F1W], ("fc1", i))
-            pre = torch.empty((M, w1.shape[0]), device=dev, dtype=BF16) if keep else None
-            a = ops.gemm(h2, w1, bias=p[_F1B], act=self._act, aux_out=pre)
-            x2 = ops.gemm(a, c.get(params[_NTOP + i * _NBLK + _F2W], ("fc2", i)), out_dtype=F32, bias=p[_F2B],
-                          residual=x1, row_scale=s_mlp, rows_per_group=T)
+            x2, rec = self._block_forward(xr, i, params, dp, B, T, keep and not ckpt)
             if keep:
-                saved["blocks"].append((xr, mean1, rstd1, h, qkv, o, lse, x1, mean2, rstd2, h2, pre, a))
+                saved["blocks"].append((xr,) if ckpt else rec)
             xr = x2
         _, y, mean, rstd = ops.layernorm_fwd(xr, params[_NW].detach(), params[_NB].detach(), self.eps,
                                              out_bf16=False, out_f32=True, save_stats=keep)
@@ -407,7 +418,11 @@ class EVAVisionTransformer(nn.Module):
         del xl, mean, rstd
         blocks = saved["blocks"]
         for i in range(L - 1, -1, -1):
-            xr, mean1, rstd1, h, qkv, o, lse, x1, mean2, rstd2, h2, pre, a = blocks.pop()
+            rec = blocks.pop()
+            if len(rec) == 1:        # checkpointed: recompute this block's forward from its input
+                rec = self._block_forward(rec[0], i, params, dp, B, T, True)[1]
+            xr, mean1, rstd1, h, qkv, o, lse, x1, mean2, rstd2, h2, pre, a = rec
+            del rec
             base = _NTOP + i * _NBLK
             p = [t.detach() for t in params[base:base + _NBLK]]
             # ---- MLP branch: x2 = x1 + s * (a W2^T + b2)

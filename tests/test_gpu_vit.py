@@ -110,3 +110,23 @@ def test_no_grad_forward_keeps_nothing_and_matches_train_forward():
     assert torch.equal(y0, y1.detach())
     cls = m.forward_features(x)           # return_all_features=False -> cls token (eva:643-648)
     assert torch.equal(cls.detach(), y1.detach()[:, 0])
+
+
+def test_activation_checkpointing_gives_identical_gradients():
+    """config.checkpointing (eva_vit_model.py:635-637): recomputing each block in backward must not change a bit."""
+    from oracle import eva_vit as O
+    cfg = O.vit_cfg(width=176, depth=3, heads=2, mlp=352)
+    torch.manual_seed(3)
+    m = _tower_from_cfg(cfg, 0.3).cuda().train()
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(1)).cuda()
+    dp = torch.tensor([[[1.0, 1.0]] * 2, [[1 / 0.85, 0.0]] * 2, [[0.0, 1 / 0.7], [1 / 0.7, 1 / 0.7]]])
+    grads = []
+    for ck in (False, True):
+        m.set_grad_checkpointing(ck)
+        m.zero_grad(set_to_none=True)
+        m.inject_drop_path_scales(dp)
+        m(x, return_all_features=True).pow(2).mean().backward()
+        grads.append({k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
+    assert grads[0].keys() == grads[1].keys() and len(grads[0]) > 30
+    for k in grads[0]:
+        assert torch.equal(grads[0][k], grads[1][k]), k
