@@ -30,6 +30,9 @@ extern "C" {
 #define MICO_ACT_QUICK_GELU 2    /* x*sigmoid(1.702x): model/clip/clip.py:168-170 */
 #define MICO_ACT_GELU_BWD 3      /* out = acc * gelu'(aux_in) */
 #define MICO_ACT_QUICK_GELU_BWD 4
+#define MICO_ACT_GELU_SAVE_GRAD 5       /* out = gelu(v), aux_out = gelu'(v): backward is one multiply (MUL_AUX) */
+#define MICO_ACT_QUICK_GELU_SAVE_GRAD 6
+#define MICO_ACT_MUL_AUX 7              /* out = acc * aux_in */
 
 int mico_version(void);
 const char* mico_last_error(void);

@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmico_b200.so")
 
 ACT_NONE, ACT_GELU, ACT_QUICK_GELU, ACT_GELU_BWD, ACT_QUICK_GELU_BWD = 0, 1, 2, 3, 4
+ACT_GELU_SAVE_GRAD, ACT_QUICK_GELU_SAVE_GRAD, ACT_MUL_AUX = 5, 6, 7
 
 
 class MicoError(RuntimeError):

@@ -29,7 +29,7 @@ import torch.nn as nn
 
 from . import ops
 from .functional import cross_entropy
-from .ops import ACT_GELU, ACT_GELU_BWD, BF16, F32, MicoError
+from .ops import ACT_GELU, ACT_GELU_SAVE_GRAD, ACT_MUL_AUX, BF16, F32, MicoError
 
 
 class BertConfig:
@@ -302,7 +302,7 @@ class BertModel(nn.Module):
             # ---- feed forward
             wi = cache.cat_w(("i", li), [P(20)])
             pre = torch.empty((M, wi.shape[0]), device=ids.device, dtype=BF16) if keep else None
-            a = ops.gemm(hb_in, wi, bias=P(21).detach(), act=ACT_GELU, aux_out=pre)
+            a = ops.gemm(hb_in, wi, bias=P(21).detach(), act=ACT_GELU_SAVE_GRAD, aux_out=pre)     # pre holds gelu'(x)
             y3 = ops.gemm(a, cache.cat_w(("o", li), [P(22)]), out_dtype=F32, bias=P(23).detach(), residual=h_in)
             hb, h, m3, r3 = ln2(y3, base + 24, base + 25)
             if keep:
@@ -343,7 +343,7 @@ class BertModel(nn.Module):
                                           want_bf16=True, dy2=g16)
             ops.gemm(dy3b, rec["a"], a_mn=True, b_mn=True, out=pg(base + 22))
             ops.colsum(dy3b, out=pg(base + 23))
-            dpre = ops.gemm(dy3b, cache.cat_w(("o", li), [P(22)]), b_mn=True, act=ACT_GELU_BWD, aux_in=rec["pre"])
+            dpre = ops.gemm(dy3b, cache.cat_w(("o", li), [P(22)]), b_mn=True, act=ACT_MUL_AUX, aux_in=rec["pre"])
             ops.gemm(dpre, hb_in, a_mn=True, b_mn=True, out=pg(base + 20))
             ops.colsum(dpre, out=pg(base + 21))
             g16 = ops.gemm(dpre, cache.cat_w(("i", li), [P(20)]), b_mn=True)

@@ -12,7 +12,7 @@ import torch.nn as nn
 
 from . import functional as MF
 from .eva_vit import EVAVisionTransformer, LayerNorm, _ParamLinear
-from .ops import ACT_QUICK_GELU, ACT_QUICK_GELU_BWD, MicoError
+from .ops import ACT_MUL_AUX, ACT_QUICK_GELU_SAVE_GRAD, MicoError
 
 
 class _MHA(nn.Module):
@@ -92,7 +92,7 @@ class VisionTransformer(EVAVisionTransformer):
         k = 3 * patch_size * patch_size
         self._kpad = (k + 63) // 64 * 64
         self._injected_dp = None
-        self._act, self._act_bwd = ACT_QUICK_GELU, ACT_QUICK_GELU_BWD
+        self._act, self._act_bwd = ACT_QUICK_GELU_SAVE_GRAD, ACT_MUL_AUX
         self._full_qkv_bias = True
         self._ln_pre = True
         self.drop_path_rng = "philox"

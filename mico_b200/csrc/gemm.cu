@@ -86,7 +86,7 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmEpi& e, EpiOperands&
         const uint4* r4 = reinterpret_cast<const uint4*>(e.residual + o.rrow * e.ldr + col0);
 #pragma unroll
         for (int i = 0; i < NC / 4; ++i) o.pre[i] = __ldg(r4 + i);
-    } else if (e.act == MICO_ACT_GELU_BWD || e.act == MICO_ACT_QUICK_GELU_BWD) {
+    } else if (e.act == MICO_ACT_GELU_BWD || e.act == MICO_ACT_QUICK_GELU_BWD || e.act == MICO_ACT_MUL_AUX) {
         const uint4* u4 = reinterpret_cast<const uint4*>(e.aux_in + o.orow * e.ld_aux_in + col0);
 #pragma unroll
         for (int i = 0; i < NC / 8; ++i) o.pre[i] = __ldg(u4 + i);
@@ -111,7 +111,33 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const EpiOperan
                 v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
             }
         }
-        if (e.act == MICO_ACT_GELU || e.act == MICO_ACT_QUICK_GELU) {
+        if (e.act == MICO_ACT_GELU_SAVE_GRAD || e.act == MICO_ACT_QUICK_GELU_SAVE_GRAD) {
+            float gr[NC];
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                gr[i] = e.act == MICO_ACT_GELU_SAVE_GRAD ? gelu_erf_grad(v[i]) : quick_gelu_grad(v[i]);
+                v[i] = e.act == MICO_ACT_GELU_SAVE_GRAD ? gelu_erf(v[i]) : quick_gelu(v[i]);
+            }
+            if (e.aux_out) {
+                uint4* a4 = reinterpret_cast<uint4*>(e.aux_out + orow * e.ld_aux_out + col0);
+#pragma unroll
+                for (int i = 0; i < NC / 8; ++i)
+                    a4[i] = make_uint4(pack_bf16x2(gr[8 * i], gr[8 * i + 1]), pack_bf16x2(gr[8 * i + 2], gr[8 * i + 3]),
+                                       pack_bf16x2(gr[8 * i + 4], gr[8 * i + 5]), pack_bf16x2(gr[8 * i + 6], gr[8 * i + 7]));
+            }
+        } else if (e.act == MICO_ACT_MUL_AUX) {
+            const uint4* u4 = reinterpret_cast<const uint4*>(e.aux_in + orow * e.ld_aux_in + col0);
+#pragma unroll
+            for (int i = 0; i < NC / 8; ++i) {
+                const uint4 u = e.residual ? __ldg(u4 + i) : o.pre[i];
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[8 * i + 2 * j] *= bf16_lo(w[j]);
+                    v[8 * i + 2 * j + 1] *= bf16_hi(w[j]);
+                }
+            }
+        } else if (e.act == MICO_ACT_GELU || e.act == MICO_ACT_QUICK_GELU) {
             if (e.aux_out) {
                 uint4* a4 = reinterpret_cast<uint4*>(e.aux_out + orow * e.ld_aux_out + col0);
 #pragma unroll
@@ -184,7 +210,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const EpiOperan
         if (col >= N) break;
         float x = v[i];
         if (e.bias) x += sbias[i];
-        if (e.act == MICO_ACT_GELU || e.act == MICO_ACT_QUICK_GELU) {
+        if (e.act == MICO_ACT_GELU_SAVE_GRAD || e.act == MICO_ACT_QUICK_GELU_SAVE_GRAD) {
+            const bool erf_gelu = e.act == MICO_ACT_GELU_SAVE_GRAD;
+            if (e.aux_out)
+                e.aux_out[orow * e.ld_aux_out + col] = __float2bfloat16(erf_gelu ? gelu_erf_grad(x) : quick_gelu_grad(x));
+            x = erf_gelu ? gelu_erf(x) : quick_gelu(x);
+        } else if (e.act == MICO_ACT_MUL_AUX) {
+            x *= __bfloat162float(e.aux_in[orow * e.ld_aux_in + col]);
+        } else if (e.act == MICO_ACT_GELU || e.act == MICO_ACT_QUICK_GELU) {
             if (e.aux_out) e.aux_out[orow * e.ld_aux_out + col] = __float2bfloat16(x);
             x = (e.act == MICO_ACT_GELU) ? gelu_erf(x) : quick_gelu(x);
         } else if (e.act == MICO_ACT_GELU_BWD) {
@@ -212,8 +245,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const EpiOperan
 // tile [32 rows x 64 B] in shared memory (16-byte groups XOR-swizzled by (row >> 1) & 3: conflict-free both ways)
 // and moves 64-byte row segments with the mapping  lane l <-> (row 8i + l/4, group l%4), i = 0..3:
 // 8 rows x 64 contiguous bytes per instruction instead of 32 rows x 16 bytes.
-__device__ __forceinline__ uint4* stage_at(uint8_t* st, int row, int g) {
-    return reinterpret_cast<uint4*>(st + row * 64 + ((g ^ ((row >> 1) & 3)) << 4));
+__device__ __forceinline__ uint32_t stage_at(uint32_t st, int row, int g) {
+    return st + row * 64 + ((g ^ ((row >> 1) & 3)) << 4);
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 __device__ __forceinline__ int64_t map_out_row(const GemmEpi& e, int row) {
     if (e.remap_gin <= 0) return row;
@@ -227,16 +268,16 @@ __device__ __forceinline__ int64_t map_res_row(const GemmEpi& e, int row) {
 }
 // own row (4 x 16 B in `own`) -> staging -> global rows base + maprow(row)*pitch_bytes + byte_off
 template <bool kResRows>
-__device__ __forceinline__ void staged_store(const GemmEpi& e, uint8_t* st, const uint4 (&own)[4], uint8_t* base,
+__device__ __forceinline__ void staged_store(const GemmEpi& e, uint32_t st, const uint4 (&own)[4], uint8_t* base,
                                              int64_t pitch_bytes, int64_t byte_off, int row0, int M) {
     const int l = (int)lane_id();
 #pragma unroll
-    for (int g = 0; g < 4; ++g) *stage_at(st, l, g) = own[g];
+    for (int g = 0; g < 4; ++g) sts128(stage_at(st, l, g), own[g]);
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int rr = 8 * i + (l >> 2), g = l & 3, row = row0 + rr;
-        const uint4 v = *stage_at(st, rr, g);
+        const uint4 v = lds128(stage_at(st, rr, g));
         if (row < M) {
             const int64_t mr = kResRows ? map_res_row(e, row) : map_out_row(e, row);
             *reinterpret_cast<uint4*>(base + mr * pitch_bytes + byte_off + g * 16) = v;
@@ -245,13 +286,13 @@ __device__ __forceinline__ void staged_store(const GemmEpi& e, uint8_t* st, cons
     __syncwarp();
 }
 // coalesced registers (pre[i] <-> row 8i + l/4, group l%4) -> staging -> own row
-__device__ __forceinline__ void staged_to_own(uint8_t* st, const uint4* pre, uint4 (&own)[4]) {
+__device__ __forceinline__ void staged_to_own(uint32_t st, const uint4* pre, uint4 (&own)[4]) {
     const int l = (int)lane_id();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) *stage_at(st, 8 * i + (l >> 2), l & 3) = pre[i];
+    for (int i = 0; i < 4; ++i) sts128(stage_at(st, 8 * i + (l >> 2), l & 3), pre[i]);
     __syncwarp();
 #pragma unroll
-    for (int g = 0; g < 4; ++g) own[g] = *stage_at(st, l, g);
+    for (int g = 0; g < 4; ++g) own[g] = lds128(stage_at(st, l, g));
     __syncwarp();
 }
 template <bool kResRows>
@@ -276,19 +317,24 @@ __device__ __forceinline__ void staged_prefetch(const GemmEpi& e, uint4 (&pre)[8
         const uint8_t* b = reinterpret_cast<const uint8_t*>(e.residual);
         coalesced_load<true>(e, pre, b, e.ldr * 4, (int64_t)col0 * 4, row0, M);
         coalesced_load<true>(e, pre + 4, b, e.ldr * 4, (int64_t)col0 * 4 + 64, row0, M);
-    } else if (e.act == MICO_ACT_GELU_BWD || e.act == MICO_ACT_QUICK_GELU_BWD) {
+    } else if (e.act == MICO_ACT_GELU_BWD || e.act == MICO_ACT_QUICK_GELU_BWD || e.act == MICO_ACT_MUL_AUX) {
         coalesced_load<false>(e, pre, reinterpret_cast<const uint8_t*>(e.aux_in), e.ld_aux_in * 2, (int64_t)col0 * 2, row0, M);
     }
 }
 
 // full 32-column chunk, all 32 lanes participate (rows >= M are predicated off at the global accesses)
-__device__ __forceinline__ void epilogue_chunk32_staged(const GemmEpi& e, uint8_t* st, const uint4 (&pre)[8],
+__device__ __forceinline__ void epilogue_chunk32_staged(const GemmEpi& e, uint32_t st, const uint4 (&pre)[8],
                                                         const float* sbias, const uint32_t (&acc)[32], int row0, int col0,
                                                         int M) {
     const int row = row0 + (int)lane_id();
     float v[32];
+    if (e.alpha != 1.0f) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * e.alpha;
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * e.alpha;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+    }
     if (e.bias) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -297,7 +343,32 @@ __device__ __forceinline__ void epilogue_chunk32_staged(const GemmEpi& e, uint8_
         }
     }
     uint4 own[4];
-    if (e.act == MICO_ACT_GELU || e.act == MICO_ACT_QUICK_GELU) {
+    if (e.act == MICO_ACT_GELU_SAVE_GRAD || e.act == MICO_ACT_QUICK_GELU_SAVE_GRAD) {
+        // out = act(v); aux_out = act'(v): the backward pass then needs one multiply per element (MICO_ACT_MUL_AUX)
+        float gr[32];
+        if (e.act == MICO_ACT_GELU_SAVE_GRAD) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float cdf, g;
+                gelu_parts(v[i], cdf, g);
+                gr[i] = fmaf(v[i] * 0.3989422804014327f, g, cdf);
+                v[i] *= cdf;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                gr[i] = quick_gelu_grad(v[i]);
+                v[i] = quick_gelu(v[i]);
+            }
+        }
+        if (e.aux_out) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                own[i] = make_uint4(pack_bf16x2(gr[8 * i], gr[8 * i + 1]), pack_bf16x2(gr[8 * i + 2], gr[8 * i + 3]),
+                                    pack_bf16x2(gr[8 * i + 4], gr[8 * i + 5]), pack_bf16x2(gr[8 * i + 6], gr[8 * i + 7]));
+            staged_store<false>(e, st, own, reinterpret_cast<uint8_t*>(e.aux_out), e.ld_aux_out * 2, (int64_t)col0 * 2, row0, M);
+        }
+    } else if (e.act == MICO_ACT_GELU || e.act == MICO_ACT_QUICK_GELU) {
         if (e.aux_out) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -311,6 +382,23 @@ __device__ __forceinline__ void epilogue_chunk32_staged(const GemmEpi& e, uint8_
         } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = quick_gelu(v[i]);
+        }
+    } else if (e.act == MICO_ACT_MUL_AUX) {
+        if (e.residual) {
+            uint4 tmp[4];
+            coalesced_load<false>(e, tmp, reinterpret_cast<const uint8_t*>(e.aux_in), e.ld_aux_in * 2, (int64_t)col0 * 2, row0, M);
+            staged_to_own(st, tmp, own);
+        } else {
+            staged_to_own(st, pre, own);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t w[4] = {own[i].x, own[i].y, own[i].z, own[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[8 * i + 2 * j] *= bf16_lo(w[j]);
+                v[8 * i + 2 * j + 1] *= bf16_hi(w[j]);
+            }
         }
     } else if (e.act == MICO_ACT_GELU_BWD || e.act == MICO_ACT_QUICK_GELU_BWD) {
         if (e.residual) {   // rare combination: the pre-activation was not prefetched
@@ -497,7 +585,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int row = m0 + q * 32 + (int)lane_id();
             const uint32_t t0 = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
             bool waited = false;
-            uint8_t* st = staging_all + (warp - 2) * 2048;
+            const uint32_t st = smem_u32(staging_all + (warp - 2) * 2048);
             const int row0 = m0 + q * 32;
             // the staged (coalesced) path needs 16-byte-aligned pitches and no read-modify-write of the output
             const bool staged_ok = epi.vec_ok && !epi.accumulate;
@@ -621,8 +709,8 @@ extern "C" int mico_gemm_bf16(const MicoGemmArgs* args, void* stream_) {
     MICO_CHECK_ARG(g.lda % 8 == 0 && g.ldb % 8 == 0);
     MICO_CHECK_ARG((reinterpret_cast<uintptr_t>(g.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.b) & 15) == 0);
     MICO_CHECK_ARG(!(g.accumulate && !g.out_fp32));
-    MICO_CHECK_ARG(g.act >= MICO_ACT_NONE && g.act <= MICO_ACT_QUICK_GELU_BWD);
-    MICO_CHECK_ARG(!((g.act == MICO_ACT_GELU_BWD || g.act == MICO_ACT_QUICK_GELU_BWD) && !g.aux_in));
+    MICO_CHECK_ARG(g.act >= MICO_ACT_NONE && g.act <= MICO_ACT_MUL_AUX);
+    MICO_CHECK_ARG(!((g.act == MICO_ACT_GELU_BWD || g.act == MICO_ACT_QUICK_GELU_BWD || g.act == MICO_ACT_MUL_AUX) && !g.aux_in));
     MICO_CHECK_ARG(!(g.row_scale && g.rows_per_group <= 0));
     MICO_CHECK_ARG(!(g.remap_gin > 0 && g.remap_gout < g.remap_gin));
     if (g.a_mn_major) MICO_CHECK_ARG(g.lda >= g.M); else MICO_CHECK_ARG(g.lda >= g.K);

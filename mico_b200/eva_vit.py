@@ -26,7 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .ops import ACT_GELU, ACT_GELU_BWD, ACT_QUICK_GELU, ACT_QUICK_GELU_BWD, BF16, F32, MicoError
+from .ops import ACT_GELU_SAVE_GRAD, ACT_MUL_AUX, ACT_QUICK_GELU_SAVE_GRAD, BF16, F32, MicoError
 
 _BLOCK_KEYS = ("norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.q_bias", "attn.v_bias", "attn.proj.weight",
                "attn.proj.bias", "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight",
@@ -235,7 +235,7 @@ class EVAVisionTransformer(nn.Module):
         self._kpad = (k + 63) // 64 * 64
         self._injected_dp = None
         # launch-sequence variant (the OpenAI-CLIP tower in clip_vit.py flips these)
-        self._act, self._act_bwd = ACT_GELU, ACT_GELU_BWD
+        self._act, self._act_bwd = ACT_GELU_SAVE_GRAD, ACT_MUL_AUX   # fc1 epilogue stores gelu'(x); fc2 dgrad multiplies by it
         self._full_qkv_bias = False      # EVA: cat(q_bias, 0, v_bias); CLIP: in_proj_bias [3D]
         self._ln_pre = False
         # "philox": all DropPath multipliers from one counter-based launch; "torch": the reference's own

@@ -9,8 +9,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_GELU_BWD, ACT_NONE, ACT_QUICK_GELU,  # noqa: F401
-                   ACT_QUICK_GELU_BWD, MicoError, check, lib)
+from ._lib import (ACT_GELU, ACT_GELU_BWD, ACT_GELU_SAVE_GRAD, ACT_MUL_AUX, ACT_NONE, ACT_QUICK_GELU,  # noqa: F401
+                   ACT_QUICK_GELU_BWD, ACT_QUICK_GELU_SAVE_GRAD, MicoError, check, lib)
 
 BF16 = torch.bfloat16
 F32 = torch.float32

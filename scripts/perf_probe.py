@@ -4,7 +4,7 @@ import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mico_b200 import ops
-from mico_b200.ops import ACT_GELU, ACT_GELU_BWD, BF16, F32
+from mico_b200.ops import ACT_GELU, ACT_GELU_BWD, ACT_GELU_SAVE_GRAD, ACT_MUL_AUX, BF16, F32
 
 
 def timeit(fn, iters=10, warm=3):
@@ -46,6 +46,8 @@ def main():
         ("proj fwd  [M,1408]x[1408,1408] +res", 2.0 * M * D * D, lambda: ops.gemm(x, w_p, out=out_d32, bias=bias_d, residual=res)),
         ("fc1 fwd   [M,1408]x[6144,1408] gelu", 2.0 * M * D * F, lambda: ops.gemm(x, w1, out=out_f, bias=bias_f, act=ACT_GELU, aux_out=pre)),
         ("fc1 fwd plain (no epilogue)", 2.0 * M * D * F, lambda: ops.gemm(x, w1, out=out_f)),
+        ("fc1 fwd gelu + store gelu' (tower path)", 2.0 * M * D * F, lambda: ops.gemm(x, w1, out=out_f, bias=bias_f, act=ACT_GELU_SAVE_GRAD, aux_out=pre)),
+        ("fc2 dgrad * saved gelu' (tower path)", 2.0 * M * D * F, lambda: ops.gemm(dy, w2, b_mn=True, out=out_f, act=ACT_MUL_AUX, aux_in=pre)),
         ("fc1 fwd bias only", 2.0 * M * D * F, lambda: ops.gemm(x, w1, out=out_f, bias=bias_f)),
         ("fc1 fwd gelu, no pre-activation store", 2.0 * M * D * F, lambda: ops.gemm(x, w1, out=out_f, bias=bias_f, act=ACT_GELU)),
         ("fc2 dgrad plain (no gelu')", 2.0 * M * D * F, lambda: ops.gemm(dy, w2, b_mn=True, out=out_f)),

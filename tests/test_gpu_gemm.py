@@ -100,6 +100,26 @@ def test_gemm_gelu_bwd_and_accumulate():
     assert rel_l2(acc, ref) < 2e-5
 
 
+@pytest.mark.parametrize("quick", [False, True])
+@pytest.mark.parametrize("M,N,K", [(514, 6144, 1408), (100, 200, 72)])
+def test_gemm_act_save_grad_then_mul_aux(M, N, K, quick):
+    """fc1 epilogue stores act'(x) (GELU or QuickGELU); the fc2-dgrad epilogue multiplies by it (MUL_AUX)."""
+    from mico_b200 import ops
+    a, b = _mk((M, K), 21), _mk((N, K), 22, 0.03)
+    bias = torch.randn(N, device="cuda") * 0.1
+    aux = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    act = ops.ACT_QUICK_GELU_SAVE_GRAD if quick else ops.ACT_GELU_SAVE_GRAD
+    out = ops.gemm(a, b, bias=bias, act=act, aux_out=aux)
+    pre = (a.float() @ b.float().t() + bias).requires_grad_(True)
+    ref = pre * torch.sigmoid(1.702 * pre) if quick else torch.nn.functional.gelu(pre)
+    ref.backward(torch.ones_like(ref))
+    assert rel_l2(out, ref.detach()) < 3e-3
+    assert rel_l2(aux, pre.grad) < 3e-3
+    dy, w2 = _mk((M, 136), 23), _mk((136, N), 24, 0.03)
+    d = ops.gemm(dy, w2, b_mn=True, act=ops.ACT_MUL_AUX, aux_in=aux)
+    assert rel_l2(d, (dy.float() @ w2.float()) * aux.float()) < 3e-3
+
+
 def test_gemm_patch_remap():
     from mico_b200 import ops
     B_, P, T, N, K = 2, 256, 257, 1408, 640
