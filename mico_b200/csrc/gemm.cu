@@ -16,6 +16,8 @@
 // Replaces F.linear/matmul call sites listed in include/mico_b200.h (reference: eva_vit_model.py:191,
 // 197, 310, 363, 446; bert.py:196-209, 293, 357, 370, 601, 607).
 #include "common.cuh"
+#include <stdlib.h>
+
 #include "host_utils.h"
 
 namespace mico {
@@ -248,12 +250,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const EpiOperan
 __device__ __forceinline__ uint32_t stage_at(uint32_t st, int row, int g) {
     return st + row * 64 + ((g ^ ((row >> 1) & 3)) << 4);
 }
+// non-volatile: the compiler may schedule these freely between the __syncwarp() fences around each staging phase
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    asm("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ int64_t map_out_row(const GemmEpi& e, int row) {
@@ -344,30 +347,31 @@ __device__ __forceinline__ void epilogue_chunk32_staged(const GemmEpi& e, uint32
     }
     uint4 own[4];
     if (e.act == MICO_ACT_GELU_SAVE_GRAD || e.act == MICO_ACT_QUICK_GELU_SAVE_GRAD) {
-        // out = act(v); aux_out = act'(v): the backward pass then needs one multiply per element (MICO_ACT_MUL_AUX)
-        float gr[32];
-        if (e.act == MICO_ACT_GELU_SAVE_GRAD) {
+        // out = act(v); aux_out = act'(v): the backward pass then needs one multiply per element (MICO_ACT_MUL_AUX).
+        // Derivatives are packed eight at a time so that only v[32] + 4 words stay live (168-register budget).
+        const bool erf_gelu = e.act == MICO_ACT_GELU_SAVE_GRAD;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                float cdf, g;
-                gelu_parts(v[i], cdf, g);
-                gr[i] = fmaf(v[i] * 0.3989422804014327f, g, cdf);
-                v[i] *= cdf;
-            }
-        } else {
+        for (int i = 0; i < 4; ++i) {
+            float gr[8];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                gr[i] = quick_gelu_grad(v[i]);
-                v[i] = quick_gelu(v[i]);
+            for (int j = 0; j < 8; ++j) {
+                const float x = v[8 * i + j];
+                if (erf_gelu) {
+                    float cdf, g;
+                    gelu_parts(x, cdf, g);
+                    gr[j] = fmaf(x * 0.3989422804014327f, g, cdf);
+                    v[8 * i + j] = x * cdf;
+                } else {
+                    const float sg = rcp_fast(1.0f + ex2_raw(x * (-1.702f * 1.4426950408889634f)));
+                    gr[j] = sg * fmaf(1.702f * x, 1.0f - sg, 1.0f);
+                    v[8 * i + j] = x * sg;
+                }
             }
+            own[i] = make_uint4(pack_bf16x2(gr[0], gr[1]), pack_bf16x2(gr[2], gr[3]), pack_bf16x2(gr[4], gr[5]),
+                                pack_bf16x2(gr[6], gr[7]));
         }
-        if (e.aux_out) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                own[i] = make_uint4(pack_bf16x2(gr[8 * i], gr[8 * i + 1]), pack_bf16x2(gr[8 * i + 2], gr[8 * i + 3]),
-                                    pack_bf16x2(gr[8 * i + 4], gr[8 * i + 5]), pack_bf16x2(gr[8 * i + 6], gr[8 * i + 7]));
+        if (e.aux_out)
             staged_store<false>(e, st, own, reinterpret_cast<uint8_t*>(e.aux_out), e.ld_aux_out * 2, (int64_t)col0 * 2, row0, M);
-        }
     } else if (e.act == MICO_ACT_GELU || e.act == MICO_ACT_QUICK_GELU) {
         if (e.aux_out) {
 #pragma unroll
@@ -454,8 +458,14 @@ __device__ __forceinline__ void epilogue_chunk32_staged(const GemmEpi& e, uint32
     }
 }
 
-template <int BN, bool A_MN, bool B_MN, int STAGES>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// CL = 2: two CTAs of a cluster (one SM pair) work on two vertically adjacent M tiles of the same N tile.  Each CTA
+// loads only HALF of the B tile and multicasts it into both CTAs' shared memory (cp.async.bulk.tensor ...
+// .multicast::cluster); smem slots are recycled when BOTH CTAs' MMAs have consumed them (multicast tcgen05.commit).
+// The mainloop of this GEMM is bound by L2 -> SM operand traffic (15 TB/s for 128x256 tiles at 1.3 PFLOP/s, which is
+// why any extra epilogue traffic used to ADD to the run time instead of overlapping); sharing B across the pair removes
+// a third of it.
+template <int BN, bool A_MN, bool B_MN, int STAGES, int CL>
+__global__ void __launch_bounds__(kGemmThreads, 1)   // 10 warps -> 3 on one SM sub-partition: 168 registers max
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                  int K, GemmEpi epi) {
     using Cfg = GemmCfg<BN, STAGES>;
@@ -472,8 +482,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int warp = threadIdx.x >> 5;
     const int num_m = (M + BM - 1) / BM;
     const int num_n = (N + BN - 1) / BN;
-    const int num_tiles = num_m * num_n;
     const int num_kb = (K + BK - 1) / BK;
+    // persistent schedule over work units = (group of CL adjacent m tiles, n tile); both CTAs of a cluster walk the
+    // same unit list in lock step
+    const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
+    const int num_tiles = ((num_m + CL - 1) / CL) * num_n;
+    const int unit0 = blockIdx.x / CL, unit_stride = gridDim.x / CL;
+    constexpr uint16_t kMask = (1u << CL) - 1;
 
     if (warp == 0) {
         if (elect_one()) {
@@ -484,7 +499,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
             for (int s = 0; s < STAGES; ++s) {
                 mbar_init(&full_bar[s], 1);
-                mbar_init(&empty_bar[s], 1);
+                mbar_init(&empty_bar[s], CL);
             }
             for (int a = 0; a < 2; ++a) {
                 mbar_init(&tfull_bar[a], 1);
@@ -497,6 +512,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();    // peer barriers are initialised before any multicast reaches them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -505,8 +521,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / num_n) * BM;
+            for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+                const int m0 = ((tile / num_n) * CL + (int)cta_rank) * BM;
                 const int n0 = (tile % num_n) * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -520,12 +536,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int j = 0; j < BM / 64; ++j)
                             tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m0 + 64 * j, kb * BK);
                     }
-                    if constexpr (!B_MN) {
-                        tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
-                    } else {
+                    if constexpr (CL == 1) {
+                        if constexpr (!B_MN) {
+                            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j)
-                            tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n0 + 64 * j, kb * BK);
+                            for (int j = 0; j < BN / 64; ++j)
+                                tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n0 + 64 * j, kb * BK);
+                        }
+                    } else {     // this CTA's half of B, multicast to both CTAs of the pair
+                        if constexpr (!B_MN) {
+                            constexpr int HALF = BN / CL;
+                            tma_load_2d_mc(sb + cta_rank * (HALF * 128), &tmB, &full_bar[stage], kb * BK,
+                                           n0 + (int)cta_rank * HALF, kMask);
+                        } else {
+                            constexpr int HB = BN / 64 / CL;
+#pragma unroll
+                            for (int jj = 0; jj < HB; ++jj) {
+                                const int j = (int)cta_rank * HB + jj;
+                                tma_load_2d_mc(sb + j * 8192, &tmB, &full_bar[stage], n0 + 64 * j, kb * BK, kMask);
+                            }
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -538,7 +569,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -557,7 +588,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                                     : umma_smem_desc_sw128(sb + k * 32, 16, 1024);
                         umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
                     }
-                    umma_commit(&empty_bar[stage]);
+                    if constexpr (CL == 1) umma_commit(&empty_bar[stage]);
+                    else umma_commit_mc(&empty_bar[stage], kMask);      // frees the slot in both CTAs
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull_bar[acc]);
@@ -568,10 +600,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int q = warp & 3;            // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;  // which of the two warps of that quarter: owns chunks c with (c & 1) == half
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int m0 = (tile / num_n) * BM;
+            const int m0 = ((tile / num_n) * CL + (int)cta_rank) * BM;
             const int n0 = (tile % num_n) * BN;
             // bias slice of this tile -> smem (one coalesced load per tile instead of 8 x 16 B per thread and chunk).
             // Stage `acc` of the buffer was last read two tiles ago; every epilogue thread has passed the named
@@ -629,13 +661,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();    // no CTA leaves while its peer may still multicast into it
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
 }
 
-template <int BN, bool A_MN, bool B_MN, int STAGES>
+template <int BN, bool A_MN, bool B_MN, int STAGES, int CL>
 int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, STAGES>;
     CUtensorMap tmA, tmB;
@@ -655,7 +688,7 @@ int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) 
     if (!B_MN) {
         const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
         const uint64_t strides[2] = {2, (uint64_t)g.ldb * 2};
-        const uint32_t box[2] = {BK, BN};
+        const uint32_t box[2] = {BK, BN / CL};       // CL = 2: each CTA of the pair loads (and multicasts) half
         rc = make_tmap_bf16(&tmB, g.b, 2, dims, strides, box);
     } else {
         const uint64_t dims[2] = {(uint64_t)g.N, (uint64_t)g.K};
@@ -665,19 +698,34 @@ int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) 
     }
     if (rc) return rc;
 
-    auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES>;
+    auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES, CL>;
     static bool attr_set = false;   // benign race: idempotent
     if (!attr_set) {
         MICO_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    const int tiles = ceil_div(g.M, BM) * ceil_div(g.N, BN);
-    const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, g.M, g.N, g.K, epi);
-    MICO_CHECK_CUDA(cudaGetLastError());
+    const int units = ceil_div(ceil_div(g.M, BM), CL) * ceil_div(g.N, BN);
+    const int max_clusters = num_sms() / CL;
+    const int grid = (units < max_clusters ? units : max_clusters) * CL;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int Mi = g.M, Ni = g.N, Ki = g.K;
+    MICO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, Mi, Ni, Ki, epi));
     count_launch();
     return MICO_OK;
 }
+
+static bool g_force_single_cta = false;     // MICO_GEMM_SINGLE_CTA=1: A/B switch for measurements
 
 template <bool A_MN, bool B_MN>
 int dispatch_bn(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) {
@@ -688,11 +736,17 @@ int dispatch_bn(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) 
     if (!B_MN && padded(176) < best_pad) { best = 176; best_pad = padded(176); }
     if (padded(128) < best_pad) { best = 128; best_pad = padded(128); }
     if (g.N <= 64 && padded(64) < best_pad) { best = 64; }
+    // CTA pairs (B multicast) whenever there are at least two M tiles to pair up
+    // (not for wgrad, A and B both MN-major with a 16k-long K loop: measured 4-15 % slower in lock step)
+    const bool pair = ceil_div(g.M, BM) >= 2 && !g_force_single_cta && !(A_MN && B_MN);
     switch (best) {
-        case 256: return launch_gemm<256, A_MN, B_MN, 4>(g, epi, stream);
-        case 176: if constexpr (!B_MN) return launch_gemm<176, A_MN, B_MN, 5>(g, epi, stream);
-        case 128: return launch_gemm<128, A_MN, B_MN, 6>(g, epi, stream);
-        default:  return launch_gemm<64, A_MN, B_MN, 8>(g, epi, stream);
+        case 256: return pair ? launch_gemm<256, A_MN, B_MN, 4, 2>(g, epi, stream)
+                              : launch_gemm<256, A_MN, B_MN, 4, 1>(g, epi, stream);
+        case 176: if constexpr (!B_MN) return pair ? launch_gemm<176, A_MN, B_MN, 5, 2>(g, epi, stream)
+                                                   : launch_gemm<176, A_MN, B_MN, 5, 1>(g, epi, stream);
+        case 128: return pair ? launch_gemm<128, A_MN, B_MN, 6, 2>(g, epi, stream)
+                              : launch_gemm<128, A_MN, B_MN, 6, 1>(g, epi, stream);
+        default:  return launch_gemm<64, A_MN, B_MN, 8, 1>(g, epi, stream);
     }
 }
 
@@ -701,6 +755,8 @@ int dispatch_bn(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) 
 
 extern "C" int mico_gemm_bf16(const MicoGemmArgs* args, void* stream_) {
     using namespace mico;
+    static const bool single = [] { const char* e = getenv("MICO_GEMM_SINGLE_CTA"); return e && e[0] == '1'; }();
+    g_force_single_cta = single;
     MICO_CHECK_ARG(args != nullptr);
     const MicoGemmArgs& g = *args;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
