@@ -34,24 +34,30 @@ struct AttnBwdParams {
 };
 
 // ------------------------------------------------------------------------------------------------ delta
+// A quad of lanes per (b, i, h) row: lane `sub` takes the 16-byte chunks sub, sub+4, ... of O and dO, so a warp
+// instruction reads 8 rows x 64 contiguous bytes (the rows of consecutive heads are adjacent in memory).
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int64_t o_bs, int64_t o_rs, int64_t o_hs,
                                   const __nv_bfloat16* __restrict__ d_o, int64_t do_bs, int64_t do_rs, int64_t do_hs,
                                   float* __restrict__ delta, int B, int H, int S, int D) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over (b, i, h), h fastest
-    if (idx >= (int64_t)B * S * H) return;
-    const int h = (int)(idx % H);
-    const int i = (int)((idx / H) % S);
-    const int b = (int)(idx / ((int64_t)H * S));
-    const uint4* po = reinterpret_cast<const uint4*>(o + b * o_bs + i * o_rs + h * o_hs);
-    const uint4* pd = reinterpret_cast<const uint4*>(d_o + b * do_bs + i * do_rs + h * do_hs);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t idx = tid >> 2;                                         // over (b, i, h), h fastest
+    const int sub = (int)(tid & 3);
+    const bool live = idx < (int64_t)B * S * H;
     float acc = 0.f;
-    for (int c0 = 0; c0 < D / 8; c0 += 4) {       // eight 16-byte loads in flight per thread
+    int h = 0, i = 0, b = 0;
+    if (live) {
+        h = (int)(idx % H);
+        i = (int)((idx / H) % S);
+        b = (int)(idx / ((int64_t)H * S));
+        const uint4* po = reinterpret_cast<const uint4*>(o + b * o_bs + i * o_rs + h * o_hs);
+        const uint4* pd = reinterpret_cast<const uint4*>(d_o + b * do_bs + i * do_rs + h * do_hs);
         uint4 a[4], g[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-            const bool ok = c0 + t < D / 8;
-            a[t] = ok ? po[c0 + t] : make_uint4(0, 0, 0, 0);
-            g[t] = ok ? pd[c0 + t] : make_uint4(0, 0, 0, 0);
+            const int c = sub + 4 * t;
+            const bool ok = c < D / 8;
+            a[t] = ok ? po[c] : make_uint4(0, 0, 0, 0);
+            g[t] = ok ? pd[c] : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t)
@@ -59,7 +65,9 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int64_t o
                    bf16_hi(a[t].y) * bf16_hi(g[t].y) + bf16_lo(a[t].z) * bf16_lo(g[t].z) + bf16_hi(a[t].z) * bf16_hi(g[t].z) +
                    bf16_lo(a[t].w) * bf16_lo(g[t].w) + bf16_hi(a[t].w) * bf16_hi(g[t].w);
     }
-    delta[((int64_t)b * H + h) * S + i] = acc;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);      // grid is a multiple of the warp size: all lanes are here
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (live && sub == 0) delta[((int64_t)b * H + h) * S + i] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------ dQ
@@ -536,7 +544,7 @@ extern "C" int mico_attention_bwd(const MicoAttnArgs* a, void* stream_) {
 
     ProfScope prof(kProfAttnBwd, 10.0 * a->B * a->H * (double)a->Sq * a->Sk * a->D, stream);
     {
-        const int64_t n = (int64_t)a->B * a->Sq * a->H;
+        const int64_t n = (int64_t)a->B * a->Sq * a->H * 4;      // a quad of lanes per row
         attn_delta_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(
             reinterpret_cast<const __nv_bfloat16*>(a->o), a->o_bs, a->o_rs, a->o_hs,
             reinterpret_cast<const __nv_bfloat16*>(a->dout), a->do_bs, a->do_rs, a->do_hs, a->delta, a->B, a->H, a->Sq, a->D);

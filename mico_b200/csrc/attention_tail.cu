@@ -31,21 +31,28 @@ __device__ __forceinline__ float dot8(const uint4& u, const float* vec) {
     return bf16_lo(u.x) * vec[0] + bf16_hi(u.x) * vec[1] + bf16_lo(u.y) * vec[2] + bf16_hi(u.y) * vec[3] +
            bf16_lo(u.z) * vec[4] + bf16_hi(u.z) * vec[5] + bf16_lo(u.w) * vec[6] + bf16_hi(u.w) * vec[7];
 }
-// All (up to 16) 16-byte chunks of the row are requested before the first use: the tail kernels are pure
-// latency chains of L2 hits, so the number of dependent round trips -- not bandwidth -- sets their run time.
-__device__ __forceinline__ float row_dot(const __nv_bfloat16* row, const float* vec, int D) {
-    const int nch = D >> 3;
-    uint4 u[16];
+// Dot product of a bf16 row with an fp32 vector, computed by a QUAD of lanes: lane `sub` of the quad takes the 16-byte
+// chunks sub, sub+4, sub+8, ... so that the four lanes read 64 contiguous bytes per instruction (8 rows x 64 B per
+// warp instruction instead of 32 rows x 16 B: the one-row-per-lane version was bound by L1 tag lookups, one per row
+// and chunk).  All four lanes return the full sum.
+__device__ __forceinline__ float row_dot_quad(const __nv_bfloat16* row, const float* vec, int D) {
+    const int nch = D >> 3, sub = (int)lane_id() & 3;
+    uint4 u[4];
 #pragma unroll
-    for (int c = 0; c < 16; ++c)
-        u[c] = c < nch ? *reinterpret_cast<const uint4*>(row + 8 * c) : make_uint4(0, 0, 0, 0);
-    float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-    for (int c = 0; c < 16; c += 2) {
-        if (c < nch) acc0 += dot8(u[c], vec + 8 * c);
-        if (c + 1 < nch) acc1 += dot8(u[c + 1], vec + 8 * c + 8);
+    for (int t = 0; t < 4; ++t) {
+        const int c = sub + 4 * t;
+        u[t] = c < nch ? *reinterpret_cast<const uint4*>(row + 8 * c) : make_uint4(0, 0, 0, 0);
     }
-    return acc0 + acc1;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int c = sub + 4 * t;
+        if (c < nch) acc += dot8(u[t], vec + 8 * c);
+    }
+    const unsigned qm = 0xFu << ((int)lane_id() & ~3);
+    acc += __shfl_xor_sync(qm, acc, 1);
+    acc += __shfl_xor_sync(qm, acc, 2);
+    return acc;
 }
 
 __device__ __forceinline__ void load_vec(const __nv_bfloat16* row, float* vec, int D) {
@@ -123,10 +130,10 @@ __global__ void __launch_bounds__(kTailThreads) attn_tail_q_kernel(TailParams p)
     const int64_t stat = ((int64_t)b * p.H + h) * p.Sq + i;
     if (MODE == 0) {
         float mx = -INFINITY;
-        for (int j = threadIdx.x; j < p.Sk; j += kTailThreads) {
-            float s = p.scale * row_dot(K + (int64_t)j * p.k_rs, qv, p.D);
+        for (int j = threadIdx.x >> 2; j < p.Sk; j += kTailThreads / 4) {
+            float s = p.scale * row_dot_quad(K + (int64_t)j * p.k_rs, qv, p.D);
             if (mrow) s += mrow[j];
-            sc[j] = s;
+            if ((threadIdx.x & 3) == 0) sc[j] = s;
             mx = fmaxf(mx, s);
         }
         mx = block_reduce(mx, small, true);
@@ -141,12 +148,12 @@ __global__ void __launch_bounds__(kTailThreads) attn_tail_q_kernel(TailParams p)
         if (p.lse && threadIdx.x == 0) p.lse[stat] = mx + __logf(sum);
     } else {
         const float lse = p.lse[stat], dlt = p.delta[stat];
-        for (int j = threadIdx.x; j < p.Sk; j += kTailThreads) {
-            float s = p.scale * row_dot(K + (int64_t)j * p.k_rs, qv, p.D);
+        for (int j = threadIdx.x >> 2; j < p.Sk; j += kTailThreads / 4) {
+            float s = p.scale * row_dot_quad(K + (int64_t)j * p.k_rs, qv, p.D);
             if (mrow) s += mrow[j];
             const float pr = __expf(s - lse);
-            const float dp = row_dot(V + (int64_t)j * p.v_rs, dov, p.D);
-            sc[j] = pr * (dp - dlt) * p.scale;
+            const float dp = row_dot_quad(V + (int64_t)j * p.v_rs, dov, p.D);
+            if ((threadIdx.x & 3) == 0) sc[j] = pr * (dp - dlt) * p.scale;
         }
         __syncthreads();
         weighted_rows(K, p.k_rs, p.Sk, sc, p.D, 1.0f, p.out0 + b * p.o0_bs + (int64_t)i * p.o0_rs + h * p.o0_hs, red);
@@ -170,13 +177,15 @@ __global__ void __launch_bounds__(kTailThreads) attn_tail_kv_kernel(TailParams p
     const __nv_bfloat16* Q = p.q + b * p.q_bs + h * p.q_hs;
     const __nv_bfloat16* DO = p.d_o + b * p.do_bs + h * p.do_hs;
     const int64_t stat0 = ((int64_t)b * p.H + h) * p.Sq;
-    for (int i = threadIdx.x; i < p.Sq; i += kTailThreads) {
-        float s = p.scale * row_dot(Q + (int64_t)i * p.q_rs, kv, p.D);
+    for (int i = threadIdx.x >> 2; i < p.Sq; i += kTailThreads / 4) {
+        float s = p.scale * row_dot_quad(Q + (int64_t)i * p.q_rs, kv, p.D);
         if (p.mask) s += (p.mask + (int64_t)(p.mask_bmod ? b % p.mask_bmod : b) * p.mask_bs + (int64_t)h * p.mask_hs)[(int64_t)i * p.mask_qs + j];
         const float pr = __expf(s - p.lse[stat0 + i]);
-        const float dp = row_dot(DO + (int64_t)i * p.do_rs, vv, p.D);
-        pa[i] = pr;
-        dsa[i] = pr * (dp - p.delta[stat0 + i]) * p.scale;
+        const float dp = row_dot_quad(DO + (int64_t)i * p.do_rs, vv, p.D);
+        if ((threadIdx.x & 3) == 0) {
+            pa[i] = pr;
+            dsa[i] = pr * (dp - p.delta[stat0 + i]) * p.scale;
+        }
     }
     __syncthreads();
     weighted_rows(Q, p.q_rs, p.Sq, dsa, p.D, 1.0f, p.out0 + b * p.o0_bs + (int64_t)j * p.o0_rs + h * p.o0_hs, red);
