@@ -277,9 +277,16 @@ def run_product(args):
     gemm_tflops = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
     fam_total = sum(v["ms"] for v in fam.values())
     step_flops = 3 * FWD_FLOPS_PER_IMAGE * B
+    traffic, traffic_src = None, None
+    tpath = os.path.join(REPO, "profiles", "gemm_traffic.json")
+    if os.path.exists(tpath):       # dram bytes per launch from the committed `ncu --set full` capture (scripts/ncu_to_traffic.py)
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj["avg_dram_bytes_per_launch"], tj["source"]
     roofline = dict(bound="tensor", kernel="gemm_bf16_kernel (tcgen05 GEMM, all linear fwd/dgrad/wgrad)",
                     achieved=gemm_tflops, peak=pk["tf_sustained"], unit="TFLOP/s",
-                    frac=gemm_tflops / pk["tf_sustained"], traffic=None, peak_source=pk["src"] + ", sustained bf16",
+                    frac=gemm_tflops / pk["tf_sustained"], traffic=traffic, traffic_unit="bytes/launch (dram read+write)",
+                    traffic_source=traffic_src, algorithmic_flops_per_launch=g["work"] / max(g["calls"], 1),
+                    peak_source=pk["src"] + ", sustained bf16",
                     launches_per_step=g["calls"] / args.steps, avg_launch_ms=g["ms"] / max(g["calls"], 1),
                     share_of_step=g["ms"] / fam_total if fam_total else None,
                     whole_step_tflops=step_flops / (ms / args.steps * 1e-3) / 1e12,

@@ -4,7 +4,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mico_b200 import ops
-from mico_b200.ops import ACT_GELU, ACT_GELU_BWD, BF16, F32
+from mico_b200.ops import ACT_GELU_SAVE_GRAD, ACT_MUL_AUX, BF16, F32
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 M, D, F = 64 * 257, 1408, 6144
@@ -16,8 +16,8 @@ if which in ("all", "gemm"):
     pre = r(M, F)
     bias = torch.randn(F, device=dev)
     for _ in range(reps):
-        ops.gemm(x, w1, bias=bias, act=ACT_GELU, aux_out=pre)            # fc1 fwd
-        ops.gemm(dy, w2, b_mn=True, act=ACT_GELU_BWD, aux_in=pre)        # fc2 dgrad
+        ops.gemm(x, w1, bias=bias, act=ACT_GELU_SAVE_GRAD, aux_out=pre)   # fc1 fwd (GELU + GELU' store)
+        ops.gemm(dy, w2, b_mn=True, act=ACT_MUL_AUX, aux_in=pre)         # fc2 dgrad (* GELU')
         ops.gemm(dy, a, a_mn=True, b_mn=True, out_dtype=F32)             # fc2 wgrad
         ops.gemm(a, w2, out_dtype=F32, residual=torch.zeros(M, D, device=dev))  # fc2 fwd
 if which in ("all", "ln"):
