@@ -124,6 +124,9 @@ typedef struct MicoAttnArgs {
      *   mask + (mask_bmod ? b % mask_bmod : b) * mask_bs + h * mask_hs + i * mask_qs + j
      * (batch entry = window; mask_bmod = windows per image; 0 / 0 reproduces the per-batch mask above) */
     int64_t mask_hs; int32_t mask_bmod;
+    /* attention-probability dropout (bert.py:243-247): P is multiplied by a counter-based Bernoulli(1-p)/(1-p) mask of
+     * element ((b*H + h)*Sq + i)*Sk + j under `dropout_seed`; forward and backward regenerate it.  p = 0 disables. */
+    float dropout_p; uint64_t dropout_seed;
 } MicoAttnArgs;
 
 int mico_attention_fwd(const MicoAttnArgs* args, void* stream);
@@ -214,6 +217,11 @@ int mico_sgemm_strided(const float* a, int64_t a_sm, int64_t a_sk, const float* 
                        int alpha_recip, int accumulate, void* stream);
 /* exact-erf GELU on a small fp32 tensor (Match_head, mico.py:44-52): out = gelu(x), or out = dy * gelu'(x) when dy != NULL */
 int mico_gelu_f32(const float* x, const float* dy, float* out, int64_t n, void* stream);
+/* hidden-state dropout (bert.py:148, 294, 372): out = [res +] x * m, m = Bernoulli(1-p)/(1-p) of element
+ * (site_offset + i) under `seed` (same counter-based generator as the attention dropout); the backward pass calls it
+ * again on the gradient with the same (seed, site_offset).  x fp32 or bf16; out as fp32 and/or bf16. */
+int mico_dropout(const void* x, int x_is_bf16, const float* res, float* out_f32, void* out_bf16, int64_t n, float p,
+                 uint64_t seed, uint64_t site_offset, void* stream);
 /* out[0] (+)= alpha * <a, b>  (d contra_temp) */
 int mico_dot_f32(const float* a, const float* b, int64_t n, float alpha, float* out, int accumulate, void* stream);
 

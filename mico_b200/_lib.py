@@ -82,6 +82,7 @@ class AttnArgs(C.Structure):
         ("dk", C.c_void_p), ("dk_bs", C.c_int64), ("dk_rs", C.c_int64), ("dk_hs", C.c_int64),
         ("dv", C.c_void_p), ("dv_bs", C.c_int64), ("dv_rs", C.c_int64), ("dv_hs", C.c_int64),
         ("mask_hs", C.c_int64), ("mask_bmod", C.c_int32),
+        ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64),
     ]
 
 

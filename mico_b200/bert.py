@@ -16,9 +16,11 @@ the LM head (dense + GELU + LN + vocab GEMM) and the cross-entropy are separate 
 1084-1090).  Masks follow the reference exactly: 2-D ``(b,S)`` or 3-D ``(b,S,S)`` attention masks become additive
 ``(1-m) * -10000`` and there is NO automatic causal mask even though ``is_decoder`` is set (bert.py:716-763).
 
-Dropout (hidden 0.1, attention 0.1 in the stock config) is not implemented by the kernels: calling the model in
-training mode with a non-zero dropout probability raises instead of silently training a different model
-(DESIGN.md "out of scope this round"); eval mode and p = 0 are exact.
+Dropout (hidden 0.1 after the embeddings and every dense output, attention-probability 0.1: bert.py:148, 243-247, 294,
+372) runs in training mode with counter-based masks (splitmix64 of a per-call seed and the element index): the
+attention kernels and `mico_dropout` regenerate the same mask in the backward pass, nothing is stored.  The masks are
+not the reference's Philox stream (no implementation could be, across devices), so parity with dropout on is checked
+against an fp32 reference driven by the same masks (tests/test_gpu_bert.py); eval mode and p = 0 are exact.
 """
 import json
 import math
@@ -181,8 +183,8 @@ _PER_LAYER = 26
 
 class _EncoderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, keep, ids, mask_self, enc, mask_enc, *params):
-        out, saved = model._launch_forward(ids, mask_self, enc, mask_enc, params, keep)
+    def forward(ctx, model, keep, drop, ids, mask_self, enc, mask_enc, *params):
+        out, saved = model._launch_forward(ids, mask_self, enc, mask_enc, params, keep, drop)
         ctx.model, ctx.saved, ctx.params = model, saved, params
         ctx.has_enc = enc is not None
         return out
@@ -193,7 +195,7 @@ class _EncoderFn(torch.autograd.Function):
             raise MicoError("BERT backward called but activations were not kept")
         denc, grads = ctx.model._launch_backward(dout, ctx.saved, ctx.params)
         ctx.saved = None
-        return (None, None, None, None, denc if ctx.needs_input_grad[4] else None, None) + tuple(grads)
+        return (None, None, None, None, None, denc if ctx.needs_input_grad[5] else None, None) + tuple(grads)
 
 
 class _Out:
@@ -216,6 +218,8 @@ class BertModel(nn.Module):
         self.encoder = BertEncoder(config)
         self.pooler = None
         self._cache = _Cache()
+        self._dropout_calls = 0
+        self.dropout_seed = None       # set to pin the dropout masks of the next training-mode calls (tests)
 
     # ------------------------------------------------------------------ parameters in launch order
     def _flat_params(self):
@@ -237,15 +241,24 @@ class BertModel(nn.Module):
     def invalidate_weight_cache(self):
         self._cache = _Cache()
 
-    def _check_dropout(self):
+    def _dropout_cfg(self):
+        """(p_hidden, p_attention, seed) for a training-mode call, else None.  Masks are counter-based (splitmix64 of
+        seed and element index): the backward pass regenerates them, and a test can reproduce them on the host."""
         c = self.config
-        if self.training and (c.hidden_dropout_prob > 0 or c.attention_probs_dropout_prob > 0):
-            raise NotImplementedError(
-                "mico_b200 BERT kernels have no dropout: set config.hidden_dropout_prob = "
-                "config.attention_probs_dropout_prob = 0 (or call .eval()) -- refusing to train a different model silently")
+        if not self.training or (c.hidden_dropout_prob <= 0 and c.attention_probs_dropout_prob <= 0):
+            return None
+        self._dropout_calls += 1
+        seed = self.dropout_seed if self.dropout_seed is not None else \
+            (torch.initial_seed() * 1000003 + self._dropout_calls * 7919) & (2 ** 62 - 1)
+        return (float(c.hidden_dropout_prob), float(c.attention_probs_dropout_prob), int(seed))
 
     # ------------------------------------------------------------------ launch sequences
-    def _launch_forward(self, ids, mask_self, enc, mask_enc, params, keep):
+    @staticmethod
+    def _site(li, k):
+        """hidden-dropout site -> element-counter offset (sites: 0 embeddings; per layer 1 self-out, 2 cross-out, 3 ffn-out)"""
+        return (0 if li < 0 else 3 * li + k) << 40
+
+    def _launch_forward(self, ids, mask_self, enc, mask_enc, params, keep, drop=None):
         c = self.config
         Dh, H = c.hidden_size, c.num_attention_heads
         d = Dh // H
@@ -258,8 +271,21 @@ class BertModel(nn.Module):
         x0 = ops.embedding_gather(ids.reshape(-1).contiguous(), det(0), det(1), det(2), S)
         # LayerNorm output in both formats: bf16 = next GEMM operand, fp32 = residual of the next sub-layer
         hb, h, mean, rstd = ops.layernorm_fwd(x0, det(3), det(4), eps, out_bf16=True, out_f32=True, save_stats=keep)
-        saved = dict(ids=ids, x0=x0, stats0=(mean, rstd), layers=[], b=b, S=S, mask_self=mask_self, mask_enc=mask_enc) \
-            if keep else None
+        ph, pa, seed = drop if drop is not None else (0.0, 0.0, 0)
+        if ph > 0:       # bert.py:148 embedding dropout
+            h, hb = ops.dropout(h, ph, seed, self._site(-1, 0), out_f32=True, out_bf16=True)
+        saved = dict(ids=ids, x0=x0, stats0=(mean, rstd), layers=[], b=b, S=S, mask_self=mask_self, mask_enc=mask_enc,
+                     drop=drop) if keep else None
+
+        def dense_res(x_b, w, bias, res, li, k):
+            """LayerNorm input of a post-LN sub-layer: dropout(dense(x)) + residual (bert.py:293-296, 370-373)"""
+            if ph > 0:
+                y = ops.gemm(x_b, w, out_dtype=F32, bias=bias)
+                return ops.dropout(y, ph, seed, self._site(li, k), res=res)[0]
+            return ops.gemm(x_b, w, out_dtype=F32, bias=bias, residual=res)
+
+        def adrop(li, cross):
+            return (pa, seed + 2 * li + (2 if cross else 1)) if pa > 0 else None
         encb = None
         Sk = 0
         if enc is not None:
@@ -279,8 +305,9 @@ class BertModel(nn.Module):
             bqkv = cache.cat_b(("sqkvb", li), [P(1), P(3), P(5)])
             qkv = ops.gemm(hb, wqkv, bias=bqkv)
             q5 = qkv.view(b, S, 3, H, d)
-            ctx, lse = ops.attention_fwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], scale, mask=mask_self, need_lse=keep)
-            y1 = ops.gemm(ctx.view(M, Dh), cache.cat_w(("so", li), [P(6)]), out_dtype=F32, bias=P(7).detach(), residual=h)
+            ctx, lse = ops.attention_fwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], scale, mask=mask_self, need_lse=keep,
+                                         dropout=adrop(li, False))
+            y1 = dense_res(ctx.view(M, Dh), cache.cat_w(("so", li), [P(6)]), P(7).detach(), h, li, 1)
             h1b, h1, m1, r1 = ln2(y1, base + 8, base + 9)
             rec = dict(hb=hb, qkv=qkv, ctx=ctx, lse=lse, y1=y1, st1=(m1, r1), h1b=h1b) if keep else None
             hb_in, h_in = h1b, h1
@@ -292,9 +319,8 @@ class BertModel(nn.Module):
                 kv = ops.gemm(encb, wkv, bias=bkv)
                 kv5 = kv.view(b, Sk, 2, H, d)
                 ctx2, lse2 = ops.attention_fwd(qc.view(b, S, H, d), kv5[:, :, 0], kv5[:, :, 1], scale, mask=mask_enc,
-                                               need_lse=keep)
-                y2 = ops.gemm(ctx2.view(M, Dh), cache.cat_w(("co", li), [P(16)]), out_dtype=F32, bias=P(17).detach(),
-                              residual=h1)
+                                               need_lse=keep, dropout=adrop(li, True))
+                y2 = dense_res(ctx2.view(M, Dh), cache.cat_w(("co", li), [P(16)]), P(17).detach(), h1, li, 2)
                 h2b, h2, m2, r2 = ln2(y2, base + 18, base + 19)
                 if keep:
                     rec.update(qc=qc, kv=kv, ctx2=ctx2, lse2=lse2, y2=y2, st2=(m2, r2), h2b=h2b)
@@ -303,7 +329,7 @@ class BertModel(nn.Module):
             wi = cache.cat_w(("i", li), [P(20)])
             pre = torch.empty((M, wi.shape[0]), device=ids.device, dtype=BF16) if keep else None
             a = ops.gemm(hb_in, wi, bias=P(21).detach(), act=ACT_GELU_SAVE_GRAD, aux_out=pre)     # pre holds gelu'(x)
-            y3 = ops.gemm(a, cache.cat_w(("o", li), [P(22)]), out_dtype=F32, bias=P(23).detach(), residual=h_in)
+            y3 = dense_res(a, cache.cat_w(("o", li), [P(22)]), P(23).detach(), h_in, li, 3)
             hb, h, m3, r3 = ln2(y3, base + 24, base + 25)
             if keep:
                 rec.update(pre=pre, a=a, y3=y3, st3=(m3, r3))
@@ -333,6 +359,15 @@ class BertModel(nn.Module):
         Sk = encb.shape[0] // b if has_enc else 0
         g32 = dout.contiguous().view(M, Dh).float()
         g16 = None
+        drop = saved.get("drop")
+        ph, pa, seed = drop if drop is not None else (0.0, 0.0, 0)
+
+        def dmask(gb, li, k):
+            """gradient entering a dense layer whose output was dropped out: the same mask again"""
+            return ops.dropout(gb, ph, seed, self._site(li, k), out_f32=False, out_bf16=True)[1] if ph > 0 else gb
+
+        def adrop(li, cross):
+            return (pa, seed + 2 * li + (2 if cross else 1)) if pa > 0 else None
         for li in range(c.num_hidden_layers - 1, -1, -1):
             rec = saved["layers"].pop()
             base = 5 + li * _PER_LAYER
@@ -341,6 +376,7 @@ class BertModel(nn.Module):
             # ---- FFN: h3 = LN(a Wo^T + bo + h_in)
             dy3, dy3b = ops.layernorm_bwd(g32, rec["y3"], *rec["st3"], det(base + 24), pg(base + 24), pg(base + 25),
                                           want_bf16=True, dy2=g16)
+            dy3b = dmask(dy3b, li, 3)
             ops.gemm(dy3b, rec["a"], a_mn=True, b_mn=True, out=pg(base + 22))
             ops.colsum(dy3b, out=pg(base + 23))
             dpre = ops.gemm(dy3b, cache.cat_w(("o", li), [P(22)]), b_mn=True, act=ACT_MUL_AUX, aux_in=rec["pre"])
@@ -352,6 +388,7 @@ class BertModel(nn.Module):
             if has_enc:
                 dy2_, dy2b = ops.layernorm_bwd(g32, rec["y2"], *rec["st2"], det(base + 18), pg(base + 18), pg(base + 19),
                                                want_bf16=True, dy2=g16)
+                dy2b = dmask(dy2b, li, 2)
                 ops.gemm(dy2b, rec["ctx2"].view(M, Dh), a_mn=True, b_mn=True, out=pg(base + 16))
                 ops.colsum(dy2b, out=pg(base + 17))
                 dctx = ops.gemm(dy2b, cache.cat_w(("co", li), [P(16)]), b_mn=True)
@@ -361,7 +398,7 @@ class BertModel(nn.Module):
                 dkv5 = dkv.view(b, Sk, 2, H, d)
                 ops.attention_bwd(rec["qc"].view(b, S, H, d), kv5[:, :, 0], kv5[:, :, 1], rec["ctx2"], rec["lse2"],
                                   dctx.view(b, S, H, d), scale, mask=saved["mask_enc"], dq=dqc.view(b, S, H, d),
-                                  dk=dkv5[:, :, 0], dv=dkv5[:, :, 1])
+                                  dk=dkv5[:, :, 0], dv=dkv5[:, :, 1], dropout=adrop(li, True))
                 ops.gemm(dqc, rec["h1b"], a_mn=True, b_mn=True, out=pg(base + 10))
                 ops.colsum(dqc, out=pg(base + 11))
                 g16 = ops.gemm(dqc, cache.cat_w(("cq", li), [P(10)]), b_mn=True)
@@ -375,6 +412,7 @@ class BertModel(nn.Module):
             # ---- self attention: h1 = LN(ctx Wo^T + bo + h)
             dy1, dy1b = ops.layernorm_bwd(g32, rec["y1"], *rec["st1"], det(base + 8), pg(base + 8), pg(base + 9),
                                           want_bf16=True, dy2=g16)
+            dy1b = dmask(dy1b, li, 1)
             ops.gemm(dy1b, rec["ctx"].view(M, Dh), a_mn=True, b_mn=True, out=pg(base + 6))
             ops.colsum(dy1b, out=pg(base + 7))
             dctx = ops.gemm(dy1b, cache.cat_w(("so", li), [P(6)]), b_mn=True)
@@ -382,7 +420,7 @@ class BertModel(nn.Module):
             dqkv = torch.empty_like(rec["qkv"])
             g5 = dqkv.view(b, S, 3, H, d)
             ops.attention_bwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], rec["ctx"], rec["lse"], dctx.view(b, S, H, d), scale,
-                              mask=saved["mask_self"], dq=g5[:, :, 0], dk=g5[:, :, 1], dv=g5[:, :, 2])
+                              mask=saved["mask_self"], dq=g5[:, :, 0], dk=g5[:, :, 1], dv=g5[:, :, 2], dropout=adrop(li, False))
             gw = torch.empty((3 * Dh, Dh), device=dev, dtype=F32)
             ops.gemm(dqkv, rec["hb"], a_mn=True, b_mn=True, out=gw)
             grads[base + 0], grads[base + 2], grads[base + 4] = gw[:Dh], gw[Dh:2 * Dh], gw[2 * Dh:]
@@ -391,6 +429,10 @@ class BertModel(nn.Module):
             g16 = ops.gemm(dqkv, cache.cat_w(("sqkv", li), [P(0), P(2), P(4)]), b_mn=True)
             g32 = dy1
         # ---- embeddings: h0 = LN(word + type + pos)
+        if ph > 0:       # embedding dropout: mask both halves of the incoming gradient
+            g32 = ops.dropout(g32.contiguous(), ph, seed, self._site(-1, 0))[0]
+            if g16 is not None:
+                g16 = ops.dropout(g16, ph, seed, self._site(-1, 0), out_f32=False, out_bf16=True)[1]
         dx0, _ = ops.layernorm_bwd(g32, saved["x0"], *saved["stats0"], det(3), pg(3), pg(4), dy2=g16)
         gword = torch.zeros_like(params[0], dtype=F32)
         ops.embedding_scatter_add(dx0, saved["ids"].reshape(-1).contiguous(), gword)
@@ -423,7 +465,7 @@ class BertModel(nn.Module):
                                       "encoder_attention_mask) are on the MiCo path")
         if not input_ids.is_cuda:
             raise MicoError("mico_b200 runs on CUDA (sm_100a) only")
-        self._check_dropout()
+        drop = self._dropout_cfg()
         b, S = input_ids.shape
         if attention_mask is None:
             attention_mask = torch.ones((b, S), device=input_ids.device)
@@ -437,7 +479,7 @@ class BertModel(nn.Module):
         keep = torch.is_grad_enabled() and (any(p.requires_grad for p in live) or (enc is not None and enc.requires_grad))
         # placeholders keep the flat indexing when the config has no cross-attention
         args = [p if p is not None else torch.empty(0, device=input_ids.device) for p in flat]
-        out = _EncoderFn.apply(self, keep, input_ids.long(), mask_self, enc, mask_enc, *args)
+        out = _EncoderFn.apply(self, keep, drop, input_ids.long(), mask_self, enc, mask_enc, *args)
         return _Out(last_hidden_state=out, pooler_output=None)
 
 

@@ -26,6 +26,7 @@ struct AttnBwdParams {
     const float* mask;
     int64_t mask_bs, mask_qs, mask_hs;
     int mask_bmod;
+    DropCfg drop;
     const float* lse;     // [B,H,Sq]
     const float* delta;   // [B,H,Sq]
     __nv_bfloat16* dq; int64_t dq_bs, dq_rs, dq_hs;
@@ -234,7 +235,8 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     tmem_ld_wait();
                     float ds[32];
                     const int lim = valid - c * 32;
-                    if (!mrow && lim >= 32) {
+                    const bool dropping = p.drop.p > 0.f;
+                    if (!mrow && lim >= 32 && !dropping) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
                             ds[i] = ex2_fast(fmaf(__uint_as_float(sv[i]), sc2, nlse2)) * fmaf(__uint_as_float(dv[i]), p.scale, ndlt);
@@ -243,7 +245,11 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         for (int i = 0; i < 32; ++i) {
                             float s = fmaf(__uint_as_float(sv[i]), sc2, nlse2);
                             if (mrow && i < lim) s = fmaf(mrow[j * kTile + c * 32 + i], kLog2e, s);
-                            ds[i] = i < lim ? ex2_fast(s) * fmaf(__uint_as_float(dv[i]), p.scale, ndlt) : 0.f;
+                            float dpv = __uint_as_float(dv[i]);
+                            if (dropping)      // dP flows only through the kept probabilities
+                                dpv *= drop_mult(p.drop, ((uint64_t)(b * p.H + h) * p.Sq + (row_ok ? qi : 0)) * p.Sk +
+                                                             (uint64_t)(j * kTile + c * 32 + i));
+                            ds[i] = i < lim ? ex2_fast(s) * fmaf(dpv, p.scale, ndlt) : 0.f;
                         }
                     }
                     tmem_store_bf16x32(tmem_dS + lane_off + c * 16, ds);
@@ -473,8 +479,13 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                             float s = fmaf(__uint_as_float(sv[q]), sc2, ls[e]);
                             if (masked && key_ok && c0 + q < validq)
                                 s = fmaf((p.mask + (int64_t)(p.mask_bmod ? b % p.mask_bmod : b) * p.mask_bs + (int64_t)h * p.mask_hs)[(int64_t)(i * kTile + c0 + q) * p.mask_qs + kj], kLog2e, s);
-                            pt[q] = ex2_fast(s);
-                            dst[q] = pt[q] * fmaf(__uint_as_float(dv[q]), p.scale, dl[e]);
+                            const float pu = ex2_fast(s);
+                            float m = 1.0f;
+                            if (p.drop.p > 0.f)
+                                m = drop_mult(p.drop, ((uint64_t)(b * p.H + h) * p.Sq + (uint64_t)min(i * kTile + c0 + q, p.Sq - 1)) * p.Sk +
+                                                          (uint64_t)min(kj, p.Sk - 1));
+                            pt[q] = pu * m;                                          // dV uses the dropped probabilities
+                            dst[q] = pu * fmaf(__uint_as_float(dv[q]) * m, p.scale, dl[e]);
                         }
                     }
                     // packed bf16 output: 16 (or 8) columns at the start of this half's own range, behind its reads
@@ -563,6 +574,7 @@ extern "C" int mico_attention_bwd(const MicoAttnArgs* a, void* stream_) {
     AttnBwdParams p;
     p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk; p.D = a->D; p.scale = a->scale;
     p.mask = a->mask; p.mask_bs = a->mask_bs; p.mask_qs = a->mask_qs; p.mask_hs = a->mask_hs; p.mask_bmod = a->mask_bmod;
+    p.drop.p = a->dropout_p; p.drop.inv_keep = a->dropout_p < 1.f ? 1.f / (1.f - a->dropout_p) : 0.f; p.drop.seed = a->dropout_seed;
     p.lse = a->lse; p.delta = a->delta;
     p.dq = reinterpret_cast<__nv_bfloat16*>(a->dq); p.dq_bs = a->dq_bs; p.dq_rs = a->dq_rs; p.dq_hs = a->dq_hs;
     p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk); p.dk_bs = a->dk_bs; p.dk_rs = a->dk_rs; p.dk_hs = a->dk_hs;

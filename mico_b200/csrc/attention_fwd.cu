@@ -25,6 +25,7 @@ struct AttnFwdParams {
     const float* mask;            // additive fp32 mask or null: mask[b*mask_bs + i*mask_qs + j]
     int64_t mask_bs, mask_qs, mask_hs;
     int mask_bmod;
+    DropCfg drop;
     __nv_bfloat16* o;             // output, element (b,i,h,d) at o + b*o_bs + i*o_rs + h*o_hs + d
     int64_t o_bs, o_rs, o_hs;
     float* lse;                   // [B,H,Sq] or null
@@ -250,7 +251,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     tmem_ld_wait();
                     float pv[32];
                     const int lim = valid - c * 32;
-                    if (!mrow && lim >= 32) {
+                    const bool dropping = p.drop.p > 0.f;
+                    if (!mrow && lim >= 32 && !dropping) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             pv[i] = ex2_fast(fmaf(__uint_as_float(v[i]), sc2, -m_new));
@@ -262,7 +264,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                             float s = fmaf(__uint_as_float(v[i]), sc2, -m_new);
                             if (mrow && i < lim) s = fmaf(mrow[j * kTile + c * 32 + i], kLog2e, s);
                             pv[i] = i < lim ? ex2_fast(s) : 0.f;
-                            sum += pv[i];
+                            sum += pv[i];                     // the softmax denominator is taken before dropout
+                            if (dropping)
+                                pv[i] *= drop_mult(p.drop, ((uint64_t)(b * p.H + h) * p.Sq + (row_ok ? qi : 0)) * p.Sk +
+                                                               (uint64_t)(j * kTile + c * 32 + i));
                         }
                     }
 #pragma unroll
@@ -349,6 +354,7 @@ extern "C" int mico_attention_fwd(const MicoAttnArgs* a, void* stream_) {
     MICO_CHECK_ARG(a && a->q && a->k && a->v && a->o);
     MICO_CHECK_ARG(a->B > 0 && a->H > 0 && a->Sq > 0 && a->Sk > 0);
     MICO_CHECK_ARG(a->scale > 0.0f);   // the row max is taken on unscaled scores
+    MICO_CHECK_ARG(a->dropout_p >= 0.0f && a->dropout_p < 1.0f);
     MICO_CHECK_ARG(a->D % 8 == 0 && a->D >= 16 && a->D <= 128);
     for (const int64_t s : {a->q_bs, a->q_rs, a->q_hs, a->k_bs, a->k_rs, a->k_hs, a->v_bs, a->v_rs, a->v_hs, a->o_bs,
                             a->o_rs, a->o_hs})
@@ -367,6 +373,7 @@ extern "C" int mico_attention_fwd(const MicoAttnArgs* a, void* stream_) {
     p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk; p.D = a->D;
     p.scale = a->scale;
     p.mask = a->mask; p.mask_bs = a->mask_bs; p.mask_qs = a->mask_qs; p.mask_hs = a->mask_hs; p.mask_bmod = a->mask_bmod;
+    p.drop.p = a->dropout_p; p.drop.inv_keep = a->dropout_p < 1.f ? 1.f / (1.f - a->dropout_p) : 0.f; p.drop.seed = a->dropout_seed;
     p.o = reinterpret_cast<__nv_bfloat16*>(a->o); p.o_bs = a->o_bs; p.o_rs = a->o_rs; p.o_hs = a->o_hs;
     p.lse = a->lse;
     const int work = a->B * a->H * m_tiles(a->Sq);

@@ -19,6 +19,7 @@ struct TailParams {
     __nv_bfloat16 *out0, *out1;     // fwd: o ; dq: dq ; dkv: dk, dv
     int64_t o0_bs, o0_rs, o0_hs, o1_bs, o1_rs, o1_hs;
     const float* mask; int64_t mask_bs, mask_qs, mask_hs; int mask_bmod;
+    DropCfg drop;
     float* lse; const float* delta;
     int B, H, Sq, Sk, D, row0, rows;
     float scale;
@@ -140,8 +141,8 @@ __global__ void __launch_bounds__(kTailThreads) attn_tail_q_kernel(TailParams p)
         float sum = 0.f;
         for (int j = threadIdx.x; j < p.Sk; j += kTailThreads) {
             const float e = __expf(sc[j] - mx);
-            sc[j] = e;
             sum += e;
+            sc[j] = p.drop.p > 0.f ? e * drop_mult(p.drop, ((uint64_t)(b * p.H + h) * p.Sq + i) * p.Sk + j) : e;
         }
         sum = block_reduce(sum, small, false);
         weighted_rows(V, p.v_rs, p.Sk, sc, p.D, 1.0f / sum, p.out0 + b * p.o0_bs + (int64_t)i * p.o0_rs + h * p.o0_hs, red);
@@ -153,7 +154,8 @@ __global__ void __launch_bounds__(kTailThreads) attn_tail_q_kernel(TailParams p)
             if (mrow) s += mrow[j];
             const float pr = __expf(s - lse);
             const float dp = row_dot_quad(V + (int64_t)j * p.v_rs, dov, p.D);
-            if ((threadIdx.x & 3) == 0) sc[j] = pr * (dp - dlt) * p.scale;
+            const float m = p.drop.p > 0.f ? drop_mult(p.drop, ((uint64_t)(b * p.H + h) * p.Sq + i) * p.Sk + j) : 1.0f;
+            if ((threadIdx.x & 3) == 0) sc[j] = pr * (dp * m - dlt) * p.scale;
         }
         __syncthreads();
         weighted_rows(K, p.k_rs, p.Sk, sc, p.D, 1.0f, p.out0 + b * p.o0_bs + (int64_t)i * p.o0_rs + h * p.o0_hs, red);
@@ -183,8 +185,9 @@ __global__ void __launch_bounds__(kTailThreads) attn_tail_kv_kernel(TailParams p
         const float pr = __expf(s - p.lse[stat0 + i]);
         const float dp = row_dot_quad(DO + (int64_t)i * p.do_rs, vv, p.D);
         if ((threadIdx.x & 3) == 0) {
-            pa[i] = pr;
-            dsa[i] = pr * (dp - p.delta[stat0 + i]) * p.scale;
+            const float m = p.drop.p > 0.f ? drop_mult(p.drop, ((uint64_t)(b * p.H + h) * p.Sq + i) * p.Sk + j) : 1.0f;
+            pa[i] = pr * m;
+            dsa[i] = pr * (dp * m - p.delta[stat0 + i]) * p.scale;
         }
     }
     __syncthreads();
@@ -242,6 +245,7 @@ TailParams base_params(const MicoAttnArgs* a) {
     p.o = reinterpret_cast<const __nv_bfloat16*>(a->o); p.o_bs = a->o_bs; p.o_rs = a->o_rs; p.o_hs = a->o_hs;
     p.d_o = reinterpret_cast<const __nv_bfloat16*>(a->dout); p.do_bs = a->do_bs; p.do_rs = a->do_rs; p.do_hs = a->do_hs;
     p.mask = a->mask; p.mask_bs = a->mask_bs; p.mask_qs = a->mask_qs; p.mask_hs = a->mask_hs; p.mask_bmod = a->mask_bmod;
+    p.drop.p = a->dropout_p; p.drop.inv_keep = a->dropout_p < 1.f ? 1.f / (1.f - a->dropout_p) : 0.f; p.drop.seed = a->dropout_seed;
     p.lse = a->lse; p.delta = a->delta;
     p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk; p.D = a->D; p.scale = a->scale;
     return p;
@@ -297,6 +301,7 @@ extern "C" int mico_attention_dmask(const MicoAttnArgs* a, float* dmask, void* s
     using namespace mico;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     MICO_CHECK_ARG(a && dmask && a->mask && a->q && a->k && a->v && a->dout && a->lse && a->delta);
+    MICO_CHECK_ARG(a->dropout_p == 0.0f);   // the learnable-bias towers (Swin) run without attention dropout
     TailParams p = base_params(a);
     const size_t smem = (size_t)2 * (a->Sk + a->Sq) * a->D * sizeof(float);
     if (smem > 200 * 1024) {

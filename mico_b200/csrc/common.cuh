@@ -291,6 +291,22 @@ __device__ __forceinline__ float ex2_fast(float x) {
     return y;
 }
 
+// Counter-based dropout (BERT hidden / attention-probability dropout, bert.py:93,148,243-247,291,369): element `ctr`
+// of a tensor is kept with probability 1-p, decided by splitmix64(seed, ctr) -- forward and backward regenerate the
+// same mask from (seed, ctr), nothing is stored.  Returns the multiplier 1/(1-p) or 0.
+struct DropCfg {
+    float p, inv_keep;
+    uint64_t seed;
+};
+__device__ __forceinline__ float drop_mult(const DropCfg& d, uint64_t ctr) {
+    uint64_t z = ctr * 0x9E3779B97F4A7C15ull + d.seed;
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 27; z *= 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const float u = (float)((uint32_t)(z >> 40)) * (1.0f / 16777216.0f);      // 24 random bits -> [0, 1)
+    return u >= d.p ? d.inv_keep : 0.0f;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -218,6 +218,20 @@ __global__ void gelu_f32_kernel(const float* __restrict__ x, const float* __rest
     out[i] = dy ? dy[i] * gelu_erf_grad(x[i]) : gelu_erf(x[i]);
 }
 
+// Hidden-state dropout (bert.py:148, 294, 372): out = [res +] x * m,  m = counter-based Bernoulli(1-p)/(1-p) of element
+// (site_offset + flat index); forward (fp32 x, optional fp32 residual, fp32 and/or bf16 outputs) and backward
+// (bf16 or fp32 gradient times the same mask) share the kernel.
+template <typename TIn>
+__global__ void dropout_kernel(const TIn* __restrict__ x, const float* __restrict__ res, float* __restrict__ out_f32,
+                               __nv_bfloat16* __restrict__ out_bf16, int64_t n, DropCfg d, uint64_t site_offset) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = ldf(x + i) * drop_mult(d, site_offset + (uint64_t)i);
+    if (res) v += res[i];
+    if (out_f32) out_f32[i] = v;
+    if (out_bf16) out_bf16[i] = __float2bfloat16(v);
+}
+
 // out[0] (+)= alpha * sum_i a[i] * b[i]   (single block, deterministic)
 __global__ void __launch_bounds__(256)
 dot_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, float alpha, float* __restrict__ out,
@@ -348,6 +362,25 @@ extern "C" int mico_gelu_f32(const float* x, const float* dy, float* out, int64_
     MICO_CHECK_ARG(x && out && n > 0);
     ProfScope prof(kProfOther, (dy ? 12.0 : 8.0) * (double)n, stream);
     gelu_f32_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(x, dy, out, n);
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return MICO_OK;
+}
+
+extern "C" int mico_dropout(const void* x, int x_is_bf16, const float* res, float* out_f32, void* out_bf16, int64_t n, float p,
+                            uint64_t seed, uint64_t site_offset, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MICO_CHECK_ARG(x && (out_f32 || out_bf16) && n > 0 && p >= 0.0f && p < 1.0f);
+    ProfScope prof(kProfOther, (double)n * ((x_is_bf16 ? 2 : 4) + (res ? 4 : 0) + (out_f32 ? 4 : 0) + (out_bf16 ? 2 : 0)), stream);
+    DropCfg d;
+    d.p = p; d.inv_keep = 1.0f / (1.0f - p); d.seed = seed;
+    const int grid = (int)((n + 255) / 256);
+    if (x_is_bf16)
+        dropout_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), res, out_f32,
+                                                               reinterpret_cast<__nv_bfloat16*>(out_bf16), n, d, site_offset);
+    else
+        dropout_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x), res, out_f32,
+                                                       reinterpret_cast<__nv_bfloat16*>(out_bf16), n, d, site_offset);
     MICO_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return MICO_OK;

@@ -98,7 +98,8 @@ def _bhsd_strides(t):
     return t.data_ptr(), t.stride(0), t.stride(1), t.stride(2)
 
 
-def _attn_args(q, k, v, o, lse, mask, scale):
+def _attn_args(q, k, v, o, lse, mask, scale, dropout=None):
+    """dropout: None or (p, seed) -- attention-probability dropout regenerated from the seed in the backward."""
     a = _lib.AttnArgs()
     B, Sq, H, D = q.shape
     Sk = k.shape[1]
@@ -126,21 +127,23 @@ def _attn_args(q, k, v, o, lse, mask, scale):
             raise MicoError("mask must be [B,Sk], [B,Sq,Sk] or [G,H,Sq,Sk] additive fp32")
     a.B, a.H, a.Sq, a.Sk, a.D = B, H, Sq, Sk, D
     a.scale = float(scale)
+    if dropout is not None and dropout[0] > 0.0:
+        a.dropout_p, a.dropout_seed = float(dropout[0]), int(dropout[1]) & (2 ** 64 - 1)
     return a
 
 
-def attention_fwd(q, k, v, scale, mask=None, out=None, need_lse=True):
+def attention_fwd(q, k, v, scale, mask=None, out=None, need_lse=True, dropout=None):
     """q,k,v: bf16 views [B,S,H,D] (e.g. slices of a fused qkv buffer). Returns (o [B,Sq,H,D], lse [B,H,Sq])."""
     B, Sq, H, D = q.shape
     if out is None:
         out = torch.empty((B, Sq, H, D), device=q.device, dtype=BF16)
     lse = torch.empty((B, H, Sq), device=q.device, dtype=F32) if need_lse else None
-    a = _attn_args(q, k, v, out, lse, mask, scale)
+    a = _attn_args(q, k, v, out, lse, mask, scale, dropout)
     check(lib.mico_attention_fwd(C.byref(a), _stream()), "mico_attention_fwd")
     return out, lse
 
 
-def attention_bwd(q, k, v, o, lse, dout, scale, mask=None, dq=None, dk=None, dv=None, dmask=None):
+def attention_bwd(q, k, v, o, lse, dout, scale, mask=None, dq=None, dk=None, dv=None, dmask=None, dropout=None):
     """dmask: optional zero-initialised fp32 tensor shaped like mask; receives the gradient of the additive bias."""
     B, Sq, H, D = q.shape
     Sk = k.shape[1]
@@ -148,7 +151,7 @@ def attention_bwd(q, k, v, o, lse, dout, scale, mask=None, dq=None, dk=None, dv=
     dk = torch.empty((B, Sk, H, D), device=q.device, dtype=BF16) if dk is None else dk
     dv = torch.empty((B, Sk, H, D), device=q.device, dtype=BF16) if dv is None else dv
     delta = torch.empty((B, H, Sq), device=q.device, dtype=F32)
-    a = _attn_args(q, k, v, o, lse, mask, scale)
+    a = _attn_args(q, k, v, o, lse, mask, scale, dropout)
     _req(dout, BF16, "dout")
     a.dout, a.do_bs, a.do_rs, a.do_hs = _bhsd_strides(dout)
     a.delta = delta.data_ptr()
@@ -446,3 +449,14 @@ def fbank(wave, window, mel, frame_shift=160, in_scale=32768.0, preemph=0.97, lo
                          C.c_float(norm_sub), C.c_float(norm_mul), _ptr(out), C.c_int64(n_frames * num_mel), _stream()),
           "mico_fbank")
     return out
+
+
+def dropout(x, p, seed, site_offset, res=None, out_f32=True, out_bf16=False):
+    """[res +] x * Bernoulli(1-p)/(1-p) mask of (seed, site_offset + flat index).  x fp32 or bf16, contiguous."""
+    if not x.is_contiguous() or (res is not None and not res.is_contiguous()):
+        raise MicoError("dropout: contiguous tensors expected")
+    yf = torch.empty(x.shape, device=x.device, dtype=F32) if out_f32 else None
+    yb = torch.empty(x.shape, device=x.device, dtype=BF16) if out_bf16 else None
+    check(lib.mico_dropout(_ptr(x), int(x.dtype == BF16), _ptr(res), _ptr(yf), _ptr(yb), C.c_int64(x.numel()), C.c_float(p),
+                           C.c_uint64(int(seed) & (2 ** 64 - 1)), C.c_uint64(int(site_offset)), _stream()), "mico_dropout")
+    return yf, yb

@@ -13,8 +13,31 @@ TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Restates, op for op,
 """
 import math
 
+import numpy as np
 import torch
 import torch.nn.functional as F
+
+
+def drop_mult(p, seed, offset, shape):
+    """Host restatement of the product's counter-based dropout (mico_b200/csrc/common.cuh drop_mult): element i of a tensor
+    gets the multiplier 1/(1-p) if splitmix64(seed, offset + i) >> 40 scaled to [0,1) is >= p, else 0.  The reference draws
+    its masks from torch's Philox stream (bert.py:93,243: nn.Dropout), which no other implementation can reproduce; tests
+    therefore feed THESE masks to the fp32 restatement and compare."""
+    n = int(np.prod(shape))
+    with np.errstate(over="ignore"):
+        z = (np.arange(n, dtype=np.uint64) + np.uint64(offset)) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed)
+        z ^= z >> np.uint64(30)
+        z *= np.uint64(0xBF58476D1CE4E5B9)
+        z ^= z >> np.uint64(27)
+        z *= np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+    u = (z >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    m = np.where(u >= np.float32(p), np.float32(1.0 / (1.0 - p)), np.float32(0.0))
+    return torch.from_numpy(m.reshape(shape))
+
+
+def _site(li, k):
+    return (0 if li < 0 else 3 * li + k) << 40
 
 
 def _lin(p, k, x):
@@ -32,7 +55,7 @@ def embeddings(p, pre, ids, eps):
     return _ln(p, pre + "LayerNorm", x, eps)
 
 
-def attention(p, pre, x, kv_src, add_mask, heads):
+def attention(p, pre, x, kv_src, add_mask, heads, adrop=None):
     b, S, D = x.shape
     d = D // heads
     q = _lin(p, pre + "self.query", x).view(b, S, heads, d).transpose(1, 2)
@@ -41,18 +64,26 @@ def attention(p, pre, x, kv_src, add_mask, heads):
     s = q @ k.transpose(-1, -2) / math.sqrt(d)
     if add_mask is not None:
         s = s + add_mask
-    ctx = (s.softmax(-1) @ v).transpose(1, 2).reshape(b, S, D)
+    pr = s.softmax(-1)
+    if adrop is not None:          # attention-probability dropout (bert.py:243-247) with the product's mask
+        pr = pr * drop_mult(adrop[0], adrop[1], 0, tuple(pr.shape))
+    ctx = (pr @ v).transpose(1, 2).reshape(b, S, D)
     return ctx
 
 
-def layer(p, pre, h, mask_self, enc, mask_enc, heads, eps):
-    ctx = attention(p, pre + "attention.", h, h, mask_self, heads)
-    h = _ln(p, pre + "attention.output.LayerNorm", _lin(p, pre + "attention.output.dense", ctx) + h, eps)
+def layer(p, pre, h, mask_self, enc, mask_enc, heads, eps, li=0, drop=None):
+    ph, pa, seed = drop if drop is not None else (0.0, 0.0, 0)
+
+    def hd(x, k):      # hidden dropout after a dense layer (bert.py:294, 372)
+        return x * drop_mult(ph, seed, _site(li, k), tuple(x.shape)) if ph > 0 else x
+
+    ctx = attention(p, pre + "attention.", h, h, mask_self, heads, (pa, seed + 2 * li + 1) if pa > 0 else None)
+    h = _ln(p, pre + "attention.output.LayerNorm", hd(_lin(p, pre + "attention.output.dense", ctx), 1) + h, eps)
     if enc is not None:
-        ctx = attention(p, pre + "crossattention.", h, enc, mask_enc, heads)
-        h = _ln(p, pre + "crossattention.output.LayerNorm", _lin(p, pre + "crossattention.output.dense", ctx) + h, eps)
+        ctx = attention(p, pre + "crossattention.", h, enc, mask_enc, heads, (pa, seed + 2 * li + 2) if pa > 0 else None)
+        h = _ln(p, pre + "crossattention.output.LayerNorm", hd(_lin(p, pre + "crossattention.output.dense", ctx), 2) + h, eps)
     a = F.gelu(_lin(p, pre + "intermediate.dense", h))
-    return _ln(p, pre + "output.LayerNorm", _lin(p, pre + "output.dense", a) + h, eps)
+    return _ln(p, pre + "output.LayerNorm", hd(_lin(p, pre + "output.dense", a), 3) + h, eps)
 
 
 def extended_mask(attention_mask):
@@ -61,7 +92,8 @@ def extended_mask(attention_mask):
     return (1.0 - m) * -10000.0
 
 
-def bert_model(p, ids, attention_mask=None, enc=None, enc_mask=None, prefix="bert.", layers=12, heads=12, eps=1e-12):
+def bert_model(p, ids, attention_mask=None, enc=None, enc_mask=None, prefix="bert.", layers=12, heads=12, eps=1e-12,
+               drop=None):
     b, S = ids.shape
     if attention_mask is None:
         attention_mask = torch.ones(b, S)
@@ -70,8 +102,10 @@ def bert_model(p, ids, attention_mask=None, enc=None, enc_mask=None, prefix="ber
     if enc is not None and enc_mask is not None:
         me = (1.0 - enc_mask.float()[:, None, None, :]) * torch.finfo(torch.float32).min
     h = embeddings(p, prefix + "embeddings.", ids, eps)
+    if drop is not None and drop[0] > 0:
+        h = h * drop_mult(drop[0], drop[2], _site(-1, 0), tuple(h.shape))
     for i in range(layers):
-        h = layer(p, f"{prefix}encoder.layer.{i}.", h, ms, enc, me, heads, eps)
+        h = layer(p, f"{prefix}encoder.layer.{i}.", h, ms, enc, me, heads, eps, i, drop)
     return h
 
 
@@ -80,8 +114,9 @@ def lm_head(p, h, prefix="cls.predictions.", eps=1e-12):
     return F.linear(t, p[prefix + "decoder.weight"], p[prefix + "bias"])
 
 
-def masked_lm(p, ids, attention_mask=None, enc=None, enc_mask=None, labels=None, layers=12, heads=12, eps=1e-12, prefix=""):
-    seq = bert_model(p, ids, attention_mask, enc, enc_mask, prefix + "bert.", layers, heads, eps)
+def masked_lm(p, ids, attention_mask=None, enc=None, enc_mask=None, labels=None, layers=12, heads=12, eps=1e-12, prefix="",
+              drop=None):
+    seq = bert_model(p, ids, attention_mask, enc, enc_mask, prefix + "bert.", layers, heads, eps, drop)
     logits = lm_head(p, seq, prefix + "cls.predictions.", eps)
     loss = None
     if labels is not None:

@@ -58,12 +58,55 @@ def test_golden_caption_loss_and_grads(golden_dir):
     print(f"bert caption: loss {out.loss.item():.5f} vs {g['loss'].item():.5f}; worst grad {worst[0]} {worst[1]:.3e}")
 
 
-def test_training_with_dropout_refuses():
-    from mico_b200.bert import BertConfig, BertForMaskedLM
-    m = BertForMaskedLM(BertConfig(vocab_size=100, hidden_size=64, num_hidden_layers=1, num_attention_heads=1,
-                                   intermediate_size=128, max_position_embeddings=16)).cuda().train()
-    with pytest.raises(NotImplementedError):
-        m(input_ids=torch.ones(1, 8, dtype=torch.long, device="cuda"))
+def test_attention_dropout_kernel_matches_masked_reference():
+    """fused attention with probability dropout (fwd + bwd, tile kernels and the SIMT tail rows) vs an fp32 reference
+    that applies the same counter-based mask to softmax(S) (bert.py:243-247)."""
+    from mico_b200 import ops
+    from oracle import bert as OB
+    for (B, H, Sq, Sk, D) in [(2, 3, 40, 257, 64), (1, 2, 130, 130, 64)]:
+        g = torch.Generator().manual_seed(Sq)
+        q, k, v, do = (torch.randn(B, s_, H, D, generator=g).to(torch.bfloat16).cuda() for s_ in (Sq, Sk, Sk, Sq))
+        p_, seed = 0.25, 123456789
+        o, lse = ops.attention_fwd(q, k, v, D ** -0.5, dropout=(p_, seed))
+        dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, do, D ** -0.5, dropout=(p_, seed))
+        qf, kf, vf = (t.float().cpu().requires_grad_(True) for t in (q, k, v))
+        pr = (torch.einsum("bihd,bjhd->bhij", qf, kf) * D ** -0.5).softmax(-1)
+        pr = pr * OB.drop_mult(p_, seed, 0, (B, H, Sq, Sk))
+        ro = torch.einsum("bhij,bjhd->bihd", pr, vf)
+        ro.backward(do.float().cpu())
+        assert rel_l2(o.cpu(), ro) < 4e-3
+        for a, r in ((dq, qf.grad), (dk, kf.grad), (dv, vf.grad)):
+            assert rel_l2(a.cpu(), r) < 1e-2
+
+
+def test_training_with_dropout_matches_masked_oracle(golden_dir):
+    """Stock dropout probabilities (hidden 0.1, attention 0.1) in training mode: loss and gradients against the fp32 oracle
+    driven by the same counter-based masks."""
+    from oracle import bert as OB
+    g = torch.load(os.path.join(golden_dir, "bert_tiny.pt"), weights_only=False)
+    cfg = dict(g["cfg"], hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1)
+    m = _model(cfg)
+    m.load_state_dict(g["state_dict"], strict=True)
+    m = m.cuda().train()
+    m.bert.dropout_seed = 20240607
+    enc = g["enc"].cuda().requires_grad_(True)
+    out = m(input_ids=g["ids"].cuda(), attention_mask=g["att3"].cuda(), encoder_hidden_states=enc, labels=g["labels"].cuda())
+    out.loss.backward()
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in g["state_dict"].items()}
+    p["cls.predictions.decoder.weight"] = p["bert.embeddings.word_embeddings.weight"]
+    encr = g["enc"].clone().requires_grad_(True)
+    loss, logits, seq = OB.masked_lm(p, g["ids"], g["att3"], encr, None, g["labels"], layers=2, heads=2,
+                                     drop=(0.1, 0.1, 20240607))
+    loss.backward()
+    print(f"bert dropout: loss {out.loss.item():.5f} vs {loss.item():.5f} (no-dropout loss {g['loss'].item():.5f})")
+    assert abs(loss.item() - g["loss"].item()) > 1e-3 * abs(g["loss"].item())      # the masks really are applied
+    assert rel_l2(out.sequence_output.detach().cpu(), seq) < FEAT_TOL
+    assert abs(out.loss.item() - loss.item()) <= LOSS_TOL * abs(loss.item())
+    assert rel_l2(enc.grad.cpu(), encr.grad) < GRAD_TOL
+    for k, v in m.named_parameters():
+        if v.grad is None or k.endswith("self.key.bias") or k.endswith("decoder.weight"):
+            continue
+        assert rel_l2(v.grad.cpu(), p[k].grad) < GRAD_TOL, k
 
 
 def test_bert_base_width_vs_oracle():
