@@ -104,6 +104,30 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     return MICO_OK;
 }
 
+
+int make_tmap_tile64(CUtensorMap* out, const void* base, bool fp32, uint64_t cols, uint64_t rows, uint64_t pitch_bytes) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+        return MICO_ERR_DRIVER;
+    }
+    const cuuint64_t gdim[2] = {cols, rows};
+    const cuuint64_t gstride[1] = {pitch_bytes};
+    const cuuint32_t bx[2] = {fp32 ? 16u : 32u, 32u};      // 64 bytes x 32 rows
+    const cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(out, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                    const_cast<void*>(base), gdim, gstride, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char msg[200];
+        snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled (epilogue tile) failed (%d): %llu x %llu pitch %llu", (int)r,
+                 (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)pitch_bytes);
+        set_last_error(__FILE__, __LINE__, msg);
+        return MICO_ERR_DRIVER;
+    }
+    return MICO_OK;
+}
+
 }  // namespace mico
 
 extern "C" int mico_version(void) { return 100; }

@@ -49,16 +49,22 @@ struct GemmEpi {
     int vec_ok;   // all pitches / bases allow 16-byte vector access
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI = 0>
 struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+    // per epilogue warp: generic = one [32 x 64 B] transpose tile; specialised = two such tiles, 64B-swizzled, that
+    // TMA stores read (512-byte aligned: they sit right behind the 1024-aligned operand stages)
+    static constexpr int STAGE_TILE = EPI != 0 ? 4096 : 2048;
+    static constexpr int STAGING_BYTES = 8 * STAGE_TILE;
+    static constexpr int BAR_BYTES = 256;            // (2 * STAGES + 4) mbarriers + the TMEM slot: <= 20 x 8 + 8
     static constexpr int BIAS_BYTES = 2 * 256 * 4;   // bias slice of the tile, one copy per accumulator stage
-    static constexpr int STAGING_BYTES = 8 * 2048;   // one [32 x 64 B] transpose tile per epilogue warp
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + STAGING_BYTES + 1024;   // + alignment slack
+    // specialised kernels rely on the 1024-byte alignment of the dynamic shared window (checked at kernel entry):
+    // 4 x 48 KB stages + 32 KB of store tiles leave no room for alignment slack
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + BIAS_BYTES + (EPI != 0 ? 0 : 1024);
 };
+static_assert(GemmCfg<256, 4, 1>::SMEM_BYTES <= 232448, "shared memory budget");
 
 // Global operands of one epilogue chunk, requested BEFORE the TMEM load is waited for so that their latency
 // overlaps it (ncu round 1: the epilogue warps sat in long-scoreboard stalls on exactly these loads).
@@ -458,26 +464,245 @@ __device__ __forceinline__ void epilogue_chunk32_staged(const GemmEpi& e, uint32
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Specialised epilogues.  The generic epilogue above decides everything at run time; inlined into the kernel it is
+// ~20k SASS instructions, spends a third of its issue slots on branches / predicates / address arithmetic and stalls
+// on instruction fetch (ncu round 1, fc1 forward: 38 warp instructions per output element, `no_inst` on every path).
+// The hot launches of the towers fall into five shapes, each compiled as its own kernel (template parameter EPI):
+//   EPI_BF16       out(bf16) = acc [+ bias]                                  qkv forward, every dgrad
+//   EPI_GELU_SAVE  out(bf16) = act(acc + bias), aux_out(bf16) = act'(..)     fc1 forward
+//   EPI_MUL_AUX    out(bf16) = acc * aux_in                                  fc2 dgrad
+//   EPI_RES32      out(f32)  = rs[row] * (acc [+ bias]) + residual           proj / fc2 forward
+//   EPI_F32        out(f32)  = acc                                           every wgrad
+// Preconditions (checked by the dispatcher; anything else runs EPI_GENERIC): 16-byte aligned operands, N % 32 == 0,
+// alpha == 1, no accumulate, no row remap.
+enum { EPI_GENERIC = 0, EPI_BF16 = 1, EPI_GELU_SAVE = 2, EPI_MUL_AUX = 3, EPI_RES32 = 4, EPI_F32 = 5 };
+
+template <int EPI>
+__device__ __forceinline__ void fast_prefetch(const GemmEpi& e, uint4 (&pre)[8], int row0, int col0, int M) {
+    if constexpr (EPI == EPI_RES32) {
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(e.residual);
+        coalesced_load<false>(e, pre, b, e.ldr * 4, (int64_t)col0 * 4, row0, M);
+        coalesced_load<false>(e, pre + 4, b, e.ldr * 4, (int64_t)col0 * 4 + 64, row0, M);
+    } else if constexpr (EPI == EPI_MUL_AUX) {
+        coalesced_load<false>(e, pre, reinterpret_cast<const uint8_t*>(e.aux_in), e.ld_aux_in * 2, (int64_t)col0 * 2, row0, M);
+    }
+}
+
+__device__ __forceinline__ void pack32_bf16(const float (&v)[32], uint4 (&own)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        own[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                            pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+}
+
+// Specialised kernels write through TMA: the warp fills one of its two [32 rows x 64 B] tiles (own row, 64B swizzle ==
+// stage_at) and lane 0 issues one bulk tensor store for the whole tile; rows >= M are clipped by the tensor map.
+// The tiles alternate, so a tile is rewritten only after all but the newest store have finished reading (ncu round 1:
+// the LDS -> STG halves of staged_store held a third of the epilogue's stall samples).
+__device__ __forceinline__ uint32_t tile_acquire(uint32_t st, uint32_t& sidx) {
+    if (lane_id() == 0) tma_store_wait_read<1>();
+    __syncwarp();
+    const uint32_t tile = st + (sidx & 1u) * 2048u;
+    ++sidx;
+    return tile;
+}
+__device__ __forceinline__ void tile_store(const CUtensorMap* tm, uint32_t tile, const uint4 (&own)[4], int c0, int row0) {
+    const int l = (int)lane_id();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) sts128(stage_at(tile, l, g), own[g]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (l == 0) {
+        tma_store_2d(tm, tile, c0, row0);
+        tma_store_commit();
+    }
+}
+
+// one full 32-column chunk; rs = DropPath row scale of this thread's row (EPI_RES32 only)
+template <int EPI>
+__device__ __forceinline__ void fast_chunk32(const GemmEpi& e, const CUtensorMap* tmOut, const CUtensorMap* tmAux, uint32_t st,
+                                             uint32_t& sidx, const uint4 (&pre)[8], const float* sbias,
+                                             const uint32_t (&acc)[32], int row0, int col0, int M, float rs) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+    if constexpr (EPI == EPI_BF16 || EPI == EPI_GELU_SAVE || EPI == EPI_RES32) {
+        if (e.bias) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 b = *reinterpret_cast<const float4*>(sbias + 4 * i);
+                v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+        }
+    }
+    uint4 own[4];
+    if constexpr (EPI == EPI_GELU_SAVE) {
+        if (e.act == MICO_ACT_GELU_SAVE_GRAD) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float gr[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float x = v[8 * i + j];
+                    float cdf, g;
+                    gelu_parts(x, cdf, g);
+                    gr[j] = fmaf(x * 0.3989422804014327f, g, cdf);
+                    v[8 * i + j] = x * cdf;
+                }
+                own[i] = make_uint4(pack_bf16x2(gr[0], gr[1]), pack_bf16x2(gr[2], gr[3]), pack_bf16x2(gr[4], gr[5]),
+                                    pack_bf16x2(gr[6], gr[7]));
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float gr[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float x = v[8 * i + j];
+                    const float sg = rcp_fast(1.0f + ex2_raw(x * (-1.702f * 1.4426950408889634f)));
+                    gr[j] = sg * fmaf(1.702f * x, 1.0f - sg, 1.0f);
+                    v[8 * i + j] = x * sg;
+                }
+                own[i] = make_uint4(pack_bf16x2(gr[0], gr[1]), pack_bf16x2(gr[2], gr[3]), pack_bf16x2(gr[4], gr[5]),
+                                    pack_bf16x2(gr[6], gr[7]));
+            }
+        }
+        tile_store(tmAux, tile_acquire(st, sidx), own, col0, row0);
+    } else if constexpr (EPI == EPI_MUL_AUX) {
+        const uint32_t tile = tile_acquire(st, sidx);      // scratch for the transpose now, output tile below
+        --sidx;
+        staged_to_own(tile, pre, own);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t w[4] = {own[i].x, own[i].y, own[i].z, own[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[8 * i + 2 * j] *= bf16_lo(w[j]);
+                v[8 * i + 2 * j + 1] *= bf16_hi(w[j]);
+            }
+        }
+    } else if constexpr (EPI == EPI_RES32) {
+        if (e.row_scale) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= rs;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t tile = tile_acquire(st, sidx);   // transpose scratch, then this half's output tile
+            staged_to_own(tile, pre + 4 * h, own);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                own[i].x = __float_as_uint(v[16 * h + 4 * i + 0] + __uint_as_float(own[i].x));
+                own[i].y = __float_as_uint(v[16 * h + 4 * i + 1] + __uint_as_float(own[i].y));
+                own[i].z = __float_as_uint(v[16 * h + 4 * i + 2] + __uint_as_float(own[i].z));
+                own[i].w = __float_as_uint(v[16 * h + 4 * i + 3] + __uint_as_float(own[i].w));
+            }
+            tile_store(tmOut, tile, own, col0 + 16 * h, row0);
+        }
+        return;
+    }
+    if constexpr (EPI == EPI_F32) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                own[i] = make_uint4(__float_as_uint(v[16 * h + 4 * i]), __float_as_uint(v[16 * h + 4 * i + 1]),
+                                    __float_as_uint(v[16 * h + 4 * i + 2]), __float_as_uint(v[16 * h + 4 * i + 3]));
+            tile_store(tmOut, tile_acquire(st, sidx), own, col0 + 16 * h, row0);
+        }
+    } else {
+        pack32_bf16(v, own);
+        tile_store(tmOut, tile_acquire(st, sidx), own, col0, row0);
+    }
+}
+
+// the 16-column remainder chunk of a 176-wide tile: per-thread vector accesses (1/11 of the columns)
+template <int EPI>
+__device__ __forceinline__ void fast_chunk16(const GemmEpi& e, const float* sbias, const uint32_t (&acc)[16], int row,
+                                             int col0, int M, float rs) {
+    if (row >= M) return;
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
+    if constexpr (EPI == EPI_BF16 || EPI == EPI_GELU_SAVE || EPI == EPI_RES32) {
+        if (e.bias) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += sbias[i];
+        }
+    }
+    if constexpr (EPI == EPI_GELU_SAVE) {
+        float gr[16];
+        const bool erf_gelu = e.act == MICO_ACT_GELU_SAVE_GRAD;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            gr[i] = erf_gelu ? gelu_erf_grad(v[i]) : quick_gelu_grad(v[i]);
+            v[i] = erf_gelu ? gelu_erf(v[i]) : quick_gelu(v[i]);
+        }
+        uint4* a4 = reinterpret_cast<uint4*>(e.aux_out + (int64_t)row * e.ld_aux_out + col0);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            a4[i] = make_uint4(pack_bf16x2(gr[8 * i], gr[8 * i + 1]), pack_bf16x2(gr[8 * i + 2], gr[8 * i + 3]),
+                               pack_bf16x2(gr[8 * i + 4], gr[8 * i + 5]), pack_bf16x2(gr[8 * i + 6], gr[8 * i + 7]));
+    } else if constexpr (EPI == EPI_MUL_AUX) {
+        const uint4* u4 = reinterpret_cast<const uint4*>(e.aux_in + (int64_t)row * e.ld_aux_in + col0);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const uint4 u = __ldg(u4 + i);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[8 * i + 2 * j] *= bf16_lo(w[j]);
+                v[8 * i + 2 * j + 1] *= bf16_hi(w[j]);
+            }
+        }
+    } else if constexpr (EPI == EPI_RES32) {
+        const float4* r4 = reinterpret_cast<const float4*>(e.residual + (int64_t)row * e.ldr + col0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 r = __ldg(r4 + i);
+            v[4 * i + 0] = fmaf(v[4 * i + 0], rs, r.x); v[4 * i + 1] = fmaf(v[4 * i + 1], rs, r.y);
+            v[4 * i + 2] = fmaf(v[4 * i + 2], rs, r.z); v[4 * i + 3] = fmaf(v[4 * i + 3], rs, r.w);
+        }
+    }
+    if constexpr (EPI == EPI_RES32 || EPI == EPI_F32) {
+        float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (int64_t)row * e.ldo + col0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+        uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) + (int64_t)row * e.ldo + col0);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            o4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                               pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+    }
+}
+
 // CL = 2: two CTAs of a cluster (one SM pair) work on two vertically adjacent M tiles of the same N tile.  Each CTA
 // loads only HALF of the B tile and multicasts it into both CTAs' shared memory (cp.async.bulk.tensor ...
 // .multicast::cluster); smem slots are recycled when BOTH CTAs' MMAs have consumed them (multicast tcgen05.commit).
 // The mainloop of this GEMM is bound by L2 -> SM operand traffic (15 TB/s for 128x256 tiles at 1.3 PFLOP/s, which is
 // why any extra epilogue traffic used to ADD to the run time instead of overlapping); sharing B across the pair removes
 // a third of it.
-template <int BN, bool A_MN, bool B_MN, int STAGES, int CL>
+template <int BN, bool A_MN, bool B_MN, int STAGES, int CL, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)   // 10 warps -> 3 on one SM sub-partition: 168 registers max
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux, int M, int N,
                  int K, GemmEpi epi) {
-    using Cfg = GemmCfg<BN, STAGES>;
-    extern __shared__ uint8_t smem_raw[];
+    using Cfg = GemmCfg<BN, STAGES, EPI>;
+    static_assert((2 * STAGES + 4) * 8 + 8 <= Cfg::BAR_BYTES, "barrier block");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    if constexpr (EPI != EPI_GENERIC) {     // no alignment slack was allocated (see GemmCfg)
+        if (smem != smem_raw) __trap();
+    }
+    uint8_t* staging_all = smem + STAGES * Cfg::STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging_all + Cfg::STAGING_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    float* sbias_all = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
-    uint8_t* staging_all = smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + Cfg::BIAS_BYTES;
+    float* sbias_all = reinterpret_cast<float*>(staging_all + Cfg::STAGING_BYTES + Cfg::BAR_BYTES);
 
     const int warp = threadIdx.x >> 5;
     const int num_m = (M + BM - 1) / BM;
@@ -494,6 +719,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
             tma_prefetch_desc(&tmA);
             tma_prefetch_desc(&tmB);
+            if constexpr (EPI != EPI_GENERIC) tma_prefetch_desc(&tmOut);
+            if constexpr (EPI == EPI_GELU_SAVE) tma_prefetch_desc(&tmAux);
         }
     } else if (warp == 1) {
         if (elect_one()) {
@@ -600,6 +827,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int q = warp & 3;            // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;  // which of the two warps of that quarter: owns chunks c with (c & 1) == half
         int it = 0;
+        uint32_t sidx = 0;                 // TMA store tiles of this warp alternate (specialised epilogues)
         for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -617,10 +845,40 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int row = m0 + q * 32 + (int)lane_id();
             const uint32_t t0 = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
             bool waited = false;
-            const uint32_t st = smem_u32(staging_all + (warp - 2) * 2048);
+            const uint32_t st = smem_u32(staging_all + (warp - 2) * Cfg::STAGE_TILE);
             const int row0 = m0 + q * 32;
             // the staged (coalesced) path needs 16-byte-aligned pitches and no read-modify-write of the output
             const bool staged_ok = epi.vec_ok && !epi.accumulate;
+            if constexpr (EPI != EPI_GENERIC) {
+                float rs = 1.0f;
+                if constexpr (EPI == EPI_RES32) {
+                    if (epi.row_scale) rs = row < M ? __ldg(epi.row_scale + row / epi.rows_per_group) : 0.f;
+                }
+#pragma unroll 1
+                for (int c = half; c < BN / 32; c += 2) {
+                    if (n0 + c * 32 >= N) break;   // warp-uniform; N % 32 == 0: a chunk is full or absent
+                    uint4 pre[8];
+                    fast_prefetch<EPI>(epi, pre, row0, n0 + c * 32, M);
+                    if (!waited) { mbar_wait(&tfull_bar[acc], acc_phase); tc_fence_after(); waited = true; }
+                    uint32_t v[32];
+                    tmem_ld_x32(t0 + c * 32, v);
+                    tmem_ld_wait();
+                    fast_chunk32<EPI>(epi, &tmOut, &tmAux, st, sidx, pre, sbias + c * 32, v, row0, n0 + c * 32, M, rs);
+                }
+                if (!waited) { mbar_wait(&tfull_bar[acc], acc_phase); tc_fence_after(); }
+                if constexpr (BN % 32 != 0) {
+                    constexpr int c0 = (BN / 32) * 32;
+                    if (half == ((BN / 32) & 1) && n0 + c0 < N) {
+                        uint32_t v[16];
+                        tmem_ld_x16(t0 + c0, v);
+                        tmem_ld_wait();
+                        fast_chunk16<EPI>(epi, sbias + c0, v, row, n0 + c0, M, rs);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane_id() == 0) mbar_arrive(&tempty_bar[acc]);
+            } else {
 #pragma unroll 1
             for (int c = half; c < BN / 32; c += 2) {
                 if (n0 + c * 32 >= N) break;   // warp-uniform
@@ -657,6 +915,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane_id() == 0) mbar_arrive(&tempty_bar[acc]);
+            }   // EPI_GENERIC
+        }
+        if constexpr (EPI != EPI_GENERIC) {
+            if (lane_id() == 0) tma_store_wait<0>();     // shared memory stays valid until every store has read it
         }
     }
     tc_fence_before();
@@ -668,9 +930,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
-template <int BN, bool A_MN, bool B_MN, int STAGES, int CL>
+template <int BN, bool A_MN, bool B_MN, int STAGES, int CL, int EPI>
 int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, STAGES>;
+    using Cfg = GemmCfg<BN, STAGES, EPI>;
     CUtensorMap tmA, tmB;
     int rc;
     if (!A_MN) {
@@ -698,7 +960,16 @@ int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) 
     }
     if (rc) return rc;
 
-    auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES, CL>;
+    CUtensorMap tmOut = tmA, tmAux = tmA;     // placeholders unless the specialised epilogue stores through them
+    if constexpr (EPI != EPI_GENERIC) {
+        const bool f32 = epi.out_fp32 != 0;
+        if ((rc = make_tmap_tile64(&tmOut, epi.out, f32, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)epi.ldo * (f32 ? 4 : 2)))) return rc;
+    }
+    if constexpr (EPI == EPI_GELU_SAVE) {
+        if ((rc = make_tmap_tile64(&tmAux, epi.aux_out, false, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)epi.ld_aux_out * 2))) return rc;
+    }
+
+    auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES, CL, EPI>;
     static bool attr_set = false;   // benign race: idempotent
     if (!attr_set) {
         MICO_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -720,12 +991,48 @@ int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int Mi = g.M, Ni = g.N, Ki = g.K;
-    MICO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, Mi, Ni, Ki, epi));
+    MICO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmAux, Mi, Ni, Ki, epi));
     count_launch();
     return MICO_OK;
 }
 
 static bool g_force_single_cta = false;     // MICO_GEMM_SINGLE_CTA=1: A/B switch for measurements
+static bool g_force_generic = false;        // MICO_GEMM_GENERIC_EPI=1: A/B switch for measurements
+
+// which specialised epilogue (if any) computes exactly what `e` asks for
+static int classify_epilogue(const MicoGemmArgs& g, const GemmEpi& e, int bn) {
+    if (g_force_generic || !e.vec_ok || e.accumulate || e.remap_gin > 0 || e.alpha != 1.0f) return EPI_GENERIC;
+    if (g.N % 32 != 0 || bn == 64 || (bn == 176 && g.N % 176 != 0)) return EPI_GENERIC;
+    const bool plain = !e.residual && !e.row_scale;
+    if (e.act == MICO_ACT_NONE && plain && !e.aux_out) {
+        if (!e.out_fp32) return EPI_BF16;
+        return e.bias ? EPI_GENERIC : EPI_F32;
+    }
+    if ((e.act == MICO_ACT_GELU_SAVE_GRAD || e.act == MICO_ACT_QUICK_GELU_SAVE_GRAD) && plain && !e.out_fp32 && e.aux_out)
+        return EPI_GELU_SAVE;
+    if (e.act == MICO_ACT_MUL_AUX && plain && !e.out_fp32 && !e.bias && !e.aux_out) return EPI_MUL_AUX;
+    if (e.act == MICO_ACT_NONE && e.residual && e.out_fp32 && !e.aux_out && !e.residual_bcast) return EPI_RES32;
+    return EPI_GENERIC;
+}
+
+template <int BN, bool A_MN, bool B_MN, int STAGES, int CL>
+int dispatch_epi(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) {
+    const int kind = classify_epilogue(g, epi, BN);
+    // only the (layout, epilogue) pairs a tower actually launches are specialised (compile time)
+    if constexpr (BN != 64) {
+        if constexpr (!A_MN && !B_MN) {          // forward: y = x W^T
+            if (kind == EPI_BF16) return launch_gemm<BN, A_MN, B_MN, STAGES, CL, EPI_BF16>(g, epi, stream);
+            if (kind == EPI_GELU_SAVE) return launch_gemm<BN, A_MN, B_MN, STAGES, CL, EPI_GELU_SAVE>(g, epi, stream);
+            if (kind == EPI_RES32) return launch_gemm<BN, A_MN, B_MN, STAGES, CL, EPI_RES32>(g, epi, stream);
+        } else if constexpr (!A_MN && B_MN) {    // dgrad: dx = dy W
+            if (kind == EPI_BF16) return launch_gemm<BN, A_MN, B_MN, STAGES, CL, EPI_BF16>(g, epi, stream);
+            if (kind == EPI_MUL_AUX) return launch_gemm<BN, A_MN, B_MN, STAGES, CL, EPI_MUL_AUX>(g, epi, stream);
+        } else if constexpr (A_MN && B_MN) {     // wgrad: dW = dy^T x
+            if (kind == EPI_F32) return launch_gemm<BN, A_MN, B_MN, STAGES, CL, EPI_F32>(g, epi, stream);
+        }
+    }
+    return launch_gemm<BN, A_MN, B_MN, STAGES, CL, EPI_GENERIC>(g, epi, stream);
+}
 
 template <bool A_MN, bool B_MN>
 int dispatch_bn(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) {
@@ -740,13 +1047,13 @@ int dispatch_bn(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) 
     // (not for wgrad, A and B both MN-major with a 16k-long K loop: measured 4-15 % slower in lock step)
     const bool pair = ceil_div(g.M, BM) >= 2 && !g_force_single_cta && !(A_MN && B_MN);
     switch (best) {
-        case 256: return pair ? launch_gemm<256, A_MN, B_MN, 4, 2>(g, epi, stream)
-                              : launch_gemm<256, A_MN, B_MN, 4, 1>(g, epi, stream);
-        case 176: if constexpr (!B_MN) return pair ? launch_gemm<176, A_MN, B_MN, 5, 2>(g, epi, stream)
-                                                   : launch_gemm<176, A_MN, B_MN, 5, 1>(g, epi, stream);
-        case 128: return pair ? launch_gemm<128, A_MN, B_MN, 6, 2>(g, epi, stream)
-                              : launch_gemm<128, A_MN, B_MN, 6, 1>(g, epi, stream);
-        default:  return launch_gemm<64, A_MN, B_MN, 8, 1>(g, epi, stream);
+        case 256: return pair ? dispatch_epi<256, A_MN, B_MN, 4, 2>(g, epi, stream)
+                              : dispatch_epi<256, A_MN, B_MN, 4, 1>(g, epi, stream);
+        case 176: if constexpr (!B_MN) return pair ? dispatch_epi<176, A_MN, B_MN, 5, 2>(g, epi, stream)
+                                                   : dispatch_epi<176, A_MN, B_MN, 5, 1>(g, epi, stream);
+        case 128: return pair ? dispatch_epi<128, A_MN, B_MN, 6, 2>(g, epi, stream)
+                              : dispatch_epi<128, A_MN, B_MN, 6, 1>(g, epi, stream);
+        default:  return launch_gemm<64, A_MN, B_MN, 8, 1, EPI_GENERIC>(g, epi, stream);
     }
 }
 
@@ -756,7 +1063,9 @@ int dispatch_bn(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) 
 extern "C" int mico_gemm_bf16(const MicoGemmArgs* args, void* stream_) {
     using namespace mico;
     static const bool single = [] { const char* e = getenv("MICO_GEMM_SINGLE_CTA"); return e && e[0] == '1'; }();
+    static const bool generic = [] { const char* e = getenv("MICO_GEMM_GENERIC_EPI"); return e && e[0] == '1'; }();
     g_force_single_cta = single;
+    g_force_generic = generic;
     MICO_CHECK_ARG(args != nullptr);
     const MicoGemmArgs& g = *args;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

@@ -33,6 +33,10 @@ void set_last_error(const char* file, int line, const char* msg);
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box);
 
+// [rows x cols] bf16 / fp32 matrix seen through 64-byte x 32-row boxes with 64-byte swizzle: the per-warp epilogue
+// tiles of the GEMM (TMA stores).  pitch in bytes (multiple of 16).
+int make_tmap_tile64(CUtensorMap* out, const void* base, bool fp32, uint64_t cols, uint64_t rows, uint64_t pitch_bytes);
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 constexpr int kDefaultSMs = 148;
