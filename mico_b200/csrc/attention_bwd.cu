@@ -83,7 +83,8 @@ struct DqSmem {
 };
 constexpr uint32_t kDqS = 0, kDqDP = 160, kDqDS = 320, kDqAcc = 400;
 
-template <int HD_PAD>
+// kPlain: no additive mask and no dropout (every ViT tower): the per-element mask / dropout code is compiled out
+template <int HD_PAD, bool kPlain>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -162,31 +163,45 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             uint32_t wcount = 0, kvcount = 0, tcount = 0;   // tcount: kv tiles processed (sdp / ds barrier phases)
             const uint32_t sQ = smem_u32(smem + DqSmem::Q), sDO = smem_u32(smem + DqSmem::DO);
             constexpr uint32_t idesc_dq = umma_idesc_bf16(HD_PAD, false, true);
-            for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
-                mbar_wait(q_full, wcount & 1);
+            auto issue_scores = [&](int j, uint32_t kvc, uint32_t tc) {
+                const int s = kvc & 1;
+                mbar_wait(&kv_full[s], (kvc >> 1) & 1);
+                mbar_wait(sdp_empty, (tc & 1) ^ 1);
                 tc_fence_after();
-                auto issue_scores = [&](int j, uint32_t kvc, uint32_t tc) {
-                    const int s = kvc & 1;
-                    mbar_wait(&kv_full[s], (kvc >> 1) & 1);
-                    mbar_wait(sdp_empty, (tc & 1) ^ 1);
-                    tc_fence_after();
-                    const int valid = n_valid(kt, j);
-                    const uint32_t idesc = umma_idesc_bf16(max(16, (valid + 15) & ~15), false, false);
-                    const uint32_t sK = smem_u32(smem + DqSmem::K0 + s * 2 * kAtomBytesN);
-                    const uint32_t sV = smem_u32(smem + DqSmem::V0 + s * 2 * kAtomBytesN);
+                const int valid = n_valid(kt, j);
+                const uint32_t idesc = umma_idesc_bf16(max(16, (valid + 15) & ~15), false, false);
+                const uint32_t sK = smem_u32(smem + DqSmem::K0 + s * 2 * kAtomBytesN);
+                const uint32_t sV = smem_u32(smem + DqSmem::V0 + s * 2 * kAtomBytesN);
 #pragma unroll
-                    for (int k = 0; k < HD_PAD / 16; ++k)
-                        umma_bf16_ss(tmem_S, umma_smem_desc_sw128(sQ + (k >> 2) * kAtomBytes + (k & 3) * 32, 16, 1024),
-                                     umma_smem_desc_sw128(sK + (k >> 2) * kAtomBytesN + (k & 3) * 32, 16, 1024), idesc, k != 0);
+                for (int k = 0; k < HD_PAD / 16; ++k)
+                    umma_bf16_ss(tmem_S, umma_smem_desc_sw128(sQ + (k >> 2) * kAtomBytes + (k & 3) * 32, 16, 1024),
+                                 umma_smem_desc_sw128(sK + (k >> 2) * kAtomBytesN + (k & 3) * 32, 16, 1024), idesc, k != 0);
 #pragma unroll
-                    for (int k = 0; k < HD_PAD / 16; ++k)
-                        umma_bf16_ss(tmem_dP, umma_smem_desc_sw128(sDO + (k >> 2) * kAtomBytes + (k & 3) * 32, 16, 1024),
-                                     umma_smem_desc_sw128(sV + (k >> 2) * kAtomBytesN + (k & 3) * 32, 16, 1024), idesc, k != 0);
-                    umma_commit(sdp_full);
-                };
+                for (int k = 0; k < HD_PAD / 16; ++k)
+                    umma_bf16_ss(tmem_dP, umma_smem_desc_sw128(sDO + (k >> 2) * kAtomBytes + (k & 3) * 32, 16, 1024),
+                                 umma_smem_desc_sw128(sV + (k >> 2) * kAtomBytesN + (k & 3) * 32, 16, 1024), idesc, k != 0);
+                umma_commit(sdp_full);
+                // Q and dO are read by the score MMAs only: once the last pair of the work item is issued, the producer
+                // may refill them for the next item while this item's softmax, dQ MMA and epilogue are still running
+                if (j == nkv - 1) umma_commit(q_empty);
+            };
+            // The (work item, kv tile) steps form one flat stream: the scores of step t+1 -- the next kv tile, or the
+            // first tile of the NEXT work item -- are issued before the dQ MMA of step t is waited for, so the TMA
+            // latency and the score MMAs of a new work item hide behind the tail of the previous one.
+            if ((int)blockIdx.x < num_work) {
+                mbar_wait(q_full, 0);
+                tc_fence_after();
                 issue_scores(0, kvcount, tcount);
+            }
+            for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
                 for (int j = 0; j < nkv; ++j) {
-                    if (j + 1 < nkv) issue_scores(j + 1, kvcount + 1, tcount + 1);
+                    if (j + 1 < nkv) {
+                        issue_scores(j + 1, kvcount + 1, tcount + 1);
+                    } else if (w + (int)gridDim.x < num_work) {
+                        mbar_wait(q_full, (wcount + 1) & 1);
+                        tc_fence_after();
+                        issue_scores(0, kvcount + 1, tcount + 1);
+                    }
                     const int s = kvcount & 1;
                     mbar_wait(ds_full, tcount & 1);
                     tc_fence_after();
@@ -201,7 +216,6 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     ++kvcount; ++tcount;
                 }
                 umma_commit(dq_full);
-                umma_commit(q_empty);
             }
         }
     } else {
@@ -211,19 +225,34 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
         const float sc2 = p.scale * kLog2e;
         uint32_t tcount = 0, wcount = 0;
+        // row statistics of a work item (rows past Sq get lse = +huge -> p = 0 -> dS = 0 with no per-element predicate);
+        // the next item's are requested during the last kv tile of the current one
+        auto load_stats = [&](int w, float& l, float& d) {
+            const int qt = w % nqt, bh = w / nqt;
+            const int qi = qt * kTile + r;
+            if (qi < p.Sq) {
+                const int64_t stat = (int64_t)bh * p.Sq + qi;
+                l = __ldg(p.lse + stat);
+                d = __ldg(p.delta + stat);
+            } else {
+                l = 1e30f;
+                d = 0.f;
+            }
+        };
+        float lse_n = 0.f, dlt_n = 0.f;
+        if ((int)blockIdx.x < num_work) load_stats(blockIdx.x, lse_n, dlt_n);
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
             const int qt = w % nqt, bh = w / nqt;
             const int h = bh % p.H, b = bh / p.H;
             const int qi = qt * kTile + r;
             const bool row_ok = qi < p.Sq;
-            const int64_t stat = ((int64_t)b * p.H + h) * p.Sq + (row_ok ? qi : 0);
-            // rows past Sq get lse = +huge -> p = 0 -> dS = 0 with no per-element predicate
-            const float nlse2 = row_ok ? -p.lse[stat] * kLog2e : -1e30f;
-            const float ndlt = row_ok ? -p.delta[stat] * p.scale : 0.f;     // dS = p * (dP*scale - delta*scale)
-            const float* mrow = p.mask ? (p.mask + (int64_t)(p.mask_bmod ? b % p.mask_bmod : b) * p.mask_bs + (int64_t)h * p.mask_hs) + (int64_t)(row_ok ? qi : 0) * p.mask_qs : nullptr;
+            const float nlse2 = -lse_n * kLog2e;
+            const float ndlt = -dlt_n * p.scale;     // dS = p * (dP*scale - delta*scale)
+            const float* mrow = (!kPlain && p.mask) ? (p.mask + (int64_t)(p.mask_bmod ? b % p.mask_bmod : b) * p.mask_bs + (int64_t)h * p.mask_hs) + (int64_t)(row_ok ? qi : 0) * p.mask_qs : nullptr;
             for (int j = 0; j < nkv; ++j, ++tcount) {
                 const int valid = n_valid(kt, j);
                 const int nch = (valid + 31) >> 5;
+                if (j == nkv - 1 && w + (int)gridDim.x < num_work) load_stats(w + gridDim.x, lse_n, dlt_n);
                 mbar_wait(sdp_full, tcount & 1);
                 tc_fence_after();
                 mbar_wait(ds_empty, (tcount & 1) ^ 1);   // previous dQ MMA no longer reads the dS operand
@@ -235,7 +264,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     tmem_ld_wait();
                     float ds[32];
                     const int lim = valid - c * 32;
-                    const bool dropping = p.drop.p > 0.f;
+                    const bool dropping = !kPlain && p.drop.p > 0.f;
                     if (!mrow && lim >= 32 && !dropping) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
@@ -300,7 +329,7 @@ constexpr uint32_t kKvST = 0, kKvDPT = 144, kKvDV = 288, kKvDK = 384;
 
 __device__ __forceinline__ int split_a(int n16) { return ((n16 / 16 + 1) / 2) * 16; }   // columns owned by half 0
 
-template <int HD_PAD>
+template <int HD_PAD, bool kPlain>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -400,6 +429,9 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         umma_bf16_ss(tmem_dPT, umma_smem_desc_sw128(sV + (k >> 2) * kAtomBytes + (k & 3) * 32, 16, 1024),
                                      umma_smem_desc_sw128(sDO + (k >> 2) * kAtomBytesN + (k & 3) * 32, 16, 1024), idesc, k != 0);
                     umma_commit(st_full);
+                    // K and V are read by the score MMAs only: after the last pair the producer may already fetch the
+                    // next work item's K / V while this item's softmax, gradient MMAs and epilogue run
+                    if (i == nqt - 1) umma_commit(kv_empty);
                     mbar_wait(pds_full, qcount & 1);
                     tc_fence_after();
                     const int ksteps = n16 >> 4;
@@ -419,7 +451,6 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     umma_commit(&qdo_empty[s]);
                 }
                 umma_commit(acc_full);
-                umma_commit(kv_empty);
             }
         }
     } else {
@@ -428,31 +459,48 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
         const float sc2 = p.scale * kLog2e;
         uint32_t qcount = 0, wcount = 0;
+        bool first_tile = true;
+        // -lse*log2(e) and -delta*scale of query t (= threadIdx.x < 160) of q tile i of work item w; queries past the
+        // tile's valid count get lse = +huge -> p = 0, dS = 0 with no per-element predicate
+        auto load_stats = [&](int w_, int i_, float& l, float& d) {
+            l = -1e30f;
+            d = 0.f;
+            const int t = threadIdx.x;
+            if (t < 160 && t < n_valid(qtl, i_)) {
+                const int64_t at = (int64_t)(w_ / nkt) * p.Sq + i_ * kTile + t;
+                l = -__ldg(p.lse + at) * kLog2e;
+                d = -__ldg(p.delta + at) * p.scale;
+            }
+        };
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
             const int jt = w % nkt, bh = w / nkt;
             const int h = bh % p.H, b = bh / p.H;
             const int kj = jt * kTile + r;
             const bool key_ok = kj < p.Sk;
-            const int64_t stat0 = ((int64_t)b * p.H + h) * p.Sq;
             for (int i = 0; i < nqt; ++i, ++qcount) {
                 const int validq = n_valid(qtl, i);
                 const int n16 = max(16, (validq + 15) & ~15);
                 const int hA = split_a(n16);
-                // stage this q tile's lse / delta in the stats buffer of parity qcount & 1: its previous readers
-                // (tile qcount - 2) all passed the 256-thread barrier of tile qcount - 1 after their last read
+                // The lse / delta of a q tile are staged in the stats buffer of parity qcount & 1 ONE TILE AHEAD: the
+                // global loads of tile qcount + 1 (possibly the first tile of the next work item) are issued here and
+                // stored after this tile's math.  The previous readers of that buffer (tile qcount - 1) all passed this
+                // tile's 256-thread barrier before the store.
                 float* s_nlse2 = reinterpret_cast<float*>(smem + DkvSmem::STATS + (qcount & 1) * 2048);
                 float* s_ndlt = s_nlse2 + 256;
-                if (threadIdx.x < 160) {
-                    // queries past the tile's valid count get lse = +huge -> p = 0, dS = 0 with no per-element predicate
-                    const int t = threadIdx.x;
-                    s_nlse2[t] = (t < validq) ? -p.lse[stat0 + i * kTile + t] * kLog2e : -1e30f;
-                    s_ndlt[t] = (t < validq) ? -p.delta[stat0 + i * kTile + t] * p.scale : 0.f;
+                if (first_tile) {      // very first tile of this CTA: nothing was prefetched
+                    float l, d;
+                    load_stats(w, i, l, d);
+                    if (threadIdx.x < 160) { s_nlse2[threadIdx.x] = l; s_ndlt[threadIdx.x] = d; }
+                    first_tile = false;
                 }
+                float l_n = 0.f, d_n = 0.f;
+                const bool more = (i + 1 < nqt) || (w + (int)gridDim.x < num_work);
+                if (more) load_stats(i + 1 < nqt ? w : w + (int)gridDim.x, i + 1 < nqt ? i + 1 : 0, l_n, d_n);
                 softmax_group_sync256();
                 mbar_wait(st_full, qcount & 1);
                 tc_fence_after();
                 const int c_begin = half == 0 ? 0 : hA, c_end = half == 0 ? hA : n16;
-                const bool masked = p.mask != nullptr;
+                const bool masked = !kPlain && p.mask != nullptr;
                 for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                     uint32_t sv[32], dv[32];
                     float pt[32], dst[32];
@@ -481,7 +529,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                                 s = fmaf((p.mask + (int64_t)(p.mask_bmod ? b % p.mask_bmod : b) * p.mask_bs + (int64_t)h * p.mask_hs)[(int64_t)(i * kTile + c0 + q) * p.mask_qs + kj], kLog2e, s);
                             const float pu = ex2_fast(s);
                             float m = 1.0f;
-                            if (p.drop.p > 0.f)
+                            if (!kPlain && p.drop.p > 0.f)
                                 m = drop_mult(p.drop, ((uint64_t)(b * p.H + h) * p.Sq + (uint64_t)min(i * kTile + c0 + q, p.Sq - 1)) * p.Sk +
                                                           (uint64_t)min(kj, p.Sk - 1));
                             pt[q] = pu * m;                                          // dV uses the dropped probabilities
@@ -508,6 +556,11 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 tc_fence_before();
                 __syncwarp();
                 if (lane_id() == 0) mbar_arrive(pds_full);
+                if (more && threadIdx.x < 160) {
+                    float* n_nlse2 = reinterpret_cast<float*>(smem + DkvSmem::STATS + ((qcount + 1) & 1) * 2048);
+                    n_nlse2[threadIdx.x] = l_n;
+                    n_nlse2[256 + threadIdx.x] = d_n;
+                }
             }
             mbar_wait(acc_full, wcount & 1);
             tc_fence_after();
@@ -593,10 +646,14 @@ extern "C" int mico_attention_bwd(const MicoAttnArgs* a, void* stream_) {
         if (m_tail_rows(a->Sq) || m_tail_rows(a->Sk)) return attention_tail_bwd(a, stream);
         return MICO_OK;
     };
+    const bool plain = a->mask == nullptr && a->dropout_p == 0.0f;
     switch (hd_pad) {
-        case 32: return launch(attn_dq_kernel<32>, attn_dkv_kernel<32>);
-        case 64: return launch(attn_dq_kernel<64>, attn_dkv_kernel<64>);
-        case 96: return launch(attn_dq_kernel<96>, attn_dkv_kernel<96>);
+        case 32: return plain ? launch(attn_dq_kernel<32, true>, attn_dkv_kernel<32, true>)
+                              : launch(attn_dq_kernel<32, false>, attn_dkv_kernel<32, false>);
+        case 64: return plain ? launch(attn_dq_kernel<64, true>, attn_dkv_kernel<64, true>)
+                              : launch(attn_dq_kernel<64, false>, attn_dkv_kernel<64, false>);
+        case 96: return plain ? launch(attn_dq_kernel<96, true>, attn_dkv_kernel<96, true>)
+                              : launch(attn_dq_kernel<96, false>, attn_dkv_kernel<96, false>);
         default:
             // head_dim 128 would need 2 x 144 + 2 x 128 TMEM columns in attn_dkv_kernel; no tower on the MiCo path
             // has it (ViT-g 88, BERT / CLIP 64, Swin 32)

@@ -41,7 +41,8 @@ struct AttnSmem {
 };
 constexpr int kSStride = 160;   // TMEM columns between the two S buffers (a 144-wide tile is read in 5 x 32 columns)
 
-template <int HD_PAD>
+// kPlain: no additive mask and no dropout (every ViT tower): that code is compiled out
+template <int HD_PAD, bool kPlain>
 __global__ void __launch_bounds__(kAttThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKx,
@@ -128,30 +129,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const uint32_t sQ = smem_u32(smem + AttnSmem::Q);
             const uint32_t sP = smem_u32(smem + AttnSmem::P);
             constexpr uint32_t idesc_pv = umma_idesc_bf16(HD_PAD, false, true);
-            for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
-                mbar_wait(q_full, wcount & 1);
+            auto issue_s = [&](int j, uint32_t kvc, uint32_t sc) {
+                const int s = kvc & 1, sb = sc & 1;
+                mbar_wait(&kv_full[s], (kvc >> 1) & 1);
+                mbar_wait(&s_empty[sb], ((sc >> 1) & 1) ^ 1);
                 tc_fence_after();
-                auto issue_s = [&](int j, uint32_t kvc, uint32_t sc) {
-                    const int s = kvc & 1, sb = sc & 1;
-                    mbar_wait(&kv_full[s], (kvc >> 1) & 1);
-                    mbar_wait(&s_empty[sb], ((sc >> 1) & 1) ^ 1);
-                    tc_fence_after();
-                    const int valid = n_valid(kt, j);
-                    const int n = max(16, (valid + 15) & ~15);
-                    const uint32_t idesc = umma_idesc_bf16(n, false, false);
-                    const uint32_t sK = smem_u32(smem + AttnSmem::K0 + s * 2 * kAtomBytesN);
+                const int valid = n_valid(kt, j);
+                const int n = max(16, (valid + 15) & ~15);
+                const uint32_t idesc = umma_idesc_bf16(n, false, false);
+                const uint32_t sK = smem_u32(smem + AttnSmem::K0 + s * 2 * kAtomBytesN);
 #pragma unroll
-                    for (int k = 0; k < HD_PAD / 16; ++k) {
-                        umma_bf16_ss(tmem_S + sb * kSStride,
-                                     umma_smem_desc_sw128(sQ + (k >> 2) * kAtomBytes + (k & 3) * 32, 16, 1024),
-                                     umma_smem_desc_sw128(sK + (k >> 2) * kAtomBytesN + (k & 3) * 32, 16, 1024), idesc,
-                                     k != 0);
-                    }
-                    umma_commit(&s_full[sb]);
-                };
+                for (int k = 0; k < HD_PAD / 16; ++k) {
+                    umma_bf16_ss(tmem_S + sb * kSStride,
+                                 umma_smem_desc_sw128(sQ + (k >> 2) * kAtomBytes + (k & 3) * 32, 16, 1024),
+                                 umma_smem_desc_sw128(sK + (k >> 2) * kAtomBytesN + (k & 3) * 32, 16, 1024), idesc,
+                                 k != 0);
+                }
+                umma_commit(&s_full[sb]);
+                // Q is read by the S MMAs only: after the last one of the work item the producer may refill it
+                if (j == nkv - 1) umma_commit(q_empty);
+            };
+            // (work item, kv tile) steps form one flat stream: S of step t+1 -- possibly the first tile of the NEXT work
+            // item -- is issued before the P V of step t, so a new item's TMA and S latency hide behind the previous tail
+            if ((int)blockIdx.x < num_work) {
+                mbar_wait(q_full, 0);
+                tc_fence_after();
                 issue_s(0, kvcount, scount);
+            }
+            for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
                 for (int j = 0; j < nkv; ++j) {
-                    if (j + 1 < nkv) issue_s(j + 1, kvcount + 1, scount + 1);
+                    if (j + 1 < nkv) {
+                        issue_s(j + 1, kvcount + 1, scount + 1);
+                    } else if (w + (int)gridDim.x < num_work) {
+                        mbar_wait(q_full, (wcount + 1) & 1);
+                        tc_fence_after();
+                        issue_s(0, kvcount + 1, scount + 1);
+                    }
                     const int s = kvcount & 1;
                     mbar_wait(p_full, pcount & 1);
                     tc_fence_after();
@@ -167,7 +180,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     umma_commit(o_full);
                     ++kvcount; ++scount; ++pcount;
                 }
-                umma_commit(q_empty);
             }
         }
     } else {
@@ -182,7 +194,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const int h = bh % p.H, b = bh / p.H;
             const int qi = qt * kTile + r;
             const bool row_ok = qi < p.Sq;
-            const float* mrow = p.mask ? (p.mask + (int64_t)(p.mask_bmod ? b % p.mask_bmod : b) * p.mask_bs + (int64_t)h * p.mask_hs) + (int64_t)(row_ok ? qi : 0) * p.mask_qs : nullptr;
+            const float* mrow = (!kPlain && p.mask) ? (p.mask + (int64_t)(p.mask_bmod ? b % p.mask_bmod : b) * p.mask_bs + (int64_t)h * p.mask_hs) + (int64_t)(row_ok ? qi : 0) * p.mask_qs : nullptr;
             float m = -INFINITY, l = 0.f;
             float oacc[HD_PAD];
 #pragma unroll
@@ -251,7 +263,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     tmem_ld_wait();
                     float pv[32];
                     const int lim = valid - c * 32;
-                    const bool dropping = p.drop.p > 0.f;
+                    const bool dropping = !kPlain && p.drop.p > 0.f;
                     if (!mrow && lim >= 32 && !dropping) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
@@ -387,11 +399,12 @@ extern "C" int mico_attention_fwd(const MicoAttnArgs* a, void* stream_) {
         if (m_tail_rows(a->Sq)) return attention_tail_fwd(a, stream);
         return MICO_OK;
     };
+    const bool plain = a->mask == nullptr && a->dropout_p == 0.0f;
     switch (hd_pad) {
-        case 32: return launch(attn_fwd_kernel<32>);
-        case 64: return launch(attn_fwd_kernel<64>);
-        case 96: return launch(attn_fwd_kernel<96>);
-        case 128: return launch(attn_fwd_kernel<128>);
+        case 32: return plain ? launch(attn_fwd_kernel<32, true>) : launch(attn_fwd_kernel<32, false>);
+        case 64: return plain ? launch(attn_fwd_kernel<64, true>) : launch(attn_fwd_kernel<64, false>);
+        case 96: return plain ? launch(attn_fwd_kernel<96, true>) : launch(attn_fwd_kernel<96, false>);
+        case 128: return plain ? launch(attn_fwd_kernel<128, true>) : launch(attn_fwd_kernel<128, false>);
         default:
             set_last_error(__FILE__, __LINE__, "head_dim must pad to 32, 64, 96 or 128");
             return MICO_ERR_UNSUPPORTED;
