@@ -142,6 +142,8 @@ int mico_attention_dmask(const MicoAttnArgs* args, float* dmask, void* stream);
  *     Backward: dx = [dres +] LN'(dy [+ dy2]); dy2 = optional second (bf16) upstream gradient, for a LayerNorm
  *     output that feeds both the next GEMM and the next residual add (post-LN BERT, bert.py:286-297); optional bf16 copy of dx scaled per row group (DropPath);
  *     dgamma/dbeta reduced deterministically through `workspace` (mico_layernorm_bwd_workspace bytes).
+ *     dxb_colsum (optional, fp32 [D], 512 <= D <= 1536): column sums of the scaled output = the bias gradient of the
+ *     upstream nn.Linear (eva_vit_model.py:197,363 backward), fused here instead of a separate pass over dx_bf16.
  * ------------------------------------------------------------------------------------------- */
 int mico_layernorm_fwd(const void* x, int x_is_bf16, int64_t ldx, const float* gamma, const float* beta,
                        void* y_bf16, float* y_f32, int64_t ldy, float* mean, float* rstd, int M, int D,
@@ -152,7 +154,8 @@ int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, const void*
                        const float* mean, const float* rstd, const float* gamma, const float* dres,
                        int64_t lddres, float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb,
                        const float* row_scale, int rows_per_group, float* dgamma, float* dbeta,
-                       int accumulate_param_grads, int M, int D, void* workspace, size_t ws_bytes, void* stream);
+                       int accumulate_param_grads, float* dxb_colsum, int M, int D, void* workspace, size_t ws_bytes,
+                       void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * HBM-bound helpers on the path (all vectorised 128-bit, grid sized in multiples of the SM count).

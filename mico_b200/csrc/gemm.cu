@@ -49,10 +49,13 @@ struct GemmEpi {
     int vec_ok;   // all pitches / bases allow 16-byte vector access
 };
 
-template <int BN, int STAGES, int EPI = 0>
+template <int BN, int STAGES, int EPI = 0, bool B_MN = false>
 struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    // an MN-major B tile is loaded as [64 k x 64 n] boxes: a 176-wide tile takes three (the last box reaches 16 columns
+    // into the neighbouring tile, or is zero-filled at the edge; the N = 176 MMA never reads them)
+    static constexpr int B_CHUNKS = (BN + 63) / 64;
+    static constexpr int B_BYTES = B_MN ? B_CHUNKS * 8192 : BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     // per epilogue warp: generic = one [32 x 64 B] transpose tile; specialised = two such tiles, 64B-swizzled, that
     // TMA stores read (512-byte aligned: they sit right behind the 1024-aligned operand stages)
@@ -64,7 +67,8 @@ struct GemmCfg {
     // 4 x 48 KB stages + 32 KB of store tiles leave no room for alignment slack
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + BIAS_BYTES + (EPI != 0 ? 0 : 1024);
 };
-static_assert(GemmCfg<256, 4, 1>::SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(GemmCfg<256, 4, 1>::SMEM_BYTES <= 232448 && GemmCfg<176, 5, 1>::SMEM_BYTES <= 232448 &&
+              GemmCfg<176, 4, 1, true>::SMEM_BYTES <= 232448, "shared memory budget");
 
 // Global operands of one epilogue chunk, requested BEFORE the TMEM load is waited for so that their latency
 // overlaps it (ncu round 1: the epilogue warps sat in long-scoreboard stalls on exactly these loads).
@@ -689,7 +693,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)   // 10 warps -> 3 on one SM 
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux, int M, int N,
                  int K, GemmEpi epi) {
-    using Cfg = GemmCfg<BN, STAGES, EPI>;
+    using Cfg = GemmCfg<BN, STAGES, EPI, B_MN>;
     static_assert((2 * STAGES + 4) * 8 + 8 <= Cfg::BAR_BYTES, "barrier block");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -768,7 +772,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < BN / 64; ++j)
+                            for (int j = 0; j < Cfg::B_CHUNKS; ++j)
                                 tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n0 + 64 * j, kb * BK);
                         }
                     } else {     // this CTA's half of B, multicast to both CTAs of the pair
@@ -777,11 +781,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             tma_load_2d_mc(sb + cta_rank * (HALF * 128), &tmB, &full_bar[stage], kb * BK,
                                            n0 + (int)cta_rank * HALF, kMask);
                         } else {
-                            constexpr int HB = BN / 64 / CL;
 #pragma unroll
-                            for (int jj = 0; jj < HB; ++jj) {
-                                const int j = (int)cta_rank * HB + jj;
-                                tma_load_2d_mc(sb + j * 8192, &tmB, &full_bar[stage], n0 + 64 * j, kb * BK, kMask);
+                            for (int j = 0; j < Cfg::B_CHUNKS; ++j) {     // chunks are dealt out to the CTAs of the pair
+                                if ((j * CL) / Cfg::B_CHUNKS == (int)cta_rank)
+                                    tma_load_2d_mc(sb + j * 8192, &tmB, &full_bar[stage], n0 + 64 * j, kb * BK, kMask);
                             }
                         }
                     }
@@ -792,13 +795,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp == 1) {
         // ------------------------------------------------------------- MMA issuer
         if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BN, A_MN, B_MN);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
             for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
+                // the last N tile issues a narrower MMA: no tensor-pipe time is spent on the columns past N (the smem rows
+                // behind them are zero-filled by TMA), which lets N = 1408 run on 256-wide tiles as 5 full tiles + 1 half
+                const int n_left = N - (tile % num_n) * BN;
+                const uint32_t idesc = umma_idesc_bf16(n_left >= BN ? BN : ((n_left + 15) & ~15), A_MN, B_MN);
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kAccStride;
@@ -932,7 +938,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <int BN, bool A_MN, bool B_MN, int STAGES, int CL, int EPI>
 int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, STAGES, EPI>;
+    using Cfg = GemmCfg<BN, STAGES, EPI, B_MN>;
     CUtensorMap tmA, tmB;
     int rc;
     if (!A_MN) {
@@ -1036,21 +1042,31 @@ int dispatch_epi(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream)
 
 template <bool A_MN, bool B_MN>
 int dispatch_bn(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) {
-    // pick the N tile that wastes the least padded work; ties -> wider tile
-    auto padded = [&](int bn) { return (int64_t)ceil_div(g.N, bn) * bn; };
+    // Pick the N tile by estimated time: whole waves of (fractional: the last N tile issues a narrower MMA) tile units
+    // over the SMs, times the tile width over its measured tensor-pipe efficiency (round 1, ViT-g shapes: 256-wide tiles
+    // run at ~1.39 PFLOP/s, 176-wide at ~1.29, 128-wide at ~1.15 -- operand reads per MMA flop grow as the tile narrows).
+    const int m_tiles = ceil_div(g.M, BM);
+    const double n16 = (double)((g.N + 15) & ~15);
+    auto est = [&](int bn, double eff) {
+        const double units = (double)m_tiles * (n16 / bn);
+        const double waves = (double)(int64_t)((units + num_sms() - 1e-9) / num_sms());
+        return (waves < 1.0 ? 1.0 : waves) * bn / eff;
+    };
     int best = 256;
-    int64_t best_pad = padded(256);
-    if (!B_MN && padded(176) < best_pad) { best = 176; best_pad = padded(176); }
-    if (padded(128) < best_pad) { best = 128; best_pad = padded(128); }
-    if (g.N <= 64 && padded(64) < best_pad) { best = 64; }
+    double best_t = est(256, 1.0);
+    // 176-wide tiles only with a K-major B: with an MN-major B the tile needs three 64-column boxes and drops to four
+    // stages -- measured slower than 128-wide tiles (fc1 dgrad 253 vs 238 us)
+    if (!B_MN && g.N % 176 == 0 && est(176, 0.93) < best_t) { best = 176; best_t = est(176, 0.93); }
+    if (est(128, 0.85) < best_t) { best = 128; best_t = est(128, 0.85); }
+    if (g.N <= 64) best = 64;
     // CTA pairs (B multicast) whenever there are at least two M tiles to pair up
     // (not for wgrad, A and B both MN-major with a 16k-long K loop: measured 4-15 % slower in lock step)
     const bool pair = ceil_div(g.M, BM) >= 2 && !g_force_single_cta && !(A_MN && B_MN);
     switch (best) {
         case 256: return pair ? dispatch_epi<256, A_MN, B_MN, 4, 2>(g, epi, stream)
                               : dispatch_epi<256, A_MN, B_MN, 4, 1>(g, epi, stream);
-        case 176: if constexpr (!B_MN) return pair ? dispatch_epi<176, A_MN, B_MN, 5, 2>(g, epi, stream)
-                                                   : dispatch_epi<176, A_MN, B_MN, 5, 1>(g, epi, stream);
+        case 176: if constexpr (!(A_MN && B_MN)) return pair ? dispatch_epi<176, A_MN, B_MN, B_MN ? 4 : 5, 2>(g, epi, stream)
+                                                             : dispatch_epi<176, A_MN, B_MN, B_MN ? 4 : 5, 1>(g, epi, stream);
         case 128: return pair ? dispatch_epi<128, A_MN, B_MN, 6, 2>(g, epi, stream)
                               : dispatch_epi<128, A_MN, B_MN, 6, 1>(g, epi, stream);
         default:  return launch_gemm<64, A_MN, B_MN, 8, 1, EPI_GENERIC>(g, epi, stream);

@@ -183,22 +183,127 @@ ln_bwd_kernel(const TDy* __restrict__ dy, int64_t lddy, const __nv_bfloat16* __r
     }
 }
 
-// partials[nblocks][2*D] -> dgamma, dbeta.  Block = 32 columns x 32 row-slices; coalesced 128-byte reads.
+
+// ---------------------------------------------------------------------------------------------------------------
+// Block-per-row backward (128 <= D/4 <= 384 vectors, i.e. every tower on the path): the 128 threads of a block share a
+// row, so a thread holds 3 float4 of each operand instead of 12 -- ~100 registers, five resident blocks per SM, and
+// ALL loads of a row (dy, x, residual gradient) are issued together: one exposed memory latency per row instead of
+// two, 70 KB in flight per SM (ncu round 1: the warp-per-row kernel reached 3.7-5.1 of 6.5 TB/s).  Each thread owns the
+// same columns of every row, so dgamma, dbeta and the column sum of the scaled bf16 output (the bias gradient of the
+// upstream linear layer: nn.Linear bias backward fused here instead of re-reading the tensor) stay in registers and go
+// straight to the per-block partials -- no cross-warp reduction.
+constexpr int kV2 = 3;
+template <typename TDy, bool kColsum>
+__global__ void __launch_bounds__(kLnThreads, 4)
+ln_bwd_row_kernel(const TDy* __restrict__ dy, int64_t lddy, const __nv_bfloat16* __restrict__ dy2, int64_t lddy2,
+                  const float* __restrict__ x, int64_t ldx, const float* __restrict__ mean,
+                  const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
+                  int64_t lddres, float* __restrict__ dx, int64_t lddx, __nv_bfloat16* __restrict__ dx_bf16,
+                  int64_t lddxb, const float* __restrict__ row_scale, int rows_per_group, float* __restrict__ partials,
+                  int M, int D) {
+    __shared__ float red[2][kLnWarps][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nvec = D >> 2;
+    float4 ag[kV2], ab[kV2], ac[kV2], gm[kV2];
+#pragma unroll
+    for (int j = 0; j < kV2; ++j) {
+        ag[j] = make_float4(0, 0, 0, 0); ab[j] = make_float4(0, 0, 0, 0); ac[j] = make_float4(0, 0, 0, 0);
+        const int i = threadIdx.x + kLnThreads * j;
+        gm[j] = i < nvec ? ld4(gamma + 4 * i) : make_float4(0, 0, 0, 0);
+    }
+    const float inv_d = 1.0f / (float)D;
+    int it = 0;
+    for (int row = blockIdx.x; row < M; row += gridDim.x, ++it) {
+        const TDy* dyr = dy + (int64_t)row * lddy;
+        const float* xr = x + (int64_t)row * ldx;
+        float4 d[kV2], xh[kV2], r[kV2];
+#pragma unroll
+        for (int j = 0; j < kV2; ++j) {     // every load of the row first
+            const int i = threadIdx.x + kLnThreads * j;
+            const bool ok = i < nvec;
+            d[j] = ok ? ld4(dyr + 4 * i) : make_float4(0, 0, 0, 0);
+            xh[j] = ok ? ld4(xr + 4 * i) : make_float4(0, 0, 0, 0);
+            r[j] = (ok && dres) ? ld4(dres + (int64_t)row * lddres + 4 * i) : make_float4(0, 0, 0, 0);
+        }
+        if (dy2) {
+            const __nv_bfloat16* d2r = dy2 + (int64_t)row * lddy2;
+#pragma unroll
+            for (int j = 0; j < kV2; ++j) {
+                const int i = threadIdx.x + kLnThreads * j;
+                if (i < nvec) {
+                    const float4 e = ld4(d2r + 4 * i);
+                    d[j].x += e.x; d[j].y += e.y; d[j].z += e.z; d[j].w += e.w;
+                }
+            }
+        }
+        const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+        const float sc = row_scale ? __ldg(row_scale + row / rows_per_group) : 1.0f;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kV2; ++j) {
+            const int i = threadIdx.x + kLnThreads * j;
+            if (i < nvec) {
+                xh[j] = make_float4((xh[j].x - mu) * rs, (xh[j].y - mu) * rs, (xh[j].z - mu) * rs, (xh[j].w - mu) * rs);
+                ag[j].x += d[j].x * xh[j].x; ag[j].y += d[j].y * xh[j].y; ag[j].z += d[j].z * xh[j].z; ag[j].w += d[j].w * xh[j].w;
+                ab[j].x += d[j].x; ab[j].y += d[j].y; ab[j].z += d[j].z; ab[j].w += d[j].w;
+                d[j] = make_float4(d[j].x * gm[j].x, d[j].y * gm[j].y, d[j].z * gm[j].z, d[j].w * gm[j].w);
+                s1 += (d[j].x + d[j].y) + (d[j].z + d[j].w);
+                s2 += (d[j].x * xh[j].x + d[j].y * xh[j].y) + (d[j].z * xh[j].z + d[j].w * xh[j].w);
+            }
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        float (*rb)[2] = red[it & 1];      // double-buffered: one __syncthreads per row
+        if (lane == 0) { rb[warp][0] = s1; rb[warp][1] = s2; }
+        __syncthreads();
+        const float m1 = ((rb[0][0] + rb[1][0]) + (rb[2][0] + rb[3][0])) * inv_d;
+        const float m2 = ((rb[0][1] + rb[1][1]) + (rb[2][1] + rb[3][1])) * inv_d;
+#pragma unroll
+        for (int j = 0; j < kV2; ++j) {
+            const int i = threadIdx.x + kLnThreads * j;
+            if (i < nvec) {
+                float4 o;
+                o.x = rs * (d[j].x - m1 - xh[j].x * m2) + r[j].x;
+                o.y = rs * (d[j].y - m1 - xh[j].y * m2) + r[j].y;
+                o.z = rs * (d[j].z - m1 - xh[j].z * m2) + r[j].z;
+                o.w = rs * (d[j].w - m1 - xh[j].w * m2) + r[j].w;
+                if (dx) st4(dx + (int64_t)row * lddx + 4 * i, o);
+                const float4 os = make_float4(o.x * sc, o.y * sc, o.z * sc, o.w * sc);
+                if (dx_bf16) st4(dx_bf16 + (int64_t)row * lddxb + 4 * i, os);
+                if constexpr (kColsum) { ac[j].x += os.x; ac[j].y += os.y; ac[j].z += os.z; ac[j].w += os.w; }
+            }
+        }
+    }
+    float* out = partials + (size_t)blockIdx.x * (kColsum ? 3 : 2) * D;
+#pragma unroll
+    for (int j = 0; j < kV2; ++j) {
+        const int i = threadIdx.x + kLnThreads * j;
+        if (i < nvec) {
+            st4(out + 4 * i, ag[j]);
+            st4(out + D + 4 * i, ab[j]);
+            if constexpr (kColsum) st4(out + 2 * D + 4 * i, ac[j]);
+        }
+    }
+}
+
+// partials[nblocks][nsets*D] -> dgamma, dbeta [, colsum].  Block = 32 columns x 32 row-slices; coalesced 128-byte reads.
 __global__ void __launch_bounds__(1024)
-ln_bwd_finalize_kernel(const float* __restrict__ partials, int nblocks, int D, float* __restrict__ dgamma,
-                       float* __restrict__ dbeta, int accumulate) {
+ln_bwd_finalize_kernel(const float* __restrict__ partials, int nblocks, int D, int nsets, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta, float* __restrict__ colsum, int accumulate) {
     __shared__ float red[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int i = blockIdx.x * 32 + tx;   // over 2*D
+    const int i = blockIdx.x * 32 + tx;   // over nsets*D
+    const int n = nsets * D;
     float a = 0.f;
-    if (i < 2 * D)
-        for (int b = ty; b < nblocks; b += 32) a += partials[(size_t)b * 2 * D + i];
+    if (i < n)
+        for (int b = ty; b < nblocks; b += 32) a += partials[(size_t)b * n + i];
     red[ty][tx] = a;
     __syncthreads();
-    if (ty == 0 && i < 2 * D) {
+    if (ty == 0 && i < n) {
         float t = 0.f;
 #pragma unroll
         for (int k = 0; k < 32; ++k) t += red[k][tx];
+        if (i >= 2 * D) { colsum[i - 2 * D] = t; return; }
         float* dst = (i < D) ? (dgamma + i) : (dbeta + (i - D));
         *dst = accumulate ? (*dst + t) : t;
     }
@@ -208,6 +313,11 @@ int ln_bwd_grid(int M) {
     const int want = ceil_div(M, kLnWarps);
     const int cap = num_sms() * 2;   // two resident blocks per SM (register-limited): exactly one wave
     return want < cap ? want : cap;
+}
+bool ln_bwd_use_rows(int D) { return (D >> 2) >= kLnThreads && (D >> 2) <= kV2 * kLnThreads; }
+int ln_bwd_row_grid(int M) {
+    const int cap = num_sms() * 4;   // four resident blocks per SM: one wave
+    return M < cap ? M : cap;
 }
 
 }  // namespace
@@ -238,7 +348,9 @@ extern "C" int mico_layernorm_fwd(const void* x, int x_is_bf16, int64_t ldx, con
 }
 
 extern "C" size_t mico_layernorm_bwd_workspace(int M, int D) {
-    return (size_t)mico::ln_bwd_grid(M) * 2 * (size_t)D * sizeof(float);
+    using namespace mico;
+    if (ln_bwd_use_rows(D)) return (size_t)ln_bwd_row_grid(M) * 3 * (size_t)D * sizeof(float);
+    return (size_t)ln_bwd_grid(M) * 2 * (size_t)D * sizeof(float);
 }
 
 extern "C" int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, const void* dy2_bf16, int64_t lddy2,
@@ -246,8 +358,8 @@ extern "C" int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, 
                                   const float* mean, const float* rstd, const float* gamma, const float* dres,
                                   int64_t lddres, float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb,
                                   const float* row_scale, int rows_per_group, float* dgamma, float* dbeta,
-                                  int accumulate_param_grads, int M, int D, void* workspace, size_t ws_bytes,
-                                  void* stream_) {
+                                  int accumulate_param_grads, float* dxb_colsum, int M, int D, void* workspace,
+                                  size_t ws_bytes, void* stream_) {
     using namespace mico;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     MICO_CHECK_ARG(dy && x && mean && rstd && gamma && dgamma && dbeta && workspace);
@@ -257,27 +369,47 @@ extern "C" int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, 
     const __nv_bfloat16* dy2 = reinterpret_cast<const __nv_bfloat16*>(dy2_bf16);
     MICO_CHECK_ARG(!(row_scale && rows_per_group <= 0));
     MICO_CHECK_ARG(ws_bytes >= mico_layernorm_bwd_workspace(M, D));
-    const int grid = ln_bwd_grid(M);
-    const size_t smem = (size_t)kLnWarps * 2 * D * sizeof(float);
+    const bool rows = ln_bwd_use_rows(D);
+    // the fused column sum lives in the block-per-row kernel only (every tower width on the path)
+    MICO_CHECK_ARG(!(dxb_colsum && !rows));
     ProfScope prof(kProfLnBwd, (double)M * D * ((dy_is_bf16 ? 2 : 4) + 4 + (dres ? 4 : 0) + (dx ? 4 : 0) + (dx_bf16 ? 2 : 0)),
                    stream);
     float* partials = reinterpret_cast<float*>(workspace);
-    if (dy_is_bf16) {
-        auto k = ln_bwd_kernel<__nv_bfloat16>;
-        if (smem > 48 * 1024) MICO_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kLnThreads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy2, lddy2, x, ldx, mean, rstd, gamma,
-                                              dres, lddres, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), lddxb,
-                                              row_scale, rows_per_group, partials, M, D);
+    __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
+    int grid;
+    if (rows) {
+        grid = ln_bwd_row_grid(M);
+        auto go = [&](auto k, auto dyp) {
+            k<<<grid, kLnThreads, 0, stream>>>(dyp, lddy, dy2, lddy2, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dxb,
+                                               lddxb, row_scale, rows_per_group, partials, M, D);
+        };
+        if (dy_is_bf16) {
+            const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(dy);
+            if (dxb_colsum) go(ln_bwd_row_kernel<__nv_bfloat16, true>, p); else go(ln_bwd_row_kernel<__nv_bfloat16, false>, p);
+        } else {
+            const float* p = reinterpret_cast<const float*>(dy);
+            if (dxb_colsum) go(ln_bwd_row_kernel<float, true>, p); else go(ln_bwd_row_kernel<float, false>, p);
+        }
     } else {
-        auto k = ln_bwd_kernel<float>;
-        if (smem > 48 * 1024) MICO_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kLnThreads, smem, stream>>>(reinterpret_cast<const float*>(dy), lddy, dy2, lddy2, x, ldx, mean, rstd, gamma, dres,
-                                              lddres, dx, lddx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), lddxb,
-                                              row_scale, rows_per_group, partials, M, D);
+        grid = ln_bwd_grid(M);
+        const size_t smem = (size_t)kLnWarps * 2 * D * sizeof(float);
+        if (dy_is_bf16) {
+            auto k = ln_bwd_kernel<__nv_bfloat16>;
+            if (smem > 48 * 1024) MICO_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k<<<grid, kLnThreads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy2, lddy2, x, ldx, mean, rstd,
+                                                  gamma, dres, lddres, dx, lddx, dxb, lddxb, row_scale, rows_per_group, partials,
+                                                  M, D);
+        } else {
+            auto k = ln_bwd_kernel<float>;
+            if (smem > 48 * 1024) MICO_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k<<<grid, kLnThreads, smem, stream>>>(reinterpret_cast<const float*>(dy), lddy, dy2, lddy2, x, ldx, mean, rstd, gamma,
+                                                  dres, lddres, dx, lddx, dxb, lddxb, row_scale, rows_per_group, partials, M, D);
+        }
     }
     MICO_CHECK_CUDA(cudaGetLastError());
-    ln_bwd_finalize_kernel<<<ceil_div(2 * D, 32), 1024, 0, stream>>>(partials, grid, D, dgamma, dbeta,
-                                                                    accumulate_param_grads);
+    const int nsets = (rows && dxb_colsum) ? 3 : 2;
+    ln_bwd_finalize_kernel<<<ceil_div(nsets * D, 32), 1024, 0, stream>>>(partials, grid, D, nsets, dgamma, dbeta, dxb_colsum,
+                                                                        accumulate_param_grads);
     MICO_CHECK_CUDA(cudaGetLastError());
     count_launch(2);
     return MICO_OK;

@@ -413,8 +413,12 @@ class EVAVisionTransformer(nn.Module):
         xl, mean, rstd = saved.pop("final")
         # gradient wrt the residual stream after the last block, plus its bf16 DropPath-scaled copy that
         # enters the last MLP branch
+        # the bias gradient of the linear layer that consumes a LayerNorm-backward output (column sums of the scaled bf16
+        # copy) is produced by the same kernel when the width allows it
+        fuse_cs = ops.layernorm_bwd_fuses_colsum(D)
         dx, dxb = ops.layernorm_bwd(dy, xl, mean, rstd, params[_NW].detach(), pgrad(_NW), pgrad(_NB),
-                                    want_bf16=True, row_scale=branch_scale(L - 1, 1), rows_per_group=T)
+                                    want_bf16=True, row_scale=branch_scale(L - 1, 1), rows_per_group=T,
+                                    colsum_out=pgrad(_NTOP + (L - 1) * _NBLK + _F2B) if (fuse_cs and L > 0) else None)
         del xl, mean, rstd
         blocks = saved["blocks"]
         for i in range(L - 1, -1, -1):
@@ -427,7 +431,8 @@ class EVAVisionTransformer(nn.Module):
             p = [t.detach() for t in params[base:base + _NBLK]]
             # ---- MLP branch: x2 = x1 + s * (a W2^T + b2)
             ops.gemm(dxb, a, a_mn=True, b_mn=True, out=pgrad(base + _F2W))           # dW2 = dY^T a
-            ops.colsum(dxb, out=pgrad(base + _F2B))
+            if not fuse_cs:
+                ops.colsum(dxb, out=pgrad(base + _F2B))
             dpre = ops.gemm(dxb, c.get(params[base + _F2W], ("fc2", i)), b_mn=True, act=self._act_bwd, aux_in=pre)
             del a, pre
             ops.gemm(dpre, h2, a_mn=True, b_mn=True, out=pgrad(base + _F1W))         # dW1
@@ -435,11 +440,13 @@ class EVAVisionTransformer(nn.Module):
             dh2 = ops.gemm(dpre, c.get(params[base + _F1W], ("fc1", i)), b_mn=True)
             del dpre, h2
             dx1, dx1b = ops.layernorm_bwd(dh2, x1, mean2, rstd2, p[_N2W], pgrad(base + _N2W), pgrad(base + _N2B),
-                                          dres=dx, want_bf16=True, row_scale=branch_scale(i, 0), rows_per_group=T)
+                                          dres=dx, want_bf16=True, row_scale=branch_scale(i, 0), rows_per_group=T,
+                                          colsum_out=pgrad(base + _PB) if fuse_cs else None)
             del dh2, x1, dx
             # ---- attention branch: x1 = x + s * (o Wp^T + bp)
             ops.gemm(dx1b, o.view(M, D), a_mn=True, b_mn=True, out=pgrad(base + _PW))
-            ops.colsum(dx1b, out=pgrad(base + _PB))
+            if not fuse_cs:
+                ops.colsum(dx1b, out=pgrad(base + _PB))
             do = ops.gemm(dx1b, c.get(params[base + _PW], ("proj", i)), b_mn=True)
             del dx1b
             dqkv = torch.empty_like(qkv)
@@ -456,7 +463,8 @@ class EVAVisionTransformer(nn.Module):
             dh = ops.gemm(dqkv, c.get(params[base + _QKVW], ("qkv", i)), b_mn=True)
             del dqkv, h
             dx, dxb = ops.layernorm_bwd(dh, xr, mean1, rstd1, p[_N1W], pgrad(base + _N1W), pgrad(base + _N1B),
-                                        dres=dx1, want_bf16=True, row_scale=branch_scale(i - 1, 1), rows_per_group=T)
+                                        dres=dx1, want_bf16=True, row_scale=branch_scale(i - 1, 1), rows_per_group=T,
+                                        colsum_out=pgrad(base - _NBLK + _F2B) if (fuse_cs and i > 0) else None)
             del dh, dx1, xr
             if self.grad_bucket_hook is not None:      # block i's gradients are final and contiguous: reduce them now
                 self.grad_bucket_hook(flat[offs[base]:offs[base + _NBLK]])

@@ -198,9 +198,15 @@ def layernorm_fwd(x, gamma, beta, eps, out_bf16=True, out_f32=False, save_stats=
     return yb, yf, mean, rstd
 
 
+def layernorm_bwd_fuses_colsum(D):
+    """True when mico_layernorm_bwd can also emit the column sums of its scaled output (block-per-row kernel)."""
+    return 512 <= D <= 1536 and D % 4 == 0
+
+
 def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, dres=None, want_f32=True, want_bf16=False,
-                  row_scale=None, rows_per_group=0, accumulate=False, dy2=None):
-    """Returns (dx_f32|None, dx_bf16|None); writes dgamma/dbeta (fp32 [D])."""
+                  row_scale=None, rows_per_group=0, accumulate=False, dy2=None, colsum_out=None):
+    """Returns (dx_f32|None, dx_bf16|None); writes dgamma/dbeta (fp32 [D]).  colsum_out (fp32 [D]): also receives the
+    column sums of the scaled output (the upstream linear layer's bias gradient)."""
     M, D = x.shape
     _req(x, F32, "x")
     dx = torch.empty((M, D), device=x.device, dtype=F32) if want_f32 else None
@@ -214,7 +220,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, dres=None, want_f3
                                  _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres),
                                  C.c_int64(dres.stride(0) if dres is not None else 0), _ptr(dx), C.c_int64(D), _ptr(dxb),
                                  C.c_int64(D), _ptr(row_scale), int(rows_per_group), _ptr(dgamma), _ptr(dbeta),
-                                 int(accumulate), M, D, _ptr(ws), C.c_size_t(ws.numel()), _stream()),
+                                 int(accumulate), _ptr(colsum_out), M, D, _ptr(ws), C.c_size_t(ws.numel()), _stream()),
           "mico_layernorm_bwd")
     return dx, dxb
 

@@ -96,6 +96,14 @@ def test_layernorm_fwd_bwd(M, D, eps):
     g2 = gamma.clone().requires_grad_(True)
     torch.nn.functional.layer_norm(xr2, (D,), g2, beta, eps).backward(dyb.float())
     assert rel_l2(dg2, dgamma + g2.grad) < 1e-5
+    # fused bias gradient of the upstream linear layer: column sums of the scaled output (block-per-row kernel widths)
+    if ops.layernorm_bwd_fuses_colsum(D):
+        cs = torch.empty(D, device="cuda")
+        dx3, dxb3 = ops.layernorm_bwd(dyb, x, mean, rstd, gamma, dg2, db2, dres=dres, want_bf16=True, row_scale=rs,
+                                      rows_per_group=T, colsum_out=cs)
+        want = ((xr2.grad + dres) * rs.repeat_interleave(T)[:, None]).sum(0)
+        assert rel_l2(cs, want) < 1e-4
+        assert rel_l2(cs, dxb3.float().sum(0)) < 2e-3
 
 
 def test_helpers():
