@@ -331,8 +331,9 @@ extern "C" int mico_layernorm_fwd(const void* x, int x_is_bf16, int64_t ldx, con
     MICO_CHECK_ARG(x && gamma && beta && (y_bf16 || y_f32));
     MICO_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= kMaxVec * 128);
     MICO_CHECK_ARG(ldx % 4 == 0 && ldy % 4 == 0);
-    const int want = ceil_div(M, kLnWarps);
-    const int grid = want < num_sms() * 16 ? want : num_sms() * 16;
+    // one row per warp, no grid cap: with ~2 rows per warp a capped grid ends in a half-empty second pass; the block
+    // scheduler balances 4k small blocks better than a strided loop does
+    const int grid = ceil_div(M, kLnWarps);
     ProfScope prof(kProfLnFwd, (double)M * D * ((x_is_bf16 ? 2 : 4) + (y_bf16 ? 2 : 0) + (y_f32 ? 4 : 0)), stream);
     if (x_is_bf16)
         ln_fwd_kernel<__nv_bfloat16><<<grid, kLnThreads, 0, stream>>>(
