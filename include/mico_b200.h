@@ -237,6 +237,28 @@ int mico_fbank(const float* wave, int64_t clip_stride, int n_clips, int n_sample
                const float* window, const float* mel, int num_mel, float in_scale, float preemph, float log_floor,
                float norm_sub, float norm_mul, float* out, int64_t out_clip_stride, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * SURVEY 8(f).1  Fused multi-tensor AdamW with the decoupled weight-decay "fix" -- replaces AdamW.step of
+ *     data/utils/build_optimizer.py:136-196 (one launch for every parameter of every group instead of ~8 torch
+ *     kernels per tensor):  m,v moment updates; p -= step_size * m/(sqrt(v)+eps); then p -= lr*wd*p.
+ *     step_size = lr * sqrt(1-beta2^t)/(1-beta1^t) is computed by the host (it knows t); lr is the group's
+ *     scheduled rate (pipeline.py:75-78).  `tensors`, `chunk_tensor`, `chunk_index` are DEVICE arrays: work item c
+ *     updates elements [chunk_index[c]*chunk_elems, +chunk_elems) of tensors[chunk_tensor[c]].  p_bf16 (optional)
+ *     receives the bf16 copy of the updated parameter (the GEMM operand the towers otherwise re-cast every step).
+ *     grad_scale multiplies every gradient first (1/world for an averaged DP sum, 1/loss-scale, or 1).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct MicoAdamTensor {
+    float* p; const float* g; float* m; float* v;   /* fp32 [n] */
+    void* p_bf16;                                    /* bf16 [n] or NULL */
+    int64_t n;
+    int32_t group;                                   /* index into the hyper-parameter table */
+    int32_t reserved;
+} MicoAdamTensor;
+typedef struct MicoAdamHyper { float lr, step_size, weight_decay, beta1, beta2, eps; } MicoAdamHyper;
+int mico_adamw_multi(const MicoAdamTensor* tensors_dev, const int32_t* chunk_tensor_dev, const int32_t* chunk_index_dev,
+                     int n_chunks, int chunk_elems, const MicoAdamHyper* hyper_host, int n_groups, float grad_scale,
+                     double total_elems, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

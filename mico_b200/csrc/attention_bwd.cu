@@ -463,13 +463,13 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // -lse*log2(e) and -delta*scale of query t (= threadIdx.x < 160) of q tile i of work item w; queries past the
         // tile's valid count get lse = +huge -> p = 0, dS = 0 with no per-element predicate
         auto load_stats = [&](int w_, int i_, float& l, float& d) {
-            l = -1e30f;
+            l = 1e30f;       // raw values: the scaling is applied where they are stored, long after the loads were issued
             d = 0.f;
             const int t = threadIdx.x;
             if (t < 160 && t < n_valid(qtl, i_)) {
                 const int64_t at = (int64_t)(w_ / nkt) * p.Sq + i_ * kTile + t;
-                l = -__ldg(p.lse + at) * kLog2e;
-                d = -__ldg(p.delta + at) * p.scale;
+                l = __ldg(p.lse + at);
+                d = __ldg(p.delta + at);
             }
         };
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
@@ -487,10 +487,11 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 // tile's 256-thread barrier before the store.
                 float* s_nlse2 = reinterpret_cast<float*>(smem + DkvSmem::STATS + (qcount & 1) * 2048);
                 float* s_ndlt = s_nlse2 + 256;
+                const uint32_t s_stats = smem_u32(s_nlse2);
                 if (first_tile) {      // very first tile of this CTA: nothing was prefetched
                     float l, d;
                     load_stats(w, i, l, d);
-                    if (threadIdx.x < 160) { s_nlse2[threadIdx.x] = l; s_ndlt[threadIdx.x] = d; }
+                    if (threadIdx.x < 160) { s_nlse2[threadIdx.x] = -l * kLog2e; s_ndlt[threadIdx.x] = -d * p.scale; }
                     first_tile = false;
                 }
                 float l_n = 0.f, d_n = 0.f;
@@ -518,8 +519,10 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     tmem_ld_wait();
 #pragma unroll
                     for (int q4 = 0; q4 < 8; ++q4) {
-                        const float4 l4 = *reinterpret_cast<const float4*>(s_nlse2 + c0 + q4 * 4);   // c0 + 32 <= 160
-                        const float4 d4 = *reinterpret_cast<const float4*>(s_ndlt + c0 + q4 * 4);
+                        const uint4 lu = lds128(s_stats + (c0 + q4 * 4) * 4);                          // c0 + 32 <= 160
+                        const uint4 du = lds128(s_stats + (256 + c0 + q4 * 4) * 4);
+                        const float4 l4 = make_float4(__uint_as_float(lu.x), __uint_as_float(lu.y), __uint_as_float(lu.z), __uint_as_float(lu.w));
+                        const float4 d4 = make_float4(__uint_as_float(du.x), __uint_as_float(du.y), __uint_as_float(du.z), __uint_as_float(du.w));
                         const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -558,8 +561,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 if (lane_id() == 0) mbar_arrive(pds_full);
                 if (more && threadIdx.x < 160) {
                     float* n_nlse2 = reinterpret_cast<float*>(smem + DkvSmem::STATS + ((qcount + 1) & 1) * 2048);
-                    n_nlse2[threadIdx.x] = l_n;
-                    n_nlse2[256 + threadIdx.x] = d_n;
+                    n_nlse2[threadIdx.x] = -l_n * kLog2e;
+                    n_nlse2[256 + threadIdx.x] = -d_n * p.scale;
                 }
             }
             mbar_wait(acc_full, wcount & 1);

@@ -260,15 +260,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const EpiOperan
 __device__ __forceinline__ uint32_t stage_at(uint32_t st, int row, int g) {
     return st + row * 64 + ((g ^ ((row >> 1) & 3)) << 4);
 }
-// non-volatile: the compiler may schedule these freely between the __syncwarp() fences around each staging phase
-__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
-    asm("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v;
-    asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-    return v;
-}
 __device__ __forceinline__ int64_t map_out_row(const GemmEpi& e, int row) {
     if (e.remap_gin <= 0) return row;
     const int g = row / e.remap_gin, r = row - g * e.remap_gin;
