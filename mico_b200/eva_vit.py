@@ -148,8 +148,19 @@ class _Bf16Cache:
             w = ops.cast_bf16_2d(src.reshape(src.shape[0], -1), pad_to)
         else:
             w = ops.cast_bf16(src.contiguous())
-        self._c[key] = (ver, w)
+        self._c[key] = (ver, w, p, pad_to is not None)
         return w
+
+    def sinks(self):
+        """(parameter, bf16 copy, key) of every unpadded entry: a fused optimizer step (mico_b200.optim.AdamW) writes the
+        updated bf16 operand itself, then calls mark_fresh()."""
+        return [(e[2], e[1], k) for k, e in self._c.items() if len(e) == 4 and not e[3] and e[1].numel() == e[2].numel()]
+
+    def mark_fresh(self):
+        for k, e in list(self._c.items()):
+            if len(e) == 4 and not e[3] and e[1].numel() == e[2].numel():
+                p = e[2]
+                self._c[k] = ((p.data_ptr(), p._version, p.device), e[1], p, False)
 
     def qkv_bias(self, qb, vb, key):
         """cat(q_bias, zeros_like(v_bias), v_bias) (eva_vit_model.py:307), rebuilt when either changes."""
@@ -280,6 +291,12 @@ class EVAVisionTransformer(nn.Module):
         """Drop the bf16 operand copies (an optimizer step that bypasses tensor versioning, or a benchmark
         that wants the per-step cast of changed weights inside the timed region)."""
         self._bf16 = _Bf16Cache()
+
+    def bf16_weight_sinks(self):
+        return self._bf16.sinks()
+
+    def mark_weights_fresh(self):
+        self._bf16.mark_fresh()
 
     def inject_drop_path_scales(self, scales):
         """Parity hook: use these (depth, 2, B) DropPath multipliers (mask / keep_prob) for the next

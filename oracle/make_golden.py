@@ -248,6 +248,63 @@ def gen_swin():
                                grads={k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None}))
 
 
+def gen_adamw():
+    """The reference's own optimizer (data/utils/build_optimizer.py: build_optimizer grouping + AdamW.step) and LR schedule
+    (data/utils/sched.py:get_lr_sched, applied as in data/utils/pipeline.py:75-78) run UNMODIFIED on CPU for 4 steps over
+    a small module whose parameter names hit all of the grouping rules; stores initial parameters, per-step gradients,
+    per-step learning rates and the parameters / moments after every step."""
+    sys.path.insert(0, os.path.join(ref_shims.REF_ROOT, "data"))
+    from utils.build_optimizer import build_optimizer
+    from utils.sched import get_lr_sched
+    from easydict import EasyDict as edict
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.vision_encoder = torch.nn.Module()
+            self.vision_encoder.visual = torch.nn.Module()
+            self.vision_encoder.visual.proj = torch.nn.Linear(24, 40)            # 'visual' -> clip groups
+            self.vision_encoder.visual.LayerNorm = torch.nn.LayerNorm(40)
+            self.multimodal_encoder = torch.nn.Linear(40, 523)                   # basic groups (two chunks, ragged tail)
+            self.LayerNorm = torch.nn.LayerNorm(7)                               # basic no-decay
+            self.contra_head_new = torch.nn.Linear(40, 8)                        # 'new' groups
+
+    torch.manual_seed(3)
+    model = Tiny()
+    args = edict(model_cfg=edict(vision_encoder_type='evaclip01_giant'),
+                 run_cfg=edict(optim='adamw', learning_rate=1e-3, clip_lr=5e-4, new_lr=2e-3, betas=[0.9, 0.98],
+                               weight_decay=0.01, new_params_name=['contra_head_new'], warmup_ratio=0.25,
+                               num_train_steps=8, scheduler='warmup_linear'))
+    opt = build_optimizer(model, args, None)
+    names = [k for k, _ in model.named_parameters()]
+    init = {k: v.detach().clone() for k, v in model.named_parameters()}
+    gen = torch.Generator().manual_seed(11)
+    steps = []
+    for step in range(1, 5):
+        lr_ratio = get_lr_sched(step, args.run_cfg)
+        for pg in opt.param_groups:
+            pg['lr'] = pg['init_lr'] * lr_ratio
+        grads = {}
+        for k, v in model.named_parameters():
+            g = torch.randn(v.shape, generator=gen) * (0.1 if step != 3 else 10.0)
+            v.grad = g.clone()
+            grads[k] = g
+        opt.step()
+        steps.append(dict(lr_ratio=lr_ratio, lrs=[pg['lr'] for pg in opt.param_groups], grads=grads,
+                          params={k: v.detach().clone() for k, v in model.named_parameters()},
+                          exp_avg={k: opt.state[v]['exp_avg'].clone() for k, v in model.named_parameters()},
+                          exp_avg_sq={k: opt.state[v]['exp_avg_sq'].clone() for k, v in model.named_parameters()}))
+    groups = {}
+    for gi, pg in enumerate(opt.param_groups):
+        for prm in pg['params']:
+            for k, v in model.named_parameters():
+                if v is prm:
+                    groups[k] = gi
+    _save("adamw.pt", dict(names=names, init=init, steps=steps, groups=groups, run_cfg=dict(args.run_cfg),
+                           group_cfg=[dict(weight_decay=pg['weight_decay'], init_lr=pg['init_lr'], betas=tuple(pg['betas']),
+                                           eps=pg['eps'], correct_bias=pg['correct_bias']) for pg in opt.param_groups]))
+
+
 def _dist_worker(rank, world, port, q):
     import torch.distributed as dist
     sys.path.insert(0, os.path.join(ref_shims.REF_ROOT, "data"))
@@ -282,7 +339,8 @@ def gen_dist():
 
 
 GENERATORS = {"vit": gen_vit, "bert": gen_bert, "mico_parts": gen_mico_parts, "dist": gen_dist,
-              "transformer": gen_transformer, "clip": gen_clip, "fbank": gen_fbank, "swin": gen_swin}
+              "transformer": gen_transformer, "clip": gen_clip, "fbank": gen_fbank, "swin": gen_swin,
+              "adamw": gen_adamw}
 
 
 def main():
