@@ -305,6 +305,33 @@ def gen_adamw():
                                            eps=pg['eps'], correct_bias=pg['correct_bias']) for pg in opt.param_groups]))
 
 
+def gen_checkpoint():
+    """MMGeneralModule.modify_checkpoint (model/mico.py:250-321) run UNMODIFIED through a stub `self` on synthetic
+    checkpoints: legacy key names ('video', 'evaclip_model', 'clip_model'), fp16 leaves, frame embeddings of the wrong
+    length (nearest resize) and position embeddings of another grid (bilinear resize), for the evaclip and the clip
+    branch."""
+    import types
+    from model.mico import MMGeneralModule
+    from easydict import EasyDict as edict
+    g = torch.Generator().manual_seed(5)
+    r = lambda *s: torch.randn(*s, generator=g)
+    cases = {}
+    ck_eva = {"evaclip_model.visual.pos_embed": r(1, 1 + 16, 8), "evaclip_model.visual.patch_embed.proj.weight": r(8, 3, 14, 14),
+              "video_frame_embedding": r(1, 4, 6), "audio_frame_embedding": r(1, 2, 6), "contra_head_t.linear.weight": r(4, 6).half(),
+              "multimodal_encoder.bert.embeddings.word_embeddings.weight": r(10, 6).half(), "video_type_embeddings": r(1, 1, 6)}
+    cfg_eva = dict(frame_embedding_type='adaptive', max_vision_sample_num=8, max_audio_sample_num=3,
+                   vision_encoder_type='evaclip01_giant', vision_resolution=98)
+    ck_clip = {"clip_model.visual.positional_embedding": r(1 + 9, 8), "clip_model.visual.conv1.weight": r(8, 3, 16, 16),
+               "vision_perceiver.video_frame_embedding": r(1, 8, 6), "itm_head.linear1.bias": r(6).half()}
+    cfg_clip = dict(frame_embedding_type='adaptive', max_vision_sample_num=3, max_audio_sample_num=1,
+                    vision_encoder_type='clip_vit_base_16', vision_resolution=80)
+    for name, ck, cfg in (("evaclip", ck_eva, cfg_eva), ("clip", ck_clip, cfg_clip)):
+        stub = types.SimpleNamespace(config=edict(cfg))
+        out = MMGeneralModule.modify_checkpoint(stub, {k: v.clone() for k, v in ck.items()})
+        cases[name] = dict(inp=ck, cfg=cfg, out=dict(out))
+    _save("modify_checkpoint.pt", cases)
+
+
 def _dist_worker(rank, world, port, q):
     import torch.distributed as dist
     sys.path.insert(0, os.path.join(ref_shims.REF_ROOT, "data"))
@@ -340,7 +367,7 @@ def gen_dist():
 
 GENERATORS = {"vit": gen_vit, "bert": gen_bert, "mico_parts": gen_mico_parts, "dist": gen_dist,
               "transformer": gen_transformer, "clip": gen_clip, "fbank": gen_fbank, "swin": gen_swin,
-              "adamw": gen_adamw}
+              "adamw": gen_adamw, "checkpoint": gen_checkpoint}
 
 
 def main():
