@@ -167,6 +167,11 @@ int mico_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 int mico_cast_f32_to_bf16_2d(const float* src, int64_t lds, int rows, int cols, void* dst, int64_t ldd, void* stream);
 /* nn.Linear bias gradient: out[n] = sum_m x[m,n] (accumulate 0), out += sum (1), out -= sum (2); x bf16 */
 size_t mico_colsum_workspace(int M, int N);
+/* column sums of two column ranges of one bf16 matrix in one launch: logical columns [0,n0) -> out0, physical columns
+ * [n0+gap, n0+gap+n1) -> out1 (the q and v thirds of the fused qkv gradient; k has no bias, eva_vit_model.py:307).
+ * n0, gap, n1 multiples of 8; workspace as for mico_colsum_workspace(M, n0 + n1). */
+int mico_colsum2_bf16(const void* x, int64_t ldx, int M, int n0, int gap, int n1, float* out0, float* out1,
+                      void* workspace, size_t ws_bytes, void* stream);
 int mico_colsum_bf16(const void* x, int64_t ldx, int M, int N, float* out, int accumulate, void* workspace,
                      size_t ws_bytes, void* stream);
 /* d pos_embed / d cls_token: out[r] (+)= sum_b x[b*R + r] */

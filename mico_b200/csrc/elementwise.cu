@@ -6,6 +6,7 @@
 //   mico_patchify           K1 im2col: (B,C,H,W) fp32 -> bf16 [B*gh*gw, Kpad]   (eva_vit_model.py:440-447)
 //   mico_cls_pos_row        token 0 = cls_token + pos_embed[0]                  (eva_vit_model.py:615-619)
 //   mico_scale_cast_bf16    bf16(x * row_scale[row/rpg])  (gradient entering a DropPath'd residual branch)
+#include <atomic>
 #include <curand_kernel.h>
 
 #include "common.cuh"
@@ -40,26 +41,46 @@ __global__ void cast_f32_bf16_2d_kernel(const float* __restrict__ src, int64_t l
 }
 
 // grid: (ceil(N/256), splits); block 256 = 8 warps; lane owns 8 consecutive columns.
+// Single pass: every block writes its partial row, takes a ticket, and the LAST block of a column group sums the partials
+// in split order (deterministic) and writes the result -- no finalize launch (ncu round 1: 8 us per finalize, 190 per step).
+// Logical column c is physical column c + (c >= gap_start ? gap_len : 0): one launch sums the q and v thirds of the fused
+// qkv gradient and skips the bias-free k third (eva_vit_model.py:307); results go to out0 (c < gap_start) / out1.
 constexpr int kColsumCols = 256;
+constexpr int kColsumSlots = 32, kColsumMaxBlocks = 256;
+__device__ unsigned int g_colsum_tickets[kColsumSlots * kColsumMaxBlocks];   // zero at load, reset by the last block
+
 __global__ void __launch_bounds__(256)
-colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int M, int N, float* __restrict__ partials) {
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int M, int N, int gap_start, int gap_len,
+                   float* __restrict__ partials, float* __restrict__ out0, float* __restrict__ out1, int accumulate,
+                   unsigned int* __restrict__ tickets) {
     __shared__ float red[8][kColsumCols];
+    __shared__ int s_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int col = blockIdx.x * kColsumCols + lane * 8;
+    const int col = blockIdx.x * kColsumCols + lane * 8;                 // logical
+    const int pcol = col + (col >= gap_start ? gap_len : 0);              // physical (gap bounds are multiples of 8)
     const int rows_per_split = (M + gridDim.y - 1) / gridDim.y;
     const int r0 = blockIdx.y * rows_per_split;
     const int r1 = min(M, r0 + rows_per_split);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (col + 8 <= N) {
-        for (int r = r0 + warp; r < r1; r += 8) {
-            const uint4 u = *reinterpret_cast<const uint4*>(x + (int64_t)r * ldx + col);
+        int r = r0 + warp;
+        for (; r + 8 < r1; r += 16) {      // two rows in flight per lane
+            const uint4 u = *reinterpret_cast<const uint4*>(x + (int64_t)r * ldx + pcol);
+            const uint4 w = *reinterpret_cast<const uint4*>(x + (int64_t)(r + 8) * ldx + pcol);
+            acc[0] += bf16_lo(u.x) + bf16_lo(w.x); acc[1] += bf16_hi(u.x) + bf16_hi(w.x);
+            acc[2] += bf16_lo(u.y) + bf16_lo(w.y); acc[3] += bf16_hi(u.y) + bf16_hi(w.y);
+            acc[4] += bf16_lo(u.z) + bf16_lo(w.z); acc[5] += bf16_hi(u.z) + bf16_hi(w.z);
+            acc[6] += bf16_lo(u.w) + bf16_lo(w.w); acc[7] += bf16_hi(u.w) + bf16_hi(w.w);
+        }
+        for (; r < r1; r += 8) {
+            const uint4 u = *reinterpret_cast<const uint4*>(x + (int64_t)r * ldx + pcol);
             acc[0] += bf16_lo(u.x); acc[1] += bf16_hi(u.x); acc[2] += bf16_lo(u.y); acc[3] += bf16_hi(u.y);
             acc[4] += bf16_lo(u.z); acc[5] += bf16_hi(u.z); acc[6] += bf16_lo(u.w); acc[7] += bf16_hi(u.w);
         }
     } else {
         for (int r = r0 + warp; r < r1; r += 8)
             for (int j = 0; j < 8; ++j)
-                if (col + j < N) acc[j] += __bfloat162float(x[(int64_t)r * ldx + col + j]);
+                if (col + j < N) acc[j] += __bfloat162float(x[(int64_t)r * ldx + pcol + j]);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
@@ -71,6 +92,20 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int M, int 
         for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
         partials[(size_t)blockIdx.y * N + c] = s;
     }
+    if (tickets == nullptr) return;          // two-kernel path (more column groups than ticket counters)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&tickets[blockIdx.x], 1u) == gridDim.y - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (c < N) {
+        float s = 0.f;
+        for (int i = 0; i < (int)gridDim.y; ++i) s += __ldcg(partials + (size_t)i * N + c);
+        float* dst = c < gap_start ? out0 + c : out1 + (c - gap_start);
+        *dst = accumulate == 1 ? *dst + s : (accumulate == 2 ? *dst - s : s);
+    }
+    if (threadIdx.x == 0) tickets[blockIdx.x] = 0;
 }
 
 __global__ void colsum_finalize_kernel(const float* __restrict__ partials, int splits, int N, float* __restrict__ out,
@@ -220,6 +255,37 @@ extern "C" int mico_cast_f32_to_bf16_2d(const float* src, int64_t lds, int rows,
 
 extern "C" size_t mico_colsum_workspace(int M, int N) { return (size_t)mico::colsum_splits(M, N) * N * sizeof(float); }
 
+namespace mico {
+namespace {
+int colsum_launch(const void* x, int64_t ldx, int M, int N, int gap_start, int gap_len, float* out0, float* out1,
+                  int accumulate, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+    static std::atomic<unsigned> slot_counter{0};
+    const int splits = colsum_splits(M, N);
+    MICO_CHECK_ARG(ws_bytes >= (size_t)splits * N * sizeof(float));
+    const int colblocks = ceil_div(N, kColsumCols);
+    dim3 grid(colblocks, splits);
+    unsigned int* tickets = nullptr;
+    if (colblocks <= kColsumMaxBlocks) {
+        unsigned int* base = nullptr;
+        MICO_CHECK_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_colsum_tickets));
+        tickets = base + (slot_counter.fetch_add(1) % kColsumSlots) * kColsumMaxBlocks;   // concurrent launches: own slice
+    }
+    colsum_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, N, gap_start, gap_len,
+                                                 reinterpret_cast<float*>(workspace), out0, out1, accumulate, tickets);
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    if (!tickets) {
+        MICO_CHECK_ARG(gap_len == 0);
+        colsum_finalize_kernel<<<ceil_div(N, 256), 256, 0, stream>>>(reinterpret_cast<const float*>(workspace), splits, N,
+                                                                    out0, accumulate);
+        MICO_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+    }
+    return MICO_OK;
+}
+}  // namespace
+}  // namespace mico
+
 extern "C" int mico_colsum_bf16(const void* x, int64_t ldx, int M, int N, float* out, int accumulate, void* workspace,
                                 size_t ws_bytes, void* stream_) {
     using namespace mico;
@@ -227,17 +293,18 @@ extern "C" int mico_colsum_bf16(const void* x, int64_t ldx, int M, int N, float*
     ProfScope prof(kProfOther, 2.0 * (double)M * N, stream);
     MICO_CHECK_ARG(x && out && workspace && M > 0 && N > 0);
     MICO_CHECK_ARG(ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0);
-    const int splits = colsum_splits(M, N);
-    MICO_CHECK_ARG(ws_bytes >= (size_t)splits * N * sizeof(float));
-    dim3 grid(ceil_div(N, kColsumCols), splits);
-    colsum_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, N,
-                                                 reinterpret_cast<float*>(workspace));
-    MICO_CHECK_CUDA(cudaGetLastError());
-    colsum_finalize_kernel<<<ceil_div(N, 256), 256, 0, stream>>>(reinterpret_cast<const float*>(workspace), splits, N,
-                                                                out, accumulate);
-    MICO_CHECK_CUDA(cudaGetLastError());
-    count_launch(2);
-    return MICO_OK;
+    return colsum_launch(x, ldx, M, N, N, 0, out, out, accumulate, workspace, ws_bytes, stream);
+}
+
+extern "C" int mico_colsum2_bf16(const void* x, int64_t ldx, int M, int n0, int gap, int n1, float* out0, float* out1,
+                                 void* workspace, size_t ws_bytes, void* stream_) {
+    using namespace mico;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    ProfScope prof(kProfOther, 2.0 * (double)M * (n0 + n1), stream);
+    MICO_CHECK_ARG(x && out0 && out1 && workspace && M > 0 && n0 > 0 && n1 > 0 && gap >= 0);
+    MICO_CHECK_ARG(ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    MICO_CHECK_ARG(n0 % 8 == 0 && gap % 8 == 0 && n1 % 8 == 0 && ceil_div(n0 + n1, kColsumCols) <= kColsumMaxBlocks);
+    return colsum_launch(x, ldx, M, n0 + n1, n0, gap, out0, out1, 0, workspace, ws_bytes, stream);
 }
 
 extern "C" int mico_batch_sum_f32(const float* x, int B, int64_t R, float* out, int accumulate, void* stream_) {

@@ -475,8 +475,7 @@ class EVAVisionTransformer(nn.Module):
             if self._full_qkv_bias:
                 ops.colsum(dqkv, out=pgrad(base + _QB))
             else:
-                ops.colsum(dqkv[:, :D], out=pgrad(base + _QB))         # k has no bias (eva_vit_model.py:307)
-                ops.colsum(dqkv[:, 2 * D:], out=pgrad(base + _VB))
+                ops.colsum2(dqkv, D, D, D, pgrad(base + _QB), pgrad(base + _VB))   # k has no bias (eva_vit_model.py:307)
             dh = ops.gemm(dqkv, c.get(params[base + _QKVW], ("qkv", i)), b_mn=True)
             del dqkv, h
             dx, dxb = ops.layernorm_bwd(dh, xr, mean1, rstd1, p[_N1W], pgrad(base + _N1W), pgrad(base + _N1B),

@@ -246,6 +246,15 @@ def cast_bf16_2d(src, ldd):
     return dst
 
 
+def colsum2(x, n0, gap, n1, out0, out1):
+    """out0[c] = sum_m x[m, c] (c < n0); out1[c] = sum_m x[m, n0 + gap + c] (c < n1): one launch for two column ranges."""
+    _req(x, BF16, "x")
+    M = x.shape[0]
+    ws = workspace(lib.mico_colsum_workspace(M, n0 + n1), x.device)
+    check(lib.mico_colsum2_bf16(_ptr(x), C.c_int64(x.stride(0)), M, int(n0), int(gap), int(n1), _ptr(out0), _ptr(out1),
+                                _ptr(ws), C.c_size_t(ws.numel()), _stream()), "mico_colsum2_bf16")
+
+
 def colsum(x, out=None, accumulate=False):
     """out[n] = sum_m x[m,n]; accumulate: False/0 overwrite, True/1 add, 2 subtract."""
     _req(x, BF16, "x")

@@ -199,3 +199,19 @@ def test_attention_timing_vitg():
     fl = 4.0 * B * H * S * S * D
     tf, tb = ev[0].elapsed_time(ev[1]) / 10, ev[1].elapsed_time(ev[2]) / 10
     print(f"attention ViT-g bs64: fwd {tf:.3f} ms ({fl / tf / 1e9:.0f} TFLOP/s)  bwd {tb:.3f} ms ({2.5 * fl / tb / 1e9:.0f} TFLOP/s)")
+
+
+def test_colsum_two_ranges_single_pass():
+    """q and v thirds of a fused [M, 3D] gradient in one launch (k skipped), repeated so that the self-resetting ticket
+    counters of the single-pass reduction are exercised; ragged N through the plain entry point."""
+    from mico_b200 import ops
+    for M, D in ((16448, 1408), (514, 176), (77, 64)):
+        x = _randn((M, 3 * D), 9, 1.0, torch.bfloat16)
+        for _ in range(3):
+            o0, o1 = torch.empty(D, device="cuda"), torch.empty(D, device="cuda")
+            ops.colsum2(x, D, D, D, o0, o1)
+            assert rel_l2(o0, x[:, :D].float().sum(0)) < 1e-5
+            assert rel_l2(o1, x[:, 2 * D:].float().sum(0)) < 1e-5
+    y = _randn((1000, 1001 + 7), 10, 1.0, torch.bfloat16)[:, :1001]
+    for _ in range(2):
+        assert rel_l2(ops.colsum(y), y.float().sum(0)) < 1e-5
