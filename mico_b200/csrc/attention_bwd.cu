@@ -232,8 +232,8 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const int qi = qt * kTile + r;
             if (qi < p.Sq) {
                 const int64_t stat = (int64_t)bh * p.Sq + qi;
-                l = __ldg(p.lse + stat);
-                d = __ldg(p.delta + stat);
+                l = ldg_f32_pinned(p.lse + stat);
+                d = ldg_f32_pinned(p.delta + stat);
             } else {
                 l = 1e30f;
                 d = 0.f;
@@ -468,8 +468,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const int t = threadIdx.x;
             if (t < 160 && t < n_valid(qtl, i_)) {
                 const int64_t at = (int64_t)(w_ / nkt) * p.Sq + i_ * kTile + t;
-                l = __ldg(p.lse + at);
-                d = __ldg(p.delta + at);
+                l = ldg_f32_pinned(p.lse + at);
+                d = ldg_f32_pinned(p.delta + at);
             }
         };
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {

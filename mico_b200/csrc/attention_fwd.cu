@@ -237,21 +237,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     mbar_wait(o_full, ocount & 1);
                     ++ocount;
                     tc_fence_after();
-#pragma unroll
-                    for (int c = 0; c < HD_PAD / 32; ++c) {
-                        uint32_t v[32];
-                        tmem_ld_x32(tmem_O + lane_off + c * 32, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) oacc[c * 32 + i] += __uint_as_float(v[i]);
-                    }
-                    if constexpr (HD_PAD % 32 != 0) {
-                        uint32_t v[16];
-                        tmem_ld_x16(tmem_O + lane_off + (HD_PAD / 32) * 32, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) oacc[(HD_PAD / 32) * 32 + i] += __uint_as_float(v[i]);
-                    }
+                    tmem_load_row<HD_PAD, true>(tmem_O + lane_off, oacc);
                 }
 #pragma unroll
                 for (int i = 0; i < HD_PAD; ++i) oacc[i] *= alpha;
@@ -307,21 +293,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mbar_wait(o_full, ocount & 1);
             ++ocount;
             tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < HD_PAD / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_x32(tmem_O + lane_off + c * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) oacc[c * 32 + i] += __uint_as_float(v[i]);
-            }
-            if constexpr (HD_PAD % 32 != 0) {
-                uint32_t v[16];
-                tmem_ld_x16(tmem_O + lane_off + (HD_PAD / 32) * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) oacc[(HD_PAD / 32) * 32 + i] += __uint_as_float(v[i]);
-            }
+            tmem_load_row<HD_PAD, true>(tmem_O + lane_off, oacc);
             tc_fence_before();
             if (row_ok) {
                 const float inv = 1.0f / l;
