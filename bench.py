@@ -187,13 +187,26 @@ def run_product(args):
     host_loss = torch.empty((), dtype=torch.float32).pin_memory()
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
 
+    bucket_blocks = int(os.environ.get("MICO_BENCH_BUCKET_BLOCKS", "5"))   # 5 blocks ~ 0.5 GB per all-reduce: 95.9 vs 94.3 % at N=2
     if world > 1:
+        pending = []
+
         def bucket_hook(bucket):
-            """DP gradient SUM (pipeline.py:93-99 semantics: no divide), one NCCL all-reduce per finished block bucket
-            on a side stream while the backward of the earlier blocks keeps the compute stream busy."""
+            """DP gradient SUM (pipeline.py:93-99 semantics: no divide), one NCCL all-reduce per `bucket_blocks` finished
+            block buckets (contiguous in the flat gradient buffer, later blocks at higher addresses) on a side stream
+            while the backward of the earlier blocks keeps the compute stream busy."""
+            pending.append(bucket)
+            if len(pending) < bucket_blocks and bucket.data_ptr() != tower._last_flat_grad[0].data_ptr():
+                return
+            lo = min(b.data_ptr() for b in pending)
+            n = sum(b.numel() for b in pending)
+            flat = tower._last_flat_grad[0]
+            off = (lo - flat.data_ptr()) // 4
+            merged = flat[off:off + n]
+            pending.clear()
             comm.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(comm):
-                dist.all_reduce(bucket)
+                dist.all_reduce(merged)
         tower.grad_bucket_hook = bucket_hook
 
     def grad_sync():
@@ -322,7 +335,7 @@ def run_product(args):
                             e2e_inputs="pinned host pixels, H2D every step on a side stream one step ahead "
                                        "(the reference's PrefetchLoader, data/utils/loader.py:100-142)",
                             l2="working set per step (~35 GB of activations) exceeds the 126 MB L2; no flush needed",
-                            grad_sync=("nccl all_reduce(SUM) per block bucket of the flat fp32 gradient buffer, overlapped with "
+                            grad_sync=("nccl all_reduce(SUM) per 5-block bucket of the flat fp32 gradient buffer, overlapped with "
                                        "backward on a side stream") if world > 1 else "none (1 GPU)"),
                 clocks=clocks,
                 e2e=dict(value=e2e, unit="tokens/s", ms_per_step=ms_e2e / args.steps,
