@@ -576,6 +576,26 @@ class BertForMaskedLM(nn.Module):
         if isinstance(module, BertEncoder):
             module.gradient_checkpointing = value
 
+    def mask_position_logits(self, input_ids, attention_mask, encoder_hidden_states=None):
+        """fp32 logits (rows, vocab) at the LAST position only -- one decode step of generation reads the prediction at the
+        appended [MASK] token (bert.py:1126-1143), so the 30522-wide LM-head GEMM runs on one row per sequence."""
+        seq = self.bert(input_ids, attention_mask=attention_mask, encoder_hidden_states=encoder_hidden_states).last_hidden_state
+        pr = self.cls.predictions
+        logits = _LMHeadFn.apply(seq[:, -1:, :].contiguous(), pr.transform.dense.weight, pr.transform.dense.bias,
+                                 pr.transform.LayerNorm.weight, pr.transform.LayerNorm.bias, pr.decoder.weight, pr.bias,
+                                 self.config.layer_norm_eps, False)
+        return logits[:, 0, :]
+
+    def generate(self, input_ids=None, attention_mask=None, encoder_hidden_states=None, max_new_tokens=20, num_beams=1,
+                 eos_token_id=None, pad_token_id=None, length_penalty=1.0, do_sample=False, top_k=None, **kwargs):
+        """The reference's `multimodal_encoder.generate(...)` call (inference_demo.py:164-171, vast.py:527-545): beam search /
+        greedy / top-k sampling over the [MASK]-append decode step; see mico_b200/generation.py."""
+        from .generation import generate as _generate
+        return _generate(self, input_ids, attention_mask, encoder_hidden_states=encoder_hidden_states,
+                         max_new_tokens=max_new_tokens, num_beams=num_beams, eos_token_id=eos_token_id,
+                         pad_token_id=pad_token_id, length_penalty=length_penalty, do_sample=do_sample, top_k=top_k,
+                         mask_token_id=kwargs.get("mask_token_id"), generator=kwargs.get("generator"))
+
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, position_ids=None, head_mask=None,
                 inputs_embeds=None, encoder_hidden_states=None, encoder_attention_mask=None, labels=None,
                 output_attentions=None, output_hidden_states=None, return_dict=None):

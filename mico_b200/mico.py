@@ -473,10 +473,42 @@ class MiCo(nn.Module):
             loss_itm.append(self.itm_ratio * MF.cross_entropy(logits, truth))
         return dict(loss_itc=sum(loss_itc) / len(loss_itc), loss_itm=sum(loss_itm) / len(loss_itm))
 
+    def _generate_captions(self, batch, subtasks):
+        """Evaluation branch of forward_cap (data/model/vast.py:514-553): beam search (or top-k sampling in captioner_mode)
+        from [CLS] over the fusion inputs of every modality combination; returns token ids, and decoded strings when a
+        tokenizer is attached."""
+        enc = self.multimodal_encoder
+        tok = enc.tokenizer
+        ids_of = lambda name, default: getattr(tok, name, None) if tok is not None and getattr(tok, name, None) is not None else default
+        bos, sep, pad, msk = ids_of("bos_token_id", 101), ids_of("sep_token_id", 102), ids_of("pad_token_id", 0), ids_of("mask_token_id", 103)
+        out = {}
+        for st in subtasks:
+            assert st in self._SUBTASKS
+            cond = self.batch_get(batch, f"condition_feats_{st[1:]}")
+            b = cond.shape[0]
+            captioner = bool(getattr(self.config, "captioner_mode", False))
+            if captioner:
+                n = int(self.config.generate_nums)
+                cond = cond.unsqueeze(1).expand(-1, n, -1, -1).reshape(-1, *cond.shape[1:])
+                b *= n
+            init_ids = torch.full((b, 1), bos, dtype=torch.long, device=cond.device)
+            init_mask = init_ids.new_ones(b, 1, 1)
+            if captioner:
+                ids = enc.generate(input_ids=init_ids, attention_mask=init_mask, do_sample=True, top_k=10,
+                                   encoder_hidden_states=cond, max_new_tokens=self.max_caption_len, eos_token_id=sep,
+                                   pad_token_id=pad, mask_token_id=msk)
+            else:
+                ids = enc.generate(input_ids=init_ids, attention_mask=init_mask, encoder_hidden_states=cond,
+                                   max_new_tokens=self.max_caption_len, num_beams=self.beam_size, eos_token_id=sep,
+                                   pad_token_id=pad, length_penalty=0.6, mask_token_id=msk)
+            new = ids[:, 1:]
+            out[f"generated_captions_{st}"] = tok.batch_decode(new, skip_special_tokens=True) if tok is not None else new
+        return out
+
     def forward_cap(self, batch, task, compute_loss=True):
-        if not compute_loss:
-            raise NotImplementedError("caption generation (beam search) is outside the pretraining hot path (SURVEY.md 8f)")
         subtasks = task.split("%")[1:]
+        if not compute_loss:
+            return self._generate_captions(batch, subtasks)
         tokens = self.batch_get(batch, "caption_tokens")
         input_ids, attention_mask = tokens.input_ids, tokens.attention_mask
         if "cap_input_ids" in batch:       # parity hook: masked ids / labels supplied by the caller
