@@ -174,8 +174,17 @@ def run_product(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    reserved = int(os.environ.get("MICO_BENCH_RESERVED_SMS", "0")) if world > 1 else 0
     if world > 1:
+        # The overlapped gradient all-reduce runs NCCL kernels next to ours.  MICO_BENCH_RESERVED_SMS=n gives NCCL n SMs of its
+        # own (and caps it there) so that its CTAs never push one of our one-CTA-per-SM persistent kernels into a second wave.
+        # Measured at N=2 (ms/step; 1 GPU 121.9): n=0 126.5, n=4 129.2, n=8 130.0, n=2 161.2 -- an uncapped NCCL finishes each
+        # bucket so quickly that the contention costs less than the SMs given away, so the default stays 0.
+        if reserved > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(reserved))
+            os.environ.setdefault("NCCL_MIN_CTAS", str(min(reserved, 4)))
         dist.init_process_group("nccl", device_id=dev)
+        _lib.check(_lib.lib.mico_set_reserved_sms(reserved), "mico_set_reserved_sms")
     B = args.batch
     torch.manual_seed(0)
     with torch.device(dev):     # random-init weights of the named architecture, created on the device
@@ -190,13 +199,17 @@ def run_product(args):
     bucket_blocks = int(os.environ.get("MICO_BENCH_BUCKET_BLOCKS", "5"))   # 5 blocks ~ 0.5 GB per all-reduce: 95.9 vs 94.3 % at N=2
     if world > 1:
         pending = []
+        hook_calls = [0]
 
         def bucket_hook(bucket):
             """DP gradient SUM (pipeline.py:93-99 semantics: no divide), one NCCL all-reduce per `bucket_blocks` finished
             block buckets (contiguous in the flat gradient buffer, later blocks at higher addresses) on a side stream
             while the backward of the earlier blocks keeps the compute stream busy."""
             pending.append(bucket)
-            if len(pending) < bucket_blocks and bucket.data_ptr() != tower._last_flat_grad[0].data_ptr():
+            is_last = bucket.data_ptr() == tower._last_flat_grad[0].data_ptr()
+            tail = len(tower.blocks) - hook_calls[0] <= 2         # the last buckets stay small: their all-reduce is exposed
+            hook_calls[0] = 0 if is_last else hook_calls[0] + 1
+            if len(pending) < bucket_blocks and not is_last and not tail:
                 return
             lo = min(b.data_ptr() for b in pending)
             n = sum(b.numel() for b in pending)
@@ -335,8 +348,9 @@ def run_product(args):
                             e2e_inputs="pinned host pixels, H2D every step on a side stream one step ahead "
                                        "(the reference's PrefetchLoader, data/utils/loader.py:100-142)",
                             l2="working set per step (~35 GB of activations) exceeds the 126 MB L2; no flush needed",
-                            grad_sync=("nccl all_reduce(SUM) per 5-block bucket of the flat fp32 gradient buffer, overlapped with "
-                                       "backward on a side stream") if world > 1 else "none (1 GPU)"),
+                            grad_sync=(f"nccl all_reduce(SUM) per {bucket_blocks}-block bucket of the flat fp32 gradient buffer, overlapped "
+                                       f"with backward on a side stream; {reserved} SMs reserved for NCCL (NCCL_MAX_CTAS)")
+                            if world > 1 else "none (1 GPU)"),
                 clocks=clocks,
                 e2e=dict(value=e2e, unit="tokens/s", ms_per_step=ms_e2e / args.steps,
                          h2d_bytes_per_step=host_pixels.numel() * 4 * 1, d2h_bytes_per_step=4),

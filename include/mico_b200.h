@@ -35,6 +35,10 @@ extern "C" {
 #define MICO_ACT_MUL_AUX 7              /* out = acc * aux_in */
 
 int mico_version(void);
+/* Persistent kernels (GEMM, attention, LayerNorm forward) launch one CTA per SM.  When a communication library runs its own
+ * kernels concurrently (the overlapped NCCL gradient all-reduce of data-parallel training, pipeline.py:93-99), leave it n SMs
+ * (even, a whole TPC each) so that its CTAs never displace one of ours into a second wave.  Default 0. */
+int mico_set_reserved_sms(int n);
 const char* mico_last_error(void);
 /* number of kernels this library has launched since load / since the last reset (bench "gpu_launches") */
 int64_t mico_launch_count(void);

@@ -47,6 +47,8 @@ ProfScope::~ProfScope() {
     if (slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].e1, stream);
 }
 
+static std::atomic<int> g_reserved_sms{0};
+
 int num_sms() {
     static int n = [] {
         int dev = 0, v = 0;
@@ -55,7 +57,8 @@ int num_sms() {
             return kDefaultSMs;
         return v;
     }();
-    return n;
+    const int r = g_reserved_sms.load(std::memory_order_relaxed);
+    return n - r > 2 ? n - r : 2;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -131,6 +134,14 @@ int make_tmap_tile64(CUtensorMap* out, const void* base, bool fp32, uint64_t col
 }  // namespace mico
 
 extern "C" int mico_version(void) { return 100; }
+extern "C" int mico_set_reserved_sms(int n) {
+    if (n < 0 || n > 64 || (n & 1)) {
+        mico::set_last_error(__FILE__, __LINE__, "reserved SMs must be an even number in [0, 64]");
+        return MICO_ERR_INVALID_ARG;
+    }
+    mico::g_reserved_sms.store(n);
+    return MICO_OK;
+}
 extern "C" const char* mico_last_error(void) { return mico::g_err; }
 extern "C" int64_t mico_launch_count(void) { return mico::g_launches.load(); }
 extern "C" void mico_reset_launch_count(void) { mico::g_launches.store(0); }

@@ -294,7 +294,7 @@ ln_bwd_kernel(const TDy* __restrict__ dy, int64_t lddy, const __nv_bfloat16* __r
 // straight to the per-block partials -- no cross-warp reduction.
 constexpr int kV2 = 3;
 template <typename TDy, bool kColsum>
-__global__ void __launch_bounds__(kLnThreads, 4)
+__global__ void __launch_bounds__(kLnThreads, 5)
 ln_bwd_row_kernel(const TDy* __restrict__ dy, int64_t lddy, const __nv_bfloat16* __restrict__ dy2, int64_t lddy2,
                   const float* __restrict__ x, int64_t ldx, const float* __restrict__ mean,
                   const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
@@ -416,7 +416,7 @@ int ln_bwd_grid(int M) {
 }
 bool ln_bwd_use_rows(int D) { return (D >> 2) >= kLnThreads && (D >> 2) <= kV2 * kLnThreads; }
 int ln_bwd_row_grid(int M) {
-    const int cap = num_sms() * 4;   // four resident blocks per SM: one wave
+    const int cap = num_sms() * 5;   // five resident blocks per SM: one wave
     return M < cap ? M : cap;
 }
 
