@@ -332,6 +332,110 @@ def gen_checkpoint():
     _save("modify_checkpoint.pt", cases)
 
 
+def gen_losses():
+    """data/model/vast.py forward_ret (:383-462: ITC with label smoothing and the learned temperature, hard-negative ITM through
+    the cross-attention BERT) and forward_cap (:485-512: TokenMasker, causal 3-D mask, masked-LM loss) run UNMODIFIED as unbound
+    methods over a stub `self` that carries the attributes the real VAST module has (reference BertForMaskedLM, reference
+    Match_head, contra_temp, itm_ratio, text_masker), on one gloo rank.  The VAST class itself cannot be constructed here
+    (weight files); its loss code can.  Process-wide patches for this generator only: Tensor.cuda() and
+    Tensor.half() are identities (CPU fp32 run; the reference casts the [CLS] state to fp16 before the ITM head, vast.py:452),
+    torch.multinomial is wrapped to RECORD the sampled hard negatives, and the masker's output is recorded -- the fixture
+    stores those discrete choices so that oracle and product replay them."""
+    import importlib
+    import importlib.util
+    import random
+    import types
+    import numpy as np
+    import torch.distributed as dist
+    from transformers.models.bert.configuration_bert import BertConfig
+    from model.bert import BertForMaskedLM
+    DATA = os.path.join(ref_shims.REF_ROOT, "data")
+    if DATA not in sys.path:
+        sys.path.insert(0, DATA)
+    spec = importlib.util.spec_from_file_location("refdata_model", os.path.join(DATA, "model", "__init__.py"),
+                                                  submodule_search_locations=[os.path.join(DATA, "model")])
+    sys.modules["refdata_model"] = importlib.util.module_from_spec(spec)       # package shell: data/model/ without its __init__
+    V = importlib.import_module("refdata_model.vast")
+    GM = importlib.import_module("refdata_model.general_module")
+    edict = sys.modules["easydict"].EasyDict
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29577", rank=0, world_size=1)
+
+    cfg = BertConfig(vocab_size=1000, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
+                     hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, max_position_embeddings=64,
+                     is_decoder=True, add_cross_attention=True, layer_norm_eps=1e-12, pad_token_id=0)
+    torch.manual_seed(0)
+    bert = BertForMaskedLM(cfg)
+    _randomize(bert, 3)
+    bert.cls.predictions.decoder.weight = bert.bert.embeddings.word_embeddings.weight
+    bert.train()
+    itm_head = GM.Match_head(128)
+    _randomize(itm_head, 4)
+    contra_temp = torch.nn.Parameter(torch.tensor(0.07))
+    masker = GM.TokenMasker(mask_token=103, range_start=106, range_end=1000)
+
+    g = torch.Generator().manual_seed(21)
+    b, S, Sk, cd = 4, 16, 9, 32
+    lens = torch.tensor([16, 11, 7, 13])
+    att = (torch.arange(S)[None] < lens[:, None]).long()
+    ids = torch.randint(106, 1000, (b, S), generator=g) * att
+    ids[:, 0] = 101
+    raw_t = torch.randn(b, cd, generator=g, requires_grad=True)
+    raw_v = torch.randn(b, cd, generator=g, requires_grad=True)
+    cond = (0.5 * torch.randn(b, Sk, 128, generator=g)).requires_grad_(True)
+
+    recorded = dict(multinomial=[], masked=None)
+    real_multinomial, real_cuda, real_half = torch.multinomial, torch.Tensor.cuda, torch.Tensor.half
+
+    def rec_multinomial(w, n, *a, **k):
+        out = real_multinomial(w, n, *a, **k)
+        recorded["multinomial"].append(int(out.item()))
+        return out
+
+    def rec_masker(tokens, prob):
+        out = masker(tokens, prob)
+        recorded["masked"] = (out[0].clone(), out[1].clone())
+        return out
+
+    stub = types.SimpleNamespace(contra_temp=contra_temp, itm_ratio=0.1, itm_head=itm_head, multimodal_encoder=bert,
+                                 text_masker=rec_masker, config=edict(captioner_mode=False))
+    stub.batch_get = lambda batch, key: batch[key]
+    torch.multinomial = rec_multinomial
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.Tensor.half = lambda self, *a, **k: self
+    try:
+        batch = edict(raw_captions=["a"] * b)
+        batch["feat_t"] = torch.nn.functional.normalize(raw_t, dim=-1)
+        batch["feat_v"] = torch.nn.functional.normalize(raw_v, dim=-1)
+        batch["condition_feats_v"] = cond
+        batch["caption_tokens"] = edict(input_ids=ids, attention_mask=att)
+        torch.manual_seed(5)
+        random.seed(5)
+        np.random.seed(5)
+        ret = V.VAST.forward_ret(stub, batch, "ret%tv", compute_loss=True)
+        cap = V.VAST.forward_cap(stub, batch, "cap%tv", compute_loss=True)
+    finally:
+        torch.multinomial, torch.Tensor.cuda, torch.Tensor.half = real_multinomial, real_cuda, real_half
+    total = ret["loss_itc"] + ret["loss_itm"] + cap["loss_cap"]
+    total.backward()
+    neg = recorded["multinomial"]
+    sd = {"multimodal_encoder." + k: v.detach().clone() for k, v in bert.state_dict().items()}
+    sd.update({"itm_head." + k: v.detach().clone() for k, v in itm_head.state_dict().items()})
+    sd["contra_temp"] = contra_temp.detach().clone()
+    keep = ("embeddings.word_embeddings.weight", "layer.0.attention.self.query.weight", "layer.1.crossattention.self.key.weight",
+            "layer.1.output.dense.bias", "cls.predictions.transform.dense.weight", "cls.predictions.bias")
+    grads = {"multimodal_encoder." + k: v.grad.clone() for k, v in bert.named_parameters()
+             if v.grad is not None and k.endswith(keep)}
+    grads.update({"itm_head." + k: v.grad.clone() for k, v in itm_head.named_parameters()})
+    grads["contra_temp"] = contra_temp.grad.clone()
+    _save("losses_tiny.pt", dict(state_dict=sd, ids=ids, att=att, raw_t=raw_t.detach(), raw_v=raw_v.detach(), cond=cond.detach(),
+                                 neg_c=torch.tensor(neg[:b]), neg_t=torch.tensor(neg[b:2 * b]),
+                                 cap_ids=recorded["masked"][0], cap_labels=recorded["masked"][1],
+                                 loss_itc=ret["loss_itc"].detach(), loss_itm=ret["loss_itm"].detach(),
+                                 loss_cap=cap["loss_cap"].detach(), grads=grads, d_raw_t=raw_t.grad.clone(),
+                                 d_raw_v=raw_v.grad.clone(), d_cond=cond.grad.clone(), layers=2, heads=2, itm_ratio=0.1))
+
+
 def _dist_worker(rank, world, port, q):
     import torch.distributed as dist
     sys.path.insert(0, os.path.join(ref_shims.REF_ROOT, "data"))
@@ -367,7 +471,7 @@ def gen_dist():
 
 GENERATORS = {"vit": gen_vit, "bert": gen_bert, "mico_parts": gen_mico_parts, "dist": gen_dist,
               "transformer": gen_transformer, "clip": gen_clip, "fbank": gen_fbank, "swin": gen_swin,
-              "adamw": gen_adamw, "checkpoint": gen_checkpoint}
+              "adamw": gen_adamw, "checkpoint": gen_checkpoint, "losses": gen_losses}
 
 
 def main():

@@ -187,3 +187,37 @@ def test_caption_generation_through_mico_forward():
     agree = (got[:, :n] == want[:, :n]).float().mean().item()
     print(f"caption generation: {agree:.2f} of tokens equal the oracle decode")
     assert agree >= 0.75     # random-init logits are nearly flat: a bf16 near-tie may flip a late token
+
+
+def test_losses_vs_reference_forward_ret_and_forward_cap(golden_dir):
+    """MiCo.forward ('ret%tv_cap%tv') against the fixture produced by the reference's OWN data/model/vast.py forward_ret /
+    forward_cap (tests/golden/losses_tiny.pt): same features, fusion inputs, hard negatives and MLM masks injected; loss values
+    1e-3 relative, gradients wrt the fusion inputs / features / heads 3e-2 rel-L2 (bf16 BERT)."""
+    import os
+    import torch.nn.functional as F
+    from mico_b200.mico import MiCo, _AttrDict
+    g = torch.load(os.path.join(golden_dir, "losses_tiny.pt"), weights_only=False)
+    torch.manual_seed(0)
+    cfg = make_cfg()
+    cfg["contra_dim"] = 32
+    model = MiCo.from_pretrained(cfg, {})
+    missing, unexpected = model.load_state_dict(g["state_dict"], strict=False)
+    assert not unexpected, unexpected
+    model = model.cuda().train()
+    raw_t, raw_v, cond = (g[k].clone().cuda().requires_grad_(True) for k in ("raw_t", "raw_v", "cond"))
+    batch = dict(feat_t=F.normalize(raw_t, dim=-1), feat_v=F.normalize(raw_v, dim=-1), condition_feats_v=cond,
+                 caption_tokens=_AttrDict(input_ids=g["ids"].cuda(), attention_mask=g["att"].cuda()),
+                 cap_input_ids=g["cap_ids"].cuda(), cap_labels=g["cap_labels"].cuda(),
+                 itm_neg_cond_tv=g["neg_c"], itm_neg_text_tv=g["neg_t"])
+    out = model(batch, "ret%tv_cap%tv", compute_loss=True)
+    for k in ("loss_itc", "loss_itm", "loss_cap"):
+        print(f"{k}: {out[k].item():.6f} vs reference {g[k].item():.6f}")
+        assert abs(out[k].item() - g[k].item()) < 1e-3 * max(1.0, abs(g[k].item())), k
+    sum(out.values()).backward()
+    errs = dict(d_raw_t=rel_l2(raw_t.grad.cpu(), g["d_raw_t"]), d_raw_v=rel_l2(raw_v.grad.cpu(), g["d_raw_v"]),
+                d_cond=rel_l2(cond.grad.cpu(), g["d_cond"]))
+    named = dict(model.named_parameters())
+    for k, want in g["grads"].items():
+        errs[k] = rel_l2(named[k].grad.cpu(), want)
+    print("gradient rel-L2 vs reference:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < 3e-2, errs

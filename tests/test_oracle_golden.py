@@ -96,3 +96,26 @@ def test_fbank_oracle_matches_torchaudio(golden_dir):
         assert (fb - g[f"fbank_{bins}"]).abs().max().item() < 2e-4      # log-mel values are O(10)
     out = OF.audio_processor(g["wave"], 224, 224, 3)
     assert out.shape == (3, 224, 224)
+
+
+def test_loss_oracle_vs_reference_forward_ret_and_forward_cap():
+    """oracle/mico.py ITC / ITM / caption losses against the fixture produced by the reference's OWN data/model/vast.py
+    forward_ret / forward_cap (run unmodified over a stub module, oracle/make_golden.py:gen_losses): values and gradients,
+    with the hard negatives and MLM masks the reference drew."""
+    import torch.nn.functional as F
+    from oracle import mico as OM
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "losses_tiny.pt"), weights_only=False)
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in g["state_dict"].items()}
+    p["multimodal_encoder.cls.predictions.decoder.weight"] = p["multimodal_encoder.bert.embeddings.word_embeddings.weight"]
+    raw_t, raw_v, cond = (g[k].clone().requires_grad_(True) for k in ("raw_t", "raw_v", "cond"))
+    ft, fv = F.normalize(raw_t, dim=-1), F.normalize(raw_v, dim=-1)
+    l_itc, _, _ = OM.itc_loss(fv, ft, fv.detach(), ft.detach(), p["contra_temp"], 0)
+    l_itm = OM.itm_loss(p, cond, cond, g["ids"], g["att"], g["ids"], g["att"], g["neg_c"], g["neg_t"], g["itm_ratio"],
+                        g["layers"], g["heads"])
+    l_cap = OM.caption_loss(p, cond, g["cap_ids"], g["att"], g["cap_labels"], g["layers"], g["heads"])
+    for got, key in ((l_itc, "loss_itc"), (l_itm, "loss_itm"), (l_cap, "loss_cap")):
+        assert abs(got.item() - g[key].item()) < 1e-5 * max(1.0, abs(g[key].item())), (key, got.item(), g[key].item())
+    (l_itc + l_itm + l_cap).backward()
+    assert rel_l2(raw_t.grad, g["d_raw_t"]) < 1e-4 and rel_l2(raw_v.grad, g["d_raw_v"]) < 1e-4 and rel_l2(cond.grad, g["d_cond"]) < 1e-4
+    for k, want in g["grads"].items():
+        assert rel_l2(p[k].grad, want) < 1e-4, k
