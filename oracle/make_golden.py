@@ -332,15 +332,13 @@ def gen_checkpoint():
     _save("modify_checkpoint.pt", cases)
 
 
-def gen_losses():
-    """data/model/vast.py forward_ret (:383-462: ITC with label smoothing and the learned temperature, hard-negative ITM through
-    the cross-attention BERT) and forward_cap (:485-512: TokenMasker, causal 3-D mask, masked-LM loss) run UNMODIFIED as unbound
-    methods over a stub `self` that carries the attributes the real VAST module has (reference BertForMaskedLM, reference
-    Match_head, contra_temp, itm_ratio, text_masker), on one gloo rank.  The VAST class itself cannot be constructed here
-    (weight files, SURVEY.md 8c); its loss code can.  Process-wide patches for this generator only: Tensor.cuda() and
-    Tensor.half() are identities (CPU fp32 run; the reference casts the [CLS] state to fp16 before the ITM head, vast.py:452),
-    torch.multinomial is wrapped to RECORD the sampled hard negatives, and the masker's output is recorded -- the fixture
-    stores those discrete choices so that oracle and product replay them."""
+def _loss_worker(rank, world, port, q):
+    """Body of gen_losses on one rank (in-process for world 1, spawned for world 2)."""
+    _data = os.path.join(ref_shims.REF_ROOT, "data")
+    while _data in sys.path:          # a spawned child inherits the parent's sys.path: keep `model` = <reference>/model
+        sys.path.remove(_data)
+    ref_shims.install()
+
     import importlib
     import importlib.util
     import random
@@ -351,15 +349,14 @@ def gen_losses():
     from model.bert import BertForMaskedLM
     DATA = os.path.join(ref_shims.REF_ROOT, "data")
     if DATA not in sys.path:
-        sys.path.insert(0, DATA)
+        sys.path.append(DATA)          # behind the reference root: only `utils.*` resolves here
     spec = importlib.util.spec_from_file_location("refdata_model", os.path.join(DATA, "model", "__init__.py"),
                                                   submodule_search_locations=[os.path.join(DATA, "model")])
     sys.modules["refdata_model"] = importlib.util.module_from_spec(spec)       # package shell: data/model/ without its __init__
     V = importlib.import_module("refdata_model.vast")
     GM = importlib.import_module("refdata_model.general_module")
     edict = sys.modules["easydict"].EasyDict
-    if not dist.is_initialized():
-        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29577", rank=0, world_size=1)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
 
     cfg = BertConfig(vocab_size=1000, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
                      hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, max_position_embeddings=64,
@@ -374,9 +371,9 @@ def gen_losses():
     contra_temp = torch.nn.Parameter(torch.tensor(0.07))
     masker = GM.TokenMasker(mask_token=103, range_start=106, range_end=1000)
 
-    g = torch.Generator().manual_seed(21)
+    g = torch.Generator().manual_seed(21 + rank)
     b, S, Sk, cd = 4, 16, 9, 32
-    lens = torch.tensor([16, 11, 7, 13])
+    lens = torch.tensor([16, 11, 7, 13]) - 2 * rank
     att = (torch.arange(S)[None] < lens[:, None]).long()
     ids = torch.randint(106, 1000, (b, S), generator=g) * att
     ids[:, 0] = 101
@@ -409,9 +406,9 @@ def gen_losses():
         batch["feat_v"] = torch.nn.functional.normalize(raw_v, dim=-1)
         batch["condition_feats_v"] = cond
         batch["caption_tokens"] = edict(input_ids=ids, attention_mask=att)
-        torch.manual_seed(5)
-        random.seed(5)
-        np.random.seed(5)
+        torch.manual_seed(5 + rank)
+        random.seed(5 + rank)
+        np.random.seed(5 + rank)
         ret = V.VAST.forward_ret(stub, batch, "ret%tv", compute_loss=True)
         cap = V.VAST.forward_cap(stub, batch, "cap%tv", compute_loss=True)
     finally:
@@ -428,12 +425,42 @@ def gen_losses():
              if v.grad is not None and k.endswith(keep)}
     grads.update({"itm_head." + k: v.grad.clone() for k, v in itm_head.named_parameters()})
     grads["contra_temp"] = contra_temp.grad.clone()
-    _save("losses_tiny.pt", dict(state_dict=sd, ids=ids, att=att, raw_t=raw_t.detach(), raw_v=raw_v.detach(), cond=cond.detach(),
-                                 neg_c=torch.tensor(neg[:b]), neg_t=torch.tensor(neg[b:2 * b]),
-                                 cap_ids=recorded["masked"][0], cap_labels=recorded["masked"][1],
-                                 loss_itc=ret["loss_itc"].detach(), loss_itm=ret["loss_itm"].detach(),
-                                 loss_cap=cap["loss_cap"].detach(), grads=grads, d_raw_t=raw_t.grad.clone(),
-                                 d_raw_v=raw_v.grad.clone(), d_cond=cond.grad.clone(), layers=2, heads=2, itm_ratio=0.1))
+    res = dict(state_dict=sd, ids=ids, att=att, raw_t=raw_t.detach(), raw_v=raw_v.detach(), cond=cond.detach(),
+               neg_c=torch.tensor(neg[:b]), neg_t=torch.tensor(neg[b:2 * b]),
+               cap_ids=recorded["masked"][0], cap_labels=recorded["masked"][1],
+               loss_itc=ret["loss_itc"].detach(), loss_itm=ret["loss_itm"].detach(),
+               loss_cap=cap["loss_cap"].detach(), grads=grads, d_raw_t=raw_t.grad.clone(),
+               d_raw_v=raw_v.grad.clone(), d_cond=cond.grad.clone(), layers=2, heads=2, itm_ratio=0.1)
+    dist.barrier()
+    dist.destroy_process_group()
+    if q is not None:                      # spawned: hand the result over through a file (q carries the directory)
+        res.pop("state_dict")              # identical on every rank and to losses_tiny.pt (same seeds)
+        torch.save(res, os.path.join(q, f"rank{rank}.pt"))
+    return res
+
+
+def gen_losses():
+    """data/model/vast.py forward_ret (:383-462: ITC with label smoothing and the learned temperature, hard-negative ITM through
+    the cross-attention BERT) and forward_cap (:485-512: TokenMasker, causal 3-D mask, masked-LM loss) run UNMODIFIED as unbound
+    methods over a stub `self` that carries the attributes the real VAST module has (reference BertForMaskedLM, reference
+    Match_head, contra_temp, itm_ratio, text_masker), on one gloo rank.  The VAST class itself cannot be constructed here
+    (weight files, SURVEY.md 8c); its loss code can.  Process-wide patches for this generator only: Tensor.cuda() and
+    Tensor.half() are identities (CPU fp32 run; the reference casts the [CLS] state to fp16 before the ITM head, vast.py:452),
+    torch.multinomial is wrapped to RECORD the sampled hard negatives, and the masker's output is recorded -- the fixture
+    stores those discrete choices so that oracle and product replay them."""
+    _save("losses_tiny.pt", _loss_worker(0, 1, 29577, None))
+    # the same on TWO gloo ranks: gathered negatives, all_gather_with_grad of the fusion inputs, per-rank batches
+    import tempfile
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with tempfile.TemporaryDirectory() as tmp:
+        procs = [ctx.Process(target=_loss_worker, args=(r, 2, 29578, tmp)) for r in range(2)]
+        for p_ in procs:
+            p_.start()
+        for p_ in procs:
+            p_.join(timeout=900)
+        ranks = [torch.load(os.path.join(tmp, f"rank{r}.pt"), weights_only=False) for r in range(2)]
+    _save("losses_2rank.pt", dict(ranks=ranks))
 
 
 def _dist_worker(rank, world, port, q):

@@ -10,7 +10,9 @@ TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Restates
   * ITM loss                                                data/model/vast.py:419-457 (negatives passed in explicitly)
   * caption loss                                            data/model/vast.py:493-510
   * concat_all_gather / all_gather_with_grad                data/utils/distributed.py:12-66 (world given as lists of per-rank tensors)
-over the reference's own state_dict key names.  The multi-rank step is simulated in ONE process by evaluating every rank's
+over the reference's own state_dict key names.  PINNED: tests/golden/losses_tiny.pt and losses_2rank.pt hold the outputs of the
+reference's own data/model/vast.py forward_ret / forward_cap (run unmodified over a stub module on 1 and 2 gloo ranks,
+oracle/make_golden.py:gen_losses); tests/test_oracle_golden.py checks itc_loss / itm_loss / caption_loss against them.  The multi-rank step is simulated in ONE process by evaluating every rank's
 tensors and concatenating them (all_gather) -- autograd through the concatenation reproduces GatherLayer's backward
 (all-reduce(SUM) of the stacked gradients, own slice) when the per-rank losses are SUMMED, which is what a DDP-less loop
 computes (pipeline.py:93-99 sums gradients without dividing).

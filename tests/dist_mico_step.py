@@ -73,9 +73,51 @@ def main():
         print("worst summed-gradient errors:", [(f"{e:.3e}", n) for e, n in errs[:4]], "median", f"{errs[len(errs) // 2][0]:.3e}")
         ok &= errs[0][0] < 1e-1 and errs[len(errs) // 2][0] < 3e-2
         print("DIST_MICO_STEP", "PASS" if ok else "FAIL", f"world={world}")
+    ok2 = reference_two_rank_check(rank, world)
     dist.barrier()
     dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    sys.exit(0 if (ok and ok2) else 1)
+
+
+def reference_two_rank_check(rank, world):
+    """World size 2 only: replay tests/golden/losses_2rank.pt -- the reference's own forward_ret / forward_cap run on two
+    gloo ranks -- through MiCo.forward over NCCL: per-rank losses (1e-3 relative) and the gradient that all_gather_with_grad
+    returns to every rank's fusion input (3e-2 rel-L2)."""
+    if world != 2:
+        return True
+    import torch.nn.functional as F
+    from test_gpu_mico import make_cfg
+    from mico_b200.mico import MiCo, _AttrDict
+    gd = os.path.join(REPO, "tests", "golden")
+    one = torch.load(os.path.join(gd, "losses_tiny.pt"), weights_only=False)
+    r = torch.load(os.path.join(gd, "losses_2rank.pt"), weights_only=False)["ranks"][rank]
+    torch.manual_seed(0)
+    cfg = make_cfg()
+    cfg["contra_dim"] = 32
+    model = MiCo.from_pretrained(cfg, {})
+    model.load_state_dict(one["state_dict"], strict=False)
+    model = model.cuda().train()
+    raw_t, raw_v, cond = (r[k].clone().cuda().requires_grad_(True) for k in ("raw_t", "raw_v", "cond"))
+    batch = dict(feat_t=F.normalize(raw_t, dim=-1), feat_v=F.normalize(raw_v, dim=-1), condition_feats_v=cond,
+                 caption_tokens=_AttrDict(input_ids=r["ids"].cuda(), attention_mask=r["att"].cuda()),
+                 cap_input_ids=r["cap_ids"].cuda(), cap_labels=r["cap_labels"].cuda(),
+                 itm_neg_cond_tv=r["neg_c"], itm_neg_text_tv=r["neg_t"])
+    out = model(batch, "ret%tv_cap%tv", compute_loss=True)
+    sum(out.values()).backward()
+    ok = True
+    for k in ("loss_itc", "loss_itm", "loss_cap"):
+        a, e = out[k].item(), r[k].item()
+        print(f"[reference 2-rank fixture] rank {rank} {k}: {a:.6f} vs {e:.6f}")
+        ok &= abs(a - e) <= 1e-3 * max(1.0, abs(e))
+    for name, got, want in (("d_cond", cond.grad, r["d_cond"]), ("d_raw_t", raw_t.grad, r["d_raw_t"]), ("d_raw_v", raw_v.grad, r["d_raw_v"])):
+        e = ((got.cpu() - want).norm() / want.norm()).item()
+        print(f"[reference 2-rank fixture] rank {rank} {name} rel-L2 {e:.3e}")
+        ok &= e < 3e-2
+    flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("DIST_REFERENCE_FIXTURE", "PASS" if flag.item() > 0 else "FAIL")
+    return flag.item() > 0
 
 
 if __name__ == "__main__":

@@ -119,3 +119,39 @@ def test_loss_oracle_vs_reference_forward_ret_and_forward_cap():
     assert rel_l2(raw_t.grad, g["d_raw_t"]) < 1e-4 and rel_l2(raw_v.grad, g["d_raw_v"]) < 1e-4 and rel_l2(cond.grad, g["d_cond"]) < 1e-4
     for k, want in g["grads"].items():
         assert rel_l2(p[k].grad, want) < 1e-4, k
+
+
+def test_loss_oracle_two_rank_world_vs_reference():
+    """The oracle's simulated 2-rank world (per-rank losses summed; gathers as concatenations) against the reference's
+    forward_ret / forward_cap run on TWO gloo ranks (tests/golden/losses_2rank.pt): per-rank loss values, the gradient of every
+    rank's fusion input (all_gather_with_grad: all-reduce(SUM) of the gathered gradient, own slice) and features, and the SUM
+    over ranks of the reference's local parameter gradients (pipeline.py:93-99 sums without dividing)."""
+    import torch.nn.functional as F
+    from oracle import mico as OM
+    gd = os.path.join(os.path.dirname(__file__), "golden")
+    one = torch.load(os.path.join(gd, "losses_tiny.pt"), weights_only=False)
+    ranks = torch.load(os.path.join(gd, "losses_2rank.pt"), weights_only=False)["ranks"]
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in one["state_dict"].items()}
+    p["multimodal_encoder.cls.predictions.decoder.weight"] = p["multimodal_encoder.bert.embeddings.word_embeddings.weight"]
+    leaves = [{k: r[k].clone().requires_grad_(True) for k in ("raw_t", "raw_v", "cond")} for r in ranks]
+    ft = [F.normalize(l["raw_t"], dim=-1) for l in leaves]
+    fv = [F.normalize(l["raw_v"], dim=-1) for l in leaves]
+    ft_all, fv_all = torch.cat(ft).detach(), torch.cat(fv).detach()
+    cond_all = torch.cat([l["cond"] for l in leaves])
+    ids_all, att_all = torch.cat([r["ids"] for r in ranks]), torch.cat([r["att"] for r in ranks])
+    total = 0.0
+    for k, r in enumerate(ranks):
+        l_itc, _, _ = OM.itc_loss(fv[k], ft[k], fv_all, ft_all, p["contra_temp"], k)
+        l_itm = OM.itm_loss(p, leaves[k]["cond"], cond_all, r["ids"], r["att"], ids_all, att_all, r["neg_c"], r["neg_t"],
+                            r["itm_ratio"], r["layers"], r["heads"])
+        l_cap = OM.caption_loss(p, leaves[k]["cond"], r["cap_ids"], r["att"], r["cap_labels"], r["layers"], r["heads"])
+        for got, key in ((l_itc, "loss_itc"), (l_itm, "loss_itm"), (l_cap, "loss_cap")):
+            assert abs(got.item() - r[key].item()) < 1e-5 * max(1.0, abs(r[key].item())), (k, key, got.item(), r[key].item())
+        total = total + l_itc + l_itm + l_cap
+    total.backward()
+    for k, r in enumerate(ranks):
+        assert rel_l2(leaves[k]["cond"].grad, r["d_cond"]) < 1e-4, k
+        assert rel_l2(leaves[k]["raw_t"].grad, r["d_raw_t"]) < 1e-4 and rel_l2(leaves[k]["raw_v"].grad, r["d_raw_v"]) < 1e-4
+    for key in ranks[0]["grads"]:
+        want = ranks[0]["grads"][key] + ranks[1]["grads"][key]
+        assert rel_l2(p[key].grad, want) < 1e-4, key
