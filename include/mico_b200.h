@@ -247,6 +247,16 @@ int mico_fbank(const float* wave, int64_t clip_stride, int n_clips, int n_sample
                float norm_sub, float norm_mul, float* out, int64_t out_clip_stride, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * SURVEY 8(f).4  Image / video-frame preprocessing (input side of the path): ToTensor -> Resize((Ho,Wo), bilinear,
+ *     align_corners=False) -> Normalize(mean, std) of model/imageprocessor.py:24-29,52-56 and model/videoprocessor.py:36-41
+ *     in one kernel.  src: n images, uint8 HWC (src_is_u8_hwc = 1, the decoder's layout; scaled by 1/255) or fp32 CHW;
+ *     img_stride in elements.  dst: fp32 [n, C, Ho, Wo].  mean / std: HOST arrays of C floats.  antialias = 1 follows
+ *     torchvision >= 0.17 (ATen's separable triangle filter), 0 the reference's pinned torchvision 0.15.2.
+ * ------------------------------------------------------------------------------------------- */
+int mico_resize_normalize(const void* src, int src_is_u8_hwc, int n, int C, int H, int W, int64_t img_stride, float* dst,
+                          int Ho, int Wo, const float* mean_host, const float* std_host, int antialias, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * SURVEY 8(f).1  Fused multi-tensor AdamW with the decoupled weight-decay "fix" -- replaces AdamW.step of
  *     data/utils/build_optimizer.py:136-196 (one launch for every parameter of every group instead of ~8 torch
  *     kernels per tensor):  m,v moment updates; p -= step_size * m/(sqrt(v)+eps); then p -= lr*wd*p.

@@ -463,6 +463,36 @@ def gen_losses():
     _save("losses_2rank.pt", dict(ranks=ranks))
 
 
+def gen_imageproc():
+    """The reference's own ImageProcessor (model/imageprocessor.py, image_transforms='none') on synthetic PNG files: a 300x400
+    photo-like image down to 224 (anti-aliased by the installed torchvision's Resize default) with the evaclip and the swin
+    normalisation, and a 97x150 image UP to 224.  Also stores torchvision's Resize(antialias=False) output for the first
+    image: the behaviour of the reference's pinned torchvision 0.15.2."""
+    import tempfile
+    import numpy as np
+    from PIL import Image
+    from torchvision import transforms
+    from model.imageprocessor import ImageProcessor
+    rng = np.random.RandomState(7)
+    yy, xx = np.mgrid[0:300, 0:400]
+    base = (127 + 90 * np.sin(xx / 23.0)[..., None] * np.cos(yy / 17.0)[..., None] * np.array([1.0, 0.6, -0.8])).clip(0, 255)
+    big = (base + rng.randint(-30, 30, (300, 400, 3))).clip(0, 255).astype(np.uint8)
+    small = rng.randint(0, 256, (97, 150, 3)).astype(np.uint8)
+    out = dict(big=torch.from_numpy(big), small=torch.from_numpy(small))
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, arr in (("big", big), ("small", small)):
+            Image.fromarray(arr).save(os.path.join(tmp, name + ".png"))
+        out["big_evaclip"] = ImageProcessor(224, "evaclip01_giant", training=True)(os.path.join(tmp, "big.png"))
+        out["big_swin"] = ImageProcessor(224, "swin_base_22k_224", training=False)(os.path.join(tmp, "big.png"))
+        out["small_evaclip"] = ImageProcessor(224, "evaclip01_giant", training=True)(os.path.join(tmp, "small.png"))
+    proc = ImageProcessor(224, "evaclip01_giant")
+    t = transforms.ToTensor()(Image.fromarray(big))
+    out["big_evaclip_noaa"] = transforms.Normalize(proc.mean, proc.std)(transforms.Resize((224, 224), antialias=False)(t)).unsqueeze(0)
+    import torchvision
+    out["torchvision"] = torchvision.__version__
+    _save("imageproc.pt", out)
+
+
 def _dist_worker(rank, world, port, q):
     import torch.distributed as dist
     sys.path.insert(0, os.path.join(ref_shims.REF_ROOT, "data"))
@@ -498,7 +528,7 @@ def gen_dist():
 
 GENERATORS = {"vit": gen_vit, "bert": gen_bert, "mico_parts": gen_mico_parts, "dist": gen_dist,
               "transformer": gen_transformer, "clip": gen_clip, "fbank": gen_fbank, "swin": gen_swin,
-              "adamw": gen_adamw, "checkpoint": gen_checkpoint, "losses": gen_losses}
+              "adamw": gen_adamw, "checkpoint": gen_checkpoint, "losses": gen_losses, "imageproc": gen_imageproc}
 
 
 def main():

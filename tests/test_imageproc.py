@@ -1,0 +1,45 @@
+"""Image preprocessing: oracle vs the fixture produced by the reference's own ImageProcessor (CPU); CUDA kernel
+vs fixture (GPU).  fp32 throughout: 1e-5 absolute on O(1) normalised pixels."""
+import os
+
+import pytest
+import torch
+
+
+def _gold(golden_dir):
+    return torch.load(os.path.join(golden_dir, "imageproc.pt"), weights_only=False)
+
+
+def test_oracle_matches_reference_image_processor(golden_dir):
+    from oracle import imageproc as OI
+    g = _gold(golden_dir)
+    for img, enc, key, aa in (("big", "evaclip01_giant", "big_evaclip", True), ("big", "swin_base_22k_224", "big_swin", True),
+                              ("small", "evaclip01_giant", "small_evaclip", True), ("big", "evaclip01_giant", "big_evaclip_noaa", False)):
+        got = torch.from_numpy(OI.image_processor(g[img].numpy(), 224, enc, antialias=aa))
+        assert got.shape == g[key].shape == (1, 3, 224, 224)
+        assert (got - g[key]).abs().max().item() < 5e-5, key          # normalised pixels are O(1)-O(4): a few fp32 ulp
+
+
+@pytest.mark.gpu
+def test_cuda_image_processor_matches_reference(golden_dir, tmp_path):
+    from mico_b200.imageprocessor import ImageProcessor, resize_normalize
+    g = _gold(golden_dir)
+    for img, enc, key, aa in (("big", "evaclip01_giant", "big_evaclip", True), ("big", "swin_base_22k_224", "big_swin", True),
+                              ("small", "evaclip01_giant", "small_evaclip", True), ("big", "evaclip01_giant", "big_evaclip_noaa", False)):
+        proc = ImageProcessor(224, enc, antialias=aa)
+        got = proc.process_uint8(g[img]).cpu()
+        assert got.shape == (1, 3, 224, 224)
+        assert (got - g[key]).abs().max().item() < 5e-5, key          # normalised pixels are O(1)-O(4): a few fp32 ulp
+    # file path + video-style batch of frames + fp32 CHW input
+    from PIL import Image
+    f = str(tmp_path / "x.png")
+    Image.fromarray(g["big"].numpy()).save(f)
+    one = ImageProcessor(224, "evaclip01_giant", antialias=True)(f).cpu()
+    assert (one - g["big_evaclip"]).abs().max().item() < 1e-5
+    frames = torch.stack([g["big"], g["big"].flip(1)])
+    two = ImageProcessor(224, "evaclip01_giant", antialias=True).process_uint8(frames).cpu()
+    assert (two[0] - g["big_evaclip"][0]).abs().max().item() < 1e-5
+    assert (two[1] - g["big_evaclip"][0].flip(2)).abs().max().item() < 1e-4       # mirrored taps: same weights, other order
+    chw = (g["big"].permute(2, 0, 1).float() / 255).cuda()
+    three = resize_normalize(chw[None], (224, 224), [0.48145466, 0.4578275, 0.40821073], [0.26862954, 0.26130258, 0.27577711], True).cpu()
+    assert (three - g["big_evaclip"]).abs().max().item() < 1e-5
