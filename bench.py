@@ -35,6 +35,7 @@ VIT_G = dict(img_size=224, patch_size=14, embed_dim=1408, depth=40, num_heads=16
 # + patch embed 2*256*588*1408; backward = 2x forward.
 FWD_FLOPS_PER_IMAGE = 40 * (2 * 257 * 1408 * (4224 + 1408 + 2 * 6144) + 4 * 257 * 257 * 1408) + 2 * 256 * 588 * 1408
 METRIC = "omni-modal pretrain tokens/sec @ ViT-g/14 (image-only fwd+bwd, bs 64/GPU)"
+WORKLOAD = "ViT-g/14 image-only fwd+bwd, bs=64 synthetic 224x224 per GPU (BASELINE configs[1])"
 
 
 def peaks():
@@ -132,8 +133,9 @@ def run_reference(args):
     line = dict(impl="reference", metric=METRIC, value=tps, unit="tokens/s", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload="ViT-g/14 image-only fwd+bwd, 224x224 synthetic (BASELINE configs[1])",
-                            batch_per_step=b, tokens_per_image=TOKENS_PER_IMAGE),
+                config=dict(workload=WORKLOAD, batch_per_gpu=args.batch, tokens_per_image=TOKENS_PER_IMAGE,
+                            drop_path_rate=0.4, loss="tokens.pow(2).mean()",
+                            reference_sample=f"{b} image(s) of the bs-{args.batch} batch per step (bounded CPU sample)"),
                 cpu_baseline=dict(value=tps, unit="tokens/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=tps, unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
@@ -342,7 +344,7 @@ def run_product(args):
     line = dict(metric=METRIC, value=value, unit="tokens/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                 data="synthetic",
-                config=dict(workload="ViT-g/14 image-only fwd+bwd, bs=64 synthetic 224x224 per GPU (BASELINE configs[1])",
+                config=dict(workload=WORKLOAD,
                             batch_per_gpu=B, tokens_per_image=TOKENS_PER_IMAGE, drop_path_rate=0.4,
                             loss="tokens.pow(2).mean()", weight_cast_in_step=True,
                             e2e_inputs="pinned host pixels, H2D every step on a side stream one step ahead "

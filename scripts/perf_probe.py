@@ -80,6 +80,11 @@ def main():
     dg, db = torch.empty_like(g), torch.empty_like(b)
     t = timeit(lambda: ops.layernorm_bwd(yb, xf, mean, rstd, g, dg, db, dres=xf, want_bf16=True))
     print(f"{'layernorm bwd (+res, +bf16 copy)':44s} {t:8.3f} ms  {M * D * (2 + 4 + 4 + 4 + 2) / t / 1e6:8.1f} GB/s")
+    cs = torch.empty(D, device=dev)
+    rs = torch.ones(64, device=dev)
+    t = timeit(lambda: ops.layernorm_bwd(yb, xf, mean, rstd, g, dg, db, dres=xf, want_bf16=True, row_scale=rs, rows_per_group=257,
+                                         colsum_out=cs))
+    print(f"{'layernorm bwd (+res, +bf16 copy, +colsum)':44s} {t:8.3f} ms  {M * D * (2 + 4 + 4 + 4 + 2) / t / 1e6:8.1f} GB/s")
     t = timeit(lambda: ops.colsum(a))
     print(f"{'colsum [M,6144] bf16':44s} {t:8.3f} ms  {M * F * 2 / t / 1e6:8.1f} GB/s")
     B, H, S, d = 64, 16, 257, 88
