@@ -37,6 +37,23 @@ def test_version_and_error_convention():
     assert b"lda" in _lib.lib.mico_last_error()
 
 
+def test_new_entry_points_validate_before_touching_cuda():
+    """Round-1 (f) entry points: bad arguments return MICO_ERR_INVALID_ARG (-1) with a message, on a box without a GPU."""
+    from mico_b200 import _lib
+    L = _lib.lib
+    assert L.mico_set_reserved_sms(3) == -1 and b"reserved SMs" in L.mico_last_error()       # odd: not whole TPCs
+    assert L.mico_set_reserved_sms(0) == 0
+    f4 = (C.c_float * 4)(0.5, 0.5, 0.5, 0.5)
+    assert L.mico_resize_normalize(None, 1, 1, 3, 8, 8, C.c_int64(192), None, 4, 4, f4, f4, 1, None) == -1
+    assert L.mico_resize_normalize(C.c_void_p(16), 1, 1, 5, 8, 8, C.c_int64(320), C.c_void_p(16), 4, 4, f4, f4, 1, None) == -1   # C > 4
+    assert L.mico_colsum2_bf16(C.c_void_p(16), C.c_int64(24), 8, 12, 0, 8, C.c_void_p(16), C.c_void_p(16), C.c_void_p(16),
+                               C.c_size_t(1 << 20), None) == -1                                                  # n0 % 8 != 0
+    assert b"invalid argument" in L.mico_last_error()
+    assert L.mico_adamw_multi(C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), 1, 16384, C.c_void_p(16), 17, C.c_float(1.0),
+                              C.c_double(1.0), None) == -1                                                       # > 16 groups
+    assert L.mico_layernorm_bwd_workspace(16448, 1408) >= 148 * 2 * 1408 * 4
+
+
 def test_product_never_imports_oracle():
     """The oracle is test infrastructure: nothing under mico_b200/ may reference it."""
     pkg = os.path.join(REPO, "mico_b200")

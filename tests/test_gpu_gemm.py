@@ -159,3 +159,36 @@ def test_gemm_full_size_fc1_timing():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     print(f"fc1 16448x6144x1408: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+
+
+@pytest.mark.parametrize("M,N,K,b_mn", [(18944, 176, 128, False),      # 148 M tiles: the cost model picks 176-wide tiles (16-col tail chunk)
+                                        (16448, 1408, 256, False),     # 256-wide tiles, last N tile issues a 128-wide MMA
+                                        (16448, 1408, 256, True),      # same with an MN-major B (dgrad layout)
+                                        (700, 352, 192, False)])       # partial last M tile, narrow last N tile (96 of 256)
+def test_specialised_epilogues_all_kinds(M, N, K, b_mn):
+    """Every specialised epilogue kernel (bf16 +/- bias, GELU + GELU' store, x saved derivative, fp32 residual with DropPath
+    row scale, fp32) on tile shapes that exercise the narrow last-N MMA, the 176-wide tile's 16-column tail chunk and a
+    ragged last M tile (rows clipped by the TMA store), against fp32 math on the same bf16 operands."""
+    from mico_b200 import ops
+    a = _mk((M, K), 11)
+    b = _mk((K, N) if b_mn else (N, K), 12, 0.05)
+    acc = a.float() @ (b.float() if b_mn else b.float().t())
+    bias = torch.randn(N, device="cuda") * 0.1
+    kw = dict(b_mn=b_mn)
+    assert rel_l2(ops.gemm(a, b, **kw), acc) < 4e-3                                         # EPI_BF16
+    assert rel_l2(ops.gemm(a, b, bias=bias, **kw), acc + bias) < 4e-3                       # EPI_BF16 + bias
+    assert rel_l2(ops.gemm(a, b, out_dtype=torch.float32, **kw), acc) < 2e-5                # EPI_F32
+    aux = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    out = ops.gemm(a, b, bias=bias, act=ops.ACT_GELU_SAVE_GRAD, aux_out=aux, **kw)          # EPI_GELU_SAVE
+    pre = (acc + bias).requires_grad_(True)
+    ref = torch.nn.functional.gelu(pre)
+    ref.sum().backward()
+    assert rel_l2(out, ref.detach()) < 4e-3 and rel_l2(aux, pre.grad) < 4e-3
+    sav = _mk((M, N), 13)
+    assert rel_l2(ops.gemm(a, b, act=ops.ACT_MUL_AUX, aux_in=sav, **kw), acc * sav.float()) < 4e-3     # EPI_MUL_AUX
+    T = 37
+    res = torch.randn(M, N, device="cuda")
+    rs = torch.rand((M + T - 1) // T, device="cuda") + 0.5
+    out = ops.gemm(a, b, bias=bias, residual=res, row_scale=rs, rows_per_group=T, out_dtype=torch.float32, **kw)   # EPI_RES32
+    ref = res + (acc + bias) * rs.repeat_interleave(T)[:M, None]
+    assert rel_l2(out, ref) < 2e-5
