@@ -490,6 +490,11 @@ def gen_imageproc():
     out["big_evaclip_noaa"] = transforms.Normalize(proc.mean, proc.std)(transforms.Resize((224, 224), antialias=False)(t)).unsqueeze(0)
     import torchvision
     out["torchvision"] = torchvision.__version__
+    # model/videoprocessor.py: the frame-segment sampler (the module imports decord at the top; only that import is stubbed)
+    import types
+    sys.modules.setdefault("decord", types.SimpleNamespace(VideoReader=None))
+    from model.videoprocessor import split as ref_split
+    out["video_split"] = {(n, k): ref_split(list(range(n)), k) for n in (1, 3, 7, 8, 30, 31, 257) for k in (1, 3, 4, 8)}
     _save("imageproc.pt", out)
 
 

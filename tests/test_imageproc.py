@@ -20,6 +20,39 @@ def test_oracle_matches_reference_image_processor(golden_dir):
         assert (got - g[key]).abs().max().item() < 5e-5, key          # normalised pixels are O(1)-O(4): a few fp32 ulp
 
 
+def test_video_frame_sampler_matches_reference(golden_dir):
+    """split() against the reference's own videoprocessor.split; eval-mode sampling takes the middle frame of every segment."""
+    pytest.importorskip("mico_b200._lib")
+    from mico_b200.videoprocessor import sample_indices, split
+    g = _gold(golden_dir)
+    for (n, k), want in g["video_split"].items():
+        got = split(list(range(n)), k)
+        assert got == want, (n, k)
+        mid = sample_indices(got, training=False)
+        assert mid == [s[(len(s) + 1) // 2 - 1] for s in want]
+        assert all(c in s for c, s in zip(sample_indices(got, training=True), got))
+
+
+@pytest.mark.gpu
+def test_cuda_video_processor_frames(golden_dir, tmp_path):
+    """A directory of frames -> (sample_num, 3, R, R): every sampled frame equals the image processor's output for that file."""
+    from PIL import Image
+    from mico_b200.imageprocessor import ImageProcessor
+    from mico_b200.videoprocessor import VideoProcessor
+    g = _gold(golden_dir)
+    d = tmp_path / "clip"
+    d.mkdir()
+    for i in range(6):
+        Image.fromarray(g["big"].roll(7 * i, 1).numpy()).save(str(d / f"img_{i:04d}.png"))
+    vp = VideoProcessor(224, "evaclip01_giant", sample_num=3, data_format="frame", training=False, antialias=True)
+    out = vp(str(d))
+    assert out.shape == (3, 3, 224, 224)
+    ip = ImageProcessor(224, "evaclip01_giant", antialias=True)
+    for j, i in enumerate((0, 2, 4)):       # middle frames of the segments [0,1] [2,3] [4,5]
+        assert torch.equal(out[j], ip(str(d / f"img_{i:04d}.png"))[0])
+    assert vp(str(tmp_path / "missing")) is None
+
+
 @pytest.mark.gpu
 def test_cuda_image_processor_matches_reference(golden_dir, tmp_path):
     from mico_b200.imageprocessor import ImageProcessor, resize_normalize
