@@ -49,13 +49,14 @@ struct GemmEpi {
     int vec_ok;   // all pitches / bases allow 16-byte vector access
 };
 
-template <int BN, int STAGES, int EPI = 0, bool B_MN = false>
+template <int BN, int STAGES, int EPI = 0, bool B_MN = false, bool P2 = false>
 struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;
     // an MN-major B tile is loaded as [64 k x 64 n] boxes: a 176-wide tile takes three (the last box reaches 16 columns
     // into the neighbouring tile, or is zero-filled at the edge; the N = 176 MMA never reads them)
     static constexpr int B_CHUNKS = (BN + 63) / 64;
-    static constexpr int B_BYTES = B_MN ? B_CHUNKS * 8192 : BN * BK * 2;
+    // P2 (one cta_group::2 MMA over the pair): each CTA holds only ITS half of the B tile (BN/2 rows)
+    static constexpr int B_BYTES = (B_MN ? B_CHUNKS * 8192 : BN * BK * 2) / (P2 ? 2 : 1);
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     // per epilogue warp: generic = one [32 x 64 B] transpose tile; specialised = two such tiles, 64B-swizzled, that
     // TMA stores read (512-byte aligned: they sit right behind the 1024-aligned operand stages)
@@ -684,7 +685,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)   // 10 warps -> 3 on one SM 
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux, int M, int N,
                  int K, GemmEpi epi) {
-    using Cfg = GemmCfg<BN, STAGES, EPI, B_MN>;
+    using Cfg = GemmCfg<BN, STAGES, EPI, B_MN, CL == 3>;
     static_assert((2 * STAGES + 4) * 8 + 8 <= Cfg::BAR_BYTES, "barrier block");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -705,15 +706,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int num_kb = (K + BK - 1) / BK;
     // persistent schedule over work units = (group of CL adjacent m tiles, n tile); both CTAs of a cluster walk the
     // same unit list in lock step
-    const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
-    const int num_tiles = ((num_m + CL - 1) / CL) * num_n;
+    // CL = 3 selects the cta_group::2 variant of the pair (P2): the leader CTA issues ONE M = 256 MMA for both CTAs, each CTA
+    // stages its own 128 A rows and its own half of the B tile (no multicast, a third less shared-memory operand traffic,
+    // six 32 KB stages instead of four 48 KB ones); CLN = CTAs per cluster.
+    constexpr bool P2 = CL == 3;
+    constexpr int CLN = CL == 1 ? 1 : 2;
+    const uint32_t cta_rank = CLN > 1 ? cluster_ctarank() : 0u;
+    const int num_tiles = ((num_m + CLN - 1) / CLN) * num_n;
     // Work units in m-group-major order: the CTAs running concurrently share A panels through L2.  (Tried: all full-width
     // N tiles first and the narrower last-N tiles at the end, to fill the last wave -- the final sweep re-reads every A
     // panel from HBM and was 5-8 % slower on the N = 1408 GEMMs.)
     auto unit_mg = [&](int u) { return u / num_n; };
     auto unit_nt = [&](int u) { return u % num_n; };
-    const int unit0 = blockIdx.x / CL, unit_stride = gridDim.x / CL;
-    constexpr uint16_t kMask = (1u << CL) - 1;
+    const int unit0 = blockIdx.x / CLN, unit_stride = gridDim.x / CLN;
+    constexpr uint16_t kMask = (1u << CLN) - 1;
 
     if (warp == 0) {
         if (elect_one()) {
@@ -726,20 +732,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
             for (int s = 0; s < STAGES; ++s) {
                 mbar_init(&full_bar[s], 1);
-                mbar_init(&empty_bar[s], CL);
+                mbar_init(&empty_bar[s], P2 ? 1 : CLN);
             }
             for (int a = 0; a < 2; ++a) {
                 mbar_init(&tfull_bar[a], 1);
-                mbar_init(&tempty_bar[a], 8);
+                mbar_init(&tempty_bar[a], P2 ? 16 : 8);      // P2: the leader also waits for the peer's eight epilogue warps
             }
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc<512>(tmem_slot);
+        if constexpr (P2) tmem_alloc_pair<512>(tmem_slot); else tmem_alloc<512>(tmem_slot);
     }
     tc_fence_before();
     __syncthreads();
-    if constexpr (CL > 1) cluster_sync_all();    // peer barriers are initialised before any multicast reaches them
+    if constexpr (CLN > 1) cluster_sync_all();    // peer barriers are initialised before any multicast reaches them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -749,12 +755,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
-                const int m0 = (unit_mg(tile) * CL + (int)cta_rank) * BM;
+                const int m0 = (unit_mg(tile) * CLN + (int)cta_rank) * BM;
                 const int n0 = unit_nt(tile) * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
+                    if constexpr (P2) {
+                        // both CTAs' loads are counted on the LEADER's full barrier (it issues the MMA for the pair)
+                        const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                        const int n_left = N - n0;
+                        const int n_eff = n_left >= BN ? BN : ((n_left + 31) & ~31);
+                        const int nb = n0 + (int)cta_rank * (n_eff / 2);        // this CTA's half of the (possibly narrow) tile
+                        if constexpr (!A_MN) {
+                            tma_load_2d_pair(sa, &tmA, fb, kb * BK, m0);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BM / 64; ++j) tma_load_2d_pair(sa + j * 8192, &tmA, fb, m0 + 64 * j, kb * BK);
+                        }
+                        if constexpr (!B_MN) {
+                            tma_load_2d_pair(sb, &tmB, fb, kb * BK, nb);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < Cfg::B_CHUNKS / 2; ++j) tma_load_2d_pair(sb + j * 8192, &tmB, fb, nb + 64 * j, kb * BK);
+                        }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     if constexpr (!A_MN) {
                         tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
@@ -763,7 +791,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int j = 0; j < BM / 64; ++j)
                             tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m0 + 64 * j, kb * BK);
                     }
-                    if constexpr (CL == 1) {
+                    if constexpr (CLN == 1) {
                         if constexpr (!B_MN) {
                             tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
                         } else {
@@ -773,13 +801,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                     } else {     // this CTA's half of B, multicast to both CTAs of the pair
                         if constexpr (!B_MN) {
-                            constexpr int HALF = BN / CL;
+                            constexpr int HALF = BN / CLN;
                             tma_load_2d_mc(sb + cta_rank * (HALF * 128), &tmB, &full_bar[stage], kb * BK,
                                            n0 + (int)cta_rank * HALF, kMask);
                         } else {
 #pragma unroll
                             for (int j = 0; j < Cfg::B_CHUNKS; ++j) {     // chunks are dealt out to the CTAs of the pair
-                                if ((j * CL) / Cfg::B_CHUNKS == (int)cta_rank)
+                                if ((j * CLN) / Cfg::B_CHUNKS == (int)cta_rank)
                                     tma_load_2d_mc(sb + j * 8192, &tmB, &full_bar[stage], n0 + 64 * j, kb * BK, kMask);
                             }
                         }
@@ -789,8 +817,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------- MMA issuer
-        if (elect_one()) {
+        // ------------------------------------------------------------- MMA issuer (P2: the leader CTA only)
+        if ((!P2 || cta_rank == 0) && elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -800,7 +828,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 // the last N tile issues a narrower MMA: no tensor-pipe time is spent on the columns past N (the smem rows
                 // behind them are zero-filled by TMA), which lets N = 1408 run on 256-wide tiles as 5 full tiles + 1 half
                 const int n_left = N - unit_nt(tile) * BN;
-                const uint32_t idesc = umma_idesc_bf16(n_left >= BN ? BN : ((n_left + 15) & ~15), A_MN, B_MN);
+                const uint32_t idesc = P2 ? umma_idesc_bf16(n_left >= BN ? BN : ((n_left + 31) & ~31), A_MN, B_MN, 256)
+                                          : umma_idesc_bf16(n_left >= BN ? BN : ((n_left + 15) & ~15), A_MN, B_MN);
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kAccStride;
@@ -815,13 +844,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                                     : umma_smem_desc_sw128(sa + k * 32, 16, 1024);
                         const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(sb + k * 2048, 8192, 1024)
                                                     : umma_smem_desc_sw128(sb + k * 32, 16, 1024);
-                        umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+                        if constexpr (P2) umma_bf16_ss_pair(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+                        else umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
                     }
-                    if constexpr (CL == 1) umma_commit(&empty_bar[stage]);
+                    if constexpr (CLN == 1) umma_commit(&empty_bar[stage]);
+                    else if constexpr (P2) umma_commit_pair(&empty_bar[stage], kMask);
                     else umma_commit_mc(&empty_bar[stage], kMask);      // frees the slot in both CTAs
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);
+                if constexpr (P2) umma_commit_pair(&tfull_bar[acc], kMask);     // both CTAs' epilogues read their half
+                else umma_commit(&tfull_bar[acc]);
             }
         }
     } else {
@@ -833,7 +865,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int m0 = (unit_mg(tile) * CL + (int)cta_rank) * BM;
+            const int m0 = (unit_mg(tile) * CLN + (int)cta_rank) * BM;
             const int n0 = unit_nt(tile) * BN;
             // bias slice of this tile -> smem (one coalesced load per tile instead of 8 x 16 B per thread and chunk).
             // Stage `acc` of the buffer was last read two tiles ago; every epilogue thread has passed the named
@@ -879,7 +911,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane_id() == 0) mbar_arrive(&tempty_bar[acc]);
+                if (lane_id() == 0) { if constexpr (P2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0)); else mbar_arrive(&tempty_bar[acc]); }
             } else {
 #pragma unroll 1
             for (int c = half; c < BN / 32; c += 2) {
@@ -916,7 +948,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane_id() == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane_id() == 0) { if constexpr (P2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0)); else mbar_arrive(&tempty_bar[acc]); }
             }   // EPI_GENERIC
         }
         if constexpr (EPI != EPI_GENERIC) {
@@ -925,16 +957,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
-    if constexpr (CL > 1) cluster_sync_all();    // no CTA leaves while its peer may still multicast into it
+    if constexpr (CLN > 1) cluster_sync_all();    // no CTA leaves while its peer may still multicast into it
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<512>(tmem_base);
+        if constexpr (P2) tmem_dealloc_pair<512>(tmem_base); else tmem_dealloc<512>(tmem_base);
     }
 }
 
 template <int BN, bool A_MN, bool B_MN, int STAGES, int CL, int EPI>
 int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, STAGES, EPI, B_MN>;
+    using Cfg = GemmCfg<BN, STAGES, EPI, B_MN, CL == 3>;
+    constexpr int CLN = CL == 1 ? 1 : 2;
     CUtensorMap tmA, tmB;
     int rc;
     if (!A_MN) {
@@ -952,7 +985,7 @@ int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) 
     if (!B_MN) {
         const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
         const uint64_t strides[2] = {2, (uint64_t)g.ldb * 2};
-        const uint32_t box[2] = {BK, BN / CL};       // CL = 2: each CTA of the pair loads (and multicasts) half
+        const uint32_t box[2] = {BK, BN / CLN};      // pairs: each CTA loads half of the B tile (CL = 2: and multicasts it)
         rc = make_tmap_bf16(&tmB, g.b, 2, dims, strides, box);
     } else {
         const uint64_t dims[2] = {(uint64_t)g.N, (uint64_t)g.K};
@@ -977,9 +1010,9 @@ int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) 
         MICO_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    const int units = ceil_div(ceil_div(g.M, BM), CL) * ceil_div(g.N, BN);
-    const int max_clusters = num_sms() / CL;
-    const int grid = (units < max_clusters ? units : max_clusters) * CL;
+    const int units = ceil_div(ceil_div(g.M, BM), CLN) * ceil_div(g.N, BN);
+    const int max_clusters = num_sms() / CLN;
+    const int grid = (units < max_clusters ? units : max_clusters) * CLN;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kGemmThreads);
@@ -987,7 +1020,7 @@ int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) 
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.x = CLN;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -1000,6 +1033,8 @@ int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) 
 
 static bool g_force_single_cta = false;     // MICO_GEMM_SINGLE_CTA=1: A/B switch for measurements
 static bool g_force_generic = false;        // MICO_GEMM_GENERIC_EPI=1: A/B switch for measurements
+static bool g_pair_mma = true;              // MICO_GEMM_PAIR_MMA=0: A/B switch for measurements
+static bool g_pair_mma_wgrad = true;        // MICO_GEMM_PAIR_MMA_WGRAD=0: A/B switch for measurements
 
 // which specialised epilogue (if any) computes exactly what `e` asks for
 static int classify_epilogue(const MicoGemmArgs& g, const GemmEpi& e, int bn) {
@@ -1058,6 +1093,17 @@ int dispatch_bn(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) 
     // CTA pairs (B multicast) whenever there are at least two M tiles to pair up
     // (not for wgrad, A and B both MN-major with a 16k-long K loop: measured 4-15 % slower in lock step)
     const bool pair = ceil_div(g.M, BM) >= 2 && !g_force_single_cta && !(A_MN && B_MN);
+    // cta_group::2 variant of the 256-wide pair: ONE M = 256 MMA per pair, each CTA staging its own A rows and its half of B
+    // (six 32 KB stages).  Measured on the ViT-g shapes: plain fc1 1.38 -> 1.47 PFLOP/s (cuBLAS 1.43-1.45), qkv fwd 1.36 -> 1.46,
+    // fc2 fwd + residual 1.16 -> 1.25, fc2 dgrad x GELU' 1.21 -> 1.29, fc2 / fc1 wgrad 1.28 -> 1.35 / 1.35 -> 1.39; bench step
+    // 123.8 -> 119.3 ms on one box.  MICO_GEMM_PAIR_MMA=0 falls back to the multicast pair, MICO_GEMM_PAIR_MMA_WGRAD=0 keeps
+    // single CTAs for wgrad (A and B both MN-major).
+    if constexpr (A_MN == B_MN || !A_MN) {
+        const bool wgrad = A_MN && B_MN;
+        if (best == 256 && ceil_div(g.M, BM) >= 2 && !g_force_single_cta && g_pair_mma && g.N % 128 == 0 &&
+            (!wgrad || g_pair_mma_wgrad))
+            return dispatch_epi<256, A_MN, B_MN, 6, 3>(g, epi, stream);
+    }
     switch (best) {
         case 256: return pair ? dispatch_epi<256, A_MN, B_MN, 4, 2>(g, epi, stream)
                               : dispatch_epi<256, A_MN, B_MN, 4, 1>(g, epi, stream);
@@ -1078,6 +1124,10 @@ extern "C" int mico_gemm_bf16(const MicoGemmArgs* args, void* stream_) {
     static const bool generic = [] { const char* e = getenv("MICO_GEMM_GENERIC_EPI"); return e && e[0] == '1'; }();
     g_force_single_cta = single;
     g_force_generic = generic;
+    static const bool pair_mma = [] { const char* e = getenv("MICO_GEMM_PAIR_MMA"); return !(e && e[0] == '0'); }();
+    static const bool pair_mma_wgrad = [] { const char* e = getenv("MICO_GEMM_PAIR_MMA_WGRAD"); return !(e && e[0] == '0'); }();
+    g_pair_mma = pair_mma;
+    g_pair_mma_wgrad = pair_mma_wgrad;
     MICO_CHECK_ARG(args != nullptr);
     const MicoGemmArgs& g = *args;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
