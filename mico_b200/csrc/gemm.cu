@@ -68,7 +68,8 @@ struct GemmCfg {
     // 4 x 48 KB stages + 32 KB of store tiles leave no room for alignment slack
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + BIAS_BYTES + (EPI != 0 ? 0 : 1024);
 };
-static_assert(GemmCfg<256, 4, 1>::SMEM_BYTES <= 232448 && GemmCfg<176, 5, 1>::SMEM_BYTES <= 232448 &&
+static_assert(GemmCfg<256, 6, 1, false, true>::SMEM_BYTES <= 232448 && GemmCfg<128, 8, 1, true, true>::SMEM_BYTES <= 232448 &&
+              GemmCfg<256, 4, 1>::SMEM_BYTES <= 232448 && GemmCfg<176, 5, 1>::SMEM_BYTES <= 232448 &&
               GemmCfg<176, 4, 1, true>::SMEM_BYTES <= 232448, "shared memory budget");
 
 // Global operands of one epilogue chunk, requested BEFORE the TMEM load is waited for so that their latency
@@ -1034,6 +1035,7 @@ int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) 
 static bool g_force_single_cta = false;     // MICO_GEMM_SINGLE_CTA=1: A/B switch for measurements
 static bool g_force_generic = false;        // MICO_GEMM_GENERIC_EPI=1: A/B switch for measurements
 static bool g_pair_mma = true;              // MICO_GEMM_PAIR_MMA=0: A/B switch for measurements
+static bool g_pair_mma_128 = true;          // MICO_GEMM_PAIR_MMA_128=0: A/B switch for measurements
 static bool g_pair_mma_wgrad = true;        // MICO_GEMM_PAIR_MMA_WGRAD=0: A/B switch for measurements
 
 // which specialised epilogue (if any) computes exactly what `e` asks for
@@ -1103,6 +1105,10 @@ int dispatch_bn(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) 
         if (best == 256 && ceil_div(g.M, BM) >= 2 && !g_force_single_cta && g_pair_mma && g.N % 128 == 0 &&
             (!wgrad || g_pair_mma_wgrad))
             return dispatch_epi<256, A_MN, B_MN, 6, 3>(g, epi, stream);
+        if (best == 128 && ceil_div(g.M, BM) >= 2 && !g_force_single_cta && g_pair_mma && g_pair_mma_128 && g.N % 128 == 0 &&
+            (!wgrad || g_pair_mma_wgrad))
+            return dispatch_epi<128, A_MN, B_MN, 8, 3>(g, epi, stream);     // 256 x 128 pair tile, eight 24 KB stages: qkv wgrad
+                                                                            // 184 -> 164 us, bench step 119.1 -> 117.5 ms
     }
     switch (best) {
         case 256: return pair ? dispatch_epi<256, A_MN, B_MN, 4, 2>(g, epi, stream)
@@ -1128,6 +1134,8 @@ extern "C" int mico_gemm_bf16(const MicoGemmArgs* args, void* stream_) {
     static const bool pair_mma_wgrad = [] { const char* e = getenv("MICO_GEMM_PAIR_MMA_WGRAD"); return !(e && e[0] == '0'); }();
     g_pair_mma = pair_mma;
     g_pair_mma_wgrad = pair_mma_wgrad;
+    static const bool pair_mma_128 = [] { const char* e = getenv("MICO_GEMM_PAIR_MMA_128"); return !(e && e[0] == '0'); }();
+    g_pair_mma_128 = pair_mma_128;
     MICO_CHECK_ARG(args != nullptr);
     const MicoGemmArgs& g = *args;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
