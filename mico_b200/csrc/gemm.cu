@@ -486,6 +486,27 @@ __device__ __forceinline__ void fast_prefetch(const GemmEpi& e, uint4 (&pre)[8],
     }
 }
 
+// L2 prefetch of the NEXT chunk's epilogue operand (same lane -> address mapping as coalesced_load, no registers held): the
+// register prefetch above is issued only one chunk ahead of its use, which leaves an HBM round trip exposed per chunk; with the
+// line already in L2 the load costs an L2 hit (proj forward, K = 1408, is bound by exactly this latency).
+template <int EPI>
+__device__ __forceinline__ void fast_prefetch_l2(const GemmEpi& e, int row0, int col0, int M) {
+    const int l = (int)lane_id();
+    if constexpr (EPI == EPI_RES32) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = row0 + 8 * i + (l >> 2);
+            if (row < M) {
+                const float* p = e.residual + (int64_t)row * e.ldr + col0 + (l & 3) * 8;      // 4 lanes x 32 B = one 128-byte line
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+            }
+        }
+    } else if constexpr (EPI == EPI_MUL_AUX) {
+        const int row = row0 + l;
+        if (row < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(e.aux_in + (int64_t)row * e.ld_aux_in + col0));   // 64 B of one line
+    }
+}
+
 __device__ __forceinline__ void pack32_bf16(const float (&v)[32], uint4 (&own)[4]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -888,6 +909,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 float rs = 1.0f;
                 if constexpr (EPI == EPI_RES32) {
                     if (epi.row_scale) rs = row < M ? __ldg(epi.row_scale + row / epi.rows_per_group) : 0.f;
+                }
+                if constexpr (EPI == EPI_RES32 || EPI == EPI_MUL_AUX) {
+                    // pull this warp's share of the tile's epilogue operand into L2 while the accumulator is still being produced
+#pragma unroll 1
+                    for (int c = half; c < BN / 32; c += 2)
+                        if (n0 + c * 32 < N) fast_prefetch_l2<EPI>(epi, row0, n0 + c * 32, M);
                 }
 #pragma unroll 1
                 for (int c = half; c < BN / 32; c += 2) {
