@@ -2,14 +2,20 @@
 //
 //   out[M,N] = epilogue(alpha * A[M,K] . B[N,K]^T)      fp32 accumulation in TMEM
 //
-// Structure (one CTA per SM, 320 threads):
+// Structure (one CTA per SM, 320 threads; CTAs paired in clusters of two along M):
 //   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled tiles -> STAGES-deep smem ring
-//   warp 1      MMA issuer:   one elected lane issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage,
-//                             tcgen05.commit releases smem slots and publishes the accumulator
-//   warps 2..9  epilogue:     tcgen05.ld TMEM -> registers -> fused bias/GELU/DropPath/residual -> HBM
-//                             (two warps per TMEM lane quarter, alternating 32-column chunks: two resident
-//                             epilogue warps per scheduler hide the global-load / MUFU latency of the fused math)
-// Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+//   warp 1      MMA issuer:   one elected lane issues tcgen05.mma (K = 16) x4 per stage; tcgen05.commit releases smem
+//                             slots and publishes the accumulator.  Pair variants:
+//                               CL = 3  ONE tcgen05.mma.cta_group::2 (M = 256) per pair, issued by the leader CTA; each CTA
+//                                       stages its own 128 A rows and its half of the B tile; barriers live in the leader
+//                                       (default for 256- and 128-wide tiles, N % 128 == 0)
+//                               CL = 2  each CTA issues its own M = 128 MMA; the B tile is shared by TMA multicast
+//                               CL = 1  single CTA (odd shapes, one M tile)
+//   warps 2..9  epilogue:     tcgen05.ld TMEM -> registers -> fused bias / GELU (+ GELU' store) / x saved GELU' / DropPath row
+//                             scale / + fp32 residual -> TMA tile stores (specialised kernels, template EPI) or the generic
+//                             run-time epilogue (two warps per TMEM lane quarter, alternating 32-column chunks)
+// Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.  The last N tile of
+// a row issues a narrower MMA, so N = 1408 runs on 256-wide tiles (5 full + 1 half).
 // Either operand may be "MN-major" (the contraction index is the slow dimension in HBM); that is how
 // wgrad (dW = dY^T X) and dgrad (dX = dY W) run on the same kernel with no transposes in HBM.
 //
