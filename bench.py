@@ -185,6 +185,8 @@ def run_product(args):
         if reserved > 0:
             os.environ.setdefault("NCCL_MAX_CTAS", str(reserved))
             os.environ.setdefault("NCCL_MIN_CTAS", str(min(reserved, 4)))
+        # NCCL prints its version banner (NCCL_DEBUG=VERSION/INFO in the environment) on stdout: keep stdout for the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
         _lib.check(_lib.lib.mico_set_reserved_sms(reserved), "mico_set_reserved_sms")
     B = args.batch
