@@ -172,6 +172,11 @@ def run_product(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line.  Native libraries write there too (NCCL prints "NCCL version ..." on fd 1 during
+    # communicator setup), so fd 1 is pointed at stderr for the whole run and the line is written to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
@@ -185,8 +190,6 @@ def run_product(args):
         if reserved > 0:
             os.environ.setdefault("NCCL_MAX_CTAS", str(reserved))
             os.environ.setdefault("NCCL_MIN_CTAS", str(min(reserved, 4)))
-        # NCCL prints its version banner (NCCL_DEBUG=VERSION/INFO in the environment) on stdout: keep stdout for the ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
         _lib.check(_lib.lib.mico_set_reserved_sms(reserved), "mico_set_reserved_sms")
     B = args.batch
@@ -359,7 +362,8 @@ def run_product(args):
                 e2e=dict(value=e2e, unit="tokens/s", ms_per_step=ms_e2e / args.steps,
                          h2d_bytes_per_step=host_pixels.numel() * 4 * 1, d2h_bytes_per_step=4),
                 gpu_launches=launches, roofline=roofline, cpu_baseline=cpu)
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
