@@ -13,7 +13,6 @@ import numpy as np
 import torch
 from torch.optim import Adam, Adamax, Optimizer
 
-from . import _lib
 from ._lib import MicoError, check, lib
 
 _CHUNK = 16384          # fp32 elements per work item (64 KB of each of p, g, m, v)

@@ -6,8 +6,6 @@ get_lr_sched.  Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may 
 """
 import math
 
-import torch
-
 
 def adamw_step(p, g, m, v, step, lr, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, correct_bias=True):
     """One AdamW update of build_optimizer.py:158-194 on clones; returns (p, m, v)."""
