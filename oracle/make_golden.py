@@ -498,6 +498,34 @@ def gen_imageproc():
     _save("imageproc.pt", out)
 
 
+def gen_eva02():
+    """Reference EVAVisionTransformer in its EVA02 configuration (rope, naiveswiglu, subln; the xformers branch is not installable
+    here, so xattn=False: the reference's own plain-attention path) at width 128 = 2 heads x 64, depth 2, mlp_ratio 2.6667
+    (hidden 341), patch 14, 224x224 -> 257 tokens, pt_hw_seq_len 16 with interpolated frequencies: eval forward and every
+    gradient of mean(y^2).  Parity target for the EVA02 CUDA tower of a later round (oracle/eva02.py)."""
+    from functools import partial
+    from model.evaclip.eva_vit_model import EVAVisionTransformer
+    from model.evaclip.transformer import LayerNorm
+    cfg = dict(width=128, depth=2, heads=2, patch=14, image=224, eps=1e-6, mlp_ratio=2.6667, pt_hw_seq_len=16)
+    torch.manual_seed(0)
+    m = EVAVisionTransformer(img_size=224, patch_size=14, num_classes=8, use_mean_pooling=False, embed_dim=128, depth=2,
+                             num_heads=2, mlp_ratio=2.6667, qkv_bias=True, drop_path_rate=0.0,
+                             norm_layer=partial(LayerNorm, eps=1e-6), xattn=False, rope=True, pt_hw_seq_len=16, intp_freq=True,
+                             naiveswiglu=True, subln=True)
+    _randomize(m, 2)
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(2, 3, 224, 224, generator=g)
+    m.eval()
+    y = m(x, return_all_features=True)
+    y.pow(2).mean().backward()
+    keep = ("blocks.0.attn.q_proj.weight", "blocks.0.attn.k_proj.weight", "blocks.1.attn.q_bias", "blocks.0.attn.inner_attn_ln.bias",
+            "blocks.1.mlp.w1.weight", "blocks.1.mlp.w2.weight", "blocks.1.mlp.ffn_ln.weight", "blocks.0.mlp.w3.bias", "pos_embed",
+            "cls_token", "norm.weight")
+    grads = {k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None and k in keep}
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items() if ".rope." not in k and not k.startswith("head.")}
+    _save("eva02_tiny.pt", dict(cfg=cfg, state_dict=sd, x=x, y=y.detach(), grads=grads))
+
+
 def _dist_worker(rank, world, port, q):
     import torch.distributed as dist
     sys.path.insert(0, os.path.join(ref_shims.REF_ROOT, "data"))
@@ -533,7 +561,7 @@ def gen_dist():
 
 GENERATORS = {"vit": gen_vit, "bert": gen_bert, "mico_parts": gen_mico_parts, "dist": gen_dist,
               "transformer": gen_transformer, "clip": gen_clip, "fbank": gen_fbank, "swin": gen_swin,
-              "adamw": gen_adamw, "checkpoint": gen_checkpoint, "losses": gen_losses, "imageproc": gen_imageproc}
+              "adamw": gen_adamw, "checkpoint": gen_checkpoint, "losses": gen_losses, "imageproc": gen_imageproc, "eva02": gen_eva02}
 
 
 def main():

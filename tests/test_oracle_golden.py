@@ -155,3 +155,17 @@ def test_loss_oracle_two_rank_world_vs_reference():
     for key in ranks[0]["grads"]:
         want = ranks[0]["grads"][key] + ranks[1]["grads"][key]
         assert rel_l2(p[key].grad, want) < 1e-4, key
+
+
+def test_eva02_oracle_matches_reference(golden_dir):
+    """oracle/eva02.py (RoPE on the patch tokens, separate q/k/v projections, sub-LN, SwiGLU) against the reference
+    EVAVisionTransformer in its EVA02 configuration: forward and gradients.  Parity target for the EVA02 CUDA tower."""
+    from oracle import eva02 as O2
+    g = torch.load(os.path.join(golden_dir, "eva02_tiny.pt"), weights_only=False)
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in g["state_dict"].items()}
+    y = O2.forward_features(p, g["x"], g["cfg"])
+    assert y.shape == g["y"].shape == (2, 257, 128)
+    assert rel_l2(y, g["y"]) < 1e-5
+    y.pow(2).mean().backward()
+    for k, want in g["grads"].items():
+        assert rel_l2(p[k].grad, want) < 1e-4, k
