@@ -166,6 +166,13 @@ int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, const void*
  * ------------------------------------------------------------------------------------------- */
 /* fp32 master parameters -> bf16 GEMM operands (the reference relies on torch.autocast, pipeline.py:43) */
 int mico_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* bf16 -> fp32: a gradient bucket reduced in bf16 back into the fp32 gradient buffer (data-parallel SUM of
+ * data/utils/pipeline.py:93-99 at half the NVLink bytes; mico_b200/dp.py) */
+int mico_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
+/* x *= (*scale_dev if scale_dev else 1) * scale_host, in place (16-byte aligned fp32): gradients of a loss group that was
+ * differentiated ahead of the outer backward pass are rescaled by the upstream scalar gradient -- the loss scale of
+ * GradScaler, data/utils/pipeline.py:86-88, or 1 (mico_b200/train_step.py) */
+int mico_scale_f32(float* x, const float* scale_dev, float scale_host, int64_t n, void* stream);
 /* same for a [rows, cols] matrix into a wider bf16 pitch ldd, zero-filling columns cols..ldd-1
  * (patch-embed weight (1408, 3*14*14=588) -> K padded to a 16-byte multiple, eva_vit_model.py:440) */
 int mico_cast_f32_to_bf16_2d(const float* src, int64_t lds, int rows, int cols, void* dst, int64_t ldd, void* stream);

@@ -69,6 +69,30 @@ class AudioProcessor(object):
                                              mode='bilinear').reshape(fb.size(0), self.resize_melbin_num)
         return (fb - self.mean) / (self.std * 2)
 
+    def batch(self, waveforms):
+        """(clips, samples) fp32 waveforms at 16 kHz -> (clips, sample_num, target_length, melbins): `__call__` for a whole
+        batch in ONE fbank launch (the reference runs its CPU front-end clip by clip in the data-loader workers,
+        audioprocessor.py:28-77).  Same padding (:54) and slice choice (:60-68) per clip."""
+        if self.melbins != self.resize_melbin_num:
+            return torch.stack([self(w) for w in waveforms], dim=0)
+        w = waveforms.to(self.device, F32).contiguous()
+        if self._window.device != w.device:
+            self._window, self._mel = self._window.to(w.device), self._mel.to(w.device)
+        fb = ops.fbank(w, self._window, self._mel, frame_shift=160, norm_sub=self.mean, norm_mul=1.0 / (self.std * 2))
+        src_length = fb.shape[1]
+        pad_len = max(self.target_length * self.sample_num - src_length,
+                      self.target_length - src_length % self.target_length)
+        n_slices = (src_length + pad_len) // self.target_length
+        slices = split(list(range(n_slices)), self.sample_num)
+        out = torch.zeros((w.shape[0], n_slices * self.target_length, self.melbins), device=w.device, dtype=F32)
+        out[:, :src_length] = fb
+        out = out.view(w.shape[0], n_slices, self.target_length, self.melbins)
+        if self.training:
+            idx = torch.tensor([[random.choice(i) for i in slices] for _ in range(w.shape[0])], device=w.device)
+        else:
+            idx = torch.tensor([[i[(len(i) + 1) // 2 - 1] for i in slices]] * w.shape[0], device=w.device)
+        return out[torch.arange(w.shape[0], device=w.device).unsqueeze(1), idx]
+
     def __call__(self, wav):
         if isinstance(wav, str):
             if not os.path.exists(wav):

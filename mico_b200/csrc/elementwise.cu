@@ -29,6 +29,33 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
         dst[i] = __float2bfloat16(src[i]);
 }
 
+// x *= s (s = *scale_dev * scale_host): gradients of a loss group differentiated ahead of time, rescaled by the upstream
+// scalar gradient when the outer backward pass reaches them (mico_b200/train_step.py)
+__global__ void scale_f32_kernel(float* __restrict__ x, const float* __restrict__ scale_dev, float scale_host, int64_t n) {
+    const float s = (scale_dev ? __ldg(scale_dev) : 1.0f) * scale_host;
+    const int64_t nvec = n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        float4 v = reinterpret_cast<float4*>(x)[i];
+        v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        reinterpret_cast<float4*>(x)[i] = v;
+    }
+    for (int64_t i = (nvec << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] *= s;
+}
+
+// bf16 -> fp32 (the reduced bf16 gradient bucket back into the fp32 gradient buffer)
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t n) {
+    const int64_t nvec = n >> 3;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        const uint4 v = reinterpret_cast<const uint4*>(src)[i];
+        reinterpret_cast<float4*>(dst)[2 * i] = make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
+        reinterpret_cast<float4*>(dst)[2 * i + 1] = make_float4(bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w));
+    }
+    for (int64_t i = (nvec << 3) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = __bfloat162float(src[i]);
+}
+
 // rows x cols fp32 (pitch lds) -> bf16 (pitch ldd >= cols); columns cols..ldd-1 are zero-filled.
 __global__ void cast_f32_bf16_2d_kernel(const float* __restrict__ src, int64_t lds, int rows, int cols,
                                         __nv_bfloat16* __restrict__ dst, int64_t ldd) {
@@ -233,6 +260,33 @@ extern "C" int mico_cast_f32_to_bf16(const float* src, void* dst, int64_t n, voi
     int64_t want = (n / 8 + 255) / 256;
     const int grid = (int)(want < 1 ? 1 : (want > num_sms() * 16 ? num_sms() * 16 : want));
     cast_f32_bf16_kernel<<<grid, 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return MICO_OK;
+}
+
+extern "C" int mico_scale_f32(float* x, const float* scale_dev, float scale_host, int64_t n, void* stream_) {
+    using namespace mico;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    ProfScope prof(kProfOther, 8.0 * (double)n, stream);
+    MICO_CHECK_ARG(x && n > 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    int64_t want = (n / 4 + 255) / 256;
+    const int grid = (int)(want < 1 ? 1 : (want > num_sms() * 16 ? num_sms() * 16 : want));
+    scale_f32_kernel<<<grid, 256, 0, stream>>>(x, scale_dev, scale_host, n);
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return MICO_OK;
+}
+
+extern "C" int mico_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream_) {
+    using namespace mico;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    ProfScope prof(kProfOther, 6.0 * (double)n, stream);
+    MICO_CHECK_ARG(src && dst && n > 0);
+    MICO_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    int64_t want = (n / 8 + 255) / 256;
+    const int grid = (int)(want < 1 ? 1 : (want > num_sms() * 16 ? num_sms() * 16 : want));
+    cast_bf16_f32_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
     MICO_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return MICO_OK;

@@ -156,10 +156,15 @@ class _Bf16Cache:
         updated bf16 operand itself, then calls mark_fresh()."""
         return [(e[2], e[1], k) for k, e in self._c.items() if len(e) == 4 and not e[3] and e[1].numel() == e[2].numel()]
 
-    def mark_fresh(self):
+    def mark_fresh(self, updated=None):
+        """Re-stamp the entries whose bf16 copy the fused optimizer step just wrote.  `updated`: ids of the parameters
+        it actually updated (a parameter it skipped -- grad None, frozen -- may have been changed by someone else since
+        the last cast and must be re-cast on its next use); None = every sink entry."""
         for k, e in list(self._c.items()):
             if len(e) == 4 and not e[3] and e[1].numel() == e[2].numel():
                 p = e[2]
+                if updated is not None and id(p) not in updated:
+                    continue
                 self._c[k] = ((p.data_ptr(), p._version, p.device), e[1], p, False)
 
     def qkv_bias(self, qb, vb, key):
@@ -240,6 +245,8 @@ class EVAVisionTransformer(nn.Module):
                 self.head.weight.mul_(init_scale)
                 self.head.bias.mul_(init_scale)
         self.grad_checkpointing = grad_checkpointing
+        self.ckpt_light_blocks = 0       # with grad_checkpointing: the last n blocks keep qkv / o / x1 (see _launch_forward)
+        self.flat_grad = None            # optional persistent fp32 gradient buffer (mico_b200.dp.FlatGrads)
         self._bf16 = _Bf16Cache()
         # K of the patch-embed GEMM padded to a multiple of 64 (one 128-byte swizzle atom of bf16)
         k = in_chans * patch_size * patch_size
@@ -256,6 +263,7 @@ class EVAVisionTransformer(nn.Module):
         # buffer (one per block, last block first; then the tower-level parameters) so that a caller can overlap the
         # gradient reduction (data/utils/pipeline.py:93-99) with the rest of the backward pass
         self.grad_bucket_hook = None
+        self.grad_begin_hook = None      # called when the tower's backward starts (see _launch_backward)
         self._dp_rates = None
         self._dp_calls = 0
 
@@ -287,6 +295,17 @@ class EVAVisionTransformer(nn.Module):
                     blk.mlp.fc1.weight, blk.mlp.fc1.bias, blk.mlp.fc2.weight, blk.mlp.fc2.bias]
         return top
 
+    @staticmethod
+    def flat_grad_sizes(params):
+        """elements reserved per parameter in the flat gradient buffer (16-byte aligned slices, launch order)"""
+        return [((p.numel() if p is not None else 0) + 3) // 4 * 4 for p in params]
+
+    _flat_grad_written = False
+    # class-level defaults (the OpenAI-CLIP subclass builds itself without this __init__)
+    flat_grad = None
+    ckpt_light_blocks = 0
+    grad_begin_hook = None
+
     def invalidate_weight_cache(self):
         """Drop the bf16 operand copies (an optimizer step that bypasses tensor versioning, or a benchmark
         that wants the per-step cast of changed weights inside the timed region)."""
@@ -295,8 +314,8 @@ class EVAVisionTransformer(nn.Module):
     def bf16_weight_sinks(self):
         return self._bf16.sinks()
 
-    def mark_weights_fresh(self):
-        self._bf16.mark_fresh()
+    def mark_weights_fresh(self, updated=None):
+        self._bf16.mark_fresh(updated)
 
     def inject_drop_path_scales(self, scales):
         """Parity hook: use these (depth, 2, B) DropPath multipliers (mask / keep_prob) for the next
@@ -359,19 +378,40 @@ class EVAVisionTransformer(nn.Module):
         rec = (xr, mean1, rstd1, h, qkv, o, lse, x1, mean2, rstd2, h2, pre, a) if keep else None
         return x2, rec
 
+    def _block_recompute_light(self, rec, i, params):
+        """Rebuild the 13-tensor block record from a 'light' one (see _launch_forward): LayerNorm outputs / statistics
+        and the fc1 activation pair are recomputed, bit-identical to the forward pass."""
+        _, xr, qkv, o, lse, x1 = rec
+        base = _NTOP + i * _NBLK
+        p = [t.detach() for t in params[base:base + _NBLK]]
+        h, _, mean1, rstd1 = ops.layernorm_fwd(xr, p[_N1W], p[_N1B], self.eps, save_stats=True)
+        h2, _, mean2, rstd2 = ops.layernorm_fwd(x1, p[_N2W], p[_N2B], self.eps, save_stats=True)
+        w1 = self._bf16.get(params[base + _F1W], ("fc1", i))
+        pre = torch.empty((h2.shape[0], w1.shape[0]), device=xr.device, dtype=BF16)
+        a = ops.gemm(h2, w1, bias=p[_F1B], act=self._act, aux_out=pre)
+        return (xr, mean1, rstd1, h, qkv, o, lse, x1, mean2, rstd2, h2, pre, a)
+
     def _launch_forward(self, x, dp, params, keep):
         P = self.patch_embed.patch_size[0]
         D, H = self.embed_dim, self.num_heads
         d = D // H
-        B = x.shape[0]
+        xs = x if isinstance(x, (tuple, list)) else (x,)
+        B = sum(t.shape[0] for t in xs)
         T = self.patch_embed.num_patches + 1
         M = B * T
-        dev = x.device
+        dev = xs[0].device
         c = self._bf16
         # K1 patch embedding: im2col -> GEMM with bias + broadcast pos_embed in the epilogue; row 0 = cls + pos[0]
         # a 3-D input (B,H,W) is one channel replicated three times (forward_audio_encoder, mico.py:139-143): the
-        # im2col kernel reads the same plane for every channel instead of materialising repeat(1,1,3,1,1)
-        cols = ops.patchify(x, P, self._kpad, tokens_per_img=T, token_off=1, replicate_channel=(x.dim() == 3))
+        # im2col kernel reads the same plane for every channel instead of materialising repeat(1,1,3,1,1).
+        # Several pixel batches (video frames, spectrogram planes, depth maps of one omni-modal step) share one pass:
+        # each is unfolded into its own row range of the same operand.
+        cols = torch.empty((M, self._kpad), device=dev, dtype=BF16)
+        r0 = 0
+        for t in xs:
+            ops.patchify(t, P, self._kpad, tokens_per_img=T, token_off=1, replicate_channel=(t.dim() == 3),
+                         out=cols[r0 * T:(r0 + t.shape[0]) * T])
+            r0 += t.shape[0]
         w_pe = c.get(params[_PEW], "pe", pad_to=self._kpad)
         pos = params[_POS].detach().reshape(T, D)
         pe_bias = params[_PEB].detach() if params[_PEB].numel() else None      # clip.py:239 conv1 has no bias
@@ -384,11 +424,20 @@ class EVAVisionTransformer(nn.Module):
                                               out_f32=True, save_stats=keep)
             if keep:
                 saved["ln_pre"] = (x0, m0, r0)
-        ckpt = keep and self.grad_checkpointing      # eva_vit_model.py:635-637: keep only each block's input
-        for i in range(len(self.blocks)):
-            x2, rec = self._block_forward(xr, i, params, dp, B, T, keep and not ckpt)
+        # eva_vit_model.py:635-637: with grad_checkpointing keep only each block's input and recompute the block in the
+        # backward pass.  `ckpt_light_blocks` = n: the LAST n blocks instead keep their GEMM-free-to-recompute half (block
+        # input, qkv, attention output, x1: 22 KB per token instead of 53) and recompute only LN1, LN2 and fc1+GELU
+        # (a third of a block forward instead of all of it) -- memory permitting, this trades HBM for recompute FLOPs.
+        L = len(self.blocks)
+        ckpt = keep and self.grad_checkpointing
+        n_light = min(L, max(0, int(self.ckpt_light_blocks))) if ckpt else 0
+        for i in range(L):
+            light = ckpt and i >= L - n_light
+            x2, rec = self._block_forward(xr, i, params, dp, B, T, keep and (not ckpt or light))
             if keep:
-                saved["blocks"].append((xr,) if ckpt else rec)
+                if light:     # (xr, mean1, rstd1, h, qkv, o, lse, x1, mean2, rstd2, h2, pre, a) -> drop h, h2, pre, a
+                    rec = ("light", rec[0], rec[4], rec[5], rec[6], rec[7])
+                saved["blocks"].append((xr,) if (ckpt and not light) else rec)
             xr = x2
         _, y, mean, rstd = ops.layernorm_fwd(xr, params[_NW].detach(), params[_NB].detach(), self.eps,
                                              out_bf16=False, out_f32=True, save_stats=keep)
@@ -409,21 +458,40 @@ class EVAVisionTransformer(nn.Module):
         grads = [None] * len(params)
         # one flat fp32 gradient buffer in parameter order (block i's gradients are contiguous: a data-parallel
         # caller can reduce them bucket by bucket while earlier blocks are still in backward)
-        sizes = [(p.numel() + 3) // 4 * 4 for p in params]
-        flat = torch.empty(sum(sizes), device=dev, dtype=F32)
+        sizes = self.flat_grad_sizes(params)
         offs = [0]
         for n in sizes:
             offs.append(offs[-1] + n)
+        # A data-parallel / optimizer layer may own the buffer (mico_b200.dp.FlatGrads): parameters' .grad are then
+        # persistent views into it, this pass WRITES them in place (one tower backward per zero_grad) and autograd
+        # receives no parameter gradients -- so a bucket all-reduce issued from the hook below really reduces p.grad
+        # (with autograd-owned gradients AccumulateGrad may clone the returned views).
+        owned = self.flat_grad is not None
+        if owned:
+            flat = self.flat_grad
+            if flat.numel() != offs[-1] or flat.device != dev:
+                raise MicoError("tower.flat_grad does not match the parameter layout (use mico_b200.dp.FlatGrads)")
+            if self._flat_grad_written:
+                raise MicoError("flat-gradient mode takes ONE tower backward per zero_grad (fold all modalities into one "
+                                "forward_multi call)")
+            self._flat_grad_written = True
+        else:
+            flat = torch.empty(offs[-1], device=dev, dtype=F32)
         self._last_flat_grad = (flat, offs)
 
         def pgrad(idx):
             g = flat[offs[idx]:offs[idx] + params[idx].numel()].view(params[idx].shape)
-            grads[idx] = g
+            if not owned:
+                grads[idx] = g
             return g
 
         def branch_scale(i, j):
             return dp[i, j] if (dp is not None and i >= 0) else None
 
+        if self.grad_begin_hook is not None:
+            # every autograd node created after the tower's forward has run by now (the engine orders ready nodes by
+            # creation sequence, newest first): all gradients outside the tower are final -- a caller can start reducing them
+            self.grad_begin_hook()
         dy = dy.contiguous().view(M, D)
         if dy.dtype != F32:
             dy = dy.float()
@@ -442,6 +510,8 @@ class EVAVisionTransformer(nn.Module):
             rec = blocks.pop()
             if len(rec) == 1:        # checkpointed: recompute this block's forward from its input
                 rec = self._block_forward(rec[0], i, params, dp, B, T, True)[1]
+            elif rec[0] == "light":  # recompute LN1, LN2, fc1 + GELU; qkv / attention / proj / fc2 outputs were kept
+                rec = self._block_recompute_light(rec, i, params)
             xr, mean1, rstd1, h, qkv, o, lse, x1, mean2, rstd2, h2, pre, a = rec
             del rec
             base = _NTOP + i * _NBLK
@@ -522,6 +592,28 @@ class EVAVisionTransformer(nn.Module):
         if not return_all_features:
             return y[:, 0]      # fc_norm is None when use_mean_pooling=False (eva_vit_model.py:643-648)
         return y
+
+    def forward_multi(self, inputs):
+        """Several pixel batches -- (B_i, C, H, W), or (B_i, H, W) for one replicated channel (spectrograms) -- through ONE
+        pass of the tower (one weight read, one backward, one gradient buffer); returns the list of (B_i, T, D) token
+        tensors.  Same result per sample as separate forward(x, return_all_features=True) calls (every op is
+        per-sample; DropPath masks are drawn per sample either way)."""
+        xs = []
+        for x in inputs:
+            if x.dim() == 4 and x.stride(1) == 0 and x.shape[1] == 3:
+                x = x[:, 0]
+            if x.dim() not in (3, 4) or not x.is_cuda:
+                raise MicoError("forward_multi expects CUDA (B, C, H, W) / (B, H, W) tensors")
+            assert x.shape[-2] == self.patch_embed.img_size[0] and x.shape[-1] == self.patch_embed.img_size[1]
+            x = x.contiguous()
+            xs.append(x if x.dtype == F32 else x.float())
+        B = sum(x.shape[0] for x in xs)
+        dp = self._draw_drop_path(B, xs[0].device)
+        flat = self._flat_params()
+        keep = torch.is_grad_enabled() and any(p.requires_grad for p in flat if p is not None)
+        flat = [p if p is not None else xs[0].new_empty(0) for p in flat]
+        y = _TowerFn.apply(self, keep, tuple(xs), dp, *flat)
+        return list(torch.split(y, [x.shape[0] for x in xs], dim=0))
 
     def forward(self, x, return_all_features=False):
         if return_all_features:

@@ -141,12 +141,23 @@ class TokenMasker:
 
 
 # ---------------------------------------------------------------------------------------------- collectives
+_GROUP = None      # process group of the data-parallel world (None = the default group)
+
+
+def set_process_group(group):
+    """Run the loss collectives over `group` instead of the default process group (a sub-world, e.g. a 2-rank replay of a
+    reference fixture inside a larger job).  Returns the previous setting."""
+    global _GROUP
+    prev, _GROUP = _GROUP, group
+    return prev
+
+
 def _world():
-    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    return dist.get_world_size(_GROUP) if dist.is_available() and dist.is_initialized() else 1
 
 
 def _rank():
-    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    return dist.get_rank(_GROUP) if dist.is_available() and dist.is_initialized() else 0
 
 
 @torch.no_grad()
@@ -157,7 +168,7 @@ def concat_all_gather(t):
         return t
     t = t.contiguous()
     out = torch.empty((w * t.shape[0],) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype)
-    dist.all_gather_into_tensor(out, t)
+    dist.all_gather_into_tensor(out, t, group=_GROUP)
     return out
 
 
@@ -169,18 +180,18 @@ class _GatherWithGrad(torch.autograd.Function):
     def forward(ctx, x):
         x = x.contiguous()
         out = torch.empty((_world() * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
-        dist.all_gather_into_tensor(out, x)
+        dist.all_gather_into_tensor(out, x, group=_GROUP)
         return out
 
     @staticmethod
     def backward(ctx, g):
         g = g.contiguous()
         n = g.shape[0] // _world()
-        if dist.get_backend() == "gloo":      # CPU test path: gloo has no reduce_scatter; the reference's own formulation
-            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        if dist.get_backend(_GROUP) == "gloo":      # CPU test path: gloo has no reduce_scatter; the reference's own formulation
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=_GROUP)
             return g[_rank() * n:(_rank() + 1) * n].clone()
         out = torch.empty((n,) + tuple(g.shape[1:]), device=g.device, dtype=g.dtype)
-        dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM)
+        dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM, group=_GROUP)
         return out
 
 
@@ -341,14 +352,16 @@ class MiCo(nn.Module):
         return self.hidden_trans_subtitle_multimodal(subtitle_output) + self.subtitle_type_embeddings
 
     # ------------------------------------------------------------------ lazy feature cache (vast.py:81-314)
-    def _tokens(self, batch, key, texts_key, max_len):
+    def _tokens(self, batch, key, texts_key, max_len, on_host=False):
+        """on_host: leave the tokenizer's CPU tensors where they are (the fused step masks them on the host before any
+        kernel is queued, mico_b200/train_step.py)."""
         if key in batch:
             return batch[key]
         tok = self.multimodal_encoder.tokenizer
         if tok is None:
             raise MicoError(f"batch has no {key!r} and no tokenizer is attached to model.multimodal_encoder.tokenizer")
         t = tok(batch[texts_key], padding="max_length", truncation=True, max_length=max_len, return_tensors="pt")
-        dev = self.contra_temp.device
+        dev = torch.device("cpu") if on_host else self.contra_temp.device
         batch[key] = _AttrDict(input_ids=t["input_ids"].to(dev), attention_mask=t["attention_mask"].to(dev))
         return batch[key]
 
@@ -411,6 +424,15 @@ class MiCo(nn.Module):
 
     def forward(self, batch, task, compute_loss=True):
         batch = _AttrDict(batch)
+        # Training (gradients on): the same losses on the schedule of mico_b200/train_step.py -- one tower pass for all
+        # modalities, ITM / caption sub-tasks differentiated group by group so that their activations never coexist.
+        # config.step_schedule = "reference" keeps the reference's lazy one-sub-task-at-a-time order below.
+        if compute_loss and torch.is_grad_enabled() and getattr(self.config, "step_schedule", "fused") == "fused" \
+                and hasattr(getattr(self.vision_encoder, "visual", None), "forward_multi"):
+            from .train_step import fused_train_forward
+            if "caption_tokens" not in batch and "raw_captions" in batch:
+                self._tokens(batch, "caption_tokens", "raw_captions", self.max_caption_len, on_host=True)
+            return fused_train_forward(self, batch, task)
         out = {}
         for t in task.split("_"):
             if t.startswith("ret"):

@@ -236,6 +236,29 @@ def cast_bf16(src, dst=None):
     return dst
 
 
+def cast_f32_from_bf16(src, dst):
+    """bf16 contiguous -> fp32 contiguous (dst written in place)"""
+    _req(src, BF16, "src")
+    _req(dst, F32, "dst")
+    if src.numel() != dst.numel() or not src.is_contiguous() or not dst.is_contiguous():
+        raise MicoError("cast_f32_from_bf16: contiguous tensors of equal size expected")
+    check(lib.mico_cast_bf16_to_f32(_ptr(src), _ptr(dst), C.c_int64(src.numel()), _stream()), "mico_cast_bf16_to_f32")
+    return dst
+
+
+def scale_(x, scale_dev=None, scale_host=1.0):
+    """x *= scale_dev[0] * scale_host in place (fp32, contiguous, 16-byte aligned)."""
+    _req(x, F32, "x")
+    if not x.is_contiguous():
+        raise MicoError("scale_: contiguous tensor expected")
+    if x.numel() == 0:
+        return x
+    if scale_dev is not None:
+        _req(scale_dev, F32, "scale_dev")
+    check(lib.mico_scale_f32(_ptr(x), _ptr(scale_dev), C.c_float(scale_host), C.c_int64(x.numel()), _stream()), "mico_scale_f32")
+    return x
+
+
 def cast_bf16_2d(src, ldd):
     """fp32 [rows, cols] (row pitch src.stride(0)) -> bf16 [rows, ldd], zero-filled past cols."""
     _req(src, F32, "src")

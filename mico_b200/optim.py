@@ -102,7 +102,9 @@ class AdamW(Optimizer):
                 ci.append(np.arange(k, dtype=np.int32))
             ct, ci = np.concatenate(ct), np.concatenate(ci)
             hit = (torch.from_numpy(ct).to(device), torch.from_numpy(ci).to(device), len(ct))
-            self._chunk_cache = {key: hit}
+            if len(self._chunk_cache) >= 8:      # the parameter set is stable from step to step: a handful of layouts
+                self._chunk_cache.clear()
+            self._chunk_cache[key] = hit
         return hit
 
     @torch.no_grad()
@@ -149,30 +151,40 @@ class AdamW(Optimizer):
                 per_dev.setdefault(p.device, []).append(
                     (p.data_ptr(), grad.data_ptr(), state['exp_avg'].data_ptr(), state['exp_avg_sq'].data_ptr(),
                      w.data_ptr() if w is not None else 0, p.numel(), hyper_idx[hk], 0, grad, p))
-        if len(hyper) > _MAX_GROUPS:
-            raise MicoError(f"AdamW: {len(hyper)} distinct (group, step) hyper-parameter sets; the kernel takes {_MAX_GROUPS}")
         if not per_dev:
             return loss
-        htab = (_Hyper * _MAX_GROUPS)()
-        for i, h in enumerate(hyper):
-            htab[i] = _Hyper(*h)
-        for dev, rows in per_dev.items():
-            tab = np.empty(len(rows), _TENSOR_DT)
-            for i, r in enumerate(rows):
-                tab[i] = r[:8]
-            sizes = [r[5] for r in rows]
-            ct, ci, n_chunks = self._chunks(dev, sizes)
-            tab_dev = torch.from_numpy(tab.view(np.uint8)).pin_memory().to(dev, non_blocking=True)
-            with torch.cuda.device(dev):
-                stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-                check(lib.mico_adamw_multi(C.c_void_p(tab_dev.data_ptr()), C.c_void_p(ct.data_ptr()),
-                                           C.c_void_p(ci.data_ptr()), int(n_chunks), int(_CHUNK), htab, len(hyper),
-                                           C.c_float(self.grad_scale), C.c_double(float(sum(sizes))), stream),
-                      "mico_adamw_multi")
-            for r in rows:       # the raw-pointer update is invisible to autograd's version counters
-                torch.autograd.graph.increment_version(r[9])
+        updated = set()
+        for dev, all_rows in per_dev.items():
+            # the kernel takes a table of _MAX_GROUPS hyper-parameter rows per launch.  Parameters that skipped steps
+            # (grad None on some batches: the audio / depth heads on image-only batches) keep older step counts, so one
+            # step can need more (group, t) rows than that: launch once per slice of _MAX_GROUPS rows -- the reference's
+            # per-parameter loop (build_optimizer.py:136-196) has no such limit either.
+            for lo in range(0, len(hyper), _MAX_GROUPS):
+                rows = [r for r in all_rows if lo <= r[6] < lo + _MAX_GROUPS]
+                if not rows:
+                    continue
+                htab = (_Hyper * _MAX_GROUPS)()
+                n_h = min(_MAX_GROUPS, len(hyper) - lo)
+                for i in range(n_h):
+                    htab[i] = _Hyper(*hyper[lo + i])
+                tab = np.empty(len(rows), _TENSOR_DT)
+                for i, r in enumerate(rows):
+                    tab[i] = r[:6] + (r[6] - lo, 0)
+                sizes = [r[5] for r in rows]
+                ct, ci, n_chunks = self._chunks(dev, sizes)
+                tab_dev = torch.from_numpy(tab.view(np.uint8)).pin_memory().to(dev, non_blocking=True)
+                with torch.cuda.device(dev):
+                    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                    check(lib.mico_adamw_multi(C.c_void_p(tab_dev.data_ptr()), C.c_void_p(ct.data_ptr()),
+                                               C.c_void_p(ci.data_ptr()), int(n_chunks), int(_CHUNK), htab, n_h,
+                                               C.c_float(self.grad_scale), C.c_double(float(sum(sizes))), stream),
+                          "mico_adamw_multi")
+                for r in rows:       # the raw-pointer update is invisible to autograd's version counters
+                    torch.autograd.graph.increment_version(r[9])
+                    if r[4]:
+                        updated.add(id(r[9]))
         for owner in self._sink_owners:
-            owner.mark_weights_fresh()
+            owner.mark_weights_fresh(updated)
         return loss
 
 

@@ -122,3 +122,40 @@ def masked_lm(p, ids, attention_mask=None, enc=None, enc_mask=None, labels=None,
     if labels is not None:
         loss = F.cross_entropy(logits.view(-1, logits.shape[-1]), labels.view(-1))
     return loss, logits, seq
+
+
+def init_params(seed=0, prefix="", layers=12, hidden=768, heads=12, inter=3072, vocab=30522, max_pos=512, types=2, std=0.02):
+    """Random-init state_dict of BertForMaskedLM as the reference builds it (bert.py:624-637 _init_weights: Linear / Embedding
+    weights ~ N(0, 0.02), biases 0, LayerNorm 1 / 0; decoder tied to the word embeddings as under transformers 4.31), for
+    the CPU baseline legs of bench.py -- no checkpoint is available offline."""
+    g = torch.Generator().manual_seed(seed)
+    n = lambda *s: std * torch.randn(*s, generator=g)
+    p = {}
+
+    def lin(k, o, i):
+        p[k + ".weight"], p[k + ".bias"] = n(o, i), torch.zeros(o)
+
+    def ln(k):
+        p[k + ".weight"], p[k + ".bias"] = torch.ones(hidden), torch.zeros(hidden)
+    e = prefix + "bert.embeddings."
+    p[e + "word_embeddings.weight"] = n(vocab, hidden)
+    p[e + "word_embeddings.weight"][0].zero_()
+    p[e + "position_embeddings.weight"] = n(max_pos, hidden)
+    p[e + "token_type_embeddings.weight"] = n(types, hidden)
+    ln(e + "LayerNorm")
+    for i in range(layers):
+        l = f"{prefix}bert.encoder.layer.{i}."
+        for att in ("attention.", "crossattention."):
+            for k in ("query", "key", "value"):
+                lin(l + att + "self." + k, hidden, hidden)
+            lin(l + att + "output.dense", hidden, hidden)
+            ln(l + att + "output.LayerNorm")
+        lin(l + "intermediate.dense", inter, hidden)
+        lin(l + "output.dense", hidden, inter)
+        ln(l + "output.LayerNorm")
+    c = prefix + "cls.predictions."
+    lin(c + "transform.dense", hidden, hidden)
+    ln(c + "transform.LayerNorm")
+    p[c + "decoder.weight"] = p[e + "word_embeddings.weight"]
+    p[c + "bias"] = torch.zeros(vocab)
+    return p

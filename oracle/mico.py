@@ -121,3 +121,75 @@ def retrieval_caption_step(p, ranks, vit_cfg, layers, heads, itm_ratio=0.1, task
             d["loss_cap"] = caption_loss(p, conds[k], r["cap_ids"], r["att"], r["cap_labels"], layers, heads)
         out.append(d)
     return out
+
+
+# ---------------------------------------------------------------------------------------------- omni-modal step (one rank)
+_COMBO = {"v": "v", "a": "a", "d": "d", "va": "va", "id": "vd"}
+_KIND = {"v": "vision", "a": "audio", "d": "depth"}
+
+
+def omni_features(p, batch, vit_cfg, need="vad", dp_scales=None):
+    """Tower outputs, pooled features and fusion inputs of every modality in `need` (mico.py:115-148, 157-248):
+    vision_pixels (b,n,3,H,W); audio_spectrograms (b,n,T,mel) -> 3x channel repeat; depth_pixels (b,n,3,H,W)."""
+    outs = {}
+    if "v" in need:
+        outs["v"] = vision_encoder(p, batch["vision_pixels"], vit_cfg, dp_scales=dp_scales)
+    if "a" in need:
+        outs["a"] = audio_encoder(p, batch["audio_spectrograms"], vit_cfg)
+    if "d" in need:
+        outs["d"] = vision_encoder(p, batch["depth_pixels"], vit_cfg)
+    pools = {m: pool_tower(o) for m, o in outs.items()}
+    conds = {m: fusion_input(p, o, _KIND[m]) for m, o in outs.items()}
+    return outs, pools, conds
+
+
+def combo_feature(p, pools, combo):
+    """feat_<combo> of data/model/vast.py:221-272: single modality -> Contra_head; fused -> biased Linear on the concatenation
+    (contra_head_va / contra_head_id, mico.py:386-394)."""
+    parts = _COMBO[combo]
+    if len(parts) == 1:
+        return F.normalize(contra_head(p, f"contra_head_{combo}", pools[parts]), dim=-1)
+    x = torch.cat([pools[m] for m in parts], dim=1)
+    return F.normalize(F.linear(x, p[f"contra_head_{combo}.weight"], p[f"contra_head_{combo}.bias"]), dim=-1)
+
+
+def omni_step(p, batch, vit_cfg, layers, heads, task, itm_ratio=0.1, negs=None, generator=None):
+    """vast.py:317-348 (task dispatch) -> forward_ret :383-464 + forward_cap :485-512 for ONE rank (world size 1) over the
+    modality combinations tv / ta / tva / td / tid.  batch: vision_pixels, audio_spectrograms, depth_pixels, ids, att
+    [, cap_ids, cap_labels]; negs: {subtask: (neg_cond, neg_text)} to pin the hard negatives, else they are drawn like
+    vast.py:430-440 (torch.multinomial on softmax(sim) + 1e-4 with the own-sample column zeroed)."""
+    ret_st, cap_st = [], []
+    for t in task.split("_"):
+        (ret_st if t.startswith("ret") else cap_st).extend(t.split("%")[1:])
+    need = set("".join(_COMBO[s[1:]] for s in ret_st + cap_st))
+    _, pools, conds = omni_features(p, batch, vit_cfg, need)
+    cond_of = lambda c: torch.cat([conds[m] for m in _COMBO[c]], dim=1)
+    ids, att = batch["ids"], batch["att"]
+    out = {}
+    if ret_st:
+        feat_t = text_feature(p, ids, att, layers, heads)
+        bs = feat_t.shape[0]
+        l_itc, l_itm = [], []
+        for st in ret_st:
+            c = st[1:]
+            feat_c = combo_feature(p, pools, c)
+            l, sim_c2t, sim_t2c = itc_loss(feat_c, feat_t, feat_c.detach(), feat_t.detach(), p["contra_temp"], 0)
+            l_itc.append(l)
+            if negs is not None and st in negs:
+                neg_c, neg_t = negs[st]
+            else:
+                with torch.no_grad():
+                    w_t2c = F.softmax(sim_t2c, dim=1) + 1e-4
+                    w_t2c.fill_diagonal_(0)
+                    w_c2t = F.softmax(sim_c2t, dim=1) + 1e-4
+                    w_c2t.fill_diagonal_(0)
+                    neg_c = torch.multinomial(w_t2c, 1, generator=generator).view(-1)
+                    neg_t = torch.multinomial(w_c2t, 1, generator=generator).view(-1)
+            cond = cond_of(c)
+            l_itm.append(itm_loss(p, cond, cond, ids, att, ids, att, neg_c, neg_t, itm_ratio, layers, heads))
+        out["loss_itc"] = sum(l_itc) / len(l_itc)
+        out["loss_itm"] = sum(l_itm) / len(l_itm)
+    if cap_st:
+        l_cap = [caption_loss(p, cond_of(st[1:]), batch["cap_ids"], att, batch["cap_labels"], layers, heads) for st in cap_st]
+        out["loss_cap"] = sum(l_cap) / len(l_cap)
+    return out

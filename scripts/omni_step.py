@@ -16,7 +16,7 @@ def main():
     b = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     ckpt = (sys.argv[3] == "ckpt") if len(sys.argv) > 3 else b > 12       # activation checkpointing in the tower (config.checkpointing)
-    n_v, n_a, n_d, S = 8, 3, 1, 40
+    n_v, n_a, n_d, S = 8, 3, 1, int(os.environ.get("OMNI_S", "128"))
     cfg = _AttrDict(vision_encoder_type="evaclip01_giant", vision_resolution=224, checkpointing=ckpt, contra_dim=512,
                     max_vision_sample_num=8, max_audio_sample_num=3, max_depth_sample_num=1, beam_size=3, itm_ratio=0.1,
                     max_omni_caption_len=70, max_caption_len=S, max_subtitle_len=70, frame_embedding_type="adaptive",
@@ -64,7 +64,7 @@ def main():
     device_calls = {k: int(v["calls"]) for k, v in fam.items()}
     frames = b * (n_v + n_a + n_d)
     text_tok = int(att.sum())
-    print(json.dumps(dict(workload="omni-modal step: video n=8 + audio n=3 + depth n=1 + text S=40, ViT-g/14 + BERT-base, task " + task,
+    print(json.dumps(dict(workload="omni-modal step: video n=8 + audio n=3 + depth n=1 + text S=" + str(S) + ", ViT-g/14 + BERT-base, task " + task,
                           samples_per_step=b, vit_frames_per_step=frames, tower_activation_checkpointing=ckpt, ms_per_step=dt * 1e3,
                           processed_tokens_per_s=(frames * 257 + text_tok) / dt,
                           north_star_tokens_per_s=b * (1568 + 3 * 257 + 257 + 128) / dt,

@@ -221,3 +221,158 @@ def test_losses_vs_reference_forward_ret_and_forward_cap(golden_dir):
         errs[k] = rel_l2(named[k].grad.cpu(), want)
     print("gradient rel-L2 vs reference:", {k: f"{v:.2e}" for k, v in errs.items()})
     assert max(errs.values()) < 3e-2, errs
+
+
+def _omni_batch(b=3, n_v=2, n_a=2, n_d=1, S=24, seed=21):
+    g = torch.Generator().manual_seed(seed)
+    r = make_rank_batch(5, b=b, n=n_v, S=S)
+    r["audio"] = torch.randn(b, n_a, 224, 224, generator=g)
+    r["depth"] = torch.randn(b, n_d, 3, 224, 224, generator=g)
+    negs = {}
+    for st in ("tv", "ta", "tva", "td"):
+        negs[st] = ((torch.arange(b) + torch.randint(1, b, (b,), generator=g)) % b,
+                    (torch.arange(b) + torch.randint(1, b, (b,), generator=g)) % b)
+    return r, negs
+
+
+def _omni_model(seed=4):
+    from mico_b200.mico import MiCo
+    torch.manual_seed(seed)
+    model = MiCo.from_pretrained(make_cfg(), {})
+    with torch.no_grad():
+        gen = torch.Generator().manual_seed(9)
+        for _, prm in sorted(model.named_parameters()):
+            if prm.dim() <= 1 and prm.numel() > 1:
+                prm.add_(0.02 * torch.randn(prm.shape, generator=gen))
+    return model
+
+
+def _run_omni(model, r, negs, task):
+    from mico_b200.mico import _AttrDict
+    batch = dict(vision_pixels=r["pixels"].cuda(), audio_spectrograms=r["audio"].cuda(), depth_pixels=r["depth"].cuda(),
+                 caption_tokens=_AttrDict(input_ids=r["ids"].cuda(), attention_mask=r["att"].cuda()),
+                 cap_input_ids=r["cap_ids"].cuda(), cap_labels=r["cap_labels"].cuda())
+    for st, (nc, nt) in negs.items():
+        batch[f"itm_neg_cond_{st}"], batch[f"itm_neg_text_{st}"] = nc, nt
+    for prm in model.parameters():
+        prm.grad = None
+    out = model(batch, task, compute_loss=True)
+    sum(out.values()).backward()
+    return {k: v.item() for k, v in out.items()}, {k: v.grad.clone() for k, v in model.named_parameters() if v.grad is not None}
+
+
+OMNI_TASK = "ret%tv%ta%tva%td_cap%tv%ta%tva"
+
+
+def test_fused_step_matches_reference_order():
+    """mico_b200/train_step.py (one tower pass, eager loss groups) computes the losses and gradients of the reference-ordered
+    MiCo.forward: same kernels on the same operands, only the summation order of gradient contributions differs."""
+    model = _omni_model().cuda().train()
+    r, negs = _omni_batch()
+    model.config["step_schedule"] = "reference"
+    l_ref, g_ref = _run_omni(model, r, negs, OMNI_TASK)
+    model.config["step_schedule"] = "fused"
+    l_fus, g_fus = _run_omni(model, r, negs, OMNI_TASK)
+    assert set(l_ref) == set(l_fus) == {"loss_itc", "loss_itm", "loss_cap"}
+    for k in l_ref:
+        assert abs(l_ref[k] - l_fus[k]) <= 1e-6 * abs(l_ref[k]), (k, l_ref[k], l_fus[k])
+    assert set(g_ref) == set(g_fus)
+    worst = max((rel_l2(g_fus[k], g_ref[k]), k) for k in g_ref if g_ref[k].norm() > 1e-7)
+    print("fused vs reference-order schedule, worst gradient difference:", worst)
+    assert worst[0] < 2e-3       # bf16 fusion-input gradients are summed in a different order
+
+
+def test_fused_step_loss_scaling_and_unequal_weights():
+    """An eager loss group rescales its stored gradients by the upstream scalar (GradScaler's loss scale); unequal weights on
+    the losses of one group poison the gradients instead of silently mis-weighting them."""
+    from mico_b200.mico import _AttrDict
+    model = _omni_model().cuda().train()
+    r, negs = _omni_batch(b=2)
+    _, g1 = _run_omni(model, r, negs, "ret%tv_cap%tv")
+    batch = dict(vision_pixels=r["pixels"].cuda(),
+                 caption_tokens=_AttrDict(input_ids=r["ids"].cuda(), attention_mask=r["att"].cuda()),
+                 cap_input_ids=r["cap_ids"].cuda(), cap_labels=r["cap_labels"].cuda(),
+                 itm_neg_cond_tv=negs["tv"][0], itm_neg_text_tv=negs["tv"][1])
+    for prm in model.parameters():
+        prm.grad = None
+    out = model(dict(batch), "ret%tv_cap%tv", compute_loss=True)
+    (sum(out.values()) * 8.0).backward()
+    k = "multimodal_encoder.bert.encoder.layer.1.crossattention.self.key.weight"
+    assert rel_l2(dict(model.named_parameters())[k].grad, 8.0 * g1[k]) < 1e-5
+    kv = "vision_encoder.visual.blocks.0.mlp.fc1.weight"
+    assert rel_l2(dict(model.named_parameters())[kv].grad, 8.0 * g1[kv]) < 2e-2
+    for prm in model.parameters():
+        prm.grad = None
+    out = model(dict(batch), "ret%tv_cap%tv", compute_loss=True)
+    (out["loss_itc"] + out["loss_itm"] + 2.0 * out["loss_cap"]).backward()
+    assert torch.isnan(dict(model.named_parameters())[k].grad).any()
+
+
+def test_omni_step_vs_oracle():
+    """The seven-sub-task omni-modal step (video + audio + depth + text; BASELINE configs[4] at test size) against the CPU
+    oracle's omni_step (oracle/mico.py, vast.py:317-512 restated): losses 1e-3 relative, gradients like the tv step."""
+    from oracle import eva_vit as OV
+    from oracle import mico as OM
+    model = _omni_model()
+    p = oracle_params(model)
+    model = model.cuda().train()
+    r, negs = _omni_batch()
+    losses, grads = _run_omni(model, r, negs, OMNI_TASK)
+    vit_cfg = OV.vit_cfg(width=176, depth=2, heads=2, mlp=352)
+    ob = dict(vision_pixels=r["pixels"], audio_spectrograms=r["audio"], depth_pixels=r["depth"], ids=r["ids"], att=r["att"],
+              cap_ids=r["cap_ids"], cap_labels=r["cap_labels"])
+    ref = OM.omni_step(p, ob, vit_cfg, 2, 2, OMNI_TASK, itm_ratio=0.1, negs=negs)
+    sum(ref.values()).backward()
+    for k in losses:
+        print(f"{k}: {losses[k]:.6f} vs oracle {ref[k].item():.6f}")
+        assert abs(losses[k] - ref[k].item()) <= 1e-3 * abs(ref[k].item()), k
+    errs = []
+    for k, g in grads.items():
+        if k.endswith("self.key.bias") or k.endswith("decoder.weight"):
+            continue
+        rg = p[k].grad
+        assert rg is not None, k
+        if rg.norm().item() < 1e-7:
+            continue
+        errs.append((rel_l2(g.cpu(), rg), k))
+    errs.sort(reverse=True)
+    print("worst gradient errors:", [(f"{e:.3e}", k) for e, k in errs[:6]], "median", f"{errs[len(errs) // 2][0]:.3e}")
+    assert errs[0][0] < 1e-1 and errs[len(errs) // 2][0] < 3e-2 and len(errs) > 70
+    assert "contra_head_a.linear.weight" in grads and "contra_head_id.weight" not in grads
+
+
+def test_flat_grads_and_tower_forward_multi():
+    """dp.FlatGrads: every p.grad aliases one flat buffer, the tower writes its segment in place, unused parameters end up
+    with grad None; forward_multi equals separate tower calls."""
+    from mico_b200 import dp
+    model = _omni_model().cuda().train()
+    r, negs = _omni_batch(b=2)
+    _, g_ref = _run_omni(model, r, negs, "ret%tv%ta_cap%tv")
+    flat = dp.FlatGrads(model)
+    from mico_b200.mico import _AttrDict
+    batch = dict(vision_pixels=r["pixels"].cuda(), audio_spectrograms=r["audio"].cuda(),
+                 caption_tokens=_AttrDict(input_ids=r["ids"].cuda(), attention_mask=r["att"].cuda()),
+                 cap_input_ids=r["cap_ids"].cuda(), cap_labels=r["cap_labels"].cuda())
+    for st in ("tv", "ta"):
+        batch[f"itm_neg_cond_{st}"], batch[f"itm_neg_text_{st}"] = negs[st]
+    for _ in range(2):       # second pass: zero_grad really resets
+        flat.zero_grad()
+        out = model(dict(batch), "ret%tv%ta_cap%tv", compute_loss=True)
+        sum(out.values()).backward()
+        n_unused = flat.detach_unused()
+    assert n_unused > 0
+    lo, hi = flat.buf.data_ptr(), flat.buf.data_ptr() + flat.buf.numel() * 4
+    named = dict(model.named_parameters())
+    for k, g in g_ref.items():
+        assert named[k].grad is not None and lo <= named[k].grad.data_ptr() < hi, k
+        if g.norm() > 1e-7:
+            assert rel_l2(named[k].grad, g) < 2e-3, k
+    assert named["contra_head_d.linear.weight"].grad is None
+    tower = model.vision_encoder.visual
+    with torch.no_grad():
+        model.eval()
+        a = r["audio"].cuda().reshape(-1, 224, 224)
+        v = r["pixels"].cuda().reshape(-1, 3, 224, 224)
+        ym = tower.forward_multi([v, a])
+        assert torch.equal(ym[0], tower(v, return_all_features=True)) and torch.equal(ym[1], tower(a, return_all_features=True))
+    flat.close()

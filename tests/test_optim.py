@@ -136,3 +136,42 @@ def test_fused_adamw_writes_tower_bf16_operands():
     tower.invalidate_weight_cache()
     y2 = tower(x, return_all_features=True)
     assert torch.equal(y1, y2)
+
+
+@pytest.mark.gpu
+def test_fused_adamw_parameters_that_skip_steps():
+    """Multi-task training: heads without gradient on a batch keep an older step count, so one step can need more than
+    the kernel's 16 (group, t) hyper-parameter rows.  Checked against the oracle's per-parameter AdamW."""
+    from mico_b200 import optim
+    from oracle import optim as O
+    torch.manual_seed(3)
+    n_groups, per_group, steps = 6, 4, 5
+    params = [[torch.nn.Parameter(torch.randn(33 + 7 * j + gi, device="cuda")) for j in range(per_group)] for gi in range(n_groups)]
+    groups = [dict(params=ps, lr=1e-2 * (gi + 1), weight_decay=0.01 * (gi % 2)) for gi, ps in enumerate(params)]
+    opt = optim.AdamW(groups, betas=(0.9, 0.98))
+    ref = {}
+    for gi, ps in enumerate(params):
+        for j, p in enumerate(ps):
+            ref[(gi, j)] = [p.detach().cpu().clone(), torch.zeros(p.numel()), torch.zeros(p.numel()), 0]
+    gen = torch.Generator().manual_seed(11)
+    max_rows = 0
+    for s in range(steps):
+        distinct = set()
+        for gi, ps in enumerate(params):
+            for j, p in enumerate(ps):
+                if s % (j + 1) != 0:        # parameter j of every group only has a gradient every (j+1)-th step
+                    p.grad = None
+                    continue
+                g = torch.randn(p.numel(), generator=gen)
+                p.grad = g.cuda()
+                r = ref[(gi, j)]
+                r[3] += 1
+                distinct.add((gi, r[3]))
+                r[0], r[1], r[2] = O.adamw_step(r[0], g, r[1], r[2], r[3], groups[gi]["lr"], (0.9, 0.98), 1e-6,
+                                                groups[gi]["weight_decay"], True)
+        max_rows = max(max_rows, len(distinct))
+        opt.step()
+        for gi, ps in enumerate(params):
+            for j, p in enumerate(ps):
+                assert torch.allclose(p.detach().cpu(), ref[(gi, j)][0], rtol=1e-5, atol=1e-7), (s, gi, j)
+    assert max_rows > 16
