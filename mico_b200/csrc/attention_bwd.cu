@@ -249,6 +249,9 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const float nlse2 = -lse_n * kLog2e;
             const float ndlt = -dlt_n * p.scale;     // dS = p * (dP*scale - delta*scale)
             const float* mrow = (!kPlain && p.mask) ? (p.mask + (int64_t)(p.mask_bmod ? b % p.mask_bmod : b) * p.mask_bs + (int64_t)h * p.mask_hs) + (int64_t)(row_ok ? qi : 0) * p.mask_qs : nullptr;
+            const bool dropping = !kPlain && p.drop.p > 0.f;
+            const uint32_t drop_key = dropping ? drop_row_key(p.drop, (uint64_t)(b * p.H + h) * p.Sq + (row_ok ? qi : 0)) : 0u;
+            const uint32_t drop_thr = drop_thresh16(p.drop);
             for (int j = 0; j < nkv; ++j, ++tcount) {
                 const int valid = n_valid(kt, j);
                 const int nch = (valid + 31) >> 5;
@@ -264,21 +267,23 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     tmem_ld_wait();
                     float ds[32];
                     const int lim = valid - c * 32;
-                    const bool dropping = !kPlain && p.drop.p > 0.f;
                     if (!mrow && lim >= 32 && !dropping) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
                             ds[i] = ex2_fast(fmaf(__uint_as_float(sv[i]), sc2, nlse2)) * fmaf(__uint_as_float(dv[i]), p.scale, ndlt);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            float s = fmaf(__uint_as_float(sv[i]), sc2, nlse2);
-                            if (mrow && i < lim) s = fmaf(mrow[j * kTile + c * 32 + i], kLog2e, s);
-                            float dpv = __uint_as_float(dv[i]);
-                            if (dropping)      // dP flows only through the kept probabilities
-                                dpv *= drop_mult(p.drop, ((uint64_t)(b * p.H + h) * p.Sq + (row_ok ? qi : 0)) * p.Sk +
-                                                             (uint64_t)(j * kTile + c * 32 + i));
-                            ds[i] = i < lim ? ex2_fast(s) * fmaf(dpv, p.scale, ndlt) : 0.f;
+                        for (int i = 0; i < 32; i += 2) {
+                            const uint32_t bits = dropping ? drop_pair_bits(drop_key, (uint32_t)(j * kTile + c * 32 + i) >> 1) : 0u;
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                float s = fmaf(__uint_as_float(sv[i + e]), sc2, nlse2);
+                                if (mrow && i + e < lim) s = fmaf(mrow[j * kTile + c * 32 + i + e], kLog2e, s);
+                                float dpv = __uint_as_float(dv[i + e]);
+                                if (dropping)      // dP flows only through the kept probabilities
+                                    dpv *= ((e ? bits >> 16 : bits & 0xFFFFu) >= drop_thr) ? p.drop.inv_keep : 0.0f;
+                                ds[i + e] = i + e < lim ? ex2_fast(s) * fmaf(dpv, p.scale, ndlt) : 0.f;
+                            }
                         }
                     }
                     tmem_store_bf16x32(tmem_dS + lane_off + c * 16, ds);
@@ -321,8 +326,8 @@ struct DkvSmem {
     static constexpr int V = 2 * kAtomBytes;
     static constexpr int Q0 = 4 * kAtomBytes;                     // 2 stages x 2 atoms x 144 rows
     static constexpr int DO0 = Q0 + 4 * kAtomBytesN;
-    static constexpr int STATS = DO0 + 4 * kAtomBytesN;           // 2 stages x (-lse*log2e [256], -delta*scale [256])
-    static constexpr int BARS = STATS + 4 * 1024;
+    static constexpr int STATS = DO0 + 4 * kAtomBytesN;           // 2 stages x (-lse*log2e [256], -delta*scale [256], dropout row key [256])
+    static constexpr int BARS = STATS + 2 * 3072;
     static constexpr int TOTAL = BARS + 256 + 1024;
 };
 constexpr uint32_t kKvST = 0, kKvDPT = 144, kKvDV = 288, kKvDK = 384;
@@ -462,14 +467,18 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         bool first_tile = true;
         // -lse*log2(e) and -delta*scale of query t (= threadIdx.x < 160) of q tile i of work item w; queries past the
         // tile's valid count get lse = +huge -> p = 0, dS = 0 with no per-element predicate
-        auto load_stats = [&](int w_, int i_, float& l, float& d) {
+        const bool dropping = !kPlain && p.drop.p > 0.f;
+        const uint32_t drop_thr = drop_thresh16(p.drop);
+        auto load_stats = [&](int w_, int i_, float& l, float& d, uint32_t& key) {
             l = 1e30f;       // raw values: the scaling is applied where they are stored, long after the loads were issued
             d = 0.f;
+            key = 0u;
             const int t = threadIdx.x;
             if (t < 160 && t < n_valid(qtl, i_)) {
                 const int64_t at = (int64_t)(w_ / nkt) * p.Sq + i_ * kTile + t;
                 l = ldg_f32_pinned(p.lse + at);
                 d = ldg_f32_pinned(p.delta + at);
+                if (dropping) key = drop_row_key(p.drop, (uint64_t)at);       // row = (b*H + h)*Sq + query
             }
         };
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
@@ -485,18 +494,24 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 // global loads of tile qcount + 1 (possibly the first tile of the next work item) are issued here and
                 // stored after this tile's math.  The previous readers of that buffer (tile qcount - 1) all passed this
                 // tile's 256-thread barrier before the store.
-                float* s_nlse2 = reinterpret_cast<float*>(smem + DkvSmem::STATS + (qcount & 1) * 2048);
+                float* s_nlse2 = reinterpret_cast<float*>(smem + DkvSmem::STATS + (qcount & 1) * 3072);
                 float* s_ndlt = s_nlse2 + 256;
+                const uint32_t* s_key = reinterpret_cast<const uint32_t*>(s_nlse2 + 512);
                 const uint32_t s_stats = smem_u32(s_nlse2);
                 if (first_tile) {      // very first tile of this CTA: nothing was prefetched
                     float l, d;
-                    load_stats(w, i, l, d);
-                    if (threadIdx.x < 160) { s_nlse2[threadIdx.x] = -l * kLog2e; s_ndlt[threadIdx.x] = -d * p.scale; }
+                    uint32_t key;
+                    load_stats(w, i, l, d, key);
+                    if (threadIdx.x < 160) {
+                        s_nlse2[threadIdx.x] = -l * kLog2e; s_ndlt[threadIdx.x] = -d * p.scale;
+                        reinterpret_cast<uint32_t*>(s_nlse2 + 512)[threadIdx.x] = key;
+                    }
                     first_tile = false;
                 }
                 float l_n = 0.f, d_n = 0.f;
+                uint32_t key_n = 0u;
                 const bool more = (i + 1 < nqt) || (w + (int)gridDim.x < num_work);
-                if (more) load_stats(i + 1 < nqt ? w : w + (int)gridDim.x, i + 1 < nqt ? i + 1 : 0, l_n, d_n);
+                if (more) load_stats(i + 1 < nqt ? w : w + (int)gridDim.x, i + 1 < nqt ? i + 1 : 0, l_n, d_n, key_n);
                 softmax_group_sync256();
                 mbar_wait(st_full, qcount & 1);
                 tc_fence_after();
@@ -532,9 +547,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                                 s = fmaf((p.mask + (int64_t)(p.mask_bmod ? b % p.mask_bmod : b) * p.mask_bs + (int64_t)h * p.mask_hs)[(int64_t)(i * kTile + c0 + q) * p.mask_qs + kj], kLog2e, s);
                             const float pu = ex2_fast(s);
                             float m = 1.0f;
-                            if (!kPlain && p.drop.p > 0.f)
-                                m = drop_mult(p.drop, ((uint64_t)(b * p.H + h) * p.Sq + (uint64_t)min(i * kTile + c0 + q, p.Sq - 1)) * p.Sk +
-                                                          (uint64_t)min(kj, p.Sk - 1));
+                            if (dropping) m = drop_mult_rc(p.drop, s_key[c0 + q], drop_thr, min(kj, p.Sk - 1));
                             pt[q] = pu * m;                                          // dV uses the dropped probabilities
                             dst[q] = pu * fmaf(__uint_as_float(dv[q]) * m, p.scale, dl[e]);
                         }
@@ -560,9 +573,10 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 __syncwarp();
                 if (lane_id() == 0) mbar_arrive(pds_full);
                 if (more && threadIdx.x < 160) {
-                    float* n_nlse2 = reinterpret_cast<float*>(smem + DkvSmem::STATS + ((qcount + 1) & 1) * 2048);
+                    float* n_nlse2 = reinterpret_cast<float*>(smem + DkvSmem::STATS + ((qcount + 1) & 1) * 3072);
                     n_nlse2[threadIdx.x] = -l_n * kLog2e;
                     n_nlse2[256 + threadIdx.x] = -d_n * p.scale;
+                    reinterpret_cast<uint32_t*>(n_nlse2 + 512)[threadIdx.x] = key_n;
                 }
             }
             mbar_wait(acc_full, wcount & 1);

@@ -196,6 +196,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const bool row_ok = qi < p.Sq;
             const float* mrow = (!kPlain && p.mask) ? (p.mask + (int64_t)(p.mask_bmod ? b % p.mask_bmod : b) * p.mask_bs + (int64_t)h * p.mask_hs) + (int64_t)(row_ok ? qi : 0) * p.mask_qs : nullptr;
             float m = -INFINITY, l = 0.f;
+            const bool dropping = !kPlain && p.drop.p > 0.f;
+            const uint32_t drop_key = dropping ? drop_row_key(p.drop, (uint64_t)(b * p.H + h) * p.Sq + (row_ok ? qi : 0)) : 0u;
+            const uint32_t drop_thr = drop_thresh16(p.drop);
             float oacc[HD_PAD];
 #pragma unroll
             for (int i = 0; i < HD_PAD; ++i) oacc[i] = 0.f;
@@ -249,7 +252,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     tmem_ld_wait();
                     float pv[32];
                     const int lim = valid - c * 32;
-                    const bool dropping = !kPlain && p.drop.p > 0.f;
                     if (!mrow && lim >= 32 && !dropping) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
@@ -258,14 +260,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            float s = fmaf(__uint_as_float(v[i]), sc2, -m_new);
-                            if (mrow && i < lim) s = fmaf(mrow[j * kTile + c * 32 + i], kLog2e, s);
-                            pv[i] = i < lim ? ex2_fast(s) : 0.f;
-                            sum += pv[i];                     // the softmax denominator is taken before dropout
-                            if (dropping)
-                                pv[i] *= drop_mult(p.drop, ((uint64_t)(b * p.H + h) * p.Sq + (row_ok ? qi : 0)) * p.Sk +
-                                                               (uint64_t)(j * kTile + c * 32 + i));
+                        for (int i = 0; i < 32; i += 2) {
+                            const uint32_t bits = dropping ? drop_pair_bits(drop_key, (uint32_t)(j * kTile + c * 32 + i) >> 1) : 0u;
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                float s = fmaf(__uint_as_float(v[i + e]), sc2, -m_new);
+                                if (mrow && i + e < lim) s = fmaf(mrow[j * kTile + c * 32 + i + e], kLog2e, s);
+                                pv[i + e] = i + e < lim ? ex2_fast(s) : 0.f;
+                                sum += pv[i + e];                 // the softmax denominator is taken before dropout
+                                if (dropping)
+                                    pv[i + e] *= ((e ? bits >> 16 : bits & 0xFFFFu) >= drop_thr) ? p.drop.inv_keep : 0.0f;
+                            }
                         }
                     }
 #pragma unroll

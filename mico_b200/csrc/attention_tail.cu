@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kTailThreads) attn_tail_q_kernel(TailParams p)
         for (int j = threadIdx.x; j < p.Sk; j += kTailThreads) {
             const float e = __expf(sc[j] - mx);
             sum += e;
-            sc[j] = p.drop.p > 0.f ? e * drop_mult(p.drop, ((uint64_t)(b * p.H + h) * p.Sq + i) * p.Sk + j) : e;
+            sc[j] = p.drop.p > 0.f ? e * drop_mult_rc(p.drop, drop_row_key(p.drop, (uint64_t)stat), drop_thresh16(p.drop), j) : e;
         }
         sum = block_reduce(sum, small, false);
         weighted_rows(V, p.v_rs, p.Sk, sc, p.D, 1.0f / sum, p.out0 + b * p.o0_bs + (int64_t)i * p.o0_rs + h * p.o0_hs, red);
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kTailThreads) attn_tail_q_kernel(TailParams p)
             if (mrow) s += mrow[j];
             const float pr = __expf(s - lse);
             const float dp = row_dot_quad(V + (int64_t)j * p.v_rs, dov, p.D);
-            const float m = p.drop.p > 0.f ? drop_mult(p.drop, ((uint64_t)(b * p.H + h) * p.Sq + i) * p.Sk + j) : 1.0f;
+            const float m = p.drop.p > 0.f ? drop_mult_rc(p.drop, drop_row_key(p.drop, (uint64_t)stat), drop_thresh16(p.drop), j) : 1.0f;
             if ((threadIdx.x & 3) == 0) sc[j] = pr * (dp * m - dlt) * p.scale;
         }
         __syncthreads();
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kTailThreads) attn_tail_kv_kernel(TailParams p
         const float pr = __expf(s - p.lse[stat0 + i]);
         const float dp = row_dot_quad(DO + (int64_t)i * p.do_rs, vv, p.D);
         if ((threadIdx.x & 3) == 0) {
-            const float m = p.drop.p > 0.f ? drop_mult(p.drop, ((uint64_t)(b * p.H + h) * p.Sq + i) * p.Sk + j) : 1.0f;
+            const float m = p.drop.p > 0.f ? drop_mult_rc(p.drop, drop_row_key(p.drop, (uint64_t)(stat0 + i)), drop_thresh16(p.drop), j) : 1.0f;
             pa[i] = pr * m;
             dsa[i] = pr * (dp * m - p.delta[stat0 + i]) * p.scale;
         }

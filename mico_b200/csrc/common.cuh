@@ -380,6 +380,35 @@ __device__ __forceinline__ float drop_mult(const DropCfg& d, uint64_t ctr) {
     return u >= d.p ? d.inv_keep : 0.0f;
 }
 
+// Attention-probability dropout (bert.py:243-247) is generated per score element inside the attention kernels, forward and
+// twice in the backward pass: splitmix64 per element (three 64-bit multiplies) cost more than the softmax itself (round 2:
+// BERT attention ran at 55 TFLOP/s, 17 % of the omni step).  Two-level scheme instead: one splitmix64 per score ROW gives a
+// 32-bit row key; a pair of adjacent keys (2t, 2t+1) of that row shares one 32-bit integer hash (lowbias32: two 32-bit
+// multiplies) whose halves are the two 16-bit uniforms.  keep <=> uniform16 >= round(p * 65536).
+//   row  = (b*H + h)*Sq + i                 row_key = low32(splitmix64(seed + row * golden))
+//   x    = lowbias32(row_key ^ ((j >> 1) * 0x9E3779B1))         u16 = (j & 1) ? x >> 16 : x & 0xFFFF
+__device__ __forceinline__ uint32_t drop_row_key(const DropCfg& d, uint64_t row) {
+    uint64_t z = row * 0x9E3779B97F4A7C15ull + d.seed;
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 27; z *= 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)z;
+}
+__device__ __forceinline__ uint32_t drop_pair_bits(uint32_t row_key, uint32_t jpair) {
+    uint32_t x = row_key ^ (jpair * 0x9E3779B1u);
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t drop_thresh16(const DropCfg& d) { return (uint32_t)(d.p * 65536.0f + 0.5f); }
+// multiplier of score element (row, j)
+__device__ __forceinline__ float drop_mult_rc(const DropCfg& d, uint32_t row_key, uint32_t thresh, int j) {
+    const uint32_t x = drop_pair_bits(row_key, (uint32_t)j >> 1);
+    const uint32_t u = (j & 1) ? (x >> 16) : (x & 0xFFFFu);
+    return u >= thresh ? d.inv_keep : 0.0f;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

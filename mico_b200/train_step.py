@@ -117,7 +117,7 @@ def prefetch_towers(model, batch, combos):
     jobs = []
     for m, key, src in (("v", "vision_output", "vision_pixels"), ("a", "audio_output", "audio_spectrograms"),
                         ("d", "depth_output", "depth_pixels")):
-        if m in need and key not in batch:
+        if m in need and key not in batch and src in batch:      # (features may be supplied precomputed)
             jobs.append((key, batch[src]))
     if len(jobs) < 2 or not hasattr(tower, "forward_multi"):
         return               # a single modality (or a tower without the multi-input pass): the lazy path does the same work

@@ -36,6 +36,33 @@ def drop_mult(p, seed, offset, shape):
     return torch.from_numpy(m.reshape(shape))
 
 
+def attn_drop_mult(p, seed, B, H, Sq, Sk):
+    """Host restatement of the attention kernels' probability-dropout mask (mico_b200/csrc/common.cuh drop_row_key /
+    drop_pair_bits): score row r = (b*H + h)*Sq + i gets the 32-bit key low32(splitmix64(seed + r * golden)); keys 2t, 2t+1
+    of the row share lowbias32(key ^ (t * 0x9E3779B1)), whose low / high half is their 16-bit uniform; an element is kept
+    (multiplier 1/(1-p)) when uniform16 >= round(p * 65536).  Returns a (B, H, Sq, Sk) fp32 tensor."""
+    rows = B * H * Sq
+    with np.errstate(over="ignore"):
+        z = np.arange(rows, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed)
+        z ^= z >> np.uint64(30)
+        z *= np.uint64(0xBF58476D1CE4E5B9)
+        z ^= z >> np.uint64(27)
+        z *= np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+        key = (z & np.uint64(0xFFFFFFFF)).astype(np.uint32)[:, None]
+        j = np.arange(Sk, dtype=np.uint32)[None, :]
+        x = key ^ ((j >> np.uint32(1)) * np.uint32(0x9E3779B1))
+        x ^= x >> np.uint32(16)
+        x *= np.uint32(0x7FEB352D)
+        x ^= x >> np.uint32(15)
+        x *= np.uint32(0x846CA68B)
+        x ^= x >> np.uint32(16)
+    u = np.where((j & np.uint32(1)) == 1, x >> np.uint32(16), x & np.uint32(0xFFFF))
+    thresh = np.uint32(int(np.float32(p) * np.float32(65536.0) + np.float32(0.5)))
+    m = np.where(u >= thresh, np.float32(1.0 / (1.0 - p)), np.float32(0.0)).astype(np.float32)
+    return torch.from_numpy(m.reshape(B, H, Sq, Sk))
+
+
 def _site(li, k):
     return (0 if li < 0 else 3 * li + k) << 40
 
@@ -66,7 +93,7 @@ def attention(p, pre, x, kv_src, add_mask, heads, adrop=None):
         s = s + add_mask
     pr = s.softmax(-1)
     if adrop is not None:          # attention-probability dropout (bert.py:243-247) with the product's mask
-        pr = pr * drop_mult(adrop[0], adrop[1], 0, tuple(pr.shape))
+        pr = pr * attn_drop_mult(adrop[0], adrop[1], *pr.shape)
     ctx = (pr @ v).transpose(1, 2).reshape(b, S, D)
     return ctx
 

@@ -1,0 +1,185 @@
+"""TEST INFRASTRUCTURE ONLY -- full-size parity cases (BASELINE sizes: the 40-block ViT-g/14, the 12-layer BERT-base with
+cross-attention, the ITC logits between them) and the bf16-autocast calibration of SURVEY.md 7(ii).
+
+`north_star` states 1e-3 relative for outputs "within fp/bf16".  Forty pre-norm blocks with bf16 GEMM operands cannot agree
+with an fp32 run elementwise to 1e-3 -- neither can the reference itself under torch.autocast.  SURVEY.md 7(ii) therefore
+defines the end-to-end bar as: error of the CUDA path against the fp32 reference <= error of the REFERENCE ITSELF run under
+bf16 autocast against its own fp32 run (and scalar losses within 1e-3).  This module builds the cases (seeded, identical on
+both sides), evaluates the fp32 oracle, and evaluates the oracle under an emulation of the reference loop's autocast
+(data/utils/pipeline.py:43: torch.cuda.amp.autocast -- matmuls / linear layers in 16-bit, LayerNorm / softmax / losses in
+fp32; bf16 here instead of the loop's fp16 because that is what the B200 path computes in).
+
+    python -m oracle.fullsize          # writes tests/golden/bf16_calibration.json (minutes of CPU)
+
+Only tests/ imports this at run time; the committed JSON holds the autocast-vs-fp32 errors so that the GPU test does not
+have to spend minutes of CPU on the bf16 emulation.
+"""
+import contextlib
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.nn.functional as F
+
+from . import bert as OB
+from . import eva_vit as OV
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CALIB = os.path.join(REPO, "tests", "golden", "bf16_calibration.json")
+
+
+def rel_l2(a, b):
+    a, b = a.detach().float().flatten(), b.detach().float().flatten()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@contextlib.contextmanager
+def autocast_bf16_like_cuda():
+    """torch.autocast on CPU, with the ops CUDA autocast keeps in fp32 (layer_norm, softmax, cross_entropy, normalize)
+    forced to fp32 inputs -- CPU autocast would otherwise run them in bf16, which the reference's GPU loop never does."""
+    ln, sm, ce, nz, tsm = F.layer_norm, F.softmax, F.cross_entropy, F.normalize, torch.Tensor.softmax
+    F.layer_norm = lambda x, *a, **k: ln(x.float(), *a, **k)
+    F.softmax = lambda x, *a, **k: sm(x.float(), *a, **k)
+    F.cross_entropy = lambda x, *a, **k: ce(x.float(), *a, **k)
+    F.normalize = lambda x, *a, **k: nz(x.float(), *a, **k)
+    torch.Tensor.softmax = lambda self, *a, **k: tsm(self.float(), *a, **k)
+    try:
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            yield
+    finally:
+        F.layer_norm, F.softmax, F.cross_entropy, F.normalize, torch.Tensor.softmax = ln, sm, ce, nz, tsm
+
+
+# ---------------------------------------------------------------------------------------------- cases
+TOWER_GRAD_KEYS = ("blocks.0.attn.qkv.weight", "blocks.0.mlp.fc1.weight", "blocks.20.mlp.fc2.weight",
+                   "blocks.39.attn.proj.weight", "blocks.39.norm2.weight", "patch_embed.proj.weight", "pos_embed")
+BERT_GRAD_KEYS = ("bert.encoder.layer.0.attention.self.query.weight", "bert.encoder.layer.0.crossattention.self.key.weight",
+                  "bert.encoder.layer.6.intermediate.dense.weight", "bert.encoder.layer.11.output.dense.weight",
+                  "bert.encoder.layer.11.crossattention.output.LayerNorm.weight", "cls.predictions.transform.dense.weight")
+
+
+def tower_case(batch=2, seed=0):
+    cfg = OV.VIT_G14
+    params = OV.init_params(cfg, seed=seed)
+    x = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(7))
+    return cfg, params, x
+
+
+def tower_eval(cfg, params, x):
+    """fwd + bwd of the 40-block tower (eval mode: no DropPath): features, cls embedding, loss, gradients."""
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    y = OV.forward_features(p, x, cfg)
+    loss = y.float().pow(2).mean()
+    loss.backward()
+    grads = {k: p[k].grad.float() for k in p if p[k].grad is not None}
+    return dict(features=y.detach().float(), cls=y[:, 0].detach().float(), loss=loss.item(), grads=grads)
+
+
+def bert_case(batch=2, S=128, Sk=257, seed=1):
+    params = OB.init_params(seed=seed, prefix="")
+    g = torch.Generator().manual_seed(11)
+    lens = torch.randint(8, S + 1, (batch,), generator=g)
+    att = (torch.arange(S)[None] < lens[:, None]).long()
+    ids = torch.randint(1000, 30522, (batch, S), generator=g) * att
+    ids[:, 0] = 101
+    pick = (torch.rand(batch, S, generator=g) < 0.6) & (att > 0)
+    pick[:, 0] = False
+    pick[:, 1] = True
+    labels = torch.where(pick, ids, torch.full_like(ids, -100))
+    cap_ids = torch.where(pick, torch.full_like(ids, 103), ids)
+    cond = torch.randn(batch, Sk, 768, generator=g)
+    return params, dict(ids=ids, att=att, cap_ids=cap_ids, labels=labels, cond=cond)
+
+
+def bert_eval(params, c, backward=True):
+    """caption-style pass (3-D causal mask, cross-attention, LM loss) of the 12-layer encoder, fwd + bwd."""
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in params.items()}
+    p["cls.predictions.decoder.weight"] = p["bert.embeddings.word_embeddings.weight"]
+    cond = c["cond"].clone().requires_grad_(True)
+    S = c["att"].shape[1]
+    att3 = torch.tril(c["att"].unsqueeze(1).expand(-1, S, -1).clone())
+    loss, _, seq = OB.masked_lm(p, c["cap_ids"], att3, cond, None, c["labels"], prefix="")
+    out = dict(seq=seq.detach().float(), loss=loss.item())
+    if backward:
+        loss.backward()
+        out["grads"] = {k: p[k].grad.float() for k in BERT_GRAD_KEYS}
+        out["d_cond"] = cond.grad.float()
+    return out
+
+
+def itc_case(batch=4, seed=3):
+    """pooled image / text embeddings through random contrastive heads -> logits / 0.07 (vast.py:405-408)."""
+    cfg, tp, x = tower_case(batch=batch, seed=0)
+    bp, c = bert_case(batch=batch, S=128, Sk=257, seed=1)
+    g = torch.Generator().manual_seed(seed)
+    wv, wt = 0.02 * torch.randn(512, 1408, generator=g), 0.02 * torch.randn(512, 768, generator=g)
+    return cfg, tp, x, bp, c, wv, wt
+
+
+def itc_eval(cfg, tp, x, bp, c, wv, wt):
+    with torch.no_grad():
+        y = OV.forward_features(tp, x, cfg)
+        h = OB.bert_model(bp, c["ids"], c["att"], prefix="bert.")
+        fv = F.normalize(F.linear(y[:, 0].float(), wv), dim=-1)
+        ft = F.normalize(F.linear(h[:, 0].float(), wt), dim=-1)
+        return dict(feat_v=fv, feat_t=ft, logits=fv @ ft.t() / 0.07)
+
+
+def compare_tower(a, ref):
+    out = dict(features=rel_l2(a["features"], ref["features"]), cls=rel_l2(a["cls"], ref["cls"]),
+               loss=abs(a["loss"] - ref["loss"]) / abs(ref["loss"]))
+    errs = sorted(rel_l2(a["grads"][k], ref["grads"][k]) for k in ref["grads"] if k in a["grads"] and ref["grads"][k].norm() > 1e-12)
+    out["grad_median"], out["grad_max"] = errs[len(errs) // 2], errs[-1]
+    for k in TOWER_GRAD_KEYS:
+        out["grad:" + k] = rel_l2(a["grads"][k], ref["grads"][k])
+    return out
+
+
+def compare_bert(a, ref):
+    out = dict(seq=rel_l2(a["seq"], ref["seq"]), loss=abs(a["loss"] - ref["loss"]) / abs(ref["loss"]))
+    if "grads" in ref and "grads" in a:
+        out["d_cond"] = rel_l2(a["d_cond"], ref["d_cond"])
+        for k in BERT_GRAD_KEYS:
+            out["grad:" + k] = rel_l2(a["grads"][k], ref["grads"][k])
+    return out
+
+
+def compare_itc(a, ref):
+    return dict(feat_v=rel_l2(a["feat_v"], ref["feat_v"]), feat_t=rel_l2(a["feat_t"], ref["feat_t"]),
+                logits=rel_l2(a["logits"], ref["logits"]), logits_max_abs=(a["logits"] - ref["logits"]).abs().max().item())
+
+
+def main():
+    torch.set_num_threads(os.cpu_count() or 1)
+    res = dict(how="oracle under torch.autocast(cpu, bf16) with layer_norm / softmax / cross_entropy / normalize in fp32 (the CUDA "
+                   "autocast policy of the reference loop, data/utils/pipeline.py:43) vs the same oracle in fp32; rel-L2 unless noted",
+               torch=torch.__version__)
+    t0 = time.time()
+    cfg, tp, x = tower_case()
+    ref = tower_eval(cfg, tp, x)
+    with autocast_bf16_like_cuda():
+        ac = tower_eval(cfg, tp, x)
+    res["tower_vitg_40blocks_bs2"] = compare_tower(ac, ref)
+    print("tower", res["tower_vitg_40blocks_bs2"], f"{time.time() - t0:.0f}s", flush=True)
+    for Sk in (257, 2056):
+        bp, c = bert_case(Sk=Sk)
+        ref = bert_eval(bp, c, backward=(Sk == 257))
+        with autocast_bf16_like_cuda():
+            ac = bert_eval(bp, c, backward=(Sk == 257))
+        res[f"bert_base_12layers_S128_Sk{Sk}"] = compare_bert(ac, ref)
+        print("bert", Sk, res[f"bert_base_12layers_S128_Sk{Sk}"], f"{time.time() - t0:.0f}s", flush=True)
+    case = itc_case()
+    ref = itc_eval(*case)
+    with autocast_bf16_like_cuda():
+        ac = itc_eval(*case)
+    res["itc_logits_bs4"] = compare_itc(ac, ref)
+    print("itc", res["itc_logits_bs4"], f"{time.time() - t0:.0f}s", flush=True)
+    with open(CALIB, "w") as f:
+        json.dump(res, f, indent=1, sort_keys=True)
+    print("wrote", CALIB)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -71,7 +71,7 @@ def test_attention_dropout_kernel_matches_masked_reference():
         dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, do, D ** -0.5, dropout=(p_, seed))
         qf, kf, vf = (t.float().cpu().requires_grad_(True) for t in (q, k, v))
         pr = (torch.einsum("bihd,bjhd->bhij", qf, kf) * D ** -0.5).softmax(-1)
-        pr = pr * OB.drop_mult(p_, seed, 0, (B, H, Sq, Sk))
+        pr = pr * OB.attn_drop_mult(p_, seed, B, H, Sq, Sk)
         ro = torch.einsum("bhij,bjhd->bihd", pr, vf)
         ro.backward(do.float().cpu())
         assert rel_l2(o.cpu(), ro) < 4e-3

@@ -1,0 +1,107 @@
+"""Parity at BASELINE sizes: the 40-block ViT-g/14 (fwd + bwd), the 12-layer BERT-base with cross-attention
+over 257 and 2056 visual tokens at S = 128 (fwd + bwd, LM loss), and the ITC logits between them -- CUDA path vs the fp32 CPU
+oracle, judged by SURVEY.md 7(ii): the error must not exceed the error of the reference itself under bf16 autocast
+(tests/golden/bf16_calibration.json, produced by `python -m oracle.fullsize`), and scalar losses agree to 1e-3 relative
+(BASELINE.json north_star).  The fp32 oracle runs on the GPU box's host cores (tens of seconds)."""
+import json
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# ours / autocast-reference error ratio allowed per quantity.  1.0 = "no worse than the reference's own mixed precision".
+# Gradient entries carry a small margin: single tensors' errors are noisy realisations of the same rounding process.
+RATIO = 1.0
+RATIO_GRAD = 1.25
+LOSS_TOL = 1e-3
+
+
+def _calib():
+    from oracle import fullsize as FS
+    with open(FS.CALIB) as f:
+        return json.load(f)
+
+
+def _check(name, errs, calib):
+    bad = []
+    for k, e in sorted(errs.items()):
+        if k == "loss":
+            ok, bar = e <= LOSS_TOL, LOSS_TOL
+        elif k == "logits_max_abs":
+            ok, bar = e <= RATIO * calib[k], RATIO * calib[k]
+        else:
+            r = RATIO_GRAD if k.startswith("grad") or k == "d_cond" else RATIO
+            ok, bar = e <= r * calib[k], r * calib[k]
+        print(f"[{name}] {k}: ours {e:.3e}  autocast-bf16 reference {calib[k]:.3e}  bar {bar:.3e}  {'ok' if ok else 'EXCEEDS'}")
+        if not ok:
+            bad.append(k)
+    assert not bad, f"{name}: worse than the reference's own bf16 autocast on {bad}"
+
+
+def test_vitg_40_blocks_fwd_bwd():
+    from mico_b200.eva_vit import EVAVisionTransformer
+    from oracle import fullsize as FS
+    cfg, tp, x = FS.tower_case()
+    ref = FS.tower_eval(cfg, tp, x)
+    m = EVAVisionTransformer(img_size=224, patch_size=14, num_classes=0, use_mean_pooling=False, embed_dim=cfg["width"],
+                             depth=cfg["depth"], num_heads=cfg["heads"], mlp_ratio=cfg["mlp"] / cfg["width"], qkv_bias=True,
+                             drop_path_rate=0.4, eps=cfg["eps"])
+    m.load_state_dict(tp, strict=True)
+    m = m.cuda().eval()
+    y = m(x.cuda(), return_all_features=True)
+    loss = y.float().pow(2).mean()
+    loss.backward()
+    ours = dict(features=y.detach().cpu(), cls=y[:, 0].detach().cpu(), loss=loss.item(),
+                grads={k: p.grad.detach().cpu() for k, p in m.named_parameters() if p.grad is not None})
+    _check("ViT-g/14 x40, bs 2", FS.compare_tower(ours, ref), _calib()["tower_vitg_40blocks_bs2"])
+
+
+@pytest.mark.parametrize("Sk", [257, 2056])
+def test_bert_base_12_layers_cross_attention(Sk):
+    from mico_b200.bert import BertConfig, BertForMaskedLM
+    from oracle import fullsize as FS
+    bp, c = FS.bert_case(Sk=Sk)
+    backward = Sk == 257
+    ref = FS.bert_eval(bp, c, backward=backward)
+    m = BertForMaskedLM(BertConfig(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0))
+    missing, unexpected = m.load_state_dict(bp, strict=False)
+    assert not unexpected and all("position_ids" in k or "decoder" in k for k in missing), (missing, unexpected)
+    m = m.cuda().eval()
+    cond = c["cond"].cuda().requires_grad_(True)
+    S = c["att"].shape[1]
+    att3 = torch.tril(c["att"].unsqueeze(1).expand(-1, S, -1).clone()).cuda()
+    with torch.set_grad_enabled(backward):
+        out = m(input_ids=c["cap_ids"].cuda(), attention_mask=att3, encoder_hidden_states=cond, labels=c["labels"].cuda())
+    ours = dict(seq=out.sequence_output.detach().cpu(), loss=out.loss.item())
+    if backward:
+        out.loss.backward()
+        named = dict(m.named_parameters())
+        ours["grads"] = {k: named[k].grad.detach().cpu() for k in FS.BERT_GRAD_KEYS}
+        ours["d_cond"] = cond.grad.detach().cpu()
+    _check(f"BERT-base x12, S 128, S_k {Sk}", FS.compare_bert(ours, ref), _calib()[f"bert_base_12layers_S128_Sk{Sk}"])
+
+
+def test_itc_logits_full_size():
+    from mico_b200 import functional as MF
+    from mico_b200.bert import BertConfig, BertForMaskedLM
+    from mico_b200.eva_vit import EVAVisionTransformer
+    from oracle import fullsize as FS
+    cfg, tp, x, bp, c, wv, wt = FS.itc_case()
+    ref = FS.itc_eval(cfg, tp, x, bp, c, wv, wt)
+    tower = EVAVisionTransformer(img_size=224, patch_size=14, num_classes=0, use_mean_pooling=False, embed_dim=cfg["width"],
+                                 depth=cfg["depth"], num_heads=cfg["heads"], mlp_ratio=cfg["mlp"] / cfg["width"], qkv_bias=True,
+                                 eps=cfg["eps"])
+    tower.load_state_dict(tp, strict=True)
+    tower = tower.cuda().eval()
+    bert = BertForMaskedLM(BertConfig(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0))
+    bert.load_state_dict(bp, strict=False)
+    bert = bert.cuda().eval()
+    with torch.no_grad():
+        y = tower(x.cuda(), return_all_features=True)
+        h = bert.bert(c["ids"].cuda(), attention_mask=c["att"].cuda()).last_hidden_state
+        fv = MF.normalize(MF.linear_f32(y[:, 0].contiguous(), wv.cuda(), None))
+        ft = MF.normalize(MF.linear_f32(h[:, 0].contiguous(), wt.cuda(), None))
+        logits = MF.contrastive_logits(fv, ft, torch.tensor(0.07, device="cuda"))
+    ours = dict(feat_v=fv.cpu(), feat_t=ft.cpu(), logits=logits.cpu())
+    _check("ITC logits, bs 4", FS.compare_itc(ours, ref), _calib()["itc_logits_bs4"])

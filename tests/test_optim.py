@@ -147,7 +147,7 @@ def test_fused_adamw_parameters_that_skip_steps():
     torch.manual_seed(3)
     n_groups, per_group, steps = 6, 4, 5
     params = [[torch.nn.Parameter(torch.randn(33 + 7 * j + gi, device="cuda")) for j in range(per_group)] for gi in range(n_groups)]
-    groups = [dict(params=ps, lr=1e-2 * (gi + 1), weight_decay=0.01 * (gi % 2)) for gi, ps in enumerate(params)]
+    groups = [dict(params=ps, lr=1e-3 * (gi + 1), weight_decay=0.01 * (gi % 2)) for gi, ps in enumerate(params)]
     opt = optim.AdamW(groups, betas=(0.9, 0.98))
     ref = {}
     for gi, ps in enumerate(params):
