@@ -131,6 +131,12 @@ typedef struct MicoAttnArgs {
     /* attention-probability dropout (bert.py:243-247): P is multiplied by a counter-based Bernoulli(1-p)/(1-p) mask of
      * element ((b*H + h)*Sq + i)*Sk + j under `dropout_seed`; forward and backward regenerate it.  p = 0 disables. */
     float dropout_p; uint64_t dropout_seed;
+    /* K/V shared by several query batch entries -- the fusion encoder's ITM (positive, hard-negative-text) and caption
+     * sequences of one sample all cross-attend to the same visual tokens (data/model/vast.py:445-451, 504-507), so their K / V
+     * projections are computed once: kv_index[b] (device int32, or NULL = identity) is the K/V batch entry that query entry b
+     * reads; K, V, dK, dV have n_kv batch entries.  The backward pass also needs the inverse map in CSR form: K/V entry e is
+     * read by query entries grp_list[grp_ptr[e] .. grp_ptr[e+1]) (device int32; every entry must have at least one reader). */
+    const int32_t* kv_index; int32_t n_kv; const int32_t* grp_ptr; const int32_t* grp_list;
 } MicoAttnArgs;
 
 int mico_attention_fwd(const MicoAttnArgs* args, void* stream);

@@ -83,6 +83,7 @@ class AttnArgs(C.Structure):
         ("dv", C.c_void_p), ("dv_bs", C.c_int64), ("dv_rs", C.c_int64), ("dv_hs", C.c_int64),
         ("mask_hs", C.c_int64), ("mask_bmod", C.c_int32),
         ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64),
+        ("kv_index", C.c_void_p), ("n_kv", C.c_int32), ("grp_ptr", C.c_void_p), ("grp_list", C.c_void_p),
     ]
 
 

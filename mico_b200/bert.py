@@ -183,8 +183,8 @@ _PER_LAYER = 26
 
 class _EncoderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, keep, drop, ids, mask_self, enc, mask_enc, *params):
-        out, saved = model._launch_forward(ids, mask_self, enc, mask_enc, params, keep, drop)
+    def forward(ctx, model, keep, drop, ids, mask_self, enc, mask_enc, enc_index, *params):
+        out, saved = model._launch_forward(ids, mask_self, enc, mask_enc, params, keep, drop, enc_index)
         ctx.model, ctx.saved, ctx.params = model, saved, params
         ctx.has_enc = enc is not None
         return out
@@ -195,7 +195,7 @@ class _EncoderFn(torch.autograd.Function):
             raise MicoError("BERT backward called but activations were not kept")
         denc, grads = ctx.model._launch_backward(dout, ctx.saved, ctx.params)
         ctx.saved = None
-        return (None, None, None, None, None, denc if ctx.needs_input_grad[5] else None, None) + tuple(grads)
+        return (None, None, None, None, None, denc if ctx.needs_input_grad[5] else None, None, None) + tuple(grads)
 
 
 class _Out:
@@ -258,7 +258,7 @@ class BertModel(nn.Module):
         """hidden-dropout site -> element-counter offset (sites: 0 embeddings; per layer 1 self-out, 2 cross-out, 3 ffn-out)"""
         return (0 if li < 0 else 3 * li + k) << 40
 
-    def _launch_forward(self, ids, mask_self, enc, mask_enc, params, keep, drop=None):
+    def _launch_forward(self, ids, mask_self, enc, mask_enc, params, keep, drop=None, enc_index=None):
         c = self.config
         Dh, H = c.hidden_size, c.num_attention_heads
         d = Dh // H
@@ -287,12 +287,21 @@ class BertModel(nn.Module):
         def adrop(li, cross):
             return (pa, seed + 2 * li + (2 if cross else 1)) if pa > 0 else None
         encb = None
-        Sk = 0
+        Sk = E = 0
+        groups = None
         if enc is not None:
-            Sk = enc.shape[1]
-            encb = ops.scale_cast_bf16(enc.reshape(b * Sk, Dh).contiguous().float())
+            # enc_index (int32 [b]): text sequence i cross-attends to encoder entry enc_index[i] -- several sequences
+            # (ITM positive / negative-text, caption) share one sample's visual tokens, whose K / V projection then runs once
+            E, Sk = enc.shape[0], enc.shape[1]
+            if enc_index is None and E != b:
+                raise MicoError("encoder_hidden_states batch differs from input_ids batch and no encoder_index was given")
+            encb = ops.scale_cast_bf16(enc.reshape(E * Sk, Dh).contiguous().float())
             if keep:
                 saved["encb"] = encb
+                saved["E"] = E
+                if enc_index is not None:
+                    groups = ops.kv_groups(enc_index, E)
+                saved["enc_index"], saved["groups"] = enc_index, groups
 
         def ln2(y, wi, bi):
             return ops.layernorm_fwd(y, det(wi), det(bi), eps, out_bf16=True, out_f32=True, save_stats=keep)
@@ -317,9 +326,9 @@ class BertModel(nn.Module):
                 wkv = cache.cat_w(("ckv", li), [P(12), P(14)])
                 bkv = cache.cat_b(("ckvb", li), [P(13), P(15)])
                 kv = ops.gemm(encb, wkv, bias=bkv)
-                kv5 = kv.view(b, Sk, 2, H, d)
+                kv5 = kv.view(E, Sk, 2, H, d)
                 ctx2, lse2 = ops.attention_fwd(qc.view(b, S, H, d), kv5[:, :, 0], kv5[:, :, 1], scale, mask=mask_enc,
-                                               need_lse=keep, dropout=adrop(li, True))
+                                               need_lse=keep, dropout=adrop(li, True), kv_index=enc_index)
                 y2 = dense_res(ctx2.view(M, Dh), cache.cat_w(("co", li), [P(16)]), P(17).detach(), h1, li, 2)
                 h2b, h2, m2, r2 = ln2(y2, base + 18, base + 19)
                 if keep:
@@ -356,7 +365,8 @@ class BertModel(nn.Module):
         encb = saved.get("encb")
         has_enc = encb is not None
         denc = torch.zeros((encb.shape[0], Dh), device=dev, dtype=F32) if has_enc else None
-        Sk = encb.shape[0] // b if has_enc else 0
+        E = saved.get("E", b)
+        Sk = encb.shape[0] // E if has_enc else 0
         g32 = dout.contiguous().view(M, Dh).float()
         g16 = None
         drop = saved.get("drop")
@@ -392,13 +402,14 @@ class BertModel(nn.Module):
                 ops.gemm(dy2b, rec["ctx2"].view(M, Dh), a_mn=True, b_mn=True, out=pg(base + 16))
                 ops.colsum(dy2b, out=pg(base + 17))
                 dctx = ops.gemm(dy2b, cache.cat_w(("co", li), [P(16)]), b_mn=True)
-                kv5 = rec["kv"].view(b, Sk, 2, H, d)
+                kv5 = rec["kv"].view(E, Sk, 2, H, d)
                 dqc = torch.empty_like(rec["qc"])
                 dkv = torch.empty_like(rec["kv"])
-                dkv5 = dkv.view(b, Sk, 2, H, d)
+                dkv5 = dkv.view(E, Sk, 2, H, d)
                 ops.attention_bwd(rec["qc"].view(b, S, H, d), kv5[:, :, 0], kv5[:, :, 1], rec["ctx2"], rec["lse2"],
                                   dctx.view(b, S, H, d), scale, mask=saved["mask_enc"], dq=dqc.view(b, S, H, d),
-                                  dk=dkv5[:, :, 0], dv=dkv5[:, :, 1], dropout=adrop(li, True))
+                                  dk=dkv5[:, :, 0], dv=dkv5[:, :, 1], dropout=adrop(li, True),
+                                  kv_index=saved.get("enc_index"), groups=saved.get("groups"))
                 ops.gemm(dqc, rec["h1b"], a_mn=True, b_mn=True, out=pg(base + 10))
                 ops.colsum(dqc, out=pg(base + 11))
                 g16 = ops.gemm(dqc, cache.cat_w(("cq", li), [P(10)]), b_mn=True)
@@ -444,7 +455,7 @@ class BertModel(nn.Module):
         ops.batch_sum(gpos[:S].contiguous(), S, out=gtype[0])       # token_type_ids are all zero (bert.py:121-127)
         grads[2] = gtype
         if has_enc:
-            denc = denc.view(b, Sk, Dh)
+            denc = denc.view(E, Sk, Dh)
         return denc, grads
 
     # ------------------------------------------------------------------ masks (bert.py:697-781, :872)
@@ -458,7 +469,9 @@ class BertModel(nn.Module):
 
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, position_ids=None, head_mask=None,
                 inputs_embeds=None, encoder_hidden_states=None, encoder_attention_mask=None, past_key_values=None,
-                use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=None):
+                use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=None, encoder_index=None):
+        """encoder_index (not in the reference signature): int tensor [batch] -- sequence i cross-attends to
+        encoder_hidden_states[encoder_index[i]], so that sequences sharing a sample's visual tokens share its K / V."""
         if input_ids is None or inputs_embeds is not None or token_type_ids is not None or position_ids is not None \
                 or past_key_values is not None or head_mask is not None:
             raise NotImplementedError("BertModel: only (input_ids, attention_mask, encoder_hidden_states, "
@@ -479,7 +492,9 @@ class BertModel(nn.Module):
         keep = torch.is_grad_enabled() and (any(p.requires_grad for p in live) or (enc is not None and enc.requires_grad))
         # placeholders keep the flat indexing when the config has no cross-attention
         args = [p if p is not None else torch.empty(0, device=input_ids.device) for p in flat]
-        out = _EncoderFn.apply(self, keep, drop, input_ids.long(), mask_self, enc, mask_enc, *args)
+        if encoder_index is not None:
+            encoder_index = encoder_index.to(device=input_ids.device, dtype=torch.int32).contiguous()
+        out = _EncoderFn.apply(self, keep, drop, input_ids.long(), mask_self, enc, mask_enc, encoder_index, *args)
         return _Out(last_hidden_state=out, pooler_output=None)
 
 
@@ -595,6 +610,14 @@ class BertForMaskedLM(nn.Module):
                          max_new_tokens=max_new_tokens, num_beams=num_beams, eos_token_id=eos_token_id,
                          pad_token_id=pad_token_id, length_penalty=length_penalty, do_sample=do_sample, top_k=top_k,
                          mask_token_id=kwargs.get("mask_token_id"), generator=kwargs.get("generator"))
+
+    def lm_loss(self, seq, labels):
+        """LM head + cross-entropy (bert.py:1084-1090) on an encoder output computed elsewhere (a slice of a larger call)."""
+        pr = self.cls.predictions
+        logits = _LMHeadFn.apply(seq, pr.transform.dense.weight, pr.transform.dense.bias, pr.transform.LayerNorm.weight,
+                                 pr.transform.LayerNorm.bias, pr.decoder.weight, pr.bias, self.config.layer_norm_eps,
+                                 torch.is_grad_enabled())
+        return cross_entropy(logits.view(-1, self.config.vocab_size), labels.reshape(-1), ignore_index=-100, grad_dtype=BF16)
 
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, position_ids=None, head_mask=None,
                 inputs_embeds=None, encoder_hidden_states=None, encoder_attention_mask=None, labels=None,

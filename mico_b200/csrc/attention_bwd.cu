@@ -32,6 +32,9 @@ struct AttnBwdParams {
     __nv_bfloat16* dq; int64_t dq_bs, dq_rs, dq_hs;
     __nv_bfloat16* dk; int64_t dk_bs, dk_rs, dk_hs;
     __nv_bfloat16* dv; int64_t dv_bs, dv_rs, dv_hs;
+    // K/V shared by several query batch entries (MicoAttnArgs::kv_index): n_kv entries; entry e is read by the query
+    // entries grp_list[grp_ptr[e] .. grp_ptr[e+1]).  kv_index == null: identity.
+    const int* kv_index; int n_kv; const int* grp_ptr; const int* grp_list;
 };
 
 // ------------------------------------------------------------------------------------------------ delta
@@ -148,13 +151,14 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     tma_load_4d(smem + DqSmem::Q + a * kAtomBytes, &tmQ, q_full, a * 64, h, qt * kTile, b);
                     tma_load_4d(smem + DqSmem::DO + a * kAtomBytes, &tmDO, q_full, a * 64, h, qt * kTile, b);
                 }
+                const int kvb = p.kv_index ? __ldg(p.kv_index + b) : b;
                 for (int j = 0; j < nkv; ++j, ++kvcount) {
                     const int s = kvcount & 1;
                     mbar_wait(&kv_empty[s], ((kvcount >> 1) & 1) ^ 1);
                     const bool ext = n_valid(kt, j) > kTile;
                     mbar_arrive_expect_tx(&kv_full[s], 2 * n_tile_bytes(kAtoms, ext));
-                    load_n_tile<kAtoms>(smem + DqSmem::K0 + s * 2 * kAtomBytesN, &tmK, &tmKx, &kv_full[s], h, j * kTile, b, ext);
-                    load_n_tile<kAtoms>(smem + DqSmem::V0 + s * 2 * kAtomBytesN, &tmV, &tmVx, &kv_full[s], h, j * kTile, b, ext);
+                    load_n_tile<kAtoms>(smem + DqSmem::K0 + s * 2 * kAtomBytesN, &tmK, &tmKx, &kv_full[s], h, j * kTile, kvb, ext);
+                    load_n_tile<kAtoms>(smem + DqSmem::V0 + s * 2 * kAtomBytesN, &tmV, &tmVx, &kv_full[s], h, j * kTile, kvb, ext);
                 }
             }
         }
@@ -352,12 +356,16 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int warp = threadIdx.x >> 5;
-    const int nkt = m_tiles(p.Sk);
+    const bool shared_kv = p.kv_index != nullptr;
+    const int nkt = m_tiles_nt(p.Sk, shared_kv);
     const NTiling qtl = n_tiling(p.Sq);
     const int nqt = qtl.n;
-    const int num_work = p.B * p.H * nkt;
+    const int num_work = (shared_kv ? p.n_kv : p.B) * p.H * nkt;
     constexpr int kAtoms = (HD_PAD + 63) / 64;
     constexpr uint32_t kTileBytes = kAtoms * kAtomBytes;
+    // readers of K/V entry e: the query batch entries whose Q / dO tiles are streamed against this entry's key tile
+    auto n_members = [&](int e) { return shared_kv ? __ldg(p.grp_ptr + e + 1) - __ldg(p.grp_ptr + e) : 1; };
+    auto member = [&](int e, int mi) { return shared_kv ? __ldg(p.grp_list + __ldg(p.grp_ptr + e) + mi) : e; };
 
     if (warp == 8) {
         if (elect_one()) {
@@ -388,21 +396,25 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             uint32_t wcount = 0, qcount = 0;
             for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
                 const int jt = w % nkt, bh = w / nkt;
-                const int h = bh % p.H, b = bh / p.H;
+                const int h = bh % p.H, e = bh / p.H;
                 mbar_wait(kv_empty, (wcount & 1) ^ 1);
                 mbar_arrive_expect_tx(kv_full, 2 * kTileBytes);
 #pragma unroll
                 for (int a = 0; a < kAtoms; ++a) {
-                    tma_load_4d(smem + DkvSmem::K + a * kAtomBytes, &tmK, kv_full, a * 64, h, jt * kTile, b);
-                    tma_load_4d(smem + DkvSmem::V + a * kAtomBytes, &tmV, kv_full, a * 64, h, jt * kTile, b);
+                    tma_load_4d(smem + DkvSmem::K + a * kAtomBytes, &tmK, kv_full, a * 64, h, jt * kTile, e);
+                    tma_load_4d(smem + DkvSmem::V + a * kAtomBytes, &tmV, kv_full, a * 64, h, jt * kTile, e);
                 }
-                for (int i = 0; i < nqt; ++i, ++qcount) {
-                    const int s = qcount & 1;
-                    mbar_wait(&qdo_empty[s], ((qcount >> 1) & 1) ^ 1);
-                    const bool ext = n_valid(qtl, i) > kTile;
-                    mbar_arrive_expect_tx(&qdo_full[s], 2 * n_tile_bytes(kAtoms, ext));
-                    load_n_tile<kAtoms>(smem + DkvSmem::Q0 + s * 2 * kAtomBytesN, &tmQ, &tmQx, &qdo_full[s], h, i * kTile, b, ext);
-                    load_n_tile<kAtoms>(smem + DkvSmem::DO0 + s * 2 * kAtomBytesN, &tmDO, &tmDOx, &qdo_full[s], h, i * kTile, b, ext);
+                const int nmem = n_members(e);
+                for (int mi = 0; mi < nmem; ++mi) {
+                    const int qb = member(e, mi);
+                    for (int i = 0; i < nqt; ++i, ++qcount) {
+                        const int s = qcount & 1;
+                        mbar_wait(&qdo_empty[s], ((qcount >> 1) & 1) ^ 1);
+                        const bool ext = n_valid(qtl, i) > kTile;
+                        mbar_arrive_expect_tx(&qdo_full[s], 2 * n_tile_bytes(kAtoms, ext));
+                        load_n_tile<kAtoms>(smem + DkvSmem::Q0 + s * 2 * kAtomBytesN, &tmQ, &tmQx, &qdo_full[s], h, i * kTile, qb, ext);
+                        load_n_tile<kAtoms>(smem + DkvSmem::DO0 + s * 2 * kAtomBytesN, &tmDO, &tmDOx, &qdo_full[s], h, i * kTile, qb, ext);
+                    }
                 }
             }
         }
@@ -414,7 +426,10 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
                 mbar_wait(kv_full, wcount & 1);
                 tc_fence_after();
-                for (int i = 0; i < nqt; ++i, ++qcount) {
+                const int nsteps = n_members((w / nkt) / p.H) * nqt;      // (reader, q tile) steps of this work item
+                if (nsteps == 0) umma_commit(kv_empty);                   // an entry nobody reads: dK = dV = 0
+                for (int st = 0; st < nsteps; ++st, ++qcount) {
+                    const int i = st % nqt;
                     const int s = qcount & 1;
                     const uint32_t sQ = smem_u32(smem + DkvSmem::Q0 + s * 2 * kAtomBytesN);
                     const uint32_t sDO = smem_u32(smem + DkvSmem::DO0 + s * 2 * kAtomBytesN);
@@ -436,7 +451,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     umma_commit(st_full);
                     // K and V are read by the score MMAs only: after the last pair the producer may already fetch the
                     // next work item's K / V while this item's softmax, gradient MMAs and epilogue run
-                    if (i == nqt - 1) umma_commit(kv_empty);
+                    if (st == nsteps - 1) umma_commit(kv_empty);
                     mbar_wait(pds_full, qcount & 1);
                     tc_fence_after();
                     const int ksteps = n16 >> 4;
@@ -445,13 +460,13 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         const int q0 = k * 16;
                         const uint32_t acol = q0 < hA ? q0 / 2 : hA + (q0 - hA) / 2;
                         umma_bf16_ts(tmem_dV, tmem_ST + acol, umma_smem_desc_sw128(sDO + k * 2048, kAtomBytesN, 1024),
-                                     idesc_g, (i | k) != 0);
+                                     idesc_g, (st | k) != 0);
                     }
                     for (int k = 0; k < ksteps; ++k) {
                         const int q0 = k * 16;
                         const uint32_t acol = q0 < hA ? q0 / 2 : hA + (q0 - hA) / 2;
                         umma_bf16_ts(tmem_dK, tmem_dPT + acol, umma_smem_desc_sw128(sQ + k * 2048, kAtomBytesN, 1024),
-                                     idesc_g, (i | k) != 0);
+                                     idesc_g, (st | k) != 0);
                     }
                     umma_commit(&qdo_empty[s]);
                 }
@@ -469,13 +484,13 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // tile's valid count get lse = +huge -> p = 0, dS = 0 with no per-element predicate
         const bool dropping = !kPlain && p.drop.p > 0.f;
         const uint32_t drop_thr = drop_thresh16(p.drop);
-        auto load_stats = [&](int w_, int i_, float& l, float& d, uint32_t& key) {
+        auto load_stats = [&](int qb_, int h_, int i_, float& l, float& d, uint32_t& key) {
             l = 1e30f;       // raw values: the scaling is applied where they are stored, long after the loads were issued
             d = 0.f;
             key = 0u;
             const int t = threadIdx.x;
             if (t < 160 && t < n_valid(qtl, i_)) {
-                const int64_t at = (int64_t)(w_ / nkt) * p.Sq + i_ * kTile + t;
+                const int64_t at = ((int64_t)qb_ * p.H + h_) * p.Sq + i_ * kTile + t;
                 l = ldg_f32_pinned(p.lse + at);
                 d = ldg_f32_pinned(p.delta + at);
                 if (dropping) key = drop_row_key(p.drop, (uint64_t)at);       // row = (b*H + h)*Sq + query
@@ -483,9 +498,12 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         };
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
             const int jt = w % nkt, bh = w / nkt;
-            const int h = bh % p.H, b = bh / p.H;
+            const int h = bh % p.H, e = bh / p.H;
             const int kj = jt * kTile + r;
             const bool key_ok = kj < p.Sk;
+            const int nmem = n_members(e);
+            for (int mi = 0; mi < nmem; ++mi) {
+            const int b = member(e, mi);           // the query batch entry of this step
             for (int i = 0; i < nqt; ++i, ++qcount) {
                 const int validq = n_valid(qtl, i);
                 const int n16 = max(16, (validq + 15) & ~15);
@@ -501,7 +519,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 if (first_tile) {      // very first tile of this CTA: nothing was prefetched
                     float l, d;
                     uint32_t key;
-                    load_stats(w, i, l, d, key);
+                    load_stats(b, h, i, l, d, key);
                     if (threadIdx.x < 160) {
                         s_nlse2[threadIdx.x] = -l * kLog2e; s_ndlt[threadIdx.x] = -d * p.scale;
                         reinterpret_cast<uint32_t*>(s_nlse2 + 512)[threadIdx.x] = key;
@@ -510,8 +528,15 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 }
                 float l_n = 0.f, d_n = 0.f;
                 uint32_t key_n = 0u;
-                const bool more = (i + 1 < nqt) || (w + (int)gridDim.x < num_work);
-                if (more) load_stats(i + 1 < nqt ? w : w + (int)gridDim.x, i + 1 < nqt ? i + 1 : 0, l_n, d_n, key_n);
+                const bool more = (i + 1 < nqt) || (mi + 1 < nmem) || (w + (int)gridDim.x < num_work);
+                if (more) {      // the step that follows: next q tile of this reader, next reader, or the next work item's first
+                    if (i + 1 < nqt) load_stats(b, h, i + 1, l_n, d_n, key_n);
+                    else if (mi + 1 < nmem) load_stats(member(e, mi + 1), h, 0, l_n, d_n, key_n);
+                    else {
+                        const int bh2 = (w + (int)gridDim.x) / nkt;
+                        load_stats(member(bh2 / p.H, 0), bh2 % p.H, 0, l_n, d_n, key_n);
+                    }
+                }
                 softmax_group_sync256();
                 mbar_wait(st_full, qcount & 1);
                 tc_fence_after();
@@ -579,18 +604,27 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     reinterpret_cast<uint32_t*>(n_nlse2 + 512)[threadIdx.x] = key_n;
                 }
             }
+            }
             mbar_wait(acc_full, wcount & 1);
             tc_fence_after();
             {
                 float acc[HD_PAD];
-                if (half == 0) {
+                if (nmem == 0) {
+#pragma unroll
+                    for (int q = 0; q < HD_PAD; ++q) acc[q] = 0.f;
+                    if (key_ok) {
+                        __nv_bfloat16* dst = half == 0 ? p.dv + (int64_t)e * p.dv_bs + (int64_t)kj * p.dv_rs + (int64_t)h * p.dv_hs
+                                                       : p.dk + (int64_t)e * p.dk_bs + (int64_t)kj * p.dk_rs + (int64_t)h * p.dk_hs;
+                        store_row_bf16<HD_PAD>(dst, acc, p.D, 1.0f);
+                    }
+                } else if (half == 0) {
                     tmem_load_row<HD_PAD, false>(tmem_dV + lane_off, acc);
                     if (key_ok)
-                        store_row_bf16<HD_PAD>(p.dv + (int64_t)b * p.dv_bs + (int64_t)kj * p.dv_rs + (int64_t)h * p.dv_hs, acc, p.D, 1.0f);
+                        store_row_bf16<HD_PAD>(p.dv + (int64_t)e * p.dv_bs + (int64_t)kj * p.dv_rs + (int64_t)h * p.dv_hs, acc, p.D, 1.0f);
                 } else {
                     tmem_load_row<HD_PAD, false>(tmem_dK + lane_off, acc);
                     if (key_ok)
-                        store_row_bf16<HD_PAD>(p.dk + (int64_t)b * p.dk_bs + (int64_t)kj * p.dk_rs + (int64_t)h * p.dk_hs, acc, p.D, 1.0f);
+                        store_row_bf16<HD_PAD>(p.dk + (int64_t)e * p.dk_bs + (int64_t)kj * p.dk_rs + (int64_t)h * p.dk_hs, acc, p.D, 1.0f);
                 }
             }
             tc_fence_before();
@@ -634,12 +668,14 @@ extern "C" int mico_attention_bwd(const MicoAttnArgs* a, void* stream_) {
     CUtensorMap tq, tk, tv, tdo, tqx, tkx, tvx, tdox;
     int rc;
     if ((rc = make_attn_tmap(&tq, a->q, a->D, a->H, a->Sq, a->B, a->q_bs, a->q_rs, a->q_hs))) return rc;
-    if ((rc = make_attn_tmap(&tk, a->k, a->D, a->H, a->Sk, a->B, a->k_bs, a->k_rs, a->k_hs))) return rc;
-    if ((rc = make_attn_tmap(&tv, a->v, a->D, a->H, a->Sk, a->B, a->v_bs, a->v_rs, a->v_hs))) return rc;
+    MICO_CHECK_ARG(a->kv_index == nullptr || (a->n_kv > 0 && a->grp_ptr && a->grp_list));
+    const int nkvb = a->kv_index ? a->n_kv : a->B;
+    if ((rc = make_attn_tmap(&tk, a->k, a->D, a->H, a->Sk, nkvb, a->k_bs, a->k_rs, a->k_hs))) return rc;
+    if ((rc = make_attn_tmap(&tv, a->v, a->D, a->H, a->Sk, nkvb, a->v_bs, a->v_rs, a->v_hs))) return rc;
     if ((rc = make_attn_tmap(&tdo, a->dout, a->D, a->H, a->Sq, a->B, a->do_bs, a->do_rs, a->do_hs))) return rc;
     if ((rc = make_attn_tmap(&tqx, a->q, a->D, a->H, a->Sq, a->B, a->q_bs, a->q_rs, a->q_hs, kExtRows))) return rc;
-    if ((rc = make_attn_tmap(&tkx, a->k, a->D, a->H, a->Sk, a->B, a->k_bs, a->k_rs, a->k_hs, kExtRows))) return rc;
-    if ((rc = make_attn_tmap(&tvx, a->v, a->D, a->H, a->Sk, a->B, a->v_bs, a->v_rs, a->v_hs, kExtRows))) return rc;
+    if ((rc = make_attn_tmap(&tkx, a->k, a->D, a->H, a->Sk, nkvb, a->k_bs, a->k_rs, a->k_hs, kExtRows))) return rc;
+    if ((rc = make_attn_tmap(&tvx, a->v, a->D, a->H, a->Sk, nkvb, a->v_bs, a->v_rs, a->v_hs, kExtRows))) return rc;
     if ((rc = make_attn_tmap(&tdox, a->dout, a->D, a->H, a->Sq, a->B, a->do_bs, a->do_rs, a->do_hs, kExtRows))) return rc;
     AttnBwdParams p;
     p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk; p.D = a->D; p.scale = a->scale;
@@ -651,7 +687,8 @@ extern "C" int mico_attention_bwd(const MicoAttnArgs* a, void* stream_) {
     p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv); p.dv_bs = a->dv_bs; p.dv_rs = a->dv_rs; p.dv_hs = a->dv_hs;
     const int hd_pad = (a->D + 15) & ~15;
     const int work_q = a->B * a->H * m_tiles(a->Sq);
-    const int work_k = a->B * a->H * m_tiles(a->Sk);
+    const int work_k = nkvb * a->H * m_tiles_nt(a->Sk, a->kv_index != nullptr);
+    p.kv_index = a->kv_index; p.n_kv = a->n_kv; p.grp_ptr = a->grp_ptr; p.grp_list = a->grp_list;
     auto launch = [&](auto kq, auto kkv) -> int {
         MICO_CHECK_CUDA(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::TOTAL));
         MICO_CHECK_CUDA(cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem::TOTAL));
@@ -660,7 +697,7 @@ extern "C" int mico_attention_bwd(const MicoAttnArgs* a, void* stream_) {
         kkv<<<work_k < num_sms() ? work_k : num_sms(), kBwdThreads, DkvSmem::TOTAL, stream>>>(tq, tk, tv, tdo, tqx, tdox, p);
         MICO_CHECK_CUDA(cudaGetLastError());
         count_launch(3);
-        if (m_tail_rows(a->Sq) || m_tail_rows(a->Sk)) return attention_tail_bwd(a, stream);
+        if (m_tail_rows(a->Sq) || (m_tail_rows(a->Sk) && a->kv_index == nullptr)) return attention_tail_bwd(a, stream);
         return MICO_OK;
     };
     const bool plain = a->mask == nullptr && a->dropout_p == 0.0f;

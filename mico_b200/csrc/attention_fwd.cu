@@ -29,6 +29,7 @@ struct AttnFwdParams {
     __nv_bfloat16* o;             // output, element (b,i,h,d) at o + b*o_bs + i*o_rs + h*o_hs + d
     int64_t o_bs, o_rs, o_hs;
     float* lse;                   // [B,H,Sq] or null
+    const int* kv_index;          // K/V batch entry of query entry b, or null (identity)
 };
 
 struct AttnSmem {
@@ -112,13 +113,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
                 for (int a = 0; a < kAtoms; ++a)
                     tma_load_4d(smem + AttnSmem::Q + a * kAtomBytes, &tmQ, q_full, a * 64, h, qt * kTile, b);
+                const int kvb = p.kv_index ? __ldg(p.kv_index + b) : b;
                 for (int j = 0; j < nkv; ++j, ++kvcount) {
                     const int s = kvcount & 1;
                     mbar_wait(&kv_empty[s], ((kvcount >> 1) & 1) ^ 1);
                     const bool ext = n_valid(kt, j) > kTile;
                     mbar_arrive_expect_tx(&kv_full[s], 2 * n_tile_bytes(kAtoms, ext));
-                    load_n_tile<kAtoms>(smem + AttnSmem::K0 + s * 2 * kAtomBytesN, &tmK, &tmKx, &kv_full[s], h, j * kTile, b, ext);
-                    load_n_tile<kAtoms>(smem + AttnSmem::V0 + s * 2 * kAtomBytesN, &tmV, &tmVx, &kv_full[s], h, j * kTile, b, ext);
+                    load_n_tile<kAtoms>(smem + AttnSmem::K0 + s * 2 * kAtomBytesN, &tmK, &tmKx, &kv_full[s], h, j * kTile, kvb, ext);
+                    load_n_tile<kAtoms>(smem + AttnSmem::V0 + s * 2 * kAtomBytesN, &tmV, &tmVx, &kv_full[s], h, j * kTile, kvb, ext);
                 }
             }
         }
@@ -354,11 +356,14 @@ extern "C" int mico_attention_fwd(const MicoAttnArgs* a, void* stream_) {
     CUtensorMap tq, tk, tv, tkx, tvx;
     int rc;
     if ((rc = make_attn_tmap(&tq, a->q, a->D, a->H, a->Sq, a->B, a->q_bs, a->q_rs, a->q_hs))) return rc;
-    if ((rc = make_attn_tmap(&tk, a->k, a->D, a->H, a->Sk, a->B, a->k_bs, a->k_rs, a->k_hs))) return rc;
-    if ((rc = make_attn_tmap(&tv, a->v, a->D, a->H, a->Sk, a->B, a->v_bs, a->v_rs, a->v_hs))) return rc;
-    if ((rc = make_attn_tmap(&tkx, a->k, a->D, a->H, a->Sk, a->B, a->k_bs, a->k_rs, a->k_hs, kExtRows))) return rc;
-    if ((rc = make_attn_tmap(&tvx, a->v, a->D, a->H, a->Sk, a->B, a->v_bs, a->v_rs, a->v_hs, kExtRows))) return rc;
+    MICO_CHECK_ARG(a->kv_index == nullptr || a->n_kv > 0);
+    const int nkvb = a->kv_index ? a->n_kv : a->B;
+    if ((rc = make_attn_tmap(&tk, a->k, a->D, a->H, a->Sk, nkvb, a->k_bs, a->k_rs, a->k_hs))) return rc;
+    if ((rc = make_attn_tmap(&tv, a->v, a->D, a->H, a->Sk, nkvb, a->v_bs, a->v_rs, a->v_hs))) return rc;
+    if ((rc = make_attn_tmap(&tkx, a->k, a->D, a->H, a->Sk, nkvb, a->k_bs, a->k_rs, a->k_hs, kExtRows))) return rc;
+    if ((rc = make_attn_tmap(&tvx, a->v, a->D, a->H, a->Sk, nkvb, a->v_bs, a->v_rs, a->v_hs, kExtRows))) return rc;
     AttnFwdParams p;
+    p.kv_index = a->kv_index;
     p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk; p.D = a->D;
     p.scale = a->scale;
     p.mask = a->mask; p.mask_bs = a->mask_bs; p.mask_qs = a->mask_qs; p.mask_hs = a->mask_hs; p.mask_bmod = a->mask_bmod;

@@ -23,6 +23,7 @@ struct TailParams {
     float* lse; const float* delta;
     int B, H, Sq, Sk, D, row0, rows;
     float scale;
+    const int* kv_index;      // q-side kernels: K/V batch entry of query entry b (null = identity)
 };
 
 constexpr int kTailThreads = 128;
@@ -125,8 +126,9 @@ __global__ void __launch_bounds__(kTailThreads) attn_tail_q_kernel(TailParams p)
     load_vec(p.q + b * p.q_bs + (int64_t)i * p.q_rs + h * p.q_hs, qv, p.D);
     if (MODE == 1) load_vec(p.d_o + b * p.do_bs + (int64_t)i * p.do_rs + h * p.do_hs, dov, p.D);
     __syncthreads();
-    const __nv_bfloat16* K = p.k + b * p.k_bs + h * p.k_hs;
-    const __nv_bfloat16* V = p.v + b * p.v_bs + h * p.v_hs;
+    const int kvb = p.kv_index ? __ldg(p.kv_index + b) : b;
+    const __nv_bfloat16* K = p.k + kvb * p.k_bs + h * p.k_hs;
+    const __nv_bfloat16* V = p.v + kvb * p.v_bs + h * p.v_hs;
     const float* mrow = p.mask ? (p.mask + (int64_t)(p.mask_bmod ? b % p.mask_bmod : b) * p.mask_bs + (int64_t)h * p.mask_hs) + (int64_t)i * p.mask_qs : nullptr;
     const int64_t stat = ((int64_t)b * p.H + h) * p.Sq + i;
     if (MODE == 0) {
@@ -248,6 +250,7 @@ TailParams base_params(const MicoAttnArgs* a) {
     p.drop.p = a->dropout_p; p.drop.inv_keep = a->dropout_p < 1.f ? 1.f / (1.f - a->dropout_p) : 0.f; p.drop.seed = a->dropout_seed;
     p.lse = a->lse; p.delta = a->delta;
     p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk; p.D = a->D; p.scale = a->scale;
+    p.kv_index = a->kv_index;
     return p;
 }
 
@@ -284,7 +287,7 @@ int attention_tail_bwd(const MicoAttnArgs* a, cudaStream_t stream) {
         p.out0 = reinterpret_cast<__nv_bfloat16*>(a->dq); p.o0_bs = a->dq_bs; p.o0_rs = a->dq_rs; p.o0_hs = a->dq_hs;
         if ((rc = launch_tail(attn_tail_q_kernel<1>, p, a->Sk, stream))) return rc;
     }
-    if (m_tail_rows(a->Sk)) {
+    if (m_tail_rows(a->Sk) && a->kv_index == nullptr) {      // shared K/V entries: the tile kernels take the remainder keys
         TailParams p = base_params(a);
         p.rows = m_tail_rows(a->Sk);
         p.row0 = a->Sk - p.rows;

@@ -45,6 +45,8 @@ __host__ __device__ inline int m_tail_rows(int S) {
     return (S > kTile && r > 0 && r <= kTailMax) ? r : 0;
 }
 __host__ __device__ inline int m_tiles(int S) { return m_tail_rows(S) ? S / kTile : (S + kTile - 1) / kTile; }
+// same with the SIMT tail path switched off (shared K/V entries: the remainder rows take one more, mostly empty, tile)
+__host__ __device__ inline int m_tiles_nt(int S, bool no_tail) { return no_tail ? (S + kTile - 1) / kTile : m_tiles(S); }
 
 // TMA-load one streamed tile (rows 128*j ..) of a [B,S,H,D] tensor into `dst` (kAtoms atoms of kAtomBytesN):
 // the 128-row box, plus the 16-row extension box when the tile holds more than 128 rows.

@@ -98,11 +98,31 @@ def _bhsd_strides(t):
     return t.data_ptr(), t.stride(0), t.stride(1), t.stride(2)
 
 
-def _attn_args(q, k, v, o, lse, mask, scale, dropout=None):
-    """dropout: None or (p, seed) -- attention-probability dropout regenerated from the seed in the backward."""
+def kv_groups(kv_index, n_kv):
+    """CSR inverse of kv_index (int32 [B] -> K/V entry): (ptr [n_kv + 1], list [B]) int32 device tensors -- K/V entry e is
+    read by the query batch entries list[ptr[e]:ptr[e+1]] (MicoAttnArgs::grp_ptr / grp_list)."""
+    idx = kv_index.long()
+    order = torch.argsort(idx, stable=True).to(torch.int32)
+    ptr = torch.zeros(n_kv + 1, device=kv_index.device, dtype=torch.int64)
+    ptr[1:] = torch.cumsum(torch.bincount(idx, minlength=n_kv), 0)
+    return ptr.to(torch.int32), order
+
+
+def _attn_args(q, k, v, o, lse, mask, scale, dropout=None, kv_index=None, groups=None):
+    """dropout: None or (p, seed) -- attention-probability dropout regenerated from the seed in the backward.
+    kv_index: int32 [B] device tensor: query batch entry b attends to K/V batch entry kv_index[b] (k, v have fewer
+    batch entries than q); groups = kv_groups(kv_index, k.shape[0]) for the backward pass."""
     a = _lib.AttnArgs()
     B, Sq, H, D = q.shape
     Sk = k.shape[1]
+    if kv_index is not None:
+        if kv_index.dtype != torch.int32 or kv_index.numel() != B or not kv_index.is_cuda or not kv_index.is_contiguous():
+            raise MicoError("kv_index must be a contiguous int32 CUDA tensor with one entry per query batch entry")
+        a.kv_index, a.n_kv = kv_index.data_ptr(), k.shape[0]
+        if groups is not None:
+            a.grp_ptr, a.grp_list = groups[0].data_ptr(), groups[1].data_ptr()
+    elif k.shape[0] != B:
+        raise MicoError("attention: q and k batch sizes differ and no kv_index was given")
     for name, t in (("q", q), ("k", k), ("v", v), ("o", o)):
         _req(t, BF16, name)
     a.q, a.q_bs, a.q_rs, a.q_hs = _bhsd_strides(q)
@@ -132,26 +152,30 @@ def _attn_args(q, k, v, o, lse, mask, scale, dropout=None):
     return a
 
 
-def attention_fwd(q, k, v, scale, mask=None, out=None, need_lse=True, dropout=None):
+def attention_fwd(q, k, v, scale, mask=None, out=None, need_lse=True, dropout=None, kv_index=None):
     """q,k,v: bf16 views [B,S,H,D] (e.g. slices of a fused qkv buffer). Returns (o [B,Sq,H,D], lse [B,H,Sq])."""
     B, Sq, H, D = q.shape
     if out is None:
         out = torch.empty((B, Sq, H, D), device=q.device, dtype=BF16)
     lse = torch.empty((B, H, Sq), device=q.device, dtype=F32) if need_lse else None
-    a = _attn_args(q, k, v, out, lse, mask, scale, dropout)
+    a = _attn_args(q, k, v, out, lse, mask, scale, dropout, kv_index)
     check(lib.mico_attention_fwd(C.byref(a), _stream()), "mico_attention_fwd")
     return out, lse
 
 
-def attention_bwd(q, k, v, o, lse, dout, scale, mask=None, dq=None, dk=None, dv=None, dmask=None, dropout=None):
-    """dmask: optional zero-initialised fp32 tensor shaped like mask; receives the gradient of the additive bias."""
+def attention_bwd(q, k, v, o, lse, dout, scale, mask=None, dq=None, dk=None, dv=None, dmask=None, dropout=None,
+                  kv_index=None, groups=None):
+    """dmask: optional zero-initialised fp32 tensor shaped like mask; receives the gradient of the additive bias.
+    kv_index / groups: shared K/V entries (see _attn_args); dk, dv then have k.shape[0] batch entries."""
     B, Sq, H, D = q.shape
-    Sk = k.shape[1]
+    Sk, Bk = k.shape[1], k.shape[0]
     dq = torch.empty((B, Sq, H, D), device=q.device, dtype=BF16) if dq is None else dq
-    dk = torch.empty((B, Sk, H, D), device=q.device, dtype=BF16) if dk is None else dk
-    dv = torch.empty((B, Sk, H, D), device=q.device, dtype=BF16) if dv is None else dv
+    dk = torch.empty((Bk, Sk, H, D), device=q.device, dtype=BF16) if dk is None else dk
+    dv = torch.empty((Bk, Sk, H, D), device=q.device, dtype=BF16) if dv is None else dv
     delta = torch.empty((B, H, Sq), device=q.device, dtype=F32)
-    a = _attn_args(q, k, v, o, lse, mask, scale, dropout)
+    if kv_index is not None and groups is None:
+        groups = kv_groups(kv_index, Bk)
+    a = _attn_args(q, k, v, o, lse, mask, scale, dropout, kv_index, groups)
     _req(dout, BF16, "dout")
     a.dout, a.do_bs, a.do_rs, a.do_hs = _bhsd_strides(dout)
     a.delta = delta.data_ptr()

@@ -134,7 +134,7 @@ def prefetch_towers(model, batch, combos):
 
 def fused_train_forward(model, batch, task):
     """Losses of ``MiCo.forward(batch, task, compute_loss=True)`` on the schedule above.  Returns the same dict."""
-    from .mico import _rank, all_gather_with_grad, concat_all_gather
+    from .mico import _rank, _world, all_gather_with_grad, concat_all_gather
     ret_st, cap_st = [], []
     for t in task.split("_"):
         subs = t.split("%")[1:]
@@ -217,22 +217,41 @@ def fused_train_forward(model, batch, task):
             neg = (neg_c, neg_t)
 
         def group(cond_leaf, do_itm=do_itm, do_cap=do_cap, neg=neg):
+            """ONE fusion-encoder call for every text sequence that reads this combination's visual tokens: ITM positive,
+            ITM negative-condition, ITM negative-text (vast.py:445-451) and the masked caption (vast.py:497-507).  The
+            sequences of sample i all cross-attend to encoder entry i (the negative-condition ones to the sampled entry):
+            `encoder_index` shares each entry's K / V projection between them."""
+            bs = cond_leaf.shape[0]
+            ar = torch.arange(bs, device=dev)
+            ids, masks, index = [], [], []
+            enc = [cond_leaf]
+            if do_itm:
+                ids += [input_ids, input_ids, ids_all[neg[1]]]
+                att_itm = torch.cat((attention_mask, attention_mask, att_all[neg[1]]), dim=0)
+                if _world() == 1:        # the negatives are local samples: read their entry in place
+                    index += [ar, neg[0], ar]
+                else:                    # negatives gathered from every rank (vast.py:422), with gradient
+                    cond_all = all_gather_with_grad(cond_leaf)
+                    enc.append(cond_all[neg[0]])
+                    index += [ar, bs + ar, ar]
+                masks.append(att_itm.unsqueeze(1).expand(-1, S, -1) if do_cap else att_itm)
+            if do_cap:
+                ids.append(cap_ids)
+                masks.append(att3)
+                index.append(ar)
+            h = model.multimodal_encoder.bert(input_ids=torch.cat(ids, dim=0),
+                                              attention_mask=torch.cat([m.to(torch.float32) for m in masks], dim=0),
+                                              encoder_hidden_states=enc[0] if len(enc) == 1 else torch.cat(enc, dim=0),
+                                              encoder_index=torch.cat(index)).last_hidden_state
             losses = []
-            if do_itm:       # ---- ITM (vast.py:419-457)
-                bs = cond_leaf.shape[0]
-                cond_all = all_gather_with_grad(cond_leaf)
-                ids_1 = torch.cat((input_ids, input_ids, ids_all[neg[1]]), dim=0)
-                att_1 = torch.cat((attention_mask, attention_mask, att_all[neg[1]]), dim=0)
-                cond_3 = torch.cat((cond_leaf, cond_all[neg[0]], cond_leaf), dim=0)
-                h = model.multimodal_encoder.bert(input_ids=ids_1, attention_mask=att_1,
-                                                  encoder_hidden_states=cond_3).last_hidden_state
-                logits = model.itm_head(h[:, 0])
+            if do_itm:       # ---- ITM head + CE (vast.py:453-457)
+                logits = model.itm_head(h[:3 * bs, 0])
                 truth = torch.zeros(bs * 3, dtype=torch.long, device=dev)
                 truth[:bs] = 1
                 losses.append(model.itm_ratio * MF.cross_entropy(logits, truth) / n_ret)
-            if do_cap:       # ---- caption (vast.py:485-512)
-                losses.append(model.multimodal_encoder(input_ids=cap_ids, attention_mask=att3, encoder_hidden_states=cond_leaf,
-                                                       labels=cap_labels).loss / n_cap)
+            if do_cap:       # ---- LM head + CE on the caption sequences (vast.py:504-510)
+                hc = h[3 * bs:] if do_itm else h
+                losses.append(model.multimodal_encoder.lm_loss(hc, cap_labels) / n_cap)
             return tuple(losses)
 
         res = eager_losses(group, [cond], params)

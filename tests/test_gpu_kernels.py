@@ -215,3 +215,40 @@ def test_colsum_two_ranges_single_pass():
     y = _randn((1000, 1001 + 7), 10, 1.0, torch.bfloat16)[:, :1001]
     for _ in range(2):
         assert rel_l2(ops.colsum(y), y.float().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("Sq,Sk,p_drop", [(128, 771, 0.0), (40, 257, 0.25), (130, 200, 0.1)])
+def test_attention_shared_kv_entries(Sq, Sk, p_drop):
+    """kv_index: several query batch entries read ONE K/V entry (fusion encoder: ITM + caption sequences of a sample).
+    Forward equals attention against the expanded K/V; dK / dV are the sums over the readers (fp32 reference with the same
+    dropout mask)."""
+    from mico_b200 import ops
+    from oracle import bert as OB
+    B, E, H, D = 7, 3, 2, 64
+    g = torch.Generator().manual_seed(Sq + Sk)
+    q, do = (torch.randn(B, Sq, H, D, generator=g).to(torch.bfloat16).cuda() for _ in range(2))
+    k, v = (torch.randn(E, Sk, H, D, generator=g).to(torch.bfloat16).cuda() for _ in range(2))
+    idx = torch.tensor([0, 2, 1, 0, 0, 2, 1], dtype=torch.int32)
+    mask = torch.zeros(B, Sk)
+    mask[:, Sk - 5:] = -10000.0          # per-query-entry key padding
+    mask[3, :7] = -10000.0
+    drop = (p_drop, 99) if p_drop > 0 else None
+    o, lse = ops.attention_fwd(q, k, v, D ** -0.5, mask=mask.cuda(), dropout=drop, kv_index=idx.cuda())
+    dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, do, D ** -0.5, mask=mask.cuda(), dropout=drop, kv_index=idx.cuda())
+    assert dk.shape == k.shape and dv.shape == v.shape
+    qf = q.float().cpu().requires_grad_(True)
+    kf, vf = (t.float().cpu().requires_grad_(True) for t in (k, v))
+    ke, ve = kf[idx.long()], vf[idx.long()]
+    pr = (torch.einsum("bihd,bjhd->bhij", qf, ke) * D ** -0.5 + mask[:, None, None, :]).softmax(-1)
+    if drop:
+        pr = pr * OB.attn_drop_mult(p_drop, 99, B, H, Sq, Sk)
+    ro = torch.einsum("bhij,bjhd->bihd", pr, ve)
+    ro.backward(do.float().cpu())
+    assert rel_l2(o.cpu(), ro) < 4e-3
+    for a, r in ((dq, qf.grad), (dk, kf.grad), (dv, vf.grad)):
+        assert rel_l2(a.cpu(), r) < 1e-2
+    # an entry nobody reads gets zero gradients
+    idx2 = torch.tensor([0, 0, 1, 0, 0, 1, 1], dtype=torch.int32).cuda()
+    o2, lse2 = ops.attention_fwd(q, k, v, D ** -0.5, kv_index=idx2)
+    _, dk2, dv2 = ops.attention_bwd(q, k, v, o2, lse2, do, D ** -0.5, kv_index=idx2)
+    assert dk2[2].abs().max().item() == 0 and dv2[2].abs().max().item() == 0 and dk2[0].abs().max().item() > 0

