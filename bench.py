@@ -35,7 +35,7 @@ VIT_G = dict(img_size=224, patch_size=14, embed_dim=1408, depth=40, num_heads=16
 # + patch embed 2*256*588*1408; backward = 2x forward.
 FWD_FLOPS_PER_FRAME = 40 * (2 * 257 * 1408 * (4224 + 1408 + 2 * 6144) + 4 * 257 * 257 * 1408) + 2 * 256 * 588 * 1408
 OMNI_TASK = "ret%tv%ta%tva%td_cap%tv%ta%tva"
-DEFAULT_LIGHT_BLOCKS = int(os.environ.get("MICO_BENCH_LIGHT_BLOCKS", "16"))
+DEFAULT_LIGHT_BLOCKS = int(os.environ.get("MICO_BENCH_LIGHT_BLOCKS", "12"))
 N_V, N_A, N_D, S_TXT = 8, 3, 1, 128
 WAVE_SAMPLES = 160000          # 10 s at 16 kHz
 METRIC = {"omni": "omni-modal pretrain tokens/sec @ ViT-g/14",

@@ -32,33 +32,52 @@ struct AttnFwdParams {
     const int* kv_index;          // K/V batch entry of query entry b, or null (identity)
 };
 
+// Shared memory per CTA, sized so that TWO CTAs fit one SM (2 x <= 113 KB): Q (kAtoms atoms of 128 rows), then kStages
+// stages of K and of V (kAtoms atoms of 144 rows each).  P never touches shared memory (see below).
+template <int HD_PAD>
 struct AttnSmem {
-    static constexpr int Q = 0;                                  // 2 atoms x 128 rows
-    static constexpr int K0 = 2 * kAtomBytes;                    // 2 stages x 2 atoms x 144 rows
-    static constexpr int V0 = K0 + 2 * 2 * kAtomBytesN;
-    static constexpr int P = V0 + 2 * 2 * kAtomBytesN;           // 128 x 144 bf16 = 3 atoms
-    static constexpr int BARS = P + 3 * kAtomBytes;
+    static constexpr int kAtoms = (HD_PAD + 63) / 64;
+    static constexpr int kStages = HD_PAD <= 64 ? 2 : 1;
+    static constexpr int kStageBytes = kAtoms * kAtomBytesN;
+    static constexpr int Q = 0;
+    static constexpr int K0 = kAtoms * kAtomBytes;
+    static constexpr int V0 = K0 + kStages * kStageBytes;
+    static constexpr int BARS = V0 + kStages * kStageBytes;
     static constexpr int TOTAL = BARS + 256 + 1024;
 };
-constexpr int kSStride = 160;   // TMEM columns between the two S buffers (a 144-wide tile is read in 5 x 32 columns)
+constexpr int kSCols = 160;          // TMEM columns of the S / P region (a 144-wide tile is read in 5 x 32 columns)
+constexpr float kRescaleLog2 = 8.0f; // the running max is only raised when it grows by more than 2^8 (see the softmax role)
 
+// Round 2 restructuring (VERDICT r1 "attention runs at 11 % of the tensor peak"; ncu: one softmax warp per SM sub-partition,
+// score MMA -> softmax -> P V strictly serial):
+//   * P stays in tensor memory: the softmax warps write it back as packed bf16 over the S columns they have already read
+//     (tcgen05.st) and the P V MMA takes it as its TMEM A operand -- no 48 KB P tile in shared memory;
+//   * O accumulates in tensor memory across the key tiles (one fp32 accumulator, use_acc = 1).  The running row max is
+//     only raised when the new tile's max exceeds it by more than 2^8: then O and the row sum are rescaled in place
+//     (tcgen05.ld / st), otherwise the stale max stays (p <= 256 is exact enough for bf16 P and an fp32 sum) -- the
+//     per-tile accumulator read-out of round 1 (96 columns per row per tile) is gone;
+//   * with P and O out of registers / shared memory a CTA needs <= 104 KB of shared memory, 256 TMEM columns and ~100
+//     registers per thread: TWO CTAs run per SM.  While one CTA's softmax warps work, the other CTA's MMAs and TMA loads
+//     proceed, and the SM sub-partitions have two softmax warps each to issue from.
 // kPlain: no additive mask and no dropout (every ViT tower): that code is compiled out
 template <int HD_PAD, bool kPlain>
-__global__ void __launch_bounds__(kAttThreads, 1)
+__global__ void __launch_bounds__(kAttThreads, HD_PAD <= 96 ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKx,
                 const __grid_constant__ CUtensorMap tmVx, AttnFwdParams p) {
+    using SM = AttnSmem<HD_PAD>;
+    constexpr int kAtoms = SM::kAtoms, kStages = SM::kStages;
+    constexpr uint32_t kTmemCols = HD_PAD <= 96 ? 256 : 512;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem::BARS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BARS);
     uint64_t* q_full = bars + 0;
     uint64_t* q_empty = bars + 1;
-    uint64_t* kv_full = bars + 2;    // [2]
-    uint64_t* kv_empty = bars + 4;   // [2]
-    uint64_t* s_full = bars + 6;     // [2]
-    uint64_t* s_empty = bars + 8;    // [2]
-    uint64_t* p_full = bars + 10;
-    uint64_t* o_full = bars + 11;
+    uint64_t* kv_full = bars + 2;    // [kStages]
+    uint64_t* kv_empty = bars + 4;   // [kStages]
+    uint64_t* s_full = bars + 6;
+    uint64_t* p_full = bars + 7;
+    uint64_t* o_full = bars + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int warp = threadIdx.x >> 5;
@@ -66,7 +85,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const NTiling kt = n_tiling(p.Sk);
     const int nkv = kt.n;
     const int num_work = p.B * p.H * nqt;
-    constexpr int kAtoms = (HD_PAD + 63) / 64;          // 64-wide d atoms per tile
     constexpr uint32_t kTileBytes = kAtoms * kAtomBytes;
 
     if (warp == 4) {
@@ -84,22 +102,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&kv_full[i], 1);
                 mbar_init(&kv_empty[i], 1);
-                mbar_init(&s_full[i], 1);
-                mbar_init(&s_empty[i], 4);
             }
+            mbar_init(s_full, 1);
             mbar_init(p_full, 4);
             mbar_init(o_full, 1);
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc<512>(tmem_slot);
+        tmem_alloc<kTmemCols>(tmem_slot);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base;                    // 2 x kSStride columns
-    const uint32_t tmem_O = tmem_base + 2 * kSStride;     // HD_PAD columns
+    const uint32_t tmem_S = tmem_base;               // kSCols columns: S (fp32), overwritten in place by P (packed bf16)
+    const uint32_t tmem_O = tmem_base + kSCols;      // HD_PAD columns
 
     if (warp == 4) {
         // ------------------------------------------------------------------ TMA producer
@@ -108,79 +125,55 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
                 const int qt = w % nqt, bh = w / nqt;
                 const int h = bh % p.H, b = bh / p.H;
-                mbar_wait(q_empty, (wcount & 1) ^ 1);
+                mbar_wait_relaxed(q_empty, (wcount & 1) ^ 1);
                 mbar_arrive_expect_tx(q_full, kTileBytes);
 #pragma unroll
                 for (int a = 0; a < kAtoms; ++a)
-                    tma_load_4d(smem + AttnSmem::Q + a * kAtomBytes, &tmQ, q_full, a * 64, h, qt * kTile, b);
+                    tma_load_4d(smem + SM::Q + a * kAtomBytes, &tmQ, q_full, a * 64, h, qt * kTile, b);
                 const int kvb = p.kv_index ? __ldg(p.kv_index + b) : b;
                 for (int j = 0; j < nkv; ++j, ++kvcount) {
-                    const int s = kvcount & 1;
-                    mbar_wait(&kv_empty[s], ((kvcount >> 1) & 1) ^ 1);
+                    const int s = kvcount % kStages;
+                    mbar_wait_relaxed(&kv_empty[s], ((kvcount / kStages) & 1) ^ 1);
                     const bool ext = n_valid(kt, j) > kTile;
                     mbar_arrive_expect_tx(&kv_full[s], 2 * n_tile_bytes(kAtoms, ext));
-                    load_n_tile<kAtoms>(smem + AttnSmem::K0 + s * 2 * kAtomBytesN, &tmK, &tmKx, &kv_full[s], h, j * kTile, kvb, ext);
-                    load_n_tile<kAtoms>(smem + AttnSmem::V0 + s * 2 * kAtomBytesN, &tmV, &tmVx, &kv_full[s], h, j * kTile, kvb, ext);
+                    load_n_tile<kAtoms>(smem + SM::K0 + s * SM::kStageBytes, &tmK, &tmKx, &kv_full[s], h, j * kTile, kvb, ext);
+                    load_n_tile<kAtoms>(smem + SM::V0 + s * SM::kStageBytes, &tmV, &tmVx, &kv_full[s], h, j * kTile, kvb, ext);
                 }
             }
         }
     } else if (warp == 5) {
         // ------------------------------------------------------------------ MMA issuer
         if (elect_one()) {
-            uint32_t wcount = 0, kvcount = 0, scount = 0, pcount = 0;
-            const uint32_t sQ = smem_u32(smem + AttnSmem::Q);
-            const uint32_t sP = smem_u32(smem + AttnSmem::P);
+            uint32_t wcount = 0, kvcount = 0, pcount = 0;
+            const uint32_t sQ = smem_u32(smem + SM::Q);
             constexpr uint32_t idesc_pv = umma_idesc_bf16(HD_PAD, false, true);
-            auto issue_s = [&](int j, uint32_t kvc, uint32_t sc) {
-                const int s = kvc & 1, sb = sc & 1;
-                mbar_wait(&kv_full[s], (kvc >> 1) & 1);
-                mbar_wait(&s_empty[sb], ((sc >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const int valid = n_valid(kt, j);
-                const int n = max(16, (valid + 15) & ~15);
-                const uint32_t idesc = umma_idesc_bf16(n, false, false);
-                const uint32_t sK = smem_u32(smem + AttnSmem::K0 + s * 2 * kAtomBytesN);
-#pragma unroll
-                for (int k = 0; k < HD_PAD / 16; ++k) {
-                    umma_bf16_ss(tmem_S + sb * kSStride,
-                                 umma_smem_desc_sw128(sQ + (k >> 2) * kAtomBytes + (k & 3) * 32, 16, 1024),
-                                 umma_smem_desc_sw128(sK + (k >> 2) * kAtomBytesN + (k & 3) * 32, 16, 1024), idesc,
-                                 k != 0);
-                }
-                umma_commit(&s_full[sb]);
-                // Q is read by the S MMAs only: after the last one of the work item the producer may refill it
-                if (j == nkv - 1) umma_commit(q_empty);
-            };
-            // (work item, kv tile) steps form one flat stream: S of step t+1 -- possibly the first tile of the NEXT work
-            // item -- is issued before the P V of step t, so a new item's TMA and S latency hide behind the previous tail
-            if ((int)blockIdx.x < num_work) {
-                mbar_wait(q_full, 0);
-                tc_fence_after();
-                issue_s(0, kvcount, scount);
-            }
             for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
-                for (int j = 0; j < nkv; ++j) {
-                    if (j + 1 < nkv) {
-                        issue_s(j + 1, kvcount + 1, scount + 1);
-                    } else if (w + (int)gridDim.x < num_work) {
-                        mbar_wait(q_full, (wcount + 1) & 1);
-                        tc_fence_after();
-                        issue_s(0, kvcount + 1, scount + 1);
-                    }
-                    const int s = kvcount & 1;
-                    mbar_wait(p_full, pcount & 1);
+                mbar_wait_relaxed(q_full, wcount & 1);
+                for (int j = 0; j < nkv; ++j, ++kvcount, ++pcount) {
+                    const int s = kvcount % kStages;
+                    mbar_wait_relaxed(&kv_full[s], (kvcount / kStages) & 1);
                     tc_fence_after();
+                    // S = Q K^T.  The S / P columns are free: the previous tile's P V (which read P from them) was issued by
+                    // this thread before, and tcgen05.mma executes in issue order.
                     const int valid = n_valid(kt, j);
+                    const uint32_t idesc = umma_idesc_bf16(max(16, (valid + 15) & ~15), false, false);
+                    const uint32_t sK = smem_u32(smem + SM::K0 + s * SM::kStageBytes);
+#pragma unroll
+                    for (int k = 0; k < HD_PAD / 16; ++k)
+                        umma_bf16_ss(tmem_S, umma_smem_desc_sw128(sQ + (k >> 2) * kAtomBytes + (k & 3) * 32, 16, 1024),
+                                     umma_smem_desc_sw128(sK + (k >> 2) * kAtomBytesN + (k & 3) * 32, 16, 1024), idesc, k != 0);
+                    umma_commit(s_full);
+                    if (j == nkv - 1) umma_commit(q_empty);     // Q is read by the S MMAs only
+                    // O (+)= P V once the softmax warps have written P (and rescaled O if the row max moved)
+                    mbar_wait_relaxed(p_full, pcount & 1);
+                    tc_fence_after();
                     const int ksteps = (valid + 15) >> 4;
-                    const uint32_t sV = smem_u32(smem + AttnSmem::V0 + s * 2 * kAtomBytesN);
-                    for (int k = 0; k < ksteps; ++k) {
-                        const uint32_t aoff = (k >> 2) * kAtomBytes + (k & 3) * 32;
-                        umma_bf16_ss(tmem_O, umma_smem_desc_sw128(sP + aoff, 16, 1024),
-                                     umma_smem_desc_sw128(sV + k * 2048, kAtomBytesN, 1024), idesc_pv, k != 0);
-                    }
+                    const uint32_t sV = smem_u32(smem + SM::V0 + s * SM::kStageBytes);
+                    for (int k = 0; k < ksteps; ++k)     // P (TMEM, 16 keys = 8 packed columns per step) . V (MN-major)
+                        umma_bf16_ts(tmem_O, tmem_S + k * 8, umma_smem_desc_sw128(sV + k * 2048, kAtomBytesN, 1024), idesc_pv,
+                                     (j | k) != 0);
                     umma_commit(&kv_empty[s]);
-                    umma_commit(o_full);
-                    ++kvcount; ++scount; ++pcount;
+                    if (j == nkv - 1) umma_commit(o_full);
                 }
             }
         }
@@ -189,9 +182,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int r = threadIdx.x;                      // row within the tile == TMEM lane
         const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
         const float sc2 = p.scale * kLog2e;
-        uint32_t scount = 0, ocount = 0;
-        uint8_t* sP = smem + AttnSmem::P;
-        for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        uint32_t scount = 0, wcount = 0;
+        for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++wcount) {
             const int qt = w % nqt, bh = w / nqt;
             const int h = bh % p.H, b = bh / p.H;
             const int qi = qt * kTile + r;
@@ -201,16 +193,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const bool dropping = !kPlain && p.drop.p > 0.f;
             const uint32_t drop_key = dropping ? drop_row_key(p.drop, (uint64_t)(b * p.H + h) * p.Sq + (row_ok ? qi : 0)) : 0u;
             const uint32_t drop_thr = drop_thresh16(p.drop);
-            float oacc[HD_PAD];
-#pragma unroll
-            for (int i = 0; i < HD_PAD; ++i) oacc[i] = 0.f;
 
             for (int j = 0; j < nkv; ++j, ++scount) {
-                const int sb = scount & 1;
                 const int valid = n_valid(kt, j);
                 const int nch = (valid + 31) >> 5;
-                const uint32_t tS = tmem_S + sb * kSStride + lane_off;
-                mbar_wait(&s_full[sb], (scount >> 1) & 1);
+                const uint32_t tS = tmem_S + lane_off;
+                mbar_wait(s_full, scount & 1);      // also: the previous tile's P V has completed (issued before this S)
                 tc_fence_after();
                 // pass 1: row max (log2 domain).  scale > 0, so without a mask the max is taken on the raw scores.
                 float mx = -INFINITY;
@@ -235,18 +223,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     }
                 }
                 if (!mrow) mx *= sc2;
-                const float m_new = fmaxf(m, mx);
-                const float alpha = ex2_fast(m - m_new);   // m = -inf on the first tile -> 0
-                // fold the previous tile's P V (its MMA finished long ago) before P smem is overwritten
-                if (j > 0) {
-                    mbar_wait(o_full, ocount & 1);
-                    ++ocount;
-                    tc_fence_after();
-                    tmem_load_row<HD_PAD, true>(tmem_O + lane_off, oacc);
-                }
+                // Raise the running max only when it is exceeded by more than 2^kRescaleLog2; the decision is taken per warp
+                // (the in-place rescale of O is a warp-wide TMEM load / store) and every row of the warp then moves to its own
+                // new max.  With a stale max, p = 2^(s - m) <= 2^8.
+                const bool grow = mx > m + kRescaleLog2;
+                if (__any_sync(0xffffffffu, grow)) {
+                    const float m_new = fmaxf(m, mx);
+                    const float alpha = ex2_fast(m - m_new);      // m = -inf on the first tile -> 0 (O is not read then)
+                    if (j > 0) {
 #pragma unroll
-                for (int i = 0; i < HD_PAD; ++i) oacc[i] *= alpha;
-                // pass 2: p = exp2(s - m_new), row sum, bf16 P -> smem (K-major, 128B swizzle)
+                        for (int c = 0; c < HD_PAD / 32; ++c) {
+                            uint32_t o[32];
+                            tmem_ld_x32(tmem_O + lane_off + c * 32, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st_x32(tmem_O + lane_off + c * 32, o);
+                        }
+                        if constexpr (HD_PAD % 32 != 0) {
+                            uint32_t o[16];
+                            tmem_ld_x16(tmem_O + lane_off + (HD_PAD / 32) * 32, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st_x16(tmem_O + lane_off + (HD_PAD / 32) * 32, o);
+                        }
+                    }
+                    l *= alpha;
+                    m = m_new;
+                }
+                // pass 2: p = exp2(s - m), row sum, bf16 P written over the S columns already consumed (chunk c of P covers
+                // columns [16c, 16c+16), always behind the S chunk being read)
                 float sum = 0.f;
                 for (int c = 0; c < nch; ++c) {
                     uint32_t v[32];
@@ -257,7 +264,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     if (!mrow && lim >= 32 && !dropping) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            pv[i] = ex2_fast(fmaf(__uint_as_float(v[i]), sc2, -m_new));
+                            pv[i] = ex2_fast(fmaf(__uint_as_float(v[i]), sc2, -m));
                             sum += pv[i];
                         }
                     } else {
@@ -266,7 +273,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                             const uint32_t bits = dropping ? drop_pair_bits(drop_key, (uint32_t)(j * kTile + c * 32 + i) >> 1) : 0u;
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
-                                float s = fmaf(__uint_as_float(v[i + e]), sc2, -m_new);
+                                float s = fmaf(__uint_as_float(v[i + e]), sc2, -m);
                                 if (mrow && i + e < lim) s = fmaf(mrow[j * kTile + c * 32 + i + e], kLog2e, s);
                                 pv[i + e] = i + e < lim ? ex2_fast(s) : 0.f;
                                 sum += pv[i + e];                 // the softmax denominator is taken before dropout
@@ -275,55 +282,54 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                             }
                         }
                     }
+                    tmem_store_bf16x32(tS + c * 16, pv);
+                }
+                l += sum;
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane_id() == 0) mbar_arrive(p_full);
+            }
+            // the work item's O is complete after the last P V
+            mbar_wait(o_full, wcount & 1);
+            tc_fence_after();
+            const float inv = 1.0f / l;
+            __nv_bfloat16* orow = p.o + (int64_t)b * p.o_bs + (int64_t)qi * p.o_rs + (int64_t)h * p.o_hs;
+            // D % 8 == 0 and 16-byte aligned rows are checked on the host
+#pragma unroll
+            for (int c = 0; c < (HD_PAD + 31) / 32; ++c) {
+                uint32_t o[32];
+                if (c * 32 + 32 <= HD_PAD) {
+                    tmem_ld_x32(tmem_O + lane_off + c * 32, o);
+                } else {
+                    uint32_t (&o16)[16] = *reinterpret_cast<uint32_t (*)[16]>(&o[0]);
+                    tmem_ld_x16(tmem_O + lane_off + c * 32, o16);
+                }
+                tmem_ld_wait();
+                if (row_ok) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const int col = c * 32 + g * 8;     // first of 8 consecutive keys
-                        const int atom = col >> 6, chunk = (col & 63) >> 3;
-                        uint8_t* dst = sP + atom * kAtomBytes + r * 128 + ((chunk ^ (r & 7)) << 4);
-                        *reinterpret_cast<uint4*>(dst) =
-                            make_uint4(pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1]), pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3]),
-                                       pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]), pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]));
+                        const int col = c * 32 + g * 8;
+                        if (col < HD_PAD && col < p.D)
+                            *reinterpret_cast<uint4*>(orow + col) = make_uint4(
+                                pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv),
+                                pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv),
+                                pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv),
+                                pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv));
                     }
                 }
-                l = l * alpha + sum;
-                m = m_new;
-                // S buffer drained; P visible to the async proxy (UMMA)
-                tc_fence_before();
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane_id() == 0) {
-                    mbar_arrive(&s_empty[sb]);
-                    mbar_arrive(p_full);
-                }
             }
-            // last tile's P V
-            mbar_wait(o_full, ocount & 1);
-            ++ocount;
-            tc_fence_after();
-            tmem_load_row<HD_PAD, true>(tmem_O + lane_off, oacc);
             tc_fence_before();
-            if (row_ok) {
-                const float inv = 1.0f / l;
-                __nv_bfloat16* orow = p.o + (int64_t)b * p.o_bs + (int64_t)qi * p.o_rs + (int64_t)h * p.o_hs;
-                // D % 8 == 0 and 16-byte aligned rows are checked on the host
-#pragma unroll
-                for (int g = 0; g < HD_PAD / 8; ++g) {
-                    if (g * 8 < p.D)
-                        *reinterpret_cast<uint4*>(orow + g * 8) = make_uint4(
-                            pack_bf16x2(oacc[g * 8 + 0] * inv, oacc[g * 8 + 1] * inv),
-                            pack_bf16x2(oacc[g * 8 + 2] * inv, oacc[g * 8 + 3] * inv),
-                            pack_bf16x2(oacc[g * 8 + 4] * inv, oacc[g * 8 + 5] * inv),
-                            pack_bf16x2(oacc[g * 8 + 6] * inv, oacc[g * 8 + 7] * inv));
-                }
-                if (p.lse) p.lse[((int64_t)b * p.H + h) * p.Sq + qi] = (m + log2f(l)) * 0.6931471805599453f;
-            }
+            if (row_ok && p.lse) p.lse[((int64_t)b * p.H + h) * p.Sq + qi] = (m + log2f(l)) * 0.6931471805599453f;
+            // the next work item's first P V (use_acc = 0) overwrites O: it waits for p_full, on which this warp arrives only
+            // after these loads in program order
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 5) {
         tc_fence_after();
-        tmem_dealloc<512>(tmem_base);
+        tmem_dealloc<kTmemCols>(tmem_base);
     }
 }
 
@@ -371,11 +377,12 @@ extern "C" int mico_attention_fwd(const MicoAttnArgs* a, void* stream_) {
     p.o = reinterpret_cast<__nv_bfloat16*>(a->o); p.o_bs = a->o_bs; p.o_rs = a->o_rs; p.o_hs = a->o_hs;
     p.lse = a->lse;
     const int work = a->B * a->H * m_tiles(a->Sq);
-    const int grid = work < num_sms() ? work : num_sms();
     const int hd_pad = (a->D + 15) & ~15;
-    auto launch = [&](auto kern) -> int {
-        MICO_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
-        kern<<<grid, kAttThreads, AttnSmem::TOTAL, stream>>>(tq, tk, tv, tkx, tvx, p);
+    auto launch = [&](auto kern, int smem_bytes, int ctas_per_sm) -> int {
+        const int slots = num_sms() * ctas_per_sm;
+        const int grid = work < slots ? work : slots;
+        MICO_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        kern<<<grid, kAttThreads, smem_bytes, stream>>>(tq, tk, tv, tkx, tvx, p);
         MICO_CHECK_CUDA(cudaGetLastError());
         count_launch();
         if (m_tail_rows(a->Sq)) return attention_tail_fwd(a, stream);
@@ -383,10 +390,10 @@ extern "C" int mico_attention_fwd(const MicoAttnArgs* a, void* stream_) {
     };
     const bool plain = a->mask == nullptr && a->dropout_p == 0.0f;
     switch (hd_pad) {
-        case 32: return plain ? launch(attn_fwd_kernel<32, true>) : launch(attn_fwd_kernel<32, false>);
-        case 64: return plain ? launch(attn_fwd_kernel<64, true>) : launch(attn_fwd_kernel<64, false>);
-        case 96: return plain ? launch(attn_fwd_kernel<96, true>) : launch(attn_fwd_kernel<96, false>);
-        case 128: return plain ? launch(attn_fwd_kernel<128, true>) : launch(attn_fwd_kernel<128, false>);
+        case 32: return plain ? launch(attn_fwd_kernel<32, true>, AttnSmem<32>::TOTAL, 2) : launch(attn_fwd_kernel<32, false>, AttnSmem<32>::TOTAL, 2);
+        case 64: return plain ? launch(attn_fwd_kernel<64, true>, AttnSmem<64>::TOTAL, 2) : launch(attn_fwd_kernel<64, false>, AttnSmem<64>::TOTAL, 2);
+        case 96: return plain ? launch(attn_fwd_kernel<96, true>, AttnSmem<96>::TOTAL, 2) : launch(attn_fwd_kernel<96, false>, AttnSmem<96>::TOTAL, 2);
+        case 128: return plain ? launch(attn_fwd_kernel<128, true>, AttnSmem<128>::TOTAL, 1) : launch(attn_fwd_kernel<128, false>, AttnSmem<128>::TOTAL, 1);
         default:
             set_last_error(__FILE__, __LINE__, "head_dim must pad to 32, 64, 96 or 128");
             return MICO_ERR_UNSUPPORTED;
