@@ -8,6 +8,8 @@ Workloads
       depth 1 frame) through the ViT-g/14 tower, 128 text tokens through the BERT-base text / fusion encoder, ITC + ITM +
       caption losses with the NCCL feature gathers at N > 1 (data/model/vast.py:317-512, data/utils/pipeline.py:35-111).
   --config vitg (BASELINE.json configs[1]): ViT-g/14 image-only fwd+bwd, bs 64 per GPU (round 1's headline).
+  --config imgtext (configs[2]): image + text ITC / ITM / caption step, bs 32 per GPU.
+  --config trimodal (configs[3]): Swin-B video + log-mel audio + text step, bs 4 per GPU.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config omni|vitg] [--batch B]
 
@@ -38,10 +40,26 @@ OMNI_TASK = "ret%tv%ta%tva%td_cap%tv%ta%tva"
 DEFAULT_LIGHT_BLOCKS = int(os.environ.get("MICO_BENCH_LIGHT_BLOCKS", "12"))
 N_V, N_A, N_D, S_TXT = 8, 3, 1, 128
 WAVE_SAMPLES = 160000          # 10 s at 16 kHz
+# MiCo.forward workloads: BASELINE.json configs[4] (the metric's own), configs[2] and configs[3] (builder-run evidence lines)
+SPECS = {
+    "omni": dict(task=OMNI_TASK, batch=64, n_v=N_V, n_a=N_A, n_d=N_D, tower="evaclip01_giant", ckpt=True,
+                 frame_tokens=T_IMG, frame_flops=None,
+                 workload="full omni-modal (video 8f + audio 3 slices + depth + text S=128) ViT-g/14 + BERT-base pretraining step, "
+                          "bs 64 per GPU (BASELINE configs[4]: 512 global on 8 GPUs), task " + OMNI_TASK),
+    "imgtext": dict(task="ret%tv_cap%tv", batch=32, n_v=1, n_a=0, n_d=0, tower="evaclip01_giant", ckpt=False,
+                    frame_tokens=T_IMG, frame_flops=None,
+                    workload="image + text contrastive / matching / caption step (EVA-CLIP ViT-g image tower + BERT text), bs 32 per "
+                             "GPU (BASELINE configs[2]: 256 global on 8 GPUs, NCCL feature all-gather), task ret%tv_cap%tv"),
+    "trimodal": dict(task="ret%tv%ta%tva_cap%tv%ta%tva", batch=4, n_v=8, n_a=3, n_d=0, tower="swin_base_22k", ckpt=False,
+                     frame_tokens=49, frame_flops=30.9e9,
+                     workload="video (Swin-B, 8 frames) + audio (10 s waveform -> log-mel, 3 slices) + text tri-modal step, bs 4 per GPU "
+                              "(BASELINE configs[3]: 32 global on 8 GPUs), task ret%tv%ta%tva_cap%tv%ta%tva"),
+}
 METRIC = {"omni": "omni-modal pretrain tokens/sec @ ViT-g/14",
+          "imgtext": "omni-modal pretrain tokens/sec @ ViT-g/14 (image + text step, bs 32/GPU)",
+          "trimodal": "omni-modal pretrain tokens/sec (Swin-B video + audio + text step, bs 4/GPU)",
           "vitg": "omni-modal pretrain tokens/sec @ ViT-g/14 (image-only fwd+bwd, bs 64/GPU)"}
-WORKLOAD = {"omni": "full omni-modal (video 8f + audio 3 slices + depth + text S=128) ViT-g/14 + BERT-base pretraining step, "
-                    "bs 64 per GPU (BASELINE configs[4]: 512 global on 8 GPUs), task " + OMNI_TASK,
+WORKLOAD = {"omni": SPECS["omni"]["workload"], "imgtext": SPECS["imgtext"]["workload"], "trimodal": SPECS["trimodal"]["workload"],
             "vitg": "ViT-g/14 image-only fwd+bwd, bs=64 synthetic 224x224 per GPU (BASELINE configs[1])"}
 
 
@@ -92,22 +110,23 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------------------------- workload description
-def omni_tokens(b, n_v=N_V, n_a=N_A, n_d=N_D, S=S_TXT):
+def omni_tokens(b, n_v=N_V, n_a=N_A, n_d=N_D, S=S_TXT, frame_tokens=T_IMG):
     """(north-star tokens, processed tokens) per step of b samples: north_star counts 1568 per video sample, 257 per image
     (each spectrogram slice and the depth map are images through the tower), 128 per text; processed = what the encoders
     actually see (257 per frame: an 8-frame video is 2056 tower tokens)."""
-    ns = b * (NS_TOKENS["video"] * n_v / N_V + NS_TOKENS["image"] * (n_a + n_d) + S)
-    processed = b * (T_IMG * (n_v + n_a + n_d) + S)
+    vis = NS_TOKENS["image"] if n_v == 1 else NS_TOKENS["video"] * n_v / N_V
+    ns = b * (vis + NS_TOKENS["image"] * (n_a + n_d) + S)
+    processed = b * (frame_tokens * (n_v + n_a + n_d) + S)
     return ns, processed
 
 
-def omni_flops(b, n_v=N_V, n_a=N_A, n_d=N_D, S=S_TXT):
-    """Algorithmic forward FLOPs of one omni step as the reference computes it (2MNK per linear layer, 4*Sq*Sk*D per
+def omni_flops(b, n_v=N_V, n_a=N_A, n_d=N_D, S=S_TXT, task=OMNI_TASK, frame_tokens=T_IMG, frame_flops=None, tower_dim=1408):
+    """Algorithmic forward FLOPs of one MiCo.forward step as the reference computes it (2MNK per linear layer, 4*Sq*Sk*D per
     attention; no recompute counted): (tower, fusion inputs, BERT + LM head).  fwd+bwd = 3x."""
     H, F, V, L = 768, 3072, 30522, 12
     frames = b * (n_v + n_a + n_d)
-    tower = frames * FWD_FLOPS_PER_FRAME
-    fusion = 2 * frames * T_IMG * 1408 * H
+    tower = frames * (frame_flops if frame_flops else FWD_FLOPS_PER_FRAME)
+    fusion = 2 * frames * frame_tokens * tower_dim * H
 
     def bert(n, Sk, lm):
         M = n * S
@@ -118,12 +137,11 @@ def omni_flops(b, n_v=N_V, n_a=N_A, n_d=N_D, S=S_TXT):
         if lm:
             tot += 2 * M * H * H + 2 * M * H * V
         return tot
-    sk = {"tv": n_v * T_IMG, "ta": n_a * T_IMG, "tva": (n_v + n_a) * T_IMG, "td": n_d * T_IMG}
+    sk = {"tv": n_v * frame_tokens, "ta": n_a * frame_tokens, "tva": (n_v + n_a) * frame_tokens, "td": n_d * frame_tokens}
     text = bert(b, 0, False)
-    for st in ("tv", "ta", "tva", "td"):
-        text += bert(3 * b, sk[st], False)
-    for st in ("tv", "ta", "tva"):
-        text += bert(b, sk[st], True)
+    for part in task.split("_"):
+        for st in part.split("%")[1:]:
+            text += bert(3 * b, sk[st], False) if part.startswith("ret") else bert(b, sk[st], True)
     return tower, fusion, text
 
 
@@ -138,17 +156,21 @@ def make_config(args):
                     grad_sync=(f"nccl all_reduce(SUM, {args.grad_dtype}) per {args.bucket_blocks}-block bucket of the flat "
                                "gradient buffer, overlapped with backward on a side stream (mico_b200/dp.py)")
                     if args.gpus > 1 else "none (1 GPU)")
-    ns, processed = omni_tokens(args.batch)
-    return dict(workload=WORKLOAD["omni"], batch_per_gpu=args.batch, video_frames=N_V, audio_slices=N_A, depth_frames=N_D,
-                text_len=S_TXT, task=OMNI_TASK, tower="EVA01-CLIP-g-14 (1408 x 40, 16 heads x 88, MLP 6144), DropPath 0.4",
+    sp = SPECS[args.config]
+    ns, processed = omni_tokens(args.batch, sp["n_v"], sp["n_a"], sp["n_d"], frame_tokens=sp["frame_tokens"])
+    ckpt = sp["ckpt"] and not args.no_ckpt
+    return dict(workload=sp["workload"], batch_per_gpu=args.batch, video_frames=sp["n_v"], audio_slices=sp["n_a"],
+                depth_frames=sp["n_d"], text_len=S_TXT, task=sp["task"],
+                tower="EVA01-CLIP-g-14 (1408 x 40, 16 heads x 88, MLP 6144), DropPath 0.4" if sp["tower"].startswith("eva")
+                else "Swin-B (embed 128, depths 2/2/18/2, window 7), DropPath 0.2",
                 text_encoder="bert-base-uncased-crossattn (12 layers, dropout 0.1), tied LM head",
                 optimizer="AdamW (fused), gradient SUM over ranks",
-                token_accounting=f"value counts north_star tokens: 1568/video + 257/image (3 audio slices, 1 depth) + 128/text = "
-                                 f"{int(ns / args.batch)} per sample; the encoders process {int(processed / args.batch)} per sample",
+                token_accounting=f"value counts north_star tokens (1568 / 8-frame video, 257 / image incl. each audio slice and depth map, "
+                                 f"128 / text) = {int(ns / args.batch)} per sample; the encoders process {int(processed / args.batch)} per sample",
                 l2="working set per step (tens of GB of activations) exceeds the 126 MB L2; no flush needed",
-                activation_checkpointing=("none" if args.no_ckpt else "tower blocks keep their input only (the reference's "
+                activation_checkpointing=("none" if not ckpt else "tower blocks keep their input only (the reference's "
                                           "config.checkpointing, eva_vit_model.py:635-637)")
-                + (f"; last {args.light_blocks} blocks keep qkv / attention output / x1" if args.light_blocks else ""),
+                + (f"; last {args.light_blocks} blocks keep qkv / attention output / x1" if (args.light_blocks and ckpt) else ""),
                 schedule="one tower pass for all modalities; ITM / caption sub-tasks differentiated group by group inside "
                          "forward (mico_b200/train_step.py)",
                 e2e_inputs="pinned host pixels + waveforms, H2D every step on a side stream one step ahead (the reference's "
@@ -158,9 +180,9 @@ def make_config(args):
                            "(mico_b200/dp.py)") if args.gpus > 1 else "none (1 GPU)")
 
 
-def model_cfg(ckpt=True):
+def model_cfg(ckpt=True, tower="evaclip01_giant"):
     from mico_b200.mico import _AttrDict
-    return _AttrDict(vision_encoder_type="evaclip01_giant", vision_resolution=224, checkpointing=ckpt, contra_dim=512,
+    return _AttrDict(vision_encoder_type=tower, vision_resolution=224, checkpointing=ckpt, contra_dim=512,
                      max_vision_sample_num=N_V, max_audio_sample_num=N_A, max_depth_sample_num=N_D, beam_size=3, itm_ratio=0.1,
                      max_omni_caption_len=70, max_caption_len=S_TXT, max_subtitle_len=70, frame_embedding_type="adaptive",
                      pool_video=False)
@@ -177,7 +199,7 @@ def host_batch(b, rank, n_v=N_V, n_d=N_D, S=S_TXT, pin=True, wave=True):
     ids[:, 0] = 101
     ids[torch.arange(b), lens - 1] = 102
     h = dict(vision_pixels=torch.randn(b, n_v, 3, 224, 224, generator=g),
-             depth_pixels=torch.randn(b, n_d, 3, 224, 224, generator=g),
+             depth_pixels=torch.randn(b, n_d, 3, 224, 224, generator=g) if n_d else None,
              audio_waveforms=0.1 * torch.randn(b, WAVE_SAMPLES, generator=g) if wave else None,
              input_ids=ids, attention_mask=att)
     if pin:
@@ -239,9 +261,9 @@ class OmniOracle:
     def batch(self, b, n_v, n_a, n_d):
         import torch
         from oracle import fbank as OF
-        h = host_batch(b, 0, n_v=n_v, n_d=n_d, pin=False)
+        h = host_batch(b, 0, n_v=n_v, n_d=n_d, pin=False, wave=n_a > 0)
         spec = torch.stack([OF.audio_processor(w.unsqueeze(0), melbins=224, target_length=224, sample_num=n_a)
-                            for w in h["audio_waveforms"]], dim=0)
+                            for w in h["audio_waveforms"]], dim=0) if n_a else None
         ids, att = h["input_ids"], h["attention_mask"]
         g = torch.Generator().manual_seed(7)
         pick = (torch.rand(ids.shape, generator=g) < 0.6) & (att > 0)
@@ -251,12 +273,12 @@ class OmniOracle:
                     cap_ids=torch.where(pick, torch.full_like(ids, 103), ids),
                     cap_labels=torch.where(pick, ids, torch.full_like(ids, -100)))
 
-    def step(self, batch):
+    def step(self, batch, task=OMNI_TASK):
         from oracle import mico as OM
         for v in self.p.values():
             if v.is_floating_point():
                 v.grad = None
-        out = OM.omni_step(self.p, batch, self.vit_cfg, 12, 12, OMNI_TASK)
+        out = OM.omni_step(self.p, batch, self.vit_cfg, 12, 12, task)
         sum(out.values()).backward()
         return {k: float(v) for k, v in out.items()}
 
@@ -298,13 +320,19 @@ def run_reference(args):
         t_frame = time.perf_counter() - t0
         # a step of b=2 samples costs ~ 2*(n_v+n_a+n_d) frames * t_frame * ~1.25 (text side); shrink the frame counts
         # (keeping every modality and every sub-task) until the run fits the budget
-        b, shapes = 2, [(8, 3, 1), (4, 2, 1), (2, 1, 1), (1, 1, 1)]
+        if args.config == "trimodal":
+            print(json.dumps(dict(impl="reference", unavailable="the CPU oracle has no Swin-B MiCo step (builder-run config)")))
+            return
+        sp = SPECS[args.config]
+        b = 2
+        shapes = [(8, 3, 1), (4, 2, 1), (2, 1, 1), (1, 1, 1)] if args.config == "omni" else [(sp["n_v"], sp["n_a"], sp["n_d"])]
         n_v, n_a, n_d = next((s for s in shapes if nsteps * b * sum(s) * t_frame * 1.25 <= budget), shapes[-1])
         batch = orc.batch(b, n_v, n_a, n_d)
-        run = lambda: orc.step(batch)
+        run = lambda: orc.step(batch, sp["task"])
         tokens = omni_tokens(b, n_v, n_a, n_d)[0]
         sample = (f"{b} samples per step with video {n_v}f / audio {n_a} slices / depth {n_d}f / text S={S_TXT} (per-rank batch is "
-                  f"{args.batch} x 8 / 3 / 1), all seven sub-tasks, full ViT-g/14 + BERT-base, fp32 eager, {args.steps} steps")
+                  f"{args.batch} x {sp['n_v']} / {sp['n_a']} / {sp['n_d']}), every sub-task of {sp['task']}, full ViT-g/14 + BERT-base, "
+                  f"fp32 eager, {args.steps} steps")
     for _ in range(args.warmup):
         run()
     t0 = time.perf_counter()
@@ -350,15 +378,17 @@ def cpu_baseline_leg(config, budget_s=25.0):
     t0 = time.perf_counter()
     vitg_oracle_step(tp, orc.vit_cfg, x1, None)
     t_frame = time.perf_counter() - t0
-    b, shapes = 2, [(8, 3, 1), (4, 2, 1), (2, 1, 1), (1, 1, 1)]
+    sp = SPECS[config]
+    b = 2
+    shapes = [(8, 3, 1), (4, 2, 1), (2, 1, 1), (1, 1, 1)] if config == "omni" else [(sp["n_v"], sp["n_a"], sp["n_d"])]
     n_v, n_a, n_d = next((s for s in shapes if b * sum(s) * t_frame * 1.25 <= budget_s), shapes[-1])
     batch = orc.batch(b, n_v, n_a, n_d)
     t0 = time.perf_counter()
-    losses = orc.step(batch)
+    losses = orc.step(batch, sp["task"])
     dt = time.perf_counter() - t0
     return dict(value=omni_tokens(b, n_v, n_a, n_d)[0] / dt, unit="tokens/s", cores=cores, kind="port",
-                sample=f"1 step of {b} samples with video {n_v}f / audio {n_a} slices / depth {n_d}f / text S={S_TXT}, all seven "
-                       f"sub-tasks, full ViT-g/14 + BERT-base, fp32 eager (after a 1-frame tower warm-up); losses {losses}")
+                sample=f"1 step of {b} samples with video {n_v}f / audio {n_a} slices / depth {n_d}f / text S={S_TXT}, every sub-task "
+                       f"of {sp['task']}, full ViT-g/14 + BERT-base, fp32 eager (after a 1-frame tower warm-up); losses {losses}")
 
 
 # --------------------------------------------------------------------------------------------- product arm (B200)
@@ -444,14 +474,17 @@ def run_product_omni(args):
     selfcheck = {}
     if world > 1 and not args.no_selfcheck:
         selfcheck["nccl_reference_fixture_2rank"] = nccl_fixture_replay(rank, world, dev)
+    sp = SPECS[args.config]
+    task = sp["task"]
     B = args.batch
     torch.manual_seed(0)
-    cfg = model_cfg(ckpt=not args.no_ckpt)
+    cfg = model_cfg(ckpt=sp["ckpt"] and not args.no_ckpt, tower=sp["tower"])
     with torch.device(dev):
         model = MiCo.from_pretrained(cfg, {})
     model = model.to(dev).train()
-    tower = model.vision_encoder.visual
-    tower.ckpt_light_blocks = args.light_blocks
+    tower = getattr(model.vision_encoder, "visual", None)       # None: Swin (the tower module itself is the encoder)
+    if tower is not None:
+        tower.ckpt_light_blocks = args.light_blocks
     flat = dp.FlatGrads(model)
     sync = dp.GradSync(flat, bucket_blocks=args.bucket_blocks,
                        dtype=torch.bfloat16 if args.grad_dtype == "bf16" else torch.float32) if world > 1 else None
@@ -460,10 +493,11 @@ def run_product_omni(args):
     opt = optim.AdamW([dict(params=[p for k, p in named if not any(s in k for s in no_decay)], weight_decay=0.01),
                        dict(params=[p for k, p in named if any(s in k for s in no_decay)], weight_decay=0.0)],
                       lr=1e-6, betas=(0.9, 0.98))
-    opt.attach_bf16_sinks(tower)
-    audio = AudioProcessor(melbins=224, target_length=224, sample_num=N_A, training=True, device=dev)
-    host = host_batch(B, rank)
-    resident = {k: v.to(dev) for k, v in host.items() if k not in ("input_ids", "attention_mask")}
+    if tower is not None:
+        opt.attach_bf16_sinks(tower)
+    audio = AudioProcessor(melbins=224, target_length=224, sample_num=max(sp["n_a"], 1), training=True, device=dev)
+    host = host_batch(B, rank, n_v=sp["n_v"], n_d=sp["n_d"], wave=sp["n_a"] > 0)
+    resident = {k: v.to(dev) for k, v in host.items() if k not in ("input_ids", "attention_mask") and v is not None}
     host_loss = torch.empty(3, dtype=torch.float32).pin_memory()
 
     def step(dev_in, verify=False):
@@ -471,11 +505,14 @@ def run_product_omni(args):
         flat.zero_grad()
         if sync is not None:
             sync.begin_step(verify=verify)
-        batch = dict(vision_pixels=dev_in["vision_pixels"], depth_pixels=dev_in["depth_pixels"],
-                     audio_spectrograms=audio.batch(dev_in["audio_waveforms"]),
+        batch = dict(vision_pixels=dev_in["vision_pixels"],
                      caption_tokens=_AttrDict(input_ids=host["input_ids"], attention_mask=host["attention_mask"]))
-        out = model(batch, OMNI_TASK, compute_loss=True)
-        loss = out["loss_itc"] + out["loss_itm"] + out["loss_cap"]
+        if "depth_pixels" in dev_in:
+            batch["depth_pixels"] = dev_in["depth_pixels"]
+        if "audio_waveforms" in dev_in:
+            batch["audio_spectrograms"] = audio.batch(dev_in["audio_waveforms"])
+        out = model(batch, task, compute_loss=True)
+        loss = sum(out.values())
         loss.backward()
         if sync is not None:
             sync.finish()
@@ -485,7 +522,7 @@ def run_product_omni(args):
 
     copy_stream = torch.cuda.Stream(device=dev)
     staged = []
-    h2d_keys = ("vision_pixels", "depth_pixels", "audio_waveforms")
+    h2d_keys = tuple(k for k in ("vision_pixels", "depth_pixels", "audio_waveforms") if host[k] is not None)
 
     def stage_next():
         # the reference's PrefetchLoader (data/utils/loader.py:100-142): the NEXT batch crosses PCIe on a side stream
@@ -568,10 +605,11 @@ def run_product_omni(args):
         return
 
     pk = peaks()
-    ns_tok, proc_tok = omni_tokens(B)
+    ns_tok, proc_tok = omni_tokens(B, sp["n_v"], sp["n_a"], sp["n_d"], frame_tokens=sp["frame_tokens"])
     value = world * ns_tok * args.steps / (ms / 1e3)
     e2e = world * ns_tok * args.steps / (ms_e2e / 1e3)
-    tower_f, fusion_f, text_f = omni_flops(B)
+    tower_f, fusion_f, text_f = omni_flops(B, sp["n_v"], sp["n_a"], sp["n_d"], task=task, frame_tokens=sp["frame_tokens"],
+                                           frame_flops=sp["frame_flops"], tower_dim=1408 if tower is not None else 1024)
     step_flops = 3 * (tower_f + fusion_f + text_f)
     step_s = ms / args.steps * 1e-3
     g = fam["gemm"]
@@ -598,12 +636,12 @@ def run_product_omni(args):
                     families={k: dict(ms_per_step=v["ms"] / nprof, calls_per_step=v["calls"] / nprof,
                                       rate=(v["work"] / (v["ms"] * 1e-3) / (1e12 if is_tf(k) else 1e9)) if v["ms"] > 0 else None,
                                       rate_unit="TFLOP/s" if is_tf(k) else "GB/s") for k, v in fam.items()})
-    cpu = cpu_baseline_leg("omni") if (world == 1 and not args.no_cpu_baseline) else None
+    cpu = cpu_baseline_leg(args.config) if (world == 1 and not args.no_cpu_baseline and args.config != "trimodal") else None
     h2d = sum(host[k].numel() * host[k].element_size() for k in h2d_keys) + 2 * host["input_ids"].numel() * 8 * 2
     config = make_config(args)
     extra = dict(processed_tokens_per_s=world * proc_tok * args.steps / (ms / 1e3), peak_hbm_gb=round(peak_mem, 1),
                  losses_after_warmup=losses0)
-    line = dict(metric=METRIC["omni"], value=value, unit="tokens/s", n_gpus=world, steps=args.steps, warmup=W,
+    line = dict(metric=METRIC[args.config], value=value, unit="tokens/s", n_gpus=world, steps=args.steps, warmup=W,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                 data="synthetic", config=config, clocks=clocks,
                 e2e=dict(value=e2e, unit="tokens/s", ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=h2d,
@@ -766,8 +804,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mico_b200", choices=["mico_b200", "reference"])
-    ap.add_argument("--config", default="omni", choices=["omni", "vitg"])
-    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--config", default="omni", choices=["omni", "imgtext", "trimodal", "vitg"])
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default: the configuration's own)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-selfcheck", action="store_true")
     ap.add_argument("--no-ckpt", action="store_true", help="omni: keep every tower activation (small --batch only)")
@@ -776,9 +814,11 @@ def main():
     ap.add_argument("--bucket-blocks", type=int, default=int(os.environ.get("MICO_BENCH_BUCKET_BLOCKS", "5")))
     ap.add_argument("--grad-dtype", default="fp32", choices=["fp32", "bf16"])
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 64 if args.config == "vitg" else SPECS[args.config]["batch"]
     if args.impl == "reference":
         run_reference(args)
-    elif args.config == "omni":
+    elif args.config in SPECS:
         run_product_omni(args)
     else:
         run_product_vitg(args)

@@ -134,6 +134,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(m), "r"(src_smem), "r"(c0), "r"(c1) : "memory");
 }
+// same, but the box is ADDED to global memory (element-wise fp32 atomic add in L2): split-K partial accumulators
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(m), "r"(src_smem), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int kPending>
 __device__ __forceinline__ void tma_store_wait_read() {      // all but the newest kPending groups have read their smem

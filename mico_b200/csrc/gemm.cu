@@ -53,6 +53,8 @@ struct GemmEpi {
     float alpha;
     int remap_gin, remap_gout, remap_off, residual_bcast;
     int vec_ok;   // all pitches / bases allow 16-byte vector access
+    int ksplit;   // > 1: the K loop of every output tile is split over `ksplit` work units whose fp32 partial tiles are
+                  // ADDED into the (zeroed) output by TMA reduce (EPI_F32 only: weight gradients with few output tiles)
 };
 
 template <int BN, int STAGES, int EPI = 0, bool B_MN = false, bool P2 = false>
@@ -531,14 +533,16 @@ __device__ __forceinline__ uint32_t tile_acquire(uint32_t st, uint32_t& sidx) {
     ++sidx;
     return tile;
 }
-__device__ __forceinline__ void tile_store(const CUtensorMap* tm, uint32_t tile, const uint4 (&own)[4], int c0, int row0) {
+__device__ __forceinline__ void tile_store(const CUtensorMap* tm, uint32_t tile, const uint4 (&own)[4], int c0, int row0,
+                                           bool reduce_add = false) {
     const int l = (int)lane_id();
 #pragma unroll
     for (int g = 0; g < 4; ++g) sts128(stage_at(tile, l, g), own[g]);
     fence_proxy_async_smem();
     __syncwarp();
     if (l == 0) {
-        tma_store_2d(tm, tile, c0, row0);
+        if (reduce_add) tma_reduce_add_2d(tm, tile, c0, row0);
+        else tma_store_2d(tm, tile, c0, row0);
         tma_store_commit();
     }
 }
@@ -633,7 +637,7 @@ __device__ __forceinline__ void fast_chunk32(const GemmEpi& e, const CUtensorMap
             for (int i = 0; i < 4; ++i)
                 own[i] = make_uint4(__float_as_uint(v[16 * h + 4 * i]), __float_as_uint(v[16 * h + 4 * i + 1]),
                                     __float_as_uint(v[16 * h + 4 * i + 2]), __float_as_uint(v[16 * h + 4 * i + 3]));
-            tile_store(tmOut, tile_acquire(st, sidx), own, col0 + 16 * h, row0);
+            tile_store(tmOut, tile_acquire(st, sidx), own, col0 + 16 * h, row0, e.ksplit > 1);
         }
     } else {
         pack32_bf16(v, own);
@@ -748,6 +752,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto unit_nt = [&](int u) { return u % num_n; };
     const int unit0 = blockIdx.x / CLN, unit_stride = gridDim.x / CLN;
     constexpr uint16_t kMask = (1u << CLN) - 1;
+    // split-K (epi.ksplit > 1, EPI_F32 only): work unit u = (tile u % num_tiles, K part u / num_tiles) -- the parts of one
+    // tile run concurrently on different CTAs and add their fp32 partial tiles into the zeroed output (TMA reduce).  A weight
+    // gradient with a 200k-row K loop and 36 output tiles otherwise leaves half of the SM pairs idle.
+    const int ksplit = EPI == EPI_F32 ? epi.ksplit : 1;
+    const int kb_per = (num_kb + ksplit - 1) / ksplit;
+    const int num_units = num_tiles * ksplit;
 
     if (warp == 0) {
         if (elect_one()) {
@@ -782,10 +792,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+            for (int unit = unit0; unit < num_units; unit += unit_stride) {
+                const int tile = unit % num_tiles, kb0 = (unit / num_tiles) * kb_per;
+                const int kb1 = kb0 + kb_per < num_kb ? kb0 + kb_per : num_kb;
                 const int m0 = (unit_mg(tile) * CLN + (int)cta_rank) * BM;
                 const int n0 = unit_nt(tile) * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
@@ -850,7 +862,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
+            for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
+                const int tile = unit % num_tiles, kb0 = (unit / num_tiles) * kb_per;
+                const int kb1 = kb0 + kb_per < num_kb ? kb0 + kb_per : num_kb;
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 // the last N tile issues a narrower MMA: no tensor-pipe time is spent on the columns past N (the smem rows
@@ -861,7 +875,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kAccStride;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -872,8 +886,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                                     : umma_smem_desc_sw128(sa + k * 32, 16, 1024);
                         const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(sb + k * 2048, 8192, 1024)
                                                     : umma_smem_desc_sw128(sb + k * 32, 16, 1024);
-                        if constexpr (P2) umma_bf16_ss_pair(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
-                        else umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+                        if constexpr (P2) umma_bf16_ss_pair(d_tmem, adesc, bdesc, idesc, ((kb - kb0) | k) != 0);
+                        else umma_bf16_ss(d_tmem, adesc, bdesc, idesc, ((kb - kb0) | k) != 0);
                     }
                     if constexpr (CLN == 1) umma_commit(&empty_bar[stage]);
                     else if constexpr (P2) umma_commit_pair(&empty_bar[stage], kMask);
@@ -890,7 +904,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int half = (warp - 2) >> 2;  // which of the two warps of that quarter: owns chunks c with (c & 1) == half
         int it = 0;
         uint32_t sidx = 0;                 // TMA store tiles of this warp alternate (specialised epilogues)
-        for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
+        for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
+            const int tile = unit % num_tiles;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int m0 = (unit_mg(tile) * CLN + (int)cta_rank) * BM;
@@ -999,7 +1014,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int BN, bool A_MN, bool B_MN, int STAGES, int CL, int EPI>
-int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) {
+int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi_in, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, STAGES, EPI, B_MN, CL == 3>;
     constexpr int CLN = CL == 1 ? 1 : 2;
     CUtensorMap tmA, tmB;
@@ -1031,11 +1046,11 @@ int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) 
 
     CUtensorMap tmOut = tmA, tmAux = tmA;     // placeholders unless the specialised epilogue stores through them
     if constexpr (EPI != EPI_GENERIC) {
-        const bool f32 = epi.out_fp32 != 0;
-        if ((rc = make_tmap_tile64(&tmOut, epi.out, f32, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)epi.ldo * (f32 ? 4 : 2)))) return rc;
+        const bool f32 = epi_in.out_fp32 != 0;
+        if ((rc = make_tmap_tile64(&tmOut, epi_in.out, f32, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)epi_in.ldo * (f32 ? 4 : 2)))) return rc;
     }
     if constexpr (EPI == EPI_GELU_SAVE) {
-        if ((rc = make_tmap_tile64(&tmAux, epi.aux_out, false, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)epi.ld_aux_out * 2))) return rc;
+        if ((rc = make_tmap_tile64(&tmAux, epi_in.aux_out, false, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)epi_in.ld_aux_out * 2))) return rc;
     }
 
     auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES, CL, EPI>;
@@ -1044,8 +1059,28 @@ int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) 
         MICO_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    const int units = ceil_div(ceil_div(g.M, BM), CLN) * ceil_div(g.N, BN);
+    int units = ceil_div(ceil_div(g.M, BM), CLN) * ceil_div(g.N, BN);
     const int max_clusters = num_sms() / CLN;
+    GemmEpi epi = epi_in;
+    epi.ksplit = 1;
+    if constexpr (EPI == EPI_F32) {
+        // Split-K for weight gradients with fewer output tiles than SM (pair) slots: pick the split whose unit count fills
+        // whole waves best, keeping >= 16 K blocks per part.  Two parts add commutatively (bit-reproducible); more than two
+        // arrive in any order (last-bit run-to-run differences, like cuBLAS split-K) -- MICO_GEMM_SPLITK_MAX=2 / =1 restricts.
+        static const int ks_max = [] { const char* e = getenv("MICO_GEMM_SPLITK_MAX"); return e ? atoi(e) : 4; }();
+        auto fill = [&](int u) { return (double)u / ((double)ceil_div(u, max_clusters) * max_clusters); };
+        const int num_kb = ceil_div(g.K, BK);
+        int ks = 1;
+        for (int cand = 2; cand <= ks_max; cand *= 2) {
+            if (num_kb / cand < 16) break;
+            if (fill(units * cand) > fill(units * ks) * 1.08) ks = cand;
+        }
+        if (ks > 1) {
+            MICO_CHECK_CUDA(cudaMemset2DAsync(epi.out, (size_t)epi.ldo * 4, 0, (size_t)g.N * 4, (size_t)g.M, stream));
+            epi.ksplit = ks;
+            units *= ks;
+        }
+    }
     const int grid = (units < max_clusters ? units : max_clusters) * CLN;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -1194,6 +1229,7 @@ extern "C" int mico_gemm_bf16(const MicoGemmArgs* args, void* stream_) {
     e.accumulate = g.accumulate; e.alpha = g.alpha;
     e.remap_gin = g.remap_gin; e.remap_gout = g.remap_gout; e.remap_off = g.remap_off;
     e.residual_bcast = g.residual_bcast;
+    e.ksplit = 1;
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const int oel = g.out_fp32 ? 4 : 8;   // elements per 16 bytes
     bool vec = al16(g.out) && (g.ldo % oel == 0);

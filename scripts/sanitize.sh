@@ -10,7 +10,7 @@ summary=gpurun_out/r2_sanitizer_summary.txt
 : > "$summary"
 run() {   # tool, family
   local out=gpurun_out/r2_sanitizer_$1_$2.txt
-  timeout 900 "$CS" --tool "$1" --print-limit 20 python scripts/sanitize_sweep.py "$2" > "$out" 2>&1
+  timeout 240 "$CS" --tool "$1" --print-limit 20 python scripts/sanitize_sweep.py "$2" > "$out" 2>&1
   local rc=$?
   echo "[$1 / $2] exit $rc : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|done' "$out" | tr '\n' ' ')" | tee -a "$summary"
 }

@@ -70,7 +70,7 @@ def rowwise():
         ops.scale_(x.clone(), scale_dev=torch.tensor([0.5], device="cuda"))
         ops.dropout(x, 0.1, 5, 0, res=x, out_f32=True, out_bf16=True)
     ops.colsum2(r(200, 528).to(BF16), 176, 176, 176, torch.empty(176, device="cuda"), torch.empty(176, device="cuda"))
-    ops.batch_sum(r(5, 999), 5)
+    ops.batch_sum(r(5, 1000), 5)
     img = r(3, 3, 224, 224)
     cols = ops.patchify(img, 14, 640, tokens_per_img=257, token_off=1)
     ops.patchify(r(2, 224, 224), 14, 640, replicate_channel=True, tokens_per_img=257, token_off=1)

@@ -192,3 +192,21 @@ def test_specialised_epilogues_all_kinds(M, N, K, b_mn):
     out = ops.gemm(a, b, bias=bias, residual=res, row_scale=rs, rows_per_group=T, out_dtype=torch.float32, **kw)   # EPI_RES32
     ref = res + (acc + bias) * rs.repeat_interleave(T)[:M, None]
     assert rel_l2(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(768, 768, 8192), (1408, 1408, 16448), (2304, 768, 4096 + 64)])
+def test_wgrad_split_k(M, N, K):
+    """Weight gradients with few output tiles and a long K loop are split over K (TMA reduce-add of fp32 partial tiles into the
+    zeroed output, gemm.cu launch_gemm): dW = dY^T X against an fp32 reference on the same bf16 operands, and against the
+    unsplit kernel (MICO_GEMM_SPLITK_MAX is read once per process, so the unsplit result comes from an accumulate launch)."""
+    from mico_b200 import ops
+    g = torch.Generator().manual_seed(M + K)
+    dy = torch.randn(K, M, generator=g).to(torch.bfloat16).cuda()
+    x = torch.randn(K, N, generator=g).to(torch.bfloat16).cuda()
+    out = torch.full((M, N), 7.0, device="cuda")           # stale contents must not leak into the result
+    ops.gemm(dy, x, a_mn=True, b_mn=True, out=out)
+    ref = dy.float().t() @ x.float()
+    assert rel_l2(out, ref) < 2e-5
+    acc = torch.zeros((M, N), device="cuda")
+    ops.gemm(dy, x, a_mn=True, b_mn=True, out=acc, accumulate=True)      # generic epilogue, never split
+    assert rel_l2(out, acc) < 2e-5       # different fp32 partial-sum grouping over K
