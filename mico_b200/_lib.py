@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmico_b200.so")
+# MICO_B200_LIB selects another build of the same library (A/B measurements of a kernel change on one box)
+LIB_PATH = os.environ.get("MICO_B200_LIB") or os.path.join(_HERE, "lib", "libmico_b200.so")
 
 ACT_NONE, ACT_GELU, ACT_QUICK_GELU, ACT_GELU_BWD, ACT_QUICK_GELU_BWD = 0, 1, 2, 3, 4
 ACT_GELU_SAVE_GRAD, ACT_QUICK_GELU_SAVE_GRAD, ACT_MUL_AUX = 5, 6, 7

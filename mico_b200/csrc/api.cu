@@ -47,6 +47,47 @@ ProfScope::~ProfScope() {
     if (slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].e1, stream);
 }
 
+// ---- side stream (see host_utils.h)
+namespace {
+struct SideCtx {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[64] = {};
+    unsigned next = 0;
+};
+std::mutex g_side_mu;
+SideCtx g_side[16];
+cudaEvent_t side_event(SideCtx& c) {
+    cudaEvent_t& e = c.ev[c.next++ & 63];
+    if (!e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    return e;
+}
+SideCtx* side_ctx() {
+    static const bool on = [] { const char* e = getenv("MICO_ATTN_TAIL_OVERLAP"); return !(e && e[0] == '0'); }();
+    int dev = 0;
+    if (!on || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    SideCtx& c = g_side[dev];
+    if (!c.stream && cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    return &c;
+}
+}  // namespace
+
+cudaStream_t side_fork(cudaStream_t main) {
+    std::lock_guard<std::mutex> lk(g_side_mu);
+    SideCtx* c = side_ctx();
+    if (!c) return nullptr;
+    cudaEvent_t e = side_event(*c);
+    if (!e || cudaEventRecord(e, main) != cudaSuccess || cudaStreamWaitEvent(c->stream, e, 0) != cudaSuccess) return nullptr;
+    return c->stream;
+}
+
+void side_join(cudaStream_t main) {
+    std::lock_guard<std::mutex> lk(g_side_mu);
+    SideCtx* c = side_ctx();
+    if (!c) return;
+    cudaEvent_t e = side_event(*c);
+    if (e && cudaEventRecord(e, c->stream) == cudaSuccess) cudaStreamWaitEvent(main, e, 0);
+}
+
 static std::atomic<int> g_reserved_sms{0};
 
 int num_sms() {

@@ -692,13 +692,21 @@ extern "C" int mico_attention_bwd(const MicoAttnArgs* a, void* stream_) {
     auto launch = [&](auto kq, auto kkv) -> int {
         MICO_CHECK_CUDA(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::TOTAL));
         MICO_CHECK_CUDA(cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem::TOTAL));
+        // remainder rows (SIMT) run on the side stream next to the tile kernels; they need delta, which is already queued
+        const bool tail = m_tail_rows(a->Sq) || (m_tail_rows(a->Sk) && a->kv_index == nullptr);
+        cudaStream_t side = tail ? side_fork(stream) : nullptr;
+        int rc_tail = MICO_OK;
         kq<<<work_q < num_sms() ? work_q : num_sms(), kBwdThreads, DqSmem::TOTAL, stream>>>(tq, tk, tv, tdo, tkx, tvx, p);
         MICO_CHECK_CUDA(cudaGetLastError());
+        // queued after the first tile kernel so that the persistent CTAs get their SMs first; the small tail blocks then fill
+        // the shared memory / thread slots the tile kernels leave free
+        if (tail && side) rc_tail = attention_tail_bwd(a, side);
         kkv<<<work_k < num_sms() ? work_k : num_sms(), kBwdThreads, DkvSmem::TOTAL, stream>>>(tq, tk, tv, tdo, tqx, tdox, p);
         MICO_CHECK_CUDA(cudaGetLastError());
         count_launch(3);
-        if (m_tail_rows(a->Sq) || (m_tail_rows(a->Sk) && a->kv_index == nullptr)) return attention_tail_bwd(a, stream);
-        return MICO_OK;
+        if (tail && !side) return attention_tail_bwd(a, stream);
+        if (side) side_join(stream);
+        return rc_tail;
     };
     const bool plain = a->mask == nullptr && a->dropout_p == 0.0f;
     switch (hd_pad) {

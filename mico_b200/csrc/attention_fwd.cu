@@ -201,6 +201,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 mbar_wait(s_full, scount & 1);      // also: the previous tile's P V has completed (issued before this S)
                 tc_fence_after();
                 // pass 1: row max (log2 domain).  scale > 0, so without a mask the max is taken on the raw scores.
+                // (Tried in round 2 and rejected: keeping the TMEM load of chunk c + 1 in flight while chunk c is processed,
+                // two register buffers -- the kernel hits the 168-register cap of two CTAs per SM and spills: tower forward
+                // 104 -> 119 us, cross-attention 1178 -> 1603 us on one box.)
                 float mx = -INFINITY;
                 for (int c = 0; c < nch; ++c) {
                     uint32_t v[32];
@@ -382,10 +385,18 @@ extern "C" int mico_attention_fwd(const MicoAttnArgs* a, void* stream_) {
         const int slots = num_sms() * ctas_per_sm;
         const int grid = work < slots ? work : slots;
         MICO_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        // the SIMT kernel for the remainder query rows touches other rows of O / lse than the tile kernel: it runs next to
+        // it on the side stream (ncu round 2: 25 us after an 81 us tile kernel per ViT-g layer when serialised)
+        const bool tail = m_tail_rows(a->Sq) > 0;
+        cudaStream_t side = tail ? side_fork(stream) : nullptr;
         kern<<<grid, kAttThreads, smem_bytes, stream>>>(tq, tk, tv, tkx, tvx, p);
         MICO_CHECK_CUDA(cudaGetLastError());
         count_launch();
-        if (m_tail_rows(a->Sq)) return attention_tail_fwd(a, stream);
+        if (tail) {
+            const int rc = attention_tail_fwd(a, side ? side : stream);
+            if (side) side_join(stream);
+            return rc;
+        }
         return MICO_OK;
     };
     const bool plain = a->mask == nullptr && a->dropout_p == 0.0f;

@@ -44,6 +44,14 @@ int num_sms();
 
 void count_launch(int n = 1);
 
+// Fork / join onto a library-owned side stream (one per device) so that a small independent kernel -- the SIMT tail rows of
+// attention -- runs CONCURRENTLY with the tile kernel it complements instead of after it.  side_fork(main): the side stream
+// waits for everything queued on `main` so far and is returned; side_join(main): `main` waits for everything queued on the
+// side stream so far.  Returns nullptr / does nothing when overlap is switched off (MICO_ATTN_TAIL_OVERLAP=0) or on error:
+// callers then launch on `main`.
+cudaStream_t side_fork(cudaStream_t main);
+void side_join(cudaStream_t main);
+
 // Per-kernel-family device timing (mico_profile_* in the C-ABI): when enabled, every entry point brackets its
 // launches with a cudaEvent pair on the launching stream; mico_profile_collect() reads them back.
 enum ProfKind { kProfGemm = 0, kProfAttnFwd, kProfAttnBwd, kProfLnFwd, kProfLnBwd, kProfOther, kProfKinds };

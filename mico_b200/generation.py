@@ -56,13 +56,29 @@ class BeamHypotheses:
         return self.worst_score >= highest_attainable_score
 
 
-def step_logits(model, input_ids, attention_mask, encoder_hidden_states, mask_token_id):
-    """One decode step of prepare_inputs_for_generation + forward: fp32 logits (rows, vocab) at the appended [MASK]."""
+def update_position_ids(position_ids):
+    """bert.py:1119-1124."""
+    b, n = position_ids.shape
+    upd = position_ids.new_zeros(b, n + 1)
+    upd[:, :n] = position_ids
+    upd[:, n] = upd[:, n - 1] + 1
+    return upd
+
+
+def prepare_inputs_for_generation(input_ids, attention_mask, mask_token_id, position_ids=None, encoder_hidden_states=None):
+    """bert.py:1126-1143: append a [MASK] token, grow the 3-D mask (and the position ids when given).  Pinned to the
+    reference's own function by tests/golden/generation_steps.pt (tests/test_generation.py)."""
     rows = input_ids.shape[0]
     dummy = torch.full((rows, 1), mask_token_id, dtype=torch.long, device=input_ids.device)
-    ids = torch.cat([input_ids, dummy], dim=1)
-    mask = update_attention_mask(attention_mask)
-    return model.mask_position_logits(ids, mask, encoder_hidden_states)
+    return dict(input_ids=torch.cat([input_ids, dummy], dim=1), attention_mask=update_attention_mask(attention_mask),
+                position_ids=update_position_ids(position_ids) if position_ids is not None else None,
+                encoder_hidden_states=encoder_hidden_states)
+
+
+def step_logits(model, input_ids, attention_mask, encoder_hidden_states, mask_token_id):
+    """One decode step of prepare_inputs_for_generation + forward: fp32 logits (rows, vocab) at the appended [MASK]."""
+    x = prepare_inputs_for_generation(input_ids, attention_mask, mask_token_id)
+    return model.mask_position_logits(x["input_ids"], x["attention_mask"], encoder_hidden_states)
 
 
 @torch.no_grad()

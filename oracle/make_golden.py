@@ -559,7 +559,38 @@ def gen_dist():
                                        ids_all=[r[4] for r in res], x_grad=[r[5] for r in res]))
 
 
-GENERATORS = {"vit": gen_vit, "bert": gen_bert, "mico_parts": gen_mico_parts, "dist": gen_dist,
+def gen_generation():
+    """The reference's own decode-step hooks (model/bert.py:1110-1143 update_attention_mask / update_position_ids /
+    prepare_inputs_for_generation, :1145-1190 _update_model_kwargs_for_generation), called UNBOUND over a stub `self`
+    (HF GenerationMixin of transformers 4.31 is not importable here, the hooks themselves are plain functions): inputs and
+    outputs of one and of several consecutive decode steps -> tests/golden/generation_steps.pt."""
+    import types
+    from model.bert import BertForMaskedLM as R
+    stub = types.SimpleNamespace(tokenizer=types.SimpleNamespace(mask_token_id=103))
+    stub.update_attention_mask = lambda m: R.update_attention_mask(stub, m)
+    stub.update_position_ids = lambda p: R.update_position_ids(stub, p)
+    stub._extract_past_from_model_output = lambda outputs, standardize_cache_format=False: None
+    g = torch.Generator().manual_seed(5)
+    cases = []
+    for b, n in ((3, 1), (2, 4), (4, 7)):
+        lens = torch.randint(1, n + 1, (b,), generator=g)
+        att = (torch.arange(n)[None] < lens[:, None]).long()
+        mask = torch.tril(att.unsqueeze(1).expand(-1, n, -1).clone())
+        ids = torch.randint(5, 1000, (b, n), generator=g)
+        pos = torch.arange(n)[None].expand(b, -1).clone()
+        enc = torch.randn(b, 5, 8, generator=g)
+        prep = R.prepare_inputs_for_generation(stub, ids, attention_mask=mask, position_ids=pos, encoder_hidden_states=enc)
+        steps = []
+        kw = {"attention_mask": mask, "position_ids": pos}
+        for _ in range(3):      # the kwargs mask after each generated token (greedy / beam loops call this once per step)
+            kw = R._update_model_kwargs_for_generation(stub, None, dict(kw))
+            steps.append(dict(attention_mask=kw["attention_mask"].clone(), position_ids=kw["position_ids"].clone()))
+        cases.append(dict(ids=ids, mask=mask, pos=pos, enc=enc, prep_input_ids=prep["input_ids"], prep_mask=prep["attention_mask"],
+                          prep_pos=prep["position_ids"], kwargs_steps=steps, mask_token_id=103))
+    _save("generation_steps.pt", dict(cases=cases))
+
+
+GENERATORS = {"generation": gen_generation, "vit": gen_vit, "bert": gen_bert, "mico_parts": gen_mico_parts, "dist": gen_dist,
               "transformer": gen_transformer, "clip": gen_clip, "fbank": gen_fbank, "swin": gen_swin,
               "adamw": gen_adamw, "checkpoint": gen_checkpoint, "losses": gen_losses, "imageproc": gen_imageproc, "eva02": gen_eva02}
 

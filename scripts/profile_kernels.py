@@ -35,4 +35,24 @@ if which in ("all", "attn"):
     for _ in range(reps):
         o, lse = ops.attention_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], d ** -0.5)
         ops.attention_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], o, lse, do, d ** -0.5, dq=dq[:, :, 0], dk=dq[:, :, 1], dv=dq[:, :, 2])
+if which in ("attn2",):
+    # round 2: (a) ViT-g tower shape, plain; (b) fusion-encoder cross-attention of the omni step's largest group: 256 text
+    # sequences x 12 heads x 128 queries against 64 shared K/V entries of 2827 visual tokens, attention dropout 0.1;
+    # (c) fusion-encoder self-attention with a 3-D causal mask
+    B, H, S, d = 64, 16, 257, 88
+    qkv = r(B, S, 3, H, d)
+    do = r(B, S, H, d)
+    dq = torch.empty_like(qkv)
+    o, lse = ops.attention_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], d ** -0.5)
+    ops.attention_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], o, lse, do, d ** -0.5, dq=dq[:, :, 0], dk=dq[:, :, 1], dv=dq[:, :, 2])
+    Bq, E, H, Sq, Sk, d = 256, 64, 12, 128, 2827, 64
+    q, do = r(Bq, Sq, H, d), r(Bq, Sq, H, d)
+    kv = r(E, Sk, 2, H, d)
+    idx = (torch.arange(Bq, device=dev) % E).to(torch.int32)
+    o, lse = ops.attention_fwd(q, kv[:, :, 0], kv[:, :, 1], d ** -0.5, dropout=(0.1, 11), kv_index=idx)
+    ops.attention_bwd(q, kv[:, :, 0], kv[:, :, 1], o, lse, do, d ** -0.5, dropout=(0.1, 11), kv_index=idx)
+    qkv = r(Bq, Sq, 3, H, d)
+    mask = torch.zeros(Bq, Sq, Sq, device=dev).masked_fill_(torch.triu(torch.ones(Sq, Sq, device=dev), 1).bool(), -10000.0)
+    o, lse = ops.attention_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], d ** -0.5, mask=mask, dropout=(0.1, 12))
+    ops.attention_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], o, lse, do, d ** -0.5, mask=mask, dropout=(0.1, 12))
 torch.cuda.synchronize()

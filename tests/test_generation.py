@@ -91,3 +91,23 @@ def test_generate_matches_oracle_decode(golden_dir):
             w, o = want[b][want[b] != pad], got[b][got[b] != pad]
             if not torch.equal(w, o):
                 assert abs(seq_score(o, b) - seq_score(w, b)) < 2e-2 * max(1.0, abs(seq_score(w, b))), (nb, b, w, o)
+
+
+def test_decode_step_hooks_match_reference_fixture(golden_dir):
+    """tests/golden/generation_steps.pt holds inputs / outputs of the reference's OWN decode-step hooks (model/bert.py:1110-1143,
+    1145-1190, called unbound over a stub by oracle/make_golden.py:gen_generation): the product's and the oracle's mask growth,
+    position-id growth and [MASK]-append step reproduce them exactly, one step and several steps ahead."""
+    pytest.importorskip("mico_b200._lib")
+    from mico_b200 import generation as G
+    from oracle import generation as OG
+    g = torch.load(os.path.join(golden_dir, "generation_steps.pt"), weights_only=False)
+    assert len(g["cases"]) >= 3
+    for c in g["cases"]:
+        x = G.prepare_inputs_for_generation(c["ids"], c["mask"], c["mask_token_id"], position_ids=c["pos"], encoder_hidden_states=c["enc"])
+        assert torch.equal(x["input_ids"], c["prep_input_ids"]) and torch.equal(x["attention_mask"], c["prep_mask"])
+        assert torch.equal(x["position_ids"], c["prep_pos"]) and x["encoder_hidden_states"] is c["enc"]
+        assert torch.equal(OG.grow_mask(c["mask"]), c["prep_mask"])
+        m, pos = c["mask"], c["pos"]
+        for st in c["kwargs_steps"]:          # what generate() carries from step to step
+            m, pos = G.update_attention_mask(m), G.update_position_ids(pos)
+            assert torch.equal(m, st["attention_mask"]) and torch.equal(pos, st["position_ids"])
