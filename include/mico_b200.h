@@ -179,6 +179,14 @@ int mico_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
  * differentiated ahead of the outer backward pass are rescaled by the upstream scalar gradient -- the loss scale of
  * GradScaler, data/utils/pipeline.py:86-88, or 1 (mico_b200/train_step.py) */
 int mico_scale_f32(float* x, const float* scale_dev, float scale_host, int64_t n, void* stream);
+/* SURVEY 8(f).4 EVA02 towers.  Rotary position embedding (model/evaclip/rope.py:79-136, applied to q and k at
+ * eva_vit_model.py:314-322): contiguous [B, T, H, d] tokens, token 0 (cls) passes through, the others are rotated pair-wise
+ * with the interleaved tables cos / sin [T-1, d]; fp32 -> bf16 (forward: the attention operand) or bf16 -> fp32 with
+ * inverse = 1 (the gradient of the rotation = its transpose). */
+int mico_rope(const void* x, int x_is_bf16, void* y, int y_is_bf16, const float* cos_table, const float* sin_table, int B,
+              int T, int H, int d, int inverse, void* stream);
+/* SwiGLU (eva_vit_model.py:201-224): dg == NULL: out0 = silu(u1) * u2; else out0 = d u1, out1 = d u2. */
+int mico_swiglu(const float* u1, const float* u2, const float* dg, float* out0, float* out1, int64_t n, void* stream);
 /* same for a [rows, cols] matrix into a wider bf16 pitch ldd, zero-filling columns cols..ldd-1
  * (patch-embed weight (1408, 3*14*14=588) -> K padded to a 16-byte multiple, eva_vit_model.py:440) */
 int mico_cast_f32_to_bf16_2d(const float* src, int64_t lds, int rows, int cols, void* dst, int64_t ldd, void* stream);

@@ -314,8 +314,20 @@ class BertModel(nn.Module):
             bqkv = cache.cat_b(("sqkvb", li), [P(1), P(3), P(5)])
             qkv = ops.gemm(hb, wqkv, bias=bqkv)
             q5 = qkv.view(b, S, 3, H, d)
-            ctx, lse = ops.attention_fwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], scale, mask=mask_self, need_lse=keep,
-                                         dropout=adrop(li, False))
+            if isinstance(mask_self, list):
+                # consecutive groups of sequences with their own mask layout (the grouped fusion-encoder call: ITM sequences
+                # carry a per-key padding mask, which every query row shares, caption sequences a per-row causal mask): one
+                # launch per group keeps the cheap broadcast mask path for the former
+                ctx = torch.empty((b, S, H, d), device=ids.device, dtype=BF16)
+                lse = []
+                for si, (lo, hi, m) in enumerate(mask_self):
+                    dr = adrop(li, False)
+                    _, l_ = ops.attention_fwd(q5[lo:hi, :, 0], q5[lo:hi, :, 1], q5[lo:hi, :, 2], scale, mask=m, out=ctx[lo:hi],
+                                              need_lse=keep, dropout=(dr[0], dr[1] + 7919 * si) if dr else None)
+                    lse.append(l_)
+            else:
+                ctx, lse = ops.attention_fwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], scale, mask=mask_self, need_lse=keep,
+                                             dropout=adrop(li, False))
             y1 = dense_res(ctx.view(M, Dh), cache.cat_w(("so", li), [P(6)]), P(7).detach(), h, li, 1)
             h1b, h1, m1, r1 = ln2(y1, base + 8, base + 9)
             rec = dict(hb=hb, qkv=qkv, ctx=ctx, lse=lse, y1=y1, st1=(m1, r1), h1b=h1b) if keep else None
@@ -430,8 +442,16 @@ class BertModel(nn.Module):
             q5 = rec["qkv"].view(b, S, 3, H, d)
             dqkv = torch.empty_like(rec["qkv"])
             g5 = dqkv.view(b, S, 3, H, d)
-            ops.attention_bwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], rec["ctx"], rec["lse"], dctx.view(b, S, H, d), scale,
-                              mask=saved["mask_self"], dq=g5[:, :, 0], dk=g5[:, :, 1], dv=g5[:, :, 2], dropout=adrop(li, False))
+            if isinstance(saved["mask_self"], list):
+                d4 = dctx.view(b, S, H, d)
+                for si, (lo, hi, m) in enumerate(saved["mask_self"]):
+                    dr = adrop(li, False)
+                    ops.attention_bwd(q5[lo:hi, :, 0], q5[lo:hi, :, 1], q5[lo:hi, :, 2], rec["ctx"][lo:hi], rec["lse"][si], d4[lo:hi],
+                                      scale, mask=m, dq=g5[lo:hi, :, 0], dk=g5[lo:hi, :, 1], dv=g5[lo:hi, :, 2],
+                                      dropout=(dr[0], dr[1] + 7919 * si) if dr else None)
+            else:
+                ops.attention_bwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], rec["ctx"], rec["lse"], dctx.view(b, S, H, d), scale,
+                                  mask=saved["mask_self"], dq=g5[:, :, 0], dk=g5[:, :, 1], dv=g5[:, :, 2], dropout=adrop(li, False))
             gw = torch.empty((3 * Dh, Dh), device=dev, dtype=F32)
             ops.gemm(dqkv, rec["hb"], a_mn=True, b_mn=True, out=gw)
             grads[base + 0], grads[base + 2], grads[base + 4] = gw[:Dh], gw[Dh:2 * Dh], gw[2 * Dh:]
@@ -482,7 +502,17 @@ class BertModel(nn.Module):
         b, S = input_ids.shape
         if attention_mask is None:
             attention_mask = torch.ones((b, S), device=input_ids.device)
-        mask_self = self._additive(attention_mask, -10000.0)
+        if isinstance(attention_mask, (list, tuple)):
+            # several masks, each for the next mask.shape[0] sequences (2-D and 3-D layouts may be mixed; not in the reference
+            # signature: used by the grouped fusion-encoder call of mico_b200/train_step.py)
+            mask_self, lo = [], 0
+            for m in attention_mask:
+                mask_self.append((lo, lo + m.shape[0], self._additive(m, -10000.0)))
+                lo += m.shape[0]
+            if lo != b:
+                raise ValueError("attention_mask list does not cover the batch")
+        else:
+            mask_self = self._additive(attention_mask, -10000.0)
         mask_enc = None
         if encoder_hidden_states is not None and encoder_attention_mask is not None:
             mask_enc = self._additive(encoder_attention_mask, torch.finfo(torch.float32).min)   # invert_attention_mask

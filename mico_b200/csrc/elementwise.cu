@@ -56,6 +56,50 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, floa
         dst[i] = __bfloat162float(src[i]);
 }
 
+// Rotary position embedding of the EVA02 towers (model/evaclip/rope.py:79-136, applied at eva_vit_model.py:314-322): every
+// token except the first (cls) is rotated pair-wise, (x1, x2) -> (x1 c - x2 s, x2 c + x1 s) with the interleaved tables
+// cos / sin [tokens-1, d] (both entries of a pair hold the same angle).  inverse: the transpose rotation (backward pass).
+template <typename TI, typename TO>
+__global__ void rope_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* __restrict__ cosv,
+                            const float* __restrict__ sinv, int64_t n_pairs, int T, int H, int d, int inverse) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int hp = d >> 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += stride) {
+        const int pr = (int)(i % hp);
+        const int64_t row = i / hp;                    // (b, t, h)
+        const int t = (int)((row / H) % T);
+        const float x1 = (float)x[2 * i], x2 = (float)x[2 * i + 1];
+        float y1 = x1, y2 = x2;
+        if (t > 0) {
+            const float c = cosv[(int64_t)(t - 1) * d + 2 * pr];
+            float sn = sinv[(int64_t)(t - 1) * d + 2 * pr];
+            if (inverse) sn = -sn;
+            y1 = x1 * c - x2 * sn;
+            y2 = x2 * c + x1 * sn;
+        }
+        y[2 * i] = (TO)y1;
+        y[2 * i + 1] = (TO)y2;
+    }
+}
+
+// SwiGLU of the EVA02 MLP (eva_vit_model.py:201-224): g = silu(u1) * u2; backward du1 = dg u2 silu'(u1), du2 = dg silu(u1)
+__global__ void swiglu_fwd_kernel(const float* __restrict__ u1, const float* __restrict__ u2, float* __restrict__ g, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float a = u1[i], sg = 1.0f / (1.0f + __expf(-a));
+        g[i] = a * sg * u2[i];
+    }
+}
+__global__ void swiglu_bwd_kernel(const float* __restrict__ u1, const float* __restrict__ u2, const float* __restrict__ dg,
+                                  float* __restrict__ du1, float* __restrict__ du2, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float a = u1[i], sg = 1.0f / (1.0f + __expf(-a)), d = dg[i];
+        du1[i] = d * u2[i] * sg * (1.0f + a * (1.0f - sg));
+        du2[i] = d * a * sg;
+    }
+}
+
 // rows x cols fp32 (pitch lds) -> bf16 (pitch ldd >= cols); columns cols..ldd-1 are zero-filled.
 __global__ void cast_f32_bf16_2d_kernel(const float* __restrict__ src, int64_t lds, int rows, int cols,
                                         __nv_bfloat16* __restrict__ dst, int64_t ldd) {
@@ -260,6 +304,41 @@ extern "C" int mico_cast_f32_to_bf16(const float* src, void* dst, int64_t n, voi
     int64_t want = (n / 8 + 255) / 256;
     const int grid = (int)(want < 1 ? 1 : (want > num_sms() * 16 ? num_sms() * 16 : want));
     cast_f32_bf16_kernel<<<grid, 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return MICO_OK;
+}
+
+extern "C" int mico_rope(const void* x, int x_is_bf16, void* y, int y_is_bf16, const float* cosv, const float* sinv, int B, int T,
+                         int H, int d, int inverse, void* stream_) {
+    using namespace mico;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MICO_CHECK_ARG(x && y && cosv && sinv && B > 0 && T > 1 && H > 0 && d > 0 && d % 2 == 0);
+    MICO_CHECK_ARG(x_is_bf16 != y_is_bf16);       // fp32 -> bf16 (forward: the attention operand) or bf16 -> fp32 (gradient)
+    const int64_t n_pairs = (int64_t)B * T * H * (d / 2);
+    ProfScope prof(kProfOther, 6.0 * 2.0 * (double)n_pairs, stream);
+    int64_t want = (n_pairs + 255) / 256;
+    const int grid = (int)(want > num_sms() * 16 ? num_sms() * 16 : want);
+    if (x_is_bf16)
+        rope_kernel<__nv_bfloat16, float><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                                   reinterpret_cast<float*>(y), cosv, sinv, n_pairs, T, H, d, inverse);
+    else
+        rope_kernel<float, __nv_bfloat16><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x),
+                                                                   reinterpret_cast<__nv_bfloat16*>(y), cosv, sinv, n_pairs, T, H, d, inverse);
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return MICO_OK;
+}
+
+extern "C" int mico_swiglu(const float* u1, const float* u2, const float* dg, float* out0, float* out1, int64_t n, void* stream_) {
+    using namespace mico;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MICO_CHECK_ARG(u1 && u2 && out0 && n > 0 && (dg == nullptr || out1 != nullptr));
+    ProfScope prof(kProfOther, (dg ? 20.0 : 12.0) * (double)n, stream);
+    int64_t want = (n + 255) / 256;
+    const int grid = (int)(want > num_sms() * 16 ? num_sms() * 16 : want);
+    if (dg) swiglu_bwd_kernel<<<grid, 256, 0, stream>>>(u1, u2, dg, out0, out1, n);
+    else swiglu_fwd_kernel<<<grid, 256, 0, stream>>>(u1, u2, out0, n);
     MICO_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return MICO_OK;

@@ -414,6 +414,85 @@ int ln_bwd_grid(int M) {
     const int cap = num_sms() * 2;   // two resident blocks per SM (register-limited): exactly one wave
     return want < cap ? want : cap;
 }
+// ---------------------------------------------------------------------------------------------- any width
+// Rows wider than the register-resident kernels hold (D > 1536: Swin-B's patch-merging LayerNorm over 4C = 2048,
+// swin.py:329) or not a multiple of 4 (EVA02-L's SwiGLU LayerNorm over 2730, eva_vit_model.py:213): one 256-thread block
+// per row, scalar accesses, two-pass statistics.  Off the hot path of every measured configuration.
+constexpr int kLnGenThreads = 256;
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane_id() == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kLnGenThreads / 32; ++w) t += red[w];
+    return t;
+}
+
+template <typename TX>
+__global__ void __launch_bounds__(kLnGenThreads)
+ln_fwd_generic_kernel(const TX* __restrict__ x, int64_t ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      __nv_bfloat16* __restrict__ yb, float* __restrict__ yf, int64_t ldy, float* __restrict__ mean,
+                      float* __restrict__ rstd, int D, float eps) {
+    __shared__ float red[kLnGenThreads / 32];
+    const int64_t row = blockIdx.x;
+    const TX* xr = x + row * ldx;
+    float s = 0.f;
+    for (int c = threadIdx.x; c < D; c += kLnGenThreads) s += (float)xr[c];
+    const float mu = block_sum_256(s, red) / D;
+    float q = 0.f;
+    for (int c = threadIdx.x; c < D; c += kLnGenThreads) { const float d = (float)xr[c] - mu; q += d * d; }
+    const float rs = rsqrtf(block_sum_256(q, red) / D + eps);
+    for (int c = threadIdx.x; c < D; c += kLnGenThreads) {
+        const float y = ((float)xr[c] - mu) * rs * gamma[c] + beta[c];
+        if (yb) yb[row * ldy + c] = __float2bfloat16(y);
+        if (yf) yf[row * ldy + c] = y;
+    }
+    if (threadIdx.x == 0) {
+        if (mean) mean[row] = mu;
+        if (rstd) rstd[row] = rs;
+    }
+}
+
+// dx = [dres +] rstd * (g - mean(g) - xhat * mean(g * xhat)), g = (dy [+ dy2]) * gamma; dgamma += sum dy*xhat, dbeta += sum dy
+// (fp32 atomics into zeroed / accumulated buffers: the summation order over rows is not fixed)
+template <typename TDY>
+__global__ void __launch_bounds__(kLnGenThreads)
+ln_bwd_generic_kernel(const TDY* __restrict__ dy, int64_t lddy, const __nv_bfloat16* __restrict__ dy2, int64_t lddy2,
+                      const float* __restrict__ x, int64_t ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
+                      const float* __restrict__ gamma, const float* __restrict__ dres, int64_t lddres, float* __restrict__ dx,
+                      int64_t lddx, __nv_bfloat16* __restrict__ dxb, int64_t lddxb, const float* __restrict__ row_scale,
+                      int rows_per_group, float* __restrict__ dgamma, float* __restrict__ dbeta, int D) {
+    __shared__ float red[kLnGenThreads / 32];
+    const int64_t row = blockIdx.x;
+    const float mu = mean[row], rs = rstd[row];
+    auto up = [&](int c) { return (float)dy[row * lddy + c] + (dy2 ? __bfloat162float(dy2[row * lddy2 + c]) : 0.f); };
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = threadIdx.x; c < D; c += kLnGenThreads) {
+        const float u = up(c), xh = (x[row * ldx + c] - mu) * rs, g = u * gamma[c];
+        s1 += g;
+        s2 += g * xh;
+        atomicAdd(dgamma + c, u * xh);
+        atomicAdd(dbeta + c, u);
+    }
+    const float m1 = block_sum_256(s1, red) / D;
+    const float m2 = block_sum_256(s2, red) / D;
+    const float sc = row_scale ? row_scale[row / rows_per_group] : 1.0f;
+    for (int c = threadIdx.x; c < D; c += kLnGenThreads) {
+        const float xh = (x[row * ldx + c] - mu) * rs;
+        float v = rs * (up(c) * gamma[c] - m1 - xh * m2);
+        if (dres) v += dres[row * lddres + c];
+        if (dx) dx[row * lddx + c] = v;
+        if (dxb) dxb[row * lddxb + c] = __float2bfloat16(v * sc);
+    }
+}
+
+bool ln_needs_generic(int D, int64_t a, int64_t b, int64_t c, int64_t d, int64_t e, int64_t f) {
+    return D > kMaxVec * 128 || D % 4 != 0 || ((a | b | c | d | e | f) & 3) != 0;
+}
+
 bool ln_bwd_use_rows(int D) { return (D >> 2) >= kLnThreads && (D >> 2) <= kV2 * kLnThreads; }
 int ln_bwd_row_grid(int M) {
     const int cap = num_sms() * 5;   // five resident blocks per SM: one wave
@@ -429,9 +508,21 @@ extern "C" int mico_layernorm_fwd(const void* x, int x_is_bf16, int64_t ldx, con
     using namespace mico;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     MICO_CHECK_ARG(x && gamma && beta && (y_bf16 || y_f32));
-    MICO_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= kMaxVec * 128);
-    MICO_CHECK_ARG(ldx % 4 == 0 && ldy % 4 == 0);
+    MICO_CHECK_ARG(M > 0 && D > 0);
     ProfScope prof(kProfLnFwd, (double)M * D * ((x_is_bf16 ? 2 : 4) + (y_bf16 ? 2 : 0) + (y_f32 ? 4 : 0)), stream);
+    if (ln_needs_generic(D, ldx, ldy, 0, 0, 0, 0)) {
+        if (x_is_bf16)
+            ln_fwd_generic_kernel<__nv_bfloat16><<<M, kLnGenThreads, 0, stream>>>(
+                reinterpret_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, ldy,
+                mean, rstd, D, eps);
+        else
+            ln_fwd_generic_kernel<float><<<M, kLnGenThreads, 0, stream>>>(reinterpret_cast<const float*>(x), ldx, gamma, beta,
+                                                                          reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, ldy,
+                                                                          mean, rstd, D, eps);
+        MICO_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+        return MICO_OK;
+    }
     {   // TMA-staged rows when the ring fits in shared memory and the rows can be bulk-copied (16-byte aligned)
         const int row_bytes = D * (x_is_bf16 ? 2 : 4);
         const int padded = (row_bytes + 127) & ~127;
@@ -477,6 +568,7 @@ extern "C" int mico_layernorm_fwd(const void* x, int x_is_bf16, int64_t ldx, con
 
 extern "C" size_t mico_layernorm_bwd_workspace(int M, int D) {
     using namespace mico;
+    if (D > kMaxVec * 128 || D % 4 != 0) return 16;      // the any-width kernels need no workspace
     if (ln_bwd_use_rows(D)) return (size_t)ln_bwd_row_grid(M) * 3 * (size_t)D * sizeof(float);
     return (size_t)ln_bwd_grid(M) * 2 * (size_t)D * sizeof(float);
 }
@@ -492,10 +584,27 @@ extern "C" int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, 
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     MICO_CHECK_ARG(dy && x && mean && rstd && gamma && dgamma && dbeta && workspace);
     MICO_CHECK_ARG(dx || dx_bf16);
-    MICO_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= kMaxVec * 128);
-    MICO_CHECK_ARG(lddy % 4 == 0 && ldx % 4 == 0 && lddx % 4 == 0 && lddxb % 4 == 0 && lddres % 4 == 0 && lddy2 % 4 == 0);
+    MICO_CHECK_ARG(M > 0 && D > 0);
     const __nv_bfloat16* dy2 = reinterpret_cast<const __nv_bfloat16*>(dy2_bf16);
     MICO_CHECK_ARG(!(row_scale && rows_per_group <= 0));
+    if (ln_needs_generic(D, lddy, ldx, lddx, lddxb, lddres, lddy2)) {
+        MICO_CHECK_ARG(!dxb_colsum);
+        ProfScope prof(kProfLnBwd, (double)M * D * ((dy_is_bf16 ? 2 : 4) + 4 + (dres ? 4 : 0) + (dx ? 4 : 0) + (dx_bf16 ? 2 : 0)), stream);
+        if (!accumulate_param_grads) {
+            MICO_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)D * sizeof(float), stream));
+            MICO_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)D * sizeof(float), stream));
+        }
+        auto go = [&](auto k, auto dyp) {
+            k<<<M, kLnGenThreads, 0, stream>>>(dyp, lddy, dy2, lddy2, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx,
+                                              reinterpret_cast<__nv_bfloat16*>(dx_bf16), lddxb, row_scale, rows_per_group, dgamma,
+                                              dbeta, D);
+        };
+        if (dy_is_bf16) go(ln_bwd_generic_kernel<__nv_bfloat16>, reinterpret_cast<const __nv_bfloat16*>(dy));
+        else go(ln_bwd_generic_kernel<float>, reinterpret_cast<const float*>(dy));
+        MICO_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+        return MICO_OK;
+    }
     MICO_CHECK_ARG(ws_bytes >= mico_layernorm_bwd_workspace(M, D));
     const bool rows = ln_bwd_use_rows(D);
     // the fused column sum lives in the block-per-row kernel only (every tower width on the path)

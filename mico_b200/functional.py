@@ -285,3 +285,86 @@ class _LinearGeluTC(torch.autograd.Function):
 def linear_gelu(x, weight, bias=None):
     """bf16 GELU(x W^T + b) on the tensor-core GEMM (returns bf16)."""
     return _LinearGeluTC.apply(x, weight, bias, ACT_GELU)
+
+
+class _Rope(torch.autograd.Function):
+    """Rotary embedding of q / k (EVA02: eva_vit_model.py:314-322): fp32 [B, T, H, d] -> rotated bf16 attention operand."""
+
+    @staticmethod
+    def forward(ctx, x, cos, sin):
+        ctx.save_for_backward(cos, sin)
+        return ops.rope(x.contiguous().float(), cos, sin)
+
+    @staticmethod
+    def backward(ctx, dy):
+        cos, sin = ctx.saved_tensors
+        dyb = dy.contiguous() if dy.dtype == BF16 else dy.to(BF16).contiguous()
+        return ops.rope(dyb, cos, sin, inverse=True), None, None
+
+
+def rope(x, cos, sin):
+    return _Rope.apply(x, cos, sin)
+
+
+class _SwiGLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u1, u2):
+        a, b = u1.contiguous().float(), u2.contiguous().float()
+        ctx.save_for_backward(a, b)
+        return ops.swiglu(a, b)
+
+    @staticmethod
+    def backward(ctx, dg):
+        a, b = ctx.saved_tensors
+        return ops.swiglu(a, b, dg.contiguous().float())
+
+
+def swiglu(u1, u2):
+    """silu(u1) * u2 (eva_vit_model.py:201-224)"""
+    return _SwiGLU.apply(u1, u2)
+
+
+class _CastBF16(torch.autograd.Function):
+    """fp32 -> bf16 operand with an fp32 gradient (v of the EVA02 attention)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.scale_cast_bf16(_flat2d(x).contiguous().float()).view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy.float()
+
+
+def cast_bf16(x):
+    return _CastBF16.apply(x)
+
+
+class _PatchEmbed(torch.autograd.Function):
+    """Conv2d(k = s = P) as im2col + tcgen05 GEMM (eva_vit_model.py:440-447): pixels (B, C, H, W) -> (B, gh*gw, D) fp32."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, P):
+        B = x.shape[0]
+        k = weight[0].numel()
+        kpad = (k + 63) // 64 * 64
+        cols = ops.patchify(x.contiguous().float(), P, kpad)
+        wb = ops.cast_bf16_2d(weight.detach().reshape(weight.shape[0], -1), kpad)
+        y = ops.gemm(cols, wb, out_dtype=F32, bias=None if bias is None else bias.detach())
+        ctx.save_for_backward(cols)
+        ctx.meta = (k, weight.shape, bias is not None)
+        return y.view(B, -1, weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        (cols,) = ctx.saved_tensors
+        k, wshape, has_bias = ctx.meta
+        dyb = ops.scale_cast_bf16(_flat2d(dy).contiguous().float())
+        dw = torch.empty((wshape[0], k), device=dy.device, dtype=F32)
+        ops.gemm(dyb, cols[:, :k], a_mn=True, b_mn=True, out=dw)
+        db = ops.colsum(dyb) if has_bias else None
+        return None, dw.view(wshape), db, None
+
+
+def patch_embed(x, weight, bias, P):
+    return _PatchEmbed.apply(x, weight, bias, P)

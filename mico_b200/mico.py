@@ -433,6 +433,10 @@ class MiCo(nn.Module):
             if "caption_tokens" not in batch and "raw_captions" in batch:
                 self._tokens(batch, "caption_tokens", "raw_captions", self.max_caption_len, on_host=True)
             return fused_train_forward(self, batch, task)
+        tok = batch.get("caption_tokens")
+        if tok is not None and not tok.input_ids.is_cuda:        # a tokenizer's host tensors
+            dev = self.contra_temp.device
+            batch["caption_tokens"] = _AttrDict(input_ids=tok.input_ids.to(dev), attention_mask=tok.attention_mask.to(dev))
         out = {}
         for t in task.split("_"):
             if t.startswith("ret"):

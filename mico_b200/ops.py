@@ -283,6 +283,33 @@ def scale_(x, scale_dev=None, scale_host=1.0):
     return x
 
 
+def rope(x, cos, sin, inverse=False):
+    """x: contiguous [B, T, H, d]; fp32 -> rotated bf16 (forward), or bf16 -> inverse-rotated fp32 (gradient)."""
+    if not x.is_contiguous() or x.dim() != 4 or x.dtype not in (F32, BF16):
+        raise MicoError("rope: contiguous fp32 / bf16 [B, T, H, d] expected")
+    _req(cos, F32, "cos")
+    _req(sin, F32, "sin")
+    B, T, H, d = x.shape
+    if tuple(cos.shape) != (T - 1, d) or tuple(sin.shape) != (T - 1, d) or not cos.is_contiguous() or not sin.is_contiguous():
+        raise MicoError("rope: tables must be contiguous [T-1, d]")
+    y = torch.empty(x.shape, device=x.device, dtype=F32 if x.dtype == BF16 else BF16)
+    check(lib.mico_rope(_ptr(x), int(x.dtype == BF16), _ptr(y), int(y.dtype == BF16), _ptr(cos), _ptr(sin), B, T, H, d,
+                        int(inverse), _stream()), "mico_rope")
+    return y
+
+
+def swiglu(u1, u2, dg=None):
+    """fp32 contiguous: silu(u1) * u2, or (d u1, d u2) when dg is given."""
+    for n_, t in (("u1", u1), ("u2", u2)):
+        _req(t, F32, n_)
+        if not t.is_contiguous():
+            raise MicoError("swiglu: contiguous tensors expected")
+    out0 = torch.empty_like(u1)
+    out1 = torch.empty_like(u1) if dg is not None else None
+    check(lib.mico_swiglu(_ptr(u1), _ptr(u2), _ptr(dg), _ptr(out0), _ptr(out1), C.c_int64(u1.numel()), _stream()), "mico_swiglu")
+    return (out0, out1) if dg is not None else out0
+
+
 def cast_bf16_2d(src, ldd):
     """fp32 [rows, cols] (row pitch src.stride(0)) -> bf16 [rows, ldd], zero-filled past cols."""
     _req(src, F32, "src")

@@ -234,13 +234,13 @@ def fused_train_forward(model, batch, task):
                     cond_all = all_gather_with_grad(cond_leaf)
                     enc.append(cond_all[neg[0]])
                     index += [ar, bs + ar, ar]
-                masks.append(att_itm.unsqueeze(1).expand(-1, S, -1) if do_cap else att_itm)
+                masks.append(att_itm)
             if do_cap:
                 ids.append(cap_ids)
                 masks.append(att3)
                 index.append(ar)
             h = model.multimodal_encoder.bert(input_ids=torch.cat(ids, dim=0),
-                                              attention_mask=torch.cat([m.to(torch.float32) for m in masks], dim=0),
+                                              attention_mask=masks if len(masks) > 1 else masks[0],
                                               encoder_hidden_states=enc[0] if len(enc) == 1 else torch.cat(enc, dim=0),
                                               encoder_index=torch.cat(index)).last_hidden_state
             losses = []

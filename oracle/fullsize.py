@@ -151,6 +151,37 @@ def compare_itc(a, ref):
                 logits=rel_l2(a["logits"], ref["logits"]), logits_max_abs=(a["logits"] - ref["logits"]).abs().max().item())
 
 
+def seeded_params_(module, seed=0):
+    """Fill every parameter of `module` in place from its own torch.Generator (seed + index in sorted-name order), so that a
+    reference model in the build container and the product model on the GPU box -- same parameter names and shapes -- hold
+    bit-identical values without a 350 MB fixture: weights 0.02 N(0,1), LayerNorm weights 1 + 0.02 N, biases 0.02 N,
+    relative position bias tables 0.5 N."""
+    with torch.no_grad():
+        for i, (name, prm) in enumerate(sorted(module.named_parameters())):
+            g = torch.Generator().manual_seed(seed * 100003 + i)
+            r = torch.randn(prm.shape, generator=g)
+            if "relative_position_bias_table" in name:
+                v = 0.5 * r
+            elif prm.dim() <= 1 and ("norm" in name.lower()) and name.endswith("weight"):
+                v = 1.0 + 0.02 * r
+            else:
+                v = 0.02 * r
+            prm.copy_(v.to(prm.dtype))
+    return module
+
+
+SWIN_B = dict(img_size=224, patch_size=4, in_chans=3, num_classes=0, embed_dim=128, depths=[2, 2, 18, 2],
+              num_heads=[4, 8, 16, 32], window_size=7, mlp_ratio=4., drop_path_rate=0.0)
+SWIN_B_GRAD_KEYS = ("patch_embed.proj.weight", "patch_embed.norm.weight", "layers.0.blocks.0.attn.relative_position_bias_table",
+                    "layers.0.blocks.1.norm2.weight", "layers.1.downsample.norm.weight",
+                    "layers.2.blocks.17.attn.relative_position_bias_table", "layers.2.blocks.9.attn.proj.bias",
+                    "layers.3.blocks.1.norm1.bias", "norm.weight")
+
+
+def swin_b_input(batch=2):
+    return torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(21))
+
+
 def main():
     torch.set_num_threads(os.cpu_count() or 1)
     res = dict(how="oracle under torch.autocast(cpu, bf16) with layer_norm / softmax / cross_entropy / normalize in fp32 (the CUDA "

@@ -559,6 +559,24 @@ def gen_dist():
                                        ids_all=[r[4] for r in res], x_grad=[r[5] for r in res]))
 
 
+def gen_swin_b():
+    """Reference SwinTransformer at Swin-B size (swin_base_patch4_window7_224_22k.yaml: embed 128, depths [2,2,18,2], heads
+    [4,8,16,32], window 7, 224 x 224), batch 2, drop_path 0: forward_features, a selection of small gradient tensors and the
+    norm of EVERY parameter gradient of mean(y^2).  Parameters come from oracle.fullsize.seeded_params_ (regenerated, not
+    stored: 88 M values)."""
+    from model.swin import SwinTransformer
+    from oracle import fullsize as FS
+    m = FS.seeded_params_(SwinTransformer(**FS.SWIN_B), seed=5)
+    x = FS.swin_b_input()
+    m.train()
+    y = m.forward_features(x)
+    y.pow(2).mean().backward()
+    named = dict(m.named_parameters())
+    _save("swin_b.pt", dict(y=y.detach().clone(), grads={k: named[k].grad.clone() for k in FS.SWIN_B_GRAD_KEYS},
+                            grad_norms={k: float(v.grad.norm()) for k, v in named.items() if v.grad is not None},
+                            n_params=sum(v.numel() for v in named.values())))
+
+
 def gen_generation():
     """The reference's own decode-step hooks (model/bert.py:1110-1143 update_attention_mask / update_position_ids /
     prepare_inputs_for_generation, :1145-1190 _update_model_kwargs_for_generation), called UNBOUND over a stub `self`
@@ -590,7 +608,7 @@ def gen_generation():
     _save("generation_steps.pt", dict(cases=cases))
 
 
-GENERATORS = {"generation": gen_generation, "vit": gen_vit, "bert": gen_bert, "mico_parts": gen_mico_parts, "dist": gen_dist,
+GENERATORS = {"generation": gen_generation, "swin_b": gen_swin_b, "vit": gen_vit, "bert": gen_bert, "mico_parts": gen_mico_parts, "dist": gen_dist,
               "transformer": gen_transformer, "clip": gen_clip, "fbank": gen_fbank, "swin": gen_swin,
               "adamw": gen_adamw, "checkpoint": gen_checkpoint, "losses": gen_losses, "imageproc": gen_imageproc, "eva02": gen_eva02}
 

@@ -252,3 +252,24 @@ def test_attention_shared_kv_entries(Sq, Sk, p_drop):
     o2, lse2 = ops.attention_fwd(q, k, v, D ** -0.5, kv_index=idx2)
     _, dk2, dv2 = ops.attention_bwd(q, k, v, o2, lse2, do, D ** -0.5, kv_index=idx2)
     assert dk2[2].abs().max().item() == 0 and dv2[2].abs().max().item() == 0 and dk2[0].abs().max().item() > 0
+
+
+@pytest.mark.parametrize("M,D", [(70, 2048), (33, 2730), (5, 6)])
+def test_layernorm_any_width(M, D):
+    """Rows wider than the register-resident kernels hold, or not a multiple of 4 (Swin-B patch merging 2048, EVA02-L SwiGLU
+    2730): forward statistics / outputs and every backward term against torch's fp32 layer_norm."""
+    from mico_b200 import ops
+    g = torch.Generator().manual_seed(D)
+    x = torch.randn(M, D, generator=g) * 2 + 0.5
+    gam, bet = torch.randn(D, generator=g), torch.randn(D, generator=g)
+    dy, dres = torch.randn(M, D, generator=g), torch.randn(M, D, generator=g)
+    yb, yf, mean, rstd = ops.layernorm_fwd(x.cuda(), gam.cuda(), bet.cuda(), 1e-5, out_bf16=True, out_f32=True)
+    xr = x.clone().requires_grad_(True)
+    gr, br = gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (D,), gr, br, 1e-5)
+    ref.backward(dy)
+    assert rel_l2(yf.cpu(), ref.detach()) < 1e-5 and rel_l2(yb.float().cpu(), ref.detach()) < 4e-3
+    dg, db = torch.empty(D, device="cuda"), torch.empty(D, device="cuda")
+    dx, dxb = ops.layernorm_bwd(dy.cuda(), x.cuda(), mean, rstd, gam.cuda(), dg, db, dres=dres.cuda(), want_bf16=True)
+    assert rel_l2(dx.cpu(), xr.grad + dres) < 1e-5 and rel_l2(dxb.float().cpu(), xr.grad + dres) < 4e-3
+    assert rel_l2(dg.cpu(), gr.grad) < 1e-5 and rel_l2(db.cpu(), br.grad) < 1e-5
