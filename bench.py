@@ -37,7 +37,12 @@ VIT_G = dict(img_size=224, patch_size=14, embed_dim=1408, depth=40, num_heads=16
 # + patch embed 2*256*588*1408; backward = 2x forward.
 FWD_FLOPS_PER_FRAME = 40 * (2 * 257 * 1408 * (4224 + 1408 + 2 * 6144) + 4 * 257 * 257 * 1408) + 2 * 256 * 588 * 1408
 OMNI_TASK = "ret%tv%ta%tva%td_cap%tv%ta%tva"
-DEFAULT_LIGHT_BLOCKS = int(os.environ.get("MICO_BENCH_LIGHT_BLOCKS", "12"))
+# tower checkpoint levels, counted from the last block backwards (mico_b200/eva_vit.py:_launch_forward): every block keeps
+# its attention output + log-sum-exp, the last DEFAULT_QKV_BLOCKS + DEFAULT_LIGHT_BLOCKS also qkv, the last
+# DEFAULT_LIGHT_BLOCKS also x1
+DEFAULT_LIGHT_BLOCKS = int(os.environ.get("MICO_BENCH_LIGHT_BLOCKS", "0"))
+DEFAULT_QKV_BLOCKS = int(os.environ.get("MICO_BENCH_QKV_BLOCKS", "14"))
+DEFAULT_ATTN_BLOCKS = int(os.environ.get("MICO_BENCH_ATTN_BLOCKS", "-1"))
 N_V, N_A, N_D, S_TXT = 8, 3, 1, 128
 WAVE_SAMPLES = 160000          # 10 s at 16 kHz
 # MiCo.forward workloads: BASELINE.json configs[4] (the metric's own), configs[2] and configs[3] (builder-run evidence lines)
@@ -170,7 +175,10 @@ def make_config(args):
                 l2="working set per step (tens of GB of activations) exceeds the 126 MB L2; no flush needed",
                 activation_checkpointing=("none" if not ckpt else "tower blocks keep their input only (the reference's "
                                           "config.checkpointing, eva_vit_model.py:635-637)")
-                + (f"; last {args.light_blocks} blocks keep qkv / attention output / x1" if (args.light_blocks and ckpt) else ""),
+                + ((f"; kept besides the input, from the last block backwards: {args.light_blocks} blocks qkv + attention "
+                    f"output + x1, {args.qkv_blocks} blocks qkv + attention output, "
+                    f"{'all remaining' if args.attn_blocks < 0 else args.attn_blocks} blocks attention output (never re-run "
+                    "the attention kernel)") if ckpt else ""),
                 schedule="one tower pass for all modalities; ITM / caption sub-tasks differentiated group by group inside "
                          "forward (mico_b200/train_step.py)",
                 e2e_inputs="pinned host pixels + waveforms, H2D every step on a side stream one step ahead (the reference's "
@@ -484,7 +492,7 @@ def run_product_omni(args):
     model = model.to(dev).train()
     tower = getattr(model.vision_encoder, "visual", None)       # None: Swin (the tower module itself is the encoder)
     if tower is not None:
-        tower.ckpt_light_blocks = args.light_blocks
+        tower.ckpt_light_blocks, tower.ckpt_qkv_blocks, tower.ckpt_attn_blocks = args.light_blocks, args.qkv_blocks, args.attn_blocks
     flat = dp.FlatGrads(model)
     sync = dp.GradSync(flat, bucket_blocks=args.bucket_blocks,
                        dtype=torch.bfloat16 if args.grad_dtype == "bf16" else torch.float32) if world > 1 else None
@@ -811,6 +819,10 @@ def main():
     ap.add_argument("--no-ckpt", action="store_true", help="omni: keep every tower activation (small --batch only)")
     ap.add_argument("--light-blocks", type=int, default=DEFAULT_LIGHT_BLOCKS,
                     help="omni: the last n tower blocks keep qkv / attention output / x1 instead of their input only")
+    ap.add_argument("--qkv-blocks", type=int, default=DEFAULT_QKV_BLOCKS,
+                    help="omni: the n tower blocks before those keep qkv / attention output")
+    ap.add_argument("--attn-blocks", type=int, default=DEFAULT_ATTN_BLOCKS,
+                    help="omni: the n tower blocks before those keep their attention output (-1: all remaining)")
     ap.add_argument("--bucket-blocks", type=int, default=int(os.environ.get("MICO_BENCH_BUCKET_BLOCKS", "5")))
     ap.add_argument("--grad-dtype", default="fp32", choices=["fp32", "bf16"])
     args = ap.parse_args()

@@ -566,6 +566,24 @@ __device__ __forceinline__ void fast_chunk32(const GemmEpi& e, const CUtensorMap
     }
     uint4 own[4];
     if constexpr (EPI == EPI_GELU_SAVE) {
+        if (!e.aux_out) {
+            // activation only (a checkpointed block's first forward pass keeps no derivative): same value as below
+            if (e.act == MICO_ACT_GELU_SAVE_GRAD) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float cdf, g;
+                    gelu_parts(v[i], cdf, g);
+                    v[i] *= cdf;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    v[i] *= rcp_fast(1.0f + ex2_raw(v[i] * (-1.702f * 1.4426950408889634f)));
+            }
+            pack32_bf16(v, own);
+            tile_store(tmOut, tile_acquire(st, sidx), own, col0, row0);
+            return;
+        }
         if (e.act == MICO_ACT_GELU_SAVE_GRAD) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -670,7 +688,7 @@ __device__ __forceinline__ void fast_chunk16(const GemmEpi& e, const float* sbia
         uint4* a4 = reinterpret_cast<uint4*>(e.aux_out + (int64_t)row * e.ld_aux_out + col0);
 #pragma unroll
         for (int i = 0; i < 2; ++i)
-            a4[i] = make_uint4(pack_bf16x2(gr[8 * i], gr[8 * i + 1]), pack_bf16x2(gr[8 * i + 2], gr[8 * i + 3]),
+            if (e.aux_out) a4[i] = make_uint4(pack_bf16x2(gr[8 * i], gr[8 * i + 1]), pack_bf16x2(gr[8 * i + 2], gr[8 * i + 3]),
                                pack_bf16x2(gr[8 * i + 4], gr[8 * i + 5]), pack_bf16x2(gr[8 * i + 6], gr[8 * i + 7]));
     } else if constexpr (EPI == EPI_MUL_AUX) {
         const uint4* u4 = reinterpret_cast<const uint4*>(e.aux_in + (int64_t)row * e.ld_aux_in + col0);
@@ -1050,6 +1068,7 @@ int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi_in, cudaStream_t strea
         if ((rc = make_tmap_tile64(&tmOut, epi_in.out, f32, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)epi_in.ldo * (f32 ? 4 : 2)))) return rc;
     }
     if constexpr (EPI == EPI_GELU_SAVE) {
+        if (epi_in.aux_out)
         if ((rc = make_tmap_tile64(&tmAux, epi_in.aux_out, false, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)epi_in.ld_aux_out * 2))) return rc;
     }
 
@@ -1115,8 +1134,8 @@ static int classify_epilogue(const MicoGemmArgs& g, const GemmEpi& e, int bn) {
         if (!e.out_fp32) return EPI_BF16;
         return e.bias ? EPI_GENERIC : EPI_F32;
     }
-    if ((e.act == MICO_ACT_GELU_SAVE_GRAD || e.act == MICO_ACT_QUICK_GELU_SAVE_GRAD) && plain && !e.out_fp32 && e.aux_out)
-        return EPI_GELU_SAVE;
+    if ((e.act == MICO_ACT_GELU_SAVE_GRAD || e.act == MICO_ACT_QUICK_GELU_SAVE_GRAD) && plain && !e.out_fp32)
+        return EPI_GELU_SAVE;      // aux_out may be null: activation only
     if (e.act == MICO_ACT_MUL_AUX && plain && !e.out_fp32 && !e.bias && !e.aux_out) return EPI_MUL_AUX;
     if (e.act == MICO_ACT_NONE && e.residual && e.out_fp32 && !e.aux_out && !e.residual_bcast) return EPI_RES32;
     return EPI_GENERIC;

@@ -245,7 +245,12 @@ class EVAVisionTransformer(nn.Module):
                 self.head.weight.mul_(init_scale)
                 self.head.bias.mul_(init_scale)
         self.grad_checkpointing = grad_checkpointing
-        self.ckpt_light_blocks = 0       # with grad_checkpointing: the last n blocks keep qkv / o / x1 (see _launch_forward)
+        # with grad_checkpointing: what each block keeps besides its input (see _launch_forward) -- counted from the last
+        # block backwards: n `light` blocks (qkv, o, lse, x1), then n `qkv` blocks (qkv, o, lse), then n `attn` blocks
+        # (o, lse; -1 = every remaining block)
+        self.ckpt_light_blocks = 0
+        self.ckpt_qkv_blocks = 0
+        self.ckpt_attn_blocks = 0
         self.flat_grad = None            # optional persistent fp32 gradient buffer (mico_b200.dp.FlatGrads)
         self._bf16 = _Bf16Cache()
         # K of the patch-embed GEMM padded to a multiple of 64 (one 128-byte swizzle atom of bf16)
@@ -304,6 +309,8 @@ class EVAVisionTransformer(nn.Module):
     # class-level defaults (the OpenAI-CLIP subclass builds itself without this __init__)
     flat_grad = None
     ckpt_light_blocks = 0
+    ckpt_qkv_blocks = 0
+    ckpt_attn_blocks = 0
     grad_begin_hook = None
 
     def invalidate_weight_cache(self):
@@ -348,8 +355,18 @@ class EVAVisionTransformer(nn.Module):
         return dp
 
     # ------------------------------------------------------------------ forward / backward launch sequences
-    def _block_forward(self, xr, i, params, dp, B, T, keep):
-        """One pre-norm block (eva_vit_model.py:409-424) as a launch sequence; returns (x_out, tensors kept for backward)."""
+    def _ckpt_levels(self, L):
+        """Checkpoint level per block (0 = input only ... 3 = light), assigned from the last block backwards."""
+        n3 = min(L, max(0, int(self.ckpt_light_blocks)))
+        n2 = min(L - n3, max(0, int(self.ckpt_qkv_blocks)))
+        n1 = int(self.ckpt_attn_blocks)
+        n1 = L - n3 - n2 if n1 < 0 else min(L - n3 - n2, n1)
+        return [0] * (L - n3 - n2 - n1) + [1] * n1 + [2] * n2 + [3] * n3
+
+    def _block_forward(self, xr, i, params, dp, B, T, keep, level=0):
+        """One pre-norm block (eva_vit_model.py:409-424) as a launch sequence; returns (x_out, tensors kept for backward).
+        keep = False with a checkpoint level > 0: nothing but the level's tensors survives the call -- ("ck", xr, qkv, o,
+        lse, x1) with None for what the level drops (1: o, lse; 2: + qkv; 3: + x1)."""
         D, H = self.embed_dim, self.num_heads
         d = D // H
         M = B * T
@@ -364,7 +381,7 @@ class EVAVisionTransformer(nn.Module):
             qkv_bias = c.qkv_bias(params[base + _QB], params[base + _VB], ("qkvb", i))
         qkv = ops.gemm(h, c.get(params[base + _QKVW], ("qkv", i)), bias=qkv_bias)
         qkv5 = qkv.view(B, T, 3, H, d)
-        o, lse = ops.attention_fwd(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], scale, need_lse=keep)
+        o, lse = ops.attention_fwd(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], scale, need_lse=keep or level > 0)
         s_attn = dp[i, 0] if dp is not None else None
         s_mlp = dp[i, 1] if dp is not None else None
         x1 = ops.gemm(o.view(M, D), c.get(params[base + _PW], ("proj", i)), out_dtype=F32, bias=p[_PB], residual=xr,
@@ -375,16 +392,34 @@ class EVAVisionTransformer(nn.Module):
         a = ops.gemm(h2, w1, bias=p[_F1B], act=self._act, aux_out=pre)
         x2 = ops.gemm(a, c.get(params[base + _F2W], ("fc2", i)), out_dtype=F32, bias=p[_F2B], residual=x1,
                       row_scale=s_mlp, rows_per_group=T)
-        rec = (xr, mean1, rstd1, h, qkv, o, lse, x1, mean2, rstd2, h2, pre, a) if keep else None
+        if keep:
+            rec = (xr, mean1, rstd1, h, qkv, o, lse, x1, mean2, rstd2, h2, pre, a)
+        elif level > 0:
+            rec = ("ck", xr, qkv if level >= 2 else None, o, lse, x1 if level >= 3 else None)
+        else:
+            rec = None
         return x2, rec
 
-    def _block_recompute_light(self, rec, i, params):
-        """Rebuild the 13-tensor block record from a 'light' one (see _launch_forward): LayerNorm outputs / statistics
-        and the fc1 activation pair are recomputed, bit-identical to the forward pass."""
+    def _block_rebuild(self, rec, i, params, dp, B, T):
+        """Rebuild the 13-tensor block record from a checkpointed one (see _launch_forward): whatever the block's level
+        dropped is recomputed from what it kept with the forward pass's own launches, so every tensor is bit-identical to
+        the forward pass.  The attention kernel never runs again (o and lse are kept from level 1 on)."""
         _, xr, qkv, o, lse, x1 = rec
+        D, H = self.embed_dim, self.num_heads
+        d = D // H
+        c = self._bf16
         base = _NTOP + i * _NBLK
         p = [t.detach() for t in params[base:base + _NBLK]]
         h, _, mean1, rstd1 = ops.layernorm_fwd(xr, p[_N1W], p[_N1B], self.eps, save_stats=True)
+        if qkv is None:
+            if self._full_qkv_bias:
+                qkv_bias = params[base + _QB].detach()
+            else:
+                qkv_bias = c.qkv_bias(params[base + _QB], params[base + _VB], ("qkvb", i))
+            qkv = ops.gemm(h, c.get(params[base + _QKVW], ("qkv", i)), bias=qkv_bias)
+        if x1 is None:
+            x1 = ops.gemm(o.view(B * T, D), c.get(params[base + _PW], ("proj", i)), out_dtype=F32, bias=p[_PB], residual=xr,
+                          row_scale=dp[i, 0] if dp is not None else None, rows_per_group=T)
         h2, _, mean2, rstd2 = ops.layernorm_fwd(x1, p[_N2W], p[_N2B], self.eps, save_stats=True)
         w1 = self._bf16.get(params[base + _F1W], ("fc1", i))
         pre = torch.empty((h2.shape[0], w1.shape[0]), device=xr.device, dtype=BF16)
@@ -425,19 +460,17 @@ class EVAVisionTransformer(nn.Module):
             if keep:
                 saved["ln_pre"] = (x0, m0, r0)
         # eva_vit_model.py:635-637: with grad_checkpointing keep only each block's input and recompute the block in the
-        # backward pass.  `ckpt_light_blocks` = n: the LAST n blocks instead keep their GEMM-free-to-recompute half (block
-        # input, qkv, attention output, x1: 22 KB per token instead of 53) and recompute only LN1, LN2 and fc1+GELU
-        # (a third of a block forward instead of all of it) -- memory permitting, this trades HBM for recompute FLOPs.
+        # backward pass.  Memory permitting, blocks keep more than that (HBM traded for recompute, most valuable first):
+        #   level 1 `attn`  + attention output and log-sum-exp (2.2 KB per token): the attention kernel is not re-run
+        #   level 2 `qkv`   + qkv (8.4 KB per token): LN1 is re-run, the qkv GEMM is not
+        #   level 3 `light` + x1 (5.6 KB per token): the proj GEMM is not re-run; LN2 and fc1 + GELU always are
         L = len(self.blocks)
         ckpt = keep and self.grad_checkpointing
-        n_light = min(L, max(0, int(self.ckpt_light_blocks))) if ckpt else 0
+        levels = self._ckpt_levels(L) if ckpt else None
         for i in range(L):
-            light = ckpt and i >= L - n_light
-            x2, rec = self._block_forward(xr, i, params, dp, B, T, keep and (not ckpt or light))
+            x2, rec = self._block_forward(xr, i, params, dp, B, T, keep and not ckpt, levels[i] if ckpt else 0)
             if keep:
-                if light:     # (xr, mean1, rstd1, h, qkv, o, lse, x1, mean2, rstd2, h2, pre, a) -> drop h, h2, pre, a
-                    rec = ("light", rec[0], rec[4], rec[5], rec[6], rec[7])
-                saved["blocks"].append((xr,) if (ckpt and not light) else rec)
+                saved["blocks"].append((xr,) if (ckpt and levels[i] == 0) else rec)
             xr = x2
         _, y, mean, rstd = ops.layernorm_fwd(xr, params[_NW].detach(), params[_NB].detach(), self.eps,
                                              out_bf16=False, out_f32=True, save_stats=keep)
@@ -510,8 +543,8 @@ class EVAVisionTransformer(nn.Module):
             rec = blocks.pop()
             if len(rec) == 1:        # checkpointed: recompute this block's forward from its input
                 rec = self._block_forward(rec[0], i, params, dp, B, T, True)[1]
-            elif rec[0] == "light":  # recompute LN1, LN2, fc1 + GELU; qkv / attention / proj / fc2 outputs were kept
-                rec = self._block_recompute_light(rec, i, params)
+            elif isinstance(rec[0], str):   # level 1-3 checkpoint: recompute what the level dropped (never the attention)
+                rec = self._block_rebuild(rec, i, params, dp, B, T)
             xr, mean1, rstd1, h, qkv, o, lse, x1, mean2, rstd2, h2, pre, a = rec
             del rec
             base = _NTOP + i * _NBLK

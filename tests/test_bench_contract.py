@@ -24,6 +24,7 @@ def test_reference_arm_json_line():
     assert "configs[4]" in d["config"]["workload"] and d["config"]["text_len"] == 128 and d["config"]["batch_per_gpu"] == 64
     # the product arm emits the identical config dict (the driver's same_config check)
     args = types.SimpleNamespace(config="omni", batch=64, gpus=1, no_ckpt=False, light_blocks=bench.DEFAULT_LIGHT_BLOCKS,
+                                 qkv_blocks=bench.DEFAULT_QKV_BLOCKS, attn_blocks=bench.DEFAULT_ATTN_BLOCKS,
                                  grad_dtype="fp32", bucket_blocks=5)
     assert d["config"] == bench.make_config(args)
     assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1

@@ -121,12 +121,16 @@ def test_activation_checkpointing_gives_identical_gradients():
     x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(1)).cuda()
     dp = torch.tensor([[[1.0, 1.0]] * 2, [[1 / 0.85, 0.0]] * 2, [[0.0, 1 / 0.7], [1 / 0.7, 1 / 0.7]]])
     grads = []
-    for ck in (False, True):
+    # (checkpointing, light, qkv, attn blocks): no checkpointing, input-only, and every mix of the three richer levels
+    for ck, n3, n2, n1 in ((False, 0, 0, 0), (True, 0, 0, 0), (True, 1, 1, 1), (True, 0, 0, -1), (True, 0, 2, 0), (True, 2, 0, 0)):
         m.set_grad_checkpointing(ck)
+        m.ckpt_light_blocks, m.ckpt_qkv_blocks, m.ckpt_attn_blocks = n3, n2, n1
         m.zero_grad(set_to_none=True)
         m.inject_drop_path_scales(dp)
         m(x, return_all_features=True).pow(2).mean().backward()
         grads.append({k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
     assert grads[0].keys() == grads[1].keys() and len(grads[0]) > 30
-    for k in grads[0]:
-        assert torch.equal(grads[0][k], grads[1][k]), k
+    for g in grads[1:]:
+        assert g.keys() == grads[0].keys()
+        for k in grads[0]:
+            assert torch.equal(grads[0][k], g[k]), k
