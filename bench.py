@@ -356,6 +356,44 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def gpu_eager_leg(config, dev, b=4):
+    """Informational context for the product line (SURVEY "facts": the reference's real competitor is PyTorch
+    eager on the same GPU): the oracle port -- plain PyTorch ops -> ATen / cuBLAS / cuDNN kernels -- on this B200 under
+    torch.autocast(bf16), full ViT-g/14 + BERT-base, the same sub-tasks, on `b` samples per step (eager keeps every
+    activation, no checkpointing: b = 64 does not fit).  Nothing of mico_b200 runs here; only bench.py imports the oracle."""
+    import torch
+    sp = SPECS[config]
+    try:
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats(dev)
+        orc = OmniOracle()
+        orc.p = {k: v.detach().to(dev).requires_grad_(v.is_floating_point()) for k, v in orc.p.items()}
+        batch = {k: (v.to(dev) if v is not None else None) for k, v in orc.batch(b, sp["n_v"], sp["n_a"], sp["n_d"]).items()}
+
+        def run():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return orc.step(batch, sp["task"])
+        run()
+        torch.cuda.synchronize()
+        n = 3
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            losses = run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        tok = omni_tokens(b, sp["n_v"], sp["n_a"], sp["n_d"], frame_tokens=sp["frame_tokens"])[0]
+        out = dict(value=tok / (ms * 1e-3), unit="tokens/s", ms_per_step=ms, samples_per_step=b, kind="oracle port on cuda, "
+                   "torch.autocast(bf16), eager ATen/cuBLAS kernels, no optimizer step, no activation checkpointing",
+                   peak_hbm_gb=round(torch.cuda.max_memory_allocated(dev) / 1e9, 1), losses=losses)
+        del orc, batch
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:          # informational leg: never fails the bench
+        return dict(unavailable=f"{type(e).__name__}: {str(e)[:200]}")
+
+
 def cpu_baseline_leg(config, budget_s=25.0):
     """cpu_baseline for the product line: the oracle timed on this box's host cores on a bounded sample (rank 0, N = 1)."""
     import torch
@@ -645,6 +683,13 @@ def run_product_omni(args):
                                       rate=(v["work"] / (v["ms"] * 1e-3) / (1e12 if is_tf(k) else 1e9)) if v["ms"] > 0 else None,
                                       rate_unit="TFLOP/s" if is_tf(k) else "GB/s") for k, v in fam.items()})
     cpu = cpu_baseline_leg(args.config) if (world == 1 and not args.no_cpu_baseline and args.config != "trimodal") else None
+    gpu_eager = None
+    if world == 1 and args.gpu_eager and args.config in ("omni", "imgtext"):
+        import gc
+        staged.clear()
+        del model, opt, flat, resident, named, tower, out, audio       # the closures above are not called again
+        gc.collect()
+        gpu_eager = gpu_eager_leg(args.config, dev)
     h2d = sum(host[k].numel() * host[k].element_size() for k in h2d_keys) + 2 * host["input_ids"].numel() * 8 * 2
     config = make_config(args)
     extra = dict(processed_tokens_per_s=world * proc_tok * args.steps / (ms / 1e3), peak_hbm_gb=round(peak_mem, 1),
@@ -654,7 +699,8 @@ def run_product_omni(args):
                 data="synthetic", config=config, clocks=clocks,
                 e2e=dict(value=e2e, unit="tokens/s", ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=h2d,
                          d2h_bytes_per_step=12, losses=e2e_losses),
-                gpu_launches=launches, roofline=roofline, cpu_baseline=cpu, selfcheck=selfcheck or None, extra=extra)
+                gpu_launches=launches, roofline=roofline, cpu_baseline=cpu, gpu_eager=gpu_eager, selfcheck=selfcheck or None,
+                extra=extra)
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
@@ -816,6 +862,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default: the configuration's own)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-selfcheck", action="store_true")
+    ap.add_argument("--gpu-eager", action="store_true",
+                    help="omni / imgtext at N=1: also time the oracle port on the GPU under bf16 autocast (context, not a baseline)")
     ap.add_argument("--no-ckpt", action="store_true", help="omni: keep every tower activation (small --batch only)")
     ap.add_argument("--light-blocks", type=int, default=DEFAULT_LIGHT_BLOCKS,
                     help="omni: the last n tower blocks keep qkv / attention output / x1 instead of their input only")

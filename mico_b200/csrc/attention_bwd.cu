@@ -643,6 +643,15 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }  // namespace
 }  // namespace mico
 
+namespace mico {
+// attention_bwd_dq.cu: the dQ kernel with double-buffered score tiles (head_dim 81..96)
+int attention_dq_pipelined(const MicoAttnArgs* a, cudaStream_t stream);
+static bool dq_pipelined_enabled() {      // MICO_ATTN_DQ_PIPELINED=0: A/B switch for measurements
+    static const bool on = [] { const char* e = getenv("MICO_ATTN_DQ_PIPELINED"); return !(e && e[0] == '0'); }();
+    return on;
+}
+}  // namespace mico
+
 extern "C" int mico_attention_bwd(const MicoAttnArgs* a, void* stream_) {
     using namespace mico;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -696,8 +705,14 @@ extern "C" int mico_attention_bwd(const MicoAttnArgs* a, void* stream_) {
         const bool tail = m_tail_rows(a->Sq) || (m_tail_rows(a->Sk) && a->kv_index == nullptr);
         cudaStream_t side = tail ? side_fork(stream) : nullptr;
         int rc_tail = MICO_OK;
-        kq<<<work_q < num_sms() ? work_q : num_sms(), kBwdThreads, DqSmem::TOTAL, stream>>>(tq, tk, tv, tdo, tkx, tvx, p);
-        MICO_CHECK_CUDA(cudaGetLastError());
+        if (hd_pad == 96 && dq_pipelined_enabled()) {
+            // ViT-g (d = 88): double-buffered score tiles + deferred read-out, 105 -> 85 us per layer at bs 64 (ncu, one box)
+            const int rc_dq = attention_dq_pipelined(a, stream);
+            if (rc_dq) return rc_dq;
+        } else {
+            kq<<<work_q < num_sms() ? work_q : num_sms(), kBwdThreads, DqSmem::TOTAL, stream>>>(tq, tk, tv, tdo, tkx, tvx, p);
+            MICO_CHECK_CUDA(cudaGetLastError());
+        }
         // queued after the first tile kernel so that the persistent CTAs get their SMs first; the small tail blocks then fill
         // the shared memory / thread slots the tile kernels leave free
         if (tail && side) rc_tail = attention_tail_bwd(a, side);

@@ -103,6 +103,12 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
         : "memory");
 }
 
+// pull a box into L2 ahead of the load that will read it (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 // multicast variant: the tile lands at the same CTA-relative smem offset of every CTA in `cta_mask`, and each
 // destination CTA's mbarrier (same CTA-relative offset) receives the complete_tx
 __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,

@@ -31,6 +31,14 @@ _EVA_CFG = {
 }
 
 
+# model/evaclip/model_configs/EVA02-CLIP-B-16.json / EVA02-CLIP-L-14.json (mico.py:326-339); drop_path_rate 0
+_EVA02_CFG = {
+    "evaclip02_base": dict(patch_size=16, embed_dim=768, depth=12, num_heads=12, mlp_ratio=2.6667, num_classes=512),
+    "evaclip02_base_self": dict(patch_size=16, embed_dim=768, depth=12, num_heads=12, mlp_ratio=2.6667, num_classes=512),
+    "evaclip02_large": dict(patch_size=14, embed_dim=1024, depth=24, num_heads=16, mlp_ratio=2.6667, num_classes=768),
+}
+
+
 _CLIP_CFG = {
     "clip_vit_base_16": dict(patch_size=16, width=768, layers=12, heads=12, output_dim=512),
     "clip_vit_large_14_336px": dict(patch_size=14, width=1024, layers=24, heads=16, output_dim=768),
@@ -250,6 +258,14 @@ class MiCo(nn.Module):
             tower = EVAVisionTransformer(img_size=self.config.vision_resolution, qkv_bias=True, use_mean_pooling=False,
                                          grad_checkpointing=bool(self.config.checkpointing), **kw)
             self.vision_encoder = _VisionEncoder(tower)
+        elif t in _EVA02_CFG:     # RoPE / SwiGLU / sub-LN towers (eva_vit_model.py with rope, naiveswiglu, subln)
+            from .eva02_vit import EVA02VisionTransformer
+            kw = dict(_EVA02_CFG[t])
+            kw.update(getattr(self.config, "vision_tower_kwargs", None) or {})
+            self.vision_dim = kw["embed_dim"]
+            tower = EVA02VisionTransformer(img_size=self.config.vision_resolution, qkv_bias=True, use_mean_pooling=False,
+                                           grad_checkpointing=bool(self.config.checkpointing), **kw)
+            self.vision_encoder = _VisionEncoder(tower)
         elif t in _CLIP_CFG:      # OpenAI CLIP towers (mico.py:354-371; reference needs JIT weights at a hard-coded path)
             from .clip_vit import VisionTransformer
             kw = dict(_CLIP_CFG[t])
@@ -265,8 +281,8 @@ class MiCo(nn.Module):
             self.vision_encoder = SwinTransformer(img_size=self.config.vision_resolution, **kw)
             self.vision_dim = self.vision_encoder.num_features
         else:
-            raise NotImplementedError(f"vision_encoder_type {t!r}: EVA01-g, the OpenAI CLIP ViTs and Swin are built; EVA02 "
-                                      "(RoPE / SwiGLU) and VideoSwin towers are not (DESIGN.md)")
+            raise NotImplementedError(f"vision_encoder_type {t!r}: EVA01-g, EVA02-B / -L, the OpenAI CLIP ViTs and Swin are built; "
+                                      "EVA02-bigE (head_dim 112, post-norm) and VideoSwin towers are not (DESIGN.md)")
 
     def construct_multimodal_encoder(self):
         bert_kw = dict(getattr(self.config, "bert_config", None) or {})

@@ -123,7 +123,7 @@ def bert_model(p, ids, attention_mask=None, enc=None, enc_mask=None, prefix="ber
                drop=None):
     b, S = ids.shape
     if attention_mask is None:
-        attention_mask = torch.ones(b, S)
+        attention_mask = torch.ones(b, S, device=ids.device)
     ms = extended_mask(attention_mask)
     me = None
     if enc is not None and enc_mask is not None:

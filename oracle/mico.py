@@ -74,7 +74,7 @@ def itc_loss(feat_c, feat_t, feat_c_all, feat_t_all, temp, rank):
     bs = feat_t.shape[0]
     sim_c2t = feat_c @ feat_t_all.t() / temp
     sim_t2c = feat_t @ feat_c_all.t() / temp
-    tgt = torch.arange(rank * bs, rank * bs + bs)
+    tgt = torch.arange(rank * bs, rank * bs + bs, device=feat_t.device)
     loss = (F.cross_entropy(sim_c2t, tgt, label_smoothing=0.1) + F.cross_entropy(sim_t2c, tgt, label_smoothing=0.1)) / 2
     return loss, sim_c2t, sim_t2c
 
@@ -86,7 +86,7 @@ def itm_loss(p, cond, cond_all, ids, att, ids_all, att_all, neg_c, neg_t, itm_ra
     cond_3 = torch.cat((cond, cond_all[neg_c], cond), 0)
     out = OB.bert_model(p, ids_1, att_1, cond_3, None, prefix="multimodal_encoder.bert.", layers=layers, heads=heads)
     logits = match_head(p, out[:, 0])
-    truth = torch.zeros(bs * 3, dtype=torch.long)
+    truth = torch.zeros(bs * 3, dtype=torch.long, device=logits.device)
     truth[:bs] = 1
     return itm_ratio * F.cross_entropy(logits, truth)
 
