@@ -405,10 +405,11 @@ __device__ __forceinline__ float drop_mult(const DropCfg& d, uint64_t ctr) {
 // Attention-probability dropout (bert.py:243-247) is generated per score element inside the attention kernels, forward and
 // twice in the backward pass: splitmix64 per element (three 64-bit multiplies) cost more than the softmax itself (round 2:
 // BERT attention ran at 55 TFLOP/s, 17 % of the omni step).  Two-level scheme instead: one splitmix64 per score ROW gives a
-// 32-bit row key; a pair of adjacent keys (2t, 2t+1) of that row shares one 32-bit integer hash (lowbias32: two 32-bit
-// multiplies) whose halves are the two 16-bit uniforms.  keep <=> uniform16 >= round(p * 65536).
+// 32-bit row key; a pair of adjacent keys (2t, 2t+1) of that row shares one 32-bit integer hash whose halves are the two
+// 16-bit uniforms.  keep <=> uniform16 >= round(p * 65536).
 //   row  = (b*H + h)*Sq + i                 row_key = low32(splitmix64(seed + row * golden))
-//   x    = lowbias32(row_key ^ ((j >> 1) * 0x9E3779B1))         u16 = (j & 1) ? x >> 16 : x & 0xFFFF
+//   x    = mix(row_key ^ ((j >> 1) * 0x9E3779B1)), mix(x) = (x * 0x85EBCA6B) ^ ((x * 0x85EBCA6B) >> 15)
+//   u16  = (j & 1) ? x >> 16 : x & 0xFFFF
 __device__ __forceinline__ uint32_t drop_row_key(const DropCfg& d, uint64_t row) {
     uint64_t z = row * 0x9E3779B97F4A7C15ull + d.seed;
     z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
@@ -417,10 +418,14 @@ __device__ __forceinline__ uint32_t drop_row_key(const DropCfg& d, uint64_t row)
     return (uint32_t)z;
 }
 __device__ __forceinline__ uint32_t drop_pair_bits(uint32_t row_key, uint32_t jpair) {
+    // one multiply + one xor-shift on top of the (already well mixed) row key: 5 instructions per key pair.  The first
+    // version ran the full lowbias32 finaliser here (two multiplies, three xor-shifts, 10 instructions): with dropout on,
+    // the fusion encoder's attention kernels are bound by instruction issue, and this hash was a third of their per-element
+    // work.  Keep-rate and lag correlations of the 16-bit halves (rows x key pairs, lags 1..512) are at the sampling-noise
+    // level for both variants (checked on the host against oracle/bert.py:attn_drop_mult, which restates this function).
     uint32_t x = row_key ^ (jpair * 0x9E3779B1u);
-    x ^= x >> 16; x *= 0x7FEB352Du;
-    x ^= x >> 15; x *= 0x846CA68Bu;
-    x ^= x >> 16;
+    x *= 0x85EBCA6Bu;
+    x ^= x >> 15;
     return x;
 }
 __device__ __forceinline__ uint32_t drop_thresh16(const DropCfg& d) { return (uint32_t)(d.p * 65536.0f + 0.5f); }

@@ -22,7 +22,7 @@ def _default_antialias():
         from torchvision.transforms.transforms import Resize
         return inspect.signature(Resize.__init__).parameters["antialias"].default is True
     except Exception:
-        return True
+        return False      # no torchvision to ask: the reference's pinned torchvision 0.15.2 does not anti-alias tensors
 
 
 def resize_normalize(src, size, mean, std, antialias=True):

@@ -5,6 +5,7 @@ device pointers to libmico_b200.so and raises if the library reports an error.  
 fallback path.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -14,6 +15,9 @@ from ._lib import (ACT_GELU, ACT_GELU_BWD, ACT_GELU_SAVE_GRAD, ACT_MUL_AUX, ACT_
 
 BF16 = torch.bfloat16
 F32 = torch.float32
+
+
+_CHECK_IDS = os.environ.get("MICO_CHECK_IDS", "0") == "1"
 
 
 def _stream():
@@ -420,6 +424,14 @@ def embedding_gather(ids, word, pos, typ, S, type_ids=None, pos_ids=None, pos_of
     """ids: int64 [M] -> fp32 [M, D] = word[ids] + type[type_ids|0] + pos[pos_ids | m % S + pos_offset]."""
     _req(ids, I64, "ids")
     M, D = ids.numel(), word.shape[1]
+    # torch's nn.Embedding raises on an out-of-range index; the kernel clamps, so the position range is checked here (host
+    # arithmetic only) and MICO_CHECK_IDS=1 adds the device-side range check of the token ids (one reduction + sync)
+    if pos_ids is None and int(S) + int(pos_offset) > pos.shape[0]:
+        raise MicoError(f"embedding_gather: sequence length {S} + offset {pos_offset} exceeds the {pos.shape[0]} position embeddings")
+    if _CHECK_IDS and M:
+        lo, hi = int(ids.min()), int(ids.max())
+        if lo < 0 or hi >= word.shape[0]:
+            raise MicoError(f"embedding_gather: token id range [{lo}, {hi}] outside the vocabulary of {word.shape[0]}")
     out = torch.empty((M, D), device=ids.device, dtype=F32)
     check(lib.mico_embedding_gather(_ptr(ids), _ptr(type_ids), _ptr(pos_ids), int(pos_offset), _ptr(word), _ptr(pos),
                                     _ptr(typ), _ptr(out), M, int(S), D, word.shape[0], pos.shape[0], typ.shape[0], _stream()),

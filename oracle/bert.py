@@ -39,7 +39,7 @@ def drop_mult(p, seed, offset, shape):
 def attn_drop_mult(p, seed, B, H, Sq, Sk):
     """Host restatement of the attention kernels' probability-dropout mask (mico_b200/csrc/common.cuh drop_row_key /
     drop_pair_bits): score row r = (b*H + h)*Sq + i gets the 32-bit key low32(splitmix64(seed + r * golden)); keys 2t, 2t+1
-    of the row share lowbias32(key ^ (t * 0x9E3779B1)), whose low / high half is their 16-bit uniform; an element is kept
+    of the row share x = (key ^ (t * 0x9E3779B1)) * 0x85EBCA6B, x ^= x >> 15, whose low / high half is their 16-bit uniform; an element is kept
     (multiplier 1/(1-p)) when uniform16 >= round(p * 65536).  Returns a (B, H, Sq, Sk) fp32 tensor."""
     rows = B * H * Sq
     with np.errstate(over="ignore"):
@@ -52,11 +52,8 @@ def attn_drop_mult(p, seed, B, H, Sq, Sk):
         key = (z & np.uint64(0xFFFFFFFF)).astype(np.uint32)[:, None]
         j = np.arange(Sk, dtype=np.uint32)[None, :]
         x = key ^ ((j >> np.uint32(1)) * np.uint32(0x9E3779B1))
-        x ^= x >> np.uint32(16)
-        x *= np.uint32(0x7FEB352D)
+        x *= np.uint32(0x85EBCA6B)
         x ^= x >> np.uint32(15)
-        x *= np.uint32(0x846CA68B)
-        x ^= x >> np.uint32(16)
     u = np.where((j & np.uint32(1)) == 1, x >> np.uint32(16), x & np.uint32(0xFFFF))
     thresh = np.uint32(int(np.float32(p) * np.float32(65536.0) + np.float32(0.5)))
     m = np.where(u >= thresh, np.float32(1.0 / (1.0 - p)), np.float32(0.0)).astype(np.float32)

@@ -1,5 +1,6 @@
-"""Same-box A/B of the tower attention backward (64 x 16 x 257 x 88): interleaved rounds of the two library builds named in
-MICO_AB_LIBS (colon-separated), each in its own process.  python scripts/ab_tower_bwd.py [child]"""
+"""Same-box A/B of the tower attention backward (64 x 16 x 257 x 88): interleaved rounds, each variant in its own process.
+Variants: the library builds named in MICO_AB_LIBS (colon-separated), or environment settings in MICO_AB_ENVS
+("NAME=VALUE:NAME=VALUE", e.g. MICO_ATTN_TAIL_MERGED=1:MICO_ATTN_TAIL_MERGED=0).  python scripts/ab_tower_bwd.py [child]"""
 import os
 import subprocess
 import sys
@@ -32,11 +33,14 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         child()
     else:
-        libs = os.environ["MICO_AB_LIBS"].split(":")
-        res = {l: [] for l in libs}
+        if os.environ.get("MICO_AB_ENVS"):
+            variants = [(v, dict([v.split("=", 1)])) for v in os.environ["MICO_AB_ENVS"].split(":")]
+        else:
+            variants = [(os.path.basename(l), dict(MICO_B200_LIB=l)) for l in os.environ["MICO_AB_LIBS"].split(":")]
+        res = {n: [] for n, _ in variants}
         for _ in range(3):
-            for l in libs:
-                out = subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, MICO_B200_LIB=l), capture_output=True, text=True)
-                res[l].append(out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-200:])
-        for l in libs:
-            print(os.path.basename(l), "us per call:", res[l])
+            for n, env in variants:
+                out = subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, **env), capture_output=True, text=True)
+                res[n].append(out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-200:])
+        for n, _ in variants:
+            print(n, "us per call:", res[n])

@@ -89,3 +89,7 @@ def test_embedding_gather_and_scatter():
     ops.embedding_scatter_add(dx, ids.view(-1), gw)
     refg = torch.zeros_like(word).index_add_(0, ids.view(-1), dx)
     assert rel_l2(gw, refg) < 1e-6
+    # a sequence longer than the position table fails loudly, like nn.Embedding (the kernel itself would clamp)
+    long_ids = torch.zeros(P + 1, dtype=torch.int64, device="cuda")
+    with pytest.raises(Exception, match="position embeddings"):
+        ops.embedding_gather(long_ids, word, pos, typ, P + 1)
