@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--qkv-blocks", type=int, default=bench.DEFAULT_QKV_BLOCKS)
     ap.add_argument("--attn-blocks", type=int, default=bench.DEFAULT_ATTN_BLOCKS)
     ap.add_argument("--out", default="")
+    ap.add_argument("--plain", type=int, default=0, help="run this many plain steps and exit (target for an ncu launch list)")
     a = ap.parse_args()
     sp = bench.SPECS[a.config]
     dev = torch.device("cuda:0")
@@ -65,6 +66,18 @@ def main():
         flat.detach_unused()
         opt.step()
 
+    if a.plain:
+        from mico_b200 import _lib
+        for i in range(a.plain):
+            _lib.reset_launch_count()
+            if i == a.plain - 1:
+                torch.cuda.profiler.start()        # ncu --profile-from-start off: only the last step is captured
+            step()
+            torch.cuda.synchronize()
+            if i == a.plain - 1:
+                torch.cuda.profiler.stop()
+            print(f"plain step {i}: {_lib.launch_count()} mico_b200 launches", flush=True)
+        return
     for _ in range(2):
         step()
     torch.cuda.synchronize()

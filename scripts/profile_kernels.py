@@ -1,4 +1,5 @@
-"""Launch each hot kernel a few times on the ViT-g bs=64 shapes (target for `ncu --set full -k regex:...`)."""
+"""Launch each hot kernel a few times on the ViT-g shapes (target for `ncu --set full -k regex:...`): 64 frames by default,
+MICO_PROFILE_FRAMES=768 for the omni-modal step's single tower pass (64 samples x 12 frames = 197 376 tokens)."""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,7 +8,7 @@ from mico_b200 import ops
 from mico_b200.ops import ACT_GELU_SAVE_GRAD, ACT_MUL_AUX, BF16, F32
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
-M, D, F = 64 * 257, 1408, 6144
+M, D, F = int(os.environ.get("MICO_PROFILE_FRAMES", "64")) * 257, 1408, 6144
 dev = "cuda"
 r = lambda *s: (torch.randn(*s, device=dev) * 0.05).to(BF16)
 reps = 3
@@ -20,6 +21,13 @@ if which in ("all", "gemm"):
         ops.gemm(dy, w2, b_mn=True, act=ACT_MUL_AUX, aux_in=pre)         # fc2 dgrad (* GELU')
         ops.gemm(dy, a, a_mn=True, b_mn=True, out_dtype=F32)             # fc2 wgrad
         ops.gemm(a, w2, out_dtype=F32, residual=torch.zeros(M, D, device=dev))  # fc2 fwd
+    if os.environ.get("MICO_PROFILE_FRAMES"):     # round 2: the step's weakest GEMMs at the omni shapes
+        wq, wp, dqkv = r(3 * D, D), r(D, D), r(M, 3 * D)
+        res = torch.zeros(M, D, device=dev)
+        for _ in range(reps):
+            ops.gemm(x, wp, out_dtype=F32, bias=torch.zeros(D, device=dev), residual=res)   # proj fwd (+residual), K = 1408
+            ops.gemm(dqkv, x, a_mn=True, b_mn=True, out_dtype=F32)                            # qkv wgrad
+            ops.gemm(x, w1, bias=bias, act=ACT_GELU_SAVE_GRAD)                                # fc1 fwd, activation only
 if which in ("all", "ln"):
     xf = torch.randn(M, D, device=dev)
     g, b = torch.ones(D, device=dev), torch.zeros(D, device=dev)
