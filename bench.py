@@ -661,16 +661,21 @@ def run_product_omni(args):
     g = fam["gemm"]
     gemm_tflops = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
     fam_total = sum(v["ms"] for v in fam.values())
-    traffic, traffic_src = None, None
+    traffic, traffic_src, traffic_note = None, None, None
     tpath = os.path.join(REPO, "profiles", "gemm_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and tower is not None:
         tj = json.load(open(tpath))
         traffic, traffic_src = tj["avg_dram_bytes_per_launch"], tj["source"]
+        traffic_note = ("average over the four representative TOWER launches of the capture (" + tj.get("note", "") + "); their "
+                        "algorithmic operand + output bytes average 4.62 GB (5.43 / 5.43 / 2.98 / 4.65): the two GEMMs with a K = 6144 "
+                        "or 197 376-row contraction re-read their streamed operand 2.4x from DRAM (DESIGN.md 4a); `achieved` "
+                        "averages all of the family's launches, including the small text-encoder GEMMs")
     is_tf = lambda k: "attention" in k or k == "gemm"
     roofline = dict(bound="tensor", kernel="gemm_bf16_kernel (tcgen05 GEMM: every linear layer fwd / dgrad / wgrad of the tower and "
                                            "the text encoder)",
                     achieved=gemm_tflops, peak=pk["tf_sustained"], unit="TFLOP/s", frac=gemm_tflops / pk["tf_sustained"],
                     traffic=traffic, traffic_unit="bytes/launch (dram read+write)", traffic_source=traffic_src,
+                    traffic_note=traffic_note,
                     algorithmic_flops_per_launch=g["work"] / max(g["calls"], 1), peak_source=pk["src"] + ", sustained bf16",
                     launches_per_step=g["calls"] / nprof, avg_launch_ms=g["ms"] / max(g["calls"], 1),
                     share_of_step=g["ms"] / fam_total if fam_total else None,
@@ -821,7 +826,7 @@ def run_product_vitg(args):
     fam_total = sum(v["ms"] for v in fam.values())
     step_flops = 3 * FWD_FLOPS_PER_FRAME * B
     traffic, traffic_src = None, None
-    tpath = os.path.join(REPO, "profiles", "gemm_traffic.json")
+    tpath = os.path.join(REPO, "profiles", "gemm_traffic_vitg.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         traffic, traffic_src = tj["avg_dram_bytes_per_launch"], tj["source"]
