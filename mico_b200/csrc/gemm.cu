@@ -1031,6 +1031,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
+// split-K factor of a weight gradient: the split whose unit count fills whole waves of `slots` best, keeping >= 16 K blocks
+// per part (see launch_gemm)
+static int pick_ksplit(int units, int slots, int num_kb) {
+    static const int ks_max = [] { const char* e = getenv("MICO_GEMM_SPLITK_MAX"); return e ? atoi(e) : 4; }();
+    auto fill = [&](int u) { return (double)u / ((double)ceil_div(u, slots) * slots); };
+    int ks = 1;
+    for (int cand = 2; cand <= ks_max; cand *= 2) {
+        if (num_kb / cand < 16) break;
+        if (fill(units * cand) > fill(units * ks) * 1.08) ks = cand;
+    }
+    return ks;
+}
+
 template <int BN, bool A_MN, bool B_MN, int STAGES, int CL, int EPI>
 int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi_in, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, STAGES, EPI, B_MN, CL == 3>;
@@ -1086,14 +1099,7 @@ int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi_in, cudaStream_t strea
         // Split-K for weight gradients with fewer output tiles than SM (pair) slots: pick the split whose unit count fills
         // whole waves best, keeping >= 16 K blocks per part.  Two parts add commutatively (bit-reproducible); more than two
         // arrive in any order (last-bit run-to-run differences, like cuBLAS split-K) -- MICO_GEMM_SPLITK_MAX=2 / =1 restricts.
-        static const int ks_max = [] { const char* e = getenv("MICO_GEMM_SPLITK_MAX"); return e ? atoi(e) : 4; }();
-        auto fill = [&](int u) { return (double)u / ((double)ceil_div(u, max_clusters) * max_clusters); };
-        const int num_kb = ceil_div(g.K, BK);
-        int ks = 1;
-        for (int cand = 2; cand <= ks_max; cand *= 2) {
-            if (num_kb / cand < 16) break;
-            if (fill(units * cand) > fill(units * ks) * 1.08) ks = cand;
-        }
+        const int ks = pick_ksplit(units, max_clusters, ceil_div(g.K, BK));
         if (ks > 1) {
             MICO_CHECK_CUDA(cudaMemset2DAsync(epi.out, (size_t)epi.ldo * 4, 0, (size_t)g.N * 4, (size_t)g.M, stream));
             epi.ksplit = ks;
@@ -1178,6 +1184,22 @@ int dispatch_bn(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) 
     // stages -- measured slower than 128-wide tiles (fc1 dgrad 253 vs 238 us)
     if (!B_MN && g.N % 176 == 0 && est(176, 0.93) < best_t) { best = 176; best_t = est(176, 0.93); }
     if (est(128, 0.85) < best_t) { best = 128; best_t = est(128, 0.85); }
+    if constexpr (A_MN && B_MN) {
+        // Weight gradients run as CTA pairs and may split K (launch_gemm): estimate with THAT unit count.  Round 2: the plain
+        // estimate above gave the qkv / proj gradients of the 197 376-token tower pass 128-wide tiles (187 / 66 pair units, no
+        // split, ~1.0 PFLOP/s); 256-wide tiles with K split in two fill the 74 SM pairs as well (204 / 72 units) at the wider
+        // tile's efficiency.
+        static const bool splitk_aware = [] { const char* e = getenv("MICO_GEMM_WGRAD_TILE_SPLITK"); return !(e && e[0] == '0'); }();
+        if (splitk_aware && m_tiles >= 2 && g.N % 128 == 0 && g_pair_mma && g_pair_mma_wgrad && g_pair_mma_128 && !g_force_single_cta) {
+            const int slots = num_sms() / 2, num_kb = ceil_div(g.K, BK);
+            auto est_w = [&](int bn, double eff) {
+                const int ug = ceil_div(m_tiles, 2) * ceil_div(g.N, bn);
+                const int ks = pick_ksplit(ug, slots, num_kb);
+                return (double)ceil_div(ug * ks, slots) * bn / ks / eff;
+            };
+            best = est_w(256, 1.0) <= est_w(128, 0.85) ? 256 : 128;
+        }
+    }
     if (g.N <= 64) best = 64;
     // CTA pairs (B multicast) whenever there are at least two M tiles to pair up
     // (not for wgrad, A and B both MN-major with a 16k-long K loop: measured 4-15 % slower in lock step)
