@@ -238,6 +238,19 @@ int mico_cross_entropy_fwd(const void* logits, int logits_bf16, int64_t ld, cons
 int mico_cross_entropy_bwd(const void* logits, int logits_bf16, int64_t ld, const int64_t* labels, int64_t ignore_index,
                            float label_smoothing, const float* lse, const float* grad, const float* loss_and_count,
                            void* dlogits, int dlogits_bf16, int64_t ldd, int M, int V, void* stream);
+/* K7, LM head + cross-entropy without the [M, 30522] logits (bert.py:606-608 decoder + bert.py:1084-1090 CrossEntropyLoss,
+ * label_smoothing 0): the caller walks the vocabulary in chunks -- logits[:, col0 : col0+Vc] = decoder GEMM into a reusable
+ * fp32 buffer -- and these entries keep an online log-sum-exp (run_max, run_sum) and the label's logit per row
+ * (mico_ce_chunk_update; first != 0 on the first chunk), turn them into lse / row losses / (loss, n_valid)
+ * (mico_ce_chunk_finalize), and in the backward pass turn a RECOMPUTED chunk of logits into its bf16 dlogits
+ * = grad[0] / n_valid * (softmax - onehot) (mico_ce_chunk_grad).  mico_b200/bert.py:_LMHeadLossFn is the caller. */
+int mico_ce_chunk_update(const float* logits, int64_t ld, int col0, int Vc, const int64_t* labels, float* run_max,
+                         float* run_sum, float* label_logit, int M, int first, void* stream);
+int mico_ce_chunk_finalize(const float* run_max, const float* run_sum, const float* label_logit, const int64_t* labels,
+                           int64_t ignore_index, int V, float* row_loss, float* lse, float* loss_and_count, int M, void* stream);
+int mico_ce_chunk_grad(const float* logits, int64_t ld, int col0, int Vc, const int64_t* labels, int64_t ignore_index, int V,
+                       const float* lse, const float* grad, const float* loss_and_count, void* dlogits_bf16, int64_t ldd, int M,
+                       void* stream);
 /* F.normalize(x, dim=-1) (vast.py:225): y = x / max(||x||, eps); norm[m] saved for the backward */
 int mico_l2norm_fwd(const float* x, float* y, float* norm, int M, int D, float eps, void* stream);
 int mico_l2norm_bwd(const float* y, const float* dy, const float* norm, float* dx, int M, int D, void* stream);

@@ -208,6 +208,26 @@ class _Out:
         return self.__dict__[k] if isinstance(k, str) else list(self.__dict__.values())[k]
 
 
+class _LazyLogitsOut(_Out):
+    """Output of BertForMaskedLM.forward(labels=...) when the loss came from the chunked LM-head kernel path (K7): `.logits`
+    runs the full LM head the first time a caller reads it (the training loops read `.loss` only)."""
+
+    def __init__(self, make_logits, **kw):
+        super().__init__(**kw)
+        self.__dict__["_make_logits"] = make_logits
+
+    def __getattr__(self, k):          # only reached when the attribute is not in __dict__ yet
+        if k == "logits":
+            self.__dict__["logits"] = self.__dict__["_make_logits"]()
+            return self.__dict__["logits"]
+        raise AttributeError(k)
+
+    def __getitem__(self, k):
+        if k == "logits" or k == 1:
+            return self.logits
+        return self.__dict__[k] if isinstance(k, str) else [self.__dict__["loss"], None, self.__dict__["sequence_output"]][k]
+
+
 class BertModel(nn.Module):
     def __init__(self, config, add_pooling_layer=False):
         super().__init__()
@@ -605,6 +625,70 @@ class _LMHeadFn(torch.autograd.Function):
         return dh, gwd, gbd, glnw, glnb, gdec, gbdec, None, None
 
 
+class _LMHeadLossFn(torch.autograd.Function):
+    """K7: mean cross-entropy of decoder(LN(gelu(dense(h)))) + bias against `labels` (bert.py:575-609 + 1084-1090) WITHOUT the
+    [rows, vocab] logits: the vocabulary is walked in chunks of `chunk` columns -- decoder GEMM into one reusable fp32 buffer,
+    online log-sum-exp per row (mico_ce_chunk_update) -- and the backward pass recomputes each chunk with the same GEMM, turns
+    it into bf16 dlogits (mico_ce_chunk_grad) and feeds the decoder's weight / bias / input gradients chunk by chunk.  Same
+    arithmetic as _LMHeadFn + cross_entropy (bf16 dlogits there too); peak memory rows x chunk x 6 B instead of rows x vocab x 6 B."""
+
+    @staticmethod
+    def forward(ctx, h, wd, bd, lnw, lnb, wdec, bdec, labels, eps, ignore_index, chunk):
+        shp = h.shape
+        h2 = h.reshape(-1, shp[-1]).contiguous().float()
+        hb = ops.scale_cast_bf16(h2)
+        wdb = ops.cast_bf16(wd.detach().contiguous())
+        pre = torch.empty((hb.shape[0], wd.shape[0]), device=h.device, dtype=BF16)
+        t = ops.gemm(hb, wdb, bias=bd.detach(), act=ACT_GELU, aux_out=pre, out_dtype=F32)
+        tb, _, mean, rstd = ops.layernorm_fwd(t, lnw.detach(), lnb.detach(), eps, save_stats=True)
+        wdecb = ops.cast_bf16(wdec.detach().contiguous())
+        V, M = wdec.shape[0], hb.shape[0]
+        lab = labels.reshape(-1).contiguous()
+        buf = torch.empty((M, chunk), device=h.device, dtype=F32)
+        run_max, run_sum = torch.empty(M, device=h.device, dtype=F32), torch.empty(M, device=h.device, dtype=F32)
+        lab_logit = torch.zeros(M, device=h.device, dtype=F32)
+        bias = bdec.detach()
+        for c0 in range(0, V, chunk):
+            c1 = min(V, c0 + chunk)
+            lg = ops.gemm(tb, wdecb[c0:c1], bias=bias[c0:c1], out=buf[:, :c1 - c0])
+            ops.ce_chunk_update(lg, c0, lab, run_max, run_sum, lab_logit, first=(c0 == 0))
+        stats, lse = ops.ce_chunk_finalize(run_max, run_sum, lab_logit, lab, V, ignore_index)
+        ctx.save_for_backward(hb, wdb, pre, t, mean, rstd, tb, wdecb, lnw, lab, lse, stats, bias)
+        ctx.meta = (shp, ignore_index, chunk)
+        return stats[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        hb, wdb, pre, t, mean, rstd, tb, wdecb, lnw, lab, lse, stats, bias = ctx.saved_tensors
+        shp, ignore_index, chunk = ctx.meta
+        V, M, H = wdecb.shape[0], hb.shape[0], tb.shape[1]
+        dev = hb.device
+        g = g.detach().reshape(1).float().contiguous()
+        buf = torch.empty((M, chunk), device=dev, dtype=F32)
+        dl = torch.empty((M, chunk), device=dev, dtype=BF16)
+        gdec = torch.empty((V, H), device=dev, dtype=F32)
+        gbdec = torch.empty(V, device=dev, dtype=F32)
+        dt = torch.zeros((M, H), device=dev, dtype=F32)
+        for c0 in range(0, V, chunk):
+            c1 = min(V, c0 + chunk)
+            n = c1 - c0
+            lg = ops.gemm(tb, wdecb[c0:c1], bias=bias[c0:c1], out=buf[:, :n])          # the forward pass's own launch
+            ops.ce_chunk_grad(lg, c0, lab, lse, g, stats, V, dl, ignore_index)
+            dlc = dl[:, :n]
+            ops.gemm(dlc, tb, a_mn=True, b_mn=True, out=gdec[c0:c1])                     # d decoder.weight rows
+            ops.colsum(dlc, out=gbdec[c0:c1])
+            ops.gemm(dlc, wdecb[c0:c1], b_mn=True, out=dt, accumulate=(c0 > 0))         # dt += dlogits_c W_c
+        dtb = ops.scale_cast_bf16(dt)
+        glnw, glnb = torch.empty_like(lnw), torch.empty_like(lnw)
+        _, dtb2 = ops.layernorm_bwd(dtb, t, mean, rstd, lnw.detach(), glnw, glnb, want_f32=False, want_bf16=True)
+        dpre = ops.gelu_f32(pre.float(), dtb2.float())
+        dpreb = ops.scale_cast_bf16(dpre)
+        gwd = ops.gemm(dpreb, hb, a_mn=True, b_mn=True, out_dtype=F32)
+        gbd = ops.colsum(dpreb)
+        dh = ops.gemm(dpreb, wdb, b_mn=True, out_dtype=F32).view(shp)
+        return dh, gwd, gbd, glnw, glnb, gdec, gbdec, None, None, None, None
+
+
 class BertForMaskedLM(nn.Module):
     def __init__(self, config):
         super().__init__()
@@ -613,6 +697,9 @@ class BertForMaskedLM(nn.Module):
         self.cls = _MLMHead(config)
         if config.tie_word_embeddings:     # transformers 4.31 post_init() ties decoder and word embeddings
             self.cls.predictions.decoder.weight = self.bert.embeddings.word_embeddings.weight
+        # lm_loss(): LM head + cross-entropy chunk by chunk over the vocabulary (K7); forward(labels=...) still returns .logits
+        self.fused_lm_loss = True
+        self.lm_loss_chunk = 4096
 
     def get_output_embeddings(self):
         return self.cls.predictions.decoder
@@ -644,6 +731,10 @@ class BertForMaskedLM(nn.Module):
     def lm_loss(self, seq, labels):
         """LM head + cross-entropy (bert.py:1084-1090) on an encoder output computed elsewhere (a slice of a larger call)."""
         pr = self.cls.predictions
+        if self.fused_lm_loss:     # K7: the [rows, vocab] logits are never materialised
+            return _LMHeadLossFn.apply(seq, pr.transform.dense.weight, pr.transform.dense.bias, pr.transform.LayerNorm.weight,
+                                       pr.transform.LayerNorm.bias, pr.decoder.weight, pr.bias, labels,
+                                       self.config.layer_norm_eps, -100, self.lm_loss_chunk)
         logits = _LMHeadFn.apply(seq, pr.transform.dense.weight, pr.transform.dense.bias, pr.transform.LayerNorm.weight,
                                  pr.transform.LayerNorm.bias, pr.decoder.weight, pr.bias, self.config.layer_norm_eps,
                                  torch.is_grad_enabled())
@@ -657,8 +748,13 @@ class BertForMaskedLM(nn.Module):
                         encoder_attention_mask=encoder_attention_mask).last_hidden_state
         pr = self.cls.predictions
         keep = torch.is_grad_enabled()
-        logits = _LMHeadFn.apply(seq, pr.transform.dense.weight, pr.transform.dense.bias, pr.transform.LayerNorm.weight,
-                                 pr.transform.LayerNorm.bias, pr.decoder.weight, pr.bias, self.config.layer_norm_eps, keep)
+
+        def make_logits():
+            return _LMHeadFn.apply(seq, pr.transform.dense.weight, pr.transform.dense.bias, pr.transform.LayerNorm.weight,
+                                   pr.transform.LayerNorm.bias, pr.decoder.weight, pr.bias, self.config.layer_norm_eps, keep)
+        if labels is not None and self.fused_lm_loss:
+            return _LazyLogitsOut(make_logits, loss=self.lm_loss(seq, labels), sequence_output=seq)
+        logits = make_logits()
         loss = None
         if labels is not None:
             loss = cross_entropy(logits.view(-1, self.config.vocab_size), labels.view(-1), ignore_index=-100,

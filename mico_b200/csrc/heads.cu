@@ -138,6 +138,64 @@ ce_bwd_kernel(const T* __restrict__ logits, int64_t ld, const int64_t* __restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------- K7: chunked LM-head loss
+// The LM head's [rows, 30522] logits are never materialised in training mode (bert.py:606-608 + 1084-1090 fused): the vocabulary
+// is walked in chunks, each chunk's logits come out of the decoder GEMM into one reusable buffer, and these kernels keep an
+// online log-sum-exp per row (running max m, running sum s of exp(x - m)) plus the label's logit; the backward pass recomputes
+// a chunk's logits with the same GEMM and turns them into dlogits in place of a second full-size tensor.
+// one 256-thread block per row
+__global__ void __launch_bounds__(256)
+ce_chunk_update_kernel(const float* __restrict__ logits, int64_t ld, int col0, int Vc, const int64_t* __restrict__ labels,
+                       float* __restrict__ run_max, float* __restrict__ run_sum, float* __restrict__ label_logit, int first) {
+    __shared__ float red[8];
+    const int row = blockIdx.x;
+    const float* x = logits + (int64_t)row * ld;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < Vc; i += 256) mx = fmaxf(mx, x[i]);
+    mx = block_reduce_256(mx, red, true);
+    float se = 0.f;
+    for (int i = threadIdx.x; i < Vc; i += 256) se += __expf(x[i] - mx);
+    se = block_reduce_256(se, red, false);
+    if (threadIdx.x == 0) {
+        const float m0 = first ? -INFINITY : run_max[row], s0 = first ? 0.f : run_sum[row];
+        const float m1 = fmaxf(m0, mx);
+        run_max[row] = m1;
+        run_sum[row] = s0 * __expf(m0 - m1) + se * __expf(mx - m1);      // exp(-inf) = 0 on the first chunk
+        const int64_t y = labels[row] - col0;
+        if (y >= 0 && y < Vc) label_logit[row] = x[y];
+    }
+}
+// lse = m + log s; row_loss = lse - x_label for rows whose label is a vocabulary index other than ignore_index, else 0
+__global__ void ce_chunk_finalize_kernel(const float* __restrict__ run_max, const float* __restrict__ run_sum,
+                                         const float* __restrict__ label_logit, const int64_t* __restrict__ labels,
+                                         int64_t ignore_index, int V, float* __restrict__ row_loss, float* __restrict__ lse, int M) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= M) return;
+    const float l = run_max[row] + __logf(run_sum[row]);
+    lse[row] = l;
+    const int64_t y = labels[row];
+    row_loss[row] = (y != ignore_index && y >= 0 && y < V) ? l - label_logit[row] : 0.f;
+}
+// dlogits chunk (bf16) = g / n_valid * (exp(x - lse) - [label == col0 + j]); zero rows for ignored labels
+__global__ void __launch_bounds__(256)
+ce_chunk_grad_kernel(const float* __restrict__ logits, int64_t ld, int col0, int Vc, const int64_t* __restrict__ labels,
+                     int64_t ignore_index, int V, const float* __restrict__ lse, const float* __restrict__ grad,
+                     const float* __restrict__ stats, __nv_bfloat16* __restrict__ dlogits, int64_t ldd) {
+    const int row = blockIdx.x;
+    const float* x = logits + (int64_t)row * ld;
+    __nv_bfloat16* d = dlogits + (int64_t)row * ldd;
+    const int64_t y = labels[row];
+    const bool valid = (y != ignore_index && y >= 0 && y < V);
+    const float g = valid ? grad[0] / stats[1] : 0.f;
+    const float l = lse[row];
+    const int64_t yc = y - col0;
+    for (int i = threadIdx.x; i < Vc; i += 256) {
+        float v = 0.f;
+        if (valid) v = g * (__expf(x[i] - l) - (i == yc ? 1.0f : 0.f));
+        d[i] = __float2bfloat16(v);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- L2 normalise
 __global__ void __launch_bounds__(256)
 l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ norm, int M, int D, float eps) {
@@ -307,6 +365,44 @@ extern "C" int mico_cross_entropy_bwd(const void* logits, int logits_bf16, int64
     else if (dlogits_bf16) MICO_CE_BWD(float, __nv_bfloat16);
     else MICO_CE_BWD(float, float);
 #undef MICO_CE_BWD
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return MICO_OK;
+}
+
+extern "C" int mico_ce_chunk_update(const float* logits, int64_t ld, int col0, int Vc, const int64_t* labels, float* run_max,
+                                    float* run_sum, float* label_logit, int M, int first, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MICO_CHECK_ARG(logits && labels && run_max && run_sum && label_logit && M > 0 && Vc > 0 && ld >= Vc && col0 >= 0);
+    ProfScope prof(kProfOther, (double)M * Vc * 4 * 2, stream);
+    ce_chunk_update_kernel<<<M, 256, 0, stream>>>(logits, ld, col0, Vc, labels, run_max, run_sum, label_logit, first);
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return MICO_OK;
+}
+
+extern "C" int mico_ce_chunk_finalize(const float* run_max, const float* run_sum, const float* label_logit, const int64_t* labels,
+                                      int64_t ignore_index, int V, float* row_loss, float* lse, float* loss_and_count, int M,
+                                      void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MICO_CHECK_ARG(run_max && run_sum && label_logit && labels && row_loss && lse && loss_and_count && M > 0 && V > 0);
+    ce_chunk_finalize_kernel<<<ceil_div(M, 256), 256, 0, stream>>>(run_max, run_sum, label_logit, labels, ignore_index, V, row_loss,
+                                                                 lse, M);
+    MICO_CHECK_CUDA(cudaGetLastError());
+    ce_reduce_kernel<<<1, 256, 0, stream>>>(row_loss, labels, ignore_index, M, V, loss_and_count);
+    MICO_CHECK_CUDA(cudaGetLastError());
+    count_launch(2);
+    return MICO_OK;
+}
+
+extern "C" int mico_ce_chunk_grad(const float* logits, int64_t ld, int col0, int Vc, const int64_t* labels, int64_t ignore_index,
+                                  int V, const float* lse, const float* grad, const float* loss_and_count, void* dlogits_bf16,
+                                  int64_t ldd, int M, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MICO_CHECK_ARG(logits && labels && lse && grad && loss_and_count && dlogits_bf16 && M > 0 && Vc > 0 && ld >= Vc && ldd >= Vc);
+    ProfScope prof(kProfOther, (double)M * Vc * (4 + 2), stream);
+    ce_chunk_grad_kernel<<<M, 256, 0, stream>>>(logits, ld, col0, Vc, labels, ignore_index, V, lse, grad, loss_and_count,
+                                              reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), ldd);
     MICO_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return MICO_OK;

@@ -470,6 +470,36 @@ def cross_entropy_bwd(logits, labels, lse, grad, stats, ignore_index=-100, label
     return d
 
 
+def ce_chunk_update(logits, col0, labels, run_max, run_sum, label_logit, first):
+    """one vocabulary chunk of the LM-head loss: logits fp32 [M, Vc] view (columns col0.. of the full vocabulary)"""
+    _req(logits, F32, "logits")
+    _req(labels, I64, "labels")
+    M, Vc = logits.shape
+    check(lib.mico_ce_chunk_update(_ptr(logits), C.c_int64(logits.stride(0)), int(col0), Vc, _ptr(labels), _ptr(run_max),
+                                   _ptr(run_sum), _ptr(label_logit), M, int(bool(first)), _stream()), "mico_ce_chunk_update")
+
+
+def ce_chunk_finalize(run_max, run_sum, label_logit, labels, V, ignore_index=-100):
+    """-> (stats [2] = (loss, n_valid), lse [M])"""
+    M = run_max.numel()
+    row_loss = torch.empty(M, device=run_max.device, dtype=F32)
+    lse = torch.empty(M, device=run_max.device, dtype=F32)
+    stats = torch.empty(2, device=run_max.device, dtype=F32)
+    check(lib.mico_ce_chunk_finalize(_ptr(run_max), _ptr(run_sum), _ptr(label_logit), _ptr(labels), C.c_int64(ignore_index),
+                                     int(V), _ptr(row_loss), _ptr(lse), _ptr(stats), M, _stream()), "mico_ce_chunk_finalize")
+    return stats, lse
+
+
+def ce_chunk_grad(logits, col0, labels, lse, grad, stats, V, out, ignore_index=-100):
+    """recomputed fp32 logits chunk [M, Vc] -> bf16 dlogits chunk written into out[:, :Vc]"""
+    _req(logits, F32, "logits")
+    _req(out, BF16, "out")
+    M, Vc = logits.shape
+    check(lib.mico_ce_chunk_grad(_ptr(logits), C.c_int64(logits.stride(0)), int(col0), Vc, _ptr(labels),
+                                 C.c_int64(ignore_index), int(V), _ptr(lse), _ptr(grad), _ptr(stats), _ptr(out),
+                                 C.c_int64(out.stride(0)), M, _stream()), "mico_ce_chunk_grad")
+
+
 def l2norm_fwd(x, eps=1e-12):
     _req(x, F32, "x")
     M, D = x.shape

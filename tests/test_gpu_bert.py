@@ -148,3 +148,43 @@ def test_bert_base_width_vs_oracle():
         if v.grad is None or k.endswith("self.key.bias"):    # key-bias gradient is identically zero (see above)
             continue
         assert rel_l2(v.grad.cpu(), p[k].grad) < GRAD_TOL, k
+
+
+def test_fused_lm_head_loss_matches_materialised_logits():
+    """K7: the chunked LM-head + cross-entropy path (no [rows, 30522] logits; 8 vocabulary chunks of 4096) gives the loss and
+    every gradient of the path that materialises the logits (same GEMMs, same bf16 dlogits), including ignored rows and a
+    chunk boundary label; `.logits` of the lazy output equals the materialised tensor."""
+    cfgd = dict(num_hidden_layers=1, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    torch.manual_seed(11)
+    m = _model(cfgd).cuda().train()
+    g = torch.Generator().manual_seed(12)
+    b, S = 3, 24
+    ids = torch.randint(1, 30522, (b, S), generator=g)
+    labels = torch.where(torch.rand(b, S, generator=g) < 0.6, ids, torch.full_like(ids, -100))
+    labels[0, 0], labels[0, 1], labels[1, 0], labels[2, 5] = 4095, 4096, 30521, 0       # chunk edges, last / first token
+    res = {}
+    for fused in (False, True):
+        m.fused_lm_loss = fused
+        m.zero_grad(set_to_none=True)
+        out = m(input_ids=ids.cuda(), labels=labels.cuda())
+        out.loss.backward()
+        res[fused] = (out.loss.item(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None},
+                      out.logits.detach().float().clone())
+    l0, g0, lg0 = res[False]
+    l1, g1, lg1 = res[True]
+    assert abs(l1 - l0) <= 1e-5 * abs(l0), (l0, l1)
+    assert torch.equal(lg0, lg1)
+    assert g0.keys() == g1.keys()
+    # key.bias: its gradient is exactly 0 in exact arithmetic (see test_golden_caption_loss_and_grads), both sides hold noise.
+    # Elsewhere the two paths differ by bf16 rounding only: the materialised path rounds d(LN input) = dlogits . W to bf16 in
+    # one GEMM, the chunked path accumulates the eight partial products in fp32 first.
+    worst = max((rel_l2(g1[k], g0[k]), k) for k in g0 if not k.endswith("self.key.bias"))
+    print(f"fused LM-head loss {l1:.6f} vs {l0:.6f}; worst gradient difference {worst[1]} {worst[0]:.2e}")
+    assert worst[0] < 1e-2
+    for k in ("cls.predictions.bias", "bert.embeddings.word_embeddings.weight", "cls.predictions.transform.dense.weight"):
+        assert rel_l2(g1[k], g0[k]) < 2e-3, k          # the LM head's own parameters: same GEMMs, same bf16 dlogits
+    # smaller chunks, not a divisor of the vocabulary
+    m.lm_loss_chunk = 1000
+    m.zero_grad(set_to_none=True)
+    out = m(input_ids=ids.cuda(), labels=labels.cuda())
+    assert abs(out.loss.item() - l0) <= 1e-5 * abs(l0)
