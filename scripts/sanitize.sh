@@ -14,7 +14,8 @@ run() {   # tool, family
   local rc=$?
   echo "[$1 / $2] exit $rc : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|done' "$out" | tr '\n' ' ')" | tee -a "$summary"
 }
-for fam in gemm attention rowwise heads; do run memcheck "$fam"; done
-for fam in gemm attention rowwise; do run racecheck "$fam"; done
-for fam in gemm attention; do run synccheck "$fam"; done
+FAMS=${SANITIZE_FAMILIES:-"gemm attention rowwise heads"}      # e.g. SANITIZE_FAMILIES="attention heads" for a partial re-run
+for fam in $FAMS; do run memcheck "$fam"; done
+for fam in $FAMS; do case $fam in gemm|attention|rowwise) run racecheck "$fam";; esac; done
+for fam in $FAMS; do case $fam in gemm|attention) run synccheck "$fam";; esac; done
 cat "$summary"

@@ -34,7 +34,10 @@ def attention():
     r = lambda *s: torch.randn(*s, device="cuda", generator=g).to(BF16)
     for (B, H, Sq, Sk, D, masked, drop, shared) in [(2, 2, 257, 257, 88, False, None, False), (2, 2, 40, 257, 64, True, (0.1, 7), False),
                                                      (3, 2, 128, 200, 64, False, (0.1, 9), True), (4, 4, 49, 49, 32, True, None, False),
-                                                     (1, 2, 130, 130, 64, True, None, False)]:
+                                                     (1, 2, 130, 130, 64, True, None, False),
+                                                     # head_dim 88 with a mask + dropout and a ragged key count: the pipelined dQ kernel's
+                                                     # predicated path (attention_bwd_dq.cu) next to the single-buffer dK/dV kernel
+                                                     (2, 2, 257, 200, 88, True, (0.1, 3), False), (1, 2, 300, 97, 88, False, None, False)]:
         E = 2 if shared else B
         q, do = r(B, Sq, H, D), r(B, Sq, H, D)
         k, v = r(E, Sk, H, D), r(E, Sk, H, D)
@@ -90,6 +93,21 @@ def heads_and_io():
     labels[::3] = -100
     stats, lse = ops.cross_entropy_fwd(logits, labels, label_smoothing=0.1)
     ops.cross_entropy_bwd(logits, labels, lse, torch.ones(1, device="cuda"), stats, label_smoothing=0.1, out_dtype=BF16)
+    # K7: chunked LM-head loss (three vocabulary chunks of 400 / 400 / 200)
+    M = 4 * S
+    rm, rs_, ll = torch.empty(M, device="cuda"), torch.empty(M, device="cuda"), torch.zeros(M, device="cuda")
+    for c0 in range(0, V, 400):
+        ops.ce_chunk_update(logits[:, c0:min(V, c0 + 400)], c0, labels, rm, rs_, ll, first=(c0 == 0))
+    st2, lse2 = ops.ce_chunk_finalize(rm, rs_, ll, labels, V)
+    dl = torch.empty(M, 400, device="cuda", dtype=BF16)
+    for c0 in range(0, V, 400):
+        ops.ce_chunk_grad(logits[:, c0:min(V, c0 + 400)], c0, labels, lse2, torch.ones(1, device="cuda"), st2, V, dl)
+    # EVA02: rotary embedding (forward / inverse) and SwiGLU (forward / backward)
+    cos, sin = r(16, 64), r(16, 64)
+    xb = ops.rope(r(2, 17, 2, 64), cos, sin)
+    ops.rope(xb, cos, sin, inverse=True)
+    ops.swiglu(r(50, 344), r(50, 344))
+    ops.swiglu(r(50, 344), r(50, 344), r(50, 344))
     y, nrm = ops.l2norm_fwd(r(9, 512))
     ops.l2norm_bwd(y, r(9, 512), nrm)
     ops.sgemm(r(9, 512), r(17, 512), alpha_dev=torch.tensor([0.07], device="cuda"), alpha_recip=True)
