@@ -623,6 +623,7 @@ def run_product_omni(args):
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count()
     peak_mem = torch.cuda.max_memory_allocated(dev) / 1e9
+    peak_reserved = torch.cuda.max_memory_reserved(dev) / 1e9
 
     e2e_losses = e2e_step()
     barrier()
@@ -698,7 +699,7 @@ def run_product_omni(args):
     h2d = sum(host[k].numel() * host[k].element_size() for k in h2d_keys) + 2 * host["input_ids"].numel() * 8 * 2
     config = make_config(args)
     extra = dict(processed_tokens_per_s=world * proc_tok * args.steps / (ms / 1e3), peak_hbm_gb=round(peak_mem, 1),
-                 losses_after_warmup=losses0)
+                 peak_hbm_reserved_gb=round(peak_reserved, 1), losses_after_warmup=losses0)
     line = dict(metric=METRIC[args.config], value=value, unit="tokens/s", n_gpus=world, steps=args.steps, warmup=W,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                 data="synthetic", config=config, clocks=clocks,
