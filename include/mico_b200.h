@@ -95,6 +95,14 @@ typedef struct MicoGemmArgs {
 
 int mico_gemm_bf16(const MicoGemmArgs* args, void* stream);
 
+/* Host-side view of the work-unit plan mico_gemm_bf16 uses for a launch (no GPU needed; tests and tuning scripts).  A launch
+ * covers num_tiles output tiles (num_n of them per M group, bn MMA columns each, the last one of every group n_last), each
+ * with num_kb K blocks, on `slots` persistent CTAs / CTA pairs.  Returns the split-K factor (1 unless allow_split), the number
+ * of rounds, the planned makespan in (MMA column x K block) units and, if table != NULL, the [slots x rounds] unit table
+ * (-1 padded): slot s runs units table[s * rounds + 0..], unit u = (tile u % num_tiles, K part u / num_tiles). */
+int mico_gemm_plan(int num_tiles, int num_n, int bn, int n_last, int num_kb, int slots, int allow_split, int* ks, int* rounds,
+                   double* makespan, int* table, int table_cap);
+
 /* ---------------------------------------------------------------------------------------------
  * K4  Fused attention (flash-style; tcgen05 QK^T and PV, online softmax, no score matrix in HBM).
  *     O = softmax(scale * Q K^T + mask) V          per (batch b, head h)

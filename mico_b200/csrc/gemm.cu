@@ -23,6 +23,11 @@
 // 197, 310, 363, 446; bert.py:196-209, 293, 357, 370, 601, 607).
 #include "common.cuh"
 #include <stdlib.h>
+#include <algorithm>
+#include <array>
+#include <map>
+#include <mutex>
+#include <vector>
 
 #include "host_utils.h"
 
@@ -55,6 +60,8 @@ struct GemmEpi {
     int vec_ok;   // all pitches / bases allow 16-byte vector access
     int ksplit;   // > 1: the K loop of every output tile is split over `ksplit` work units whose fp32 partial tiles are
                   // ADDED into the (zeroed) output by TMA reduce (EPI_F32 only: weight gradients with few output tiles)
+    const int* sched;   // balanced unit schedule (plan_schedule below): slot s runs sched[s * sched_rounds + it], -1 ends its
+    int sched_rounds;   // list; null = the strided default (slot s runs units s, s + slots, ...)
 };
 
 template <int BN, int STAGES, int EPI = 0, bool B_MN = false, bool P2 = false>
@@ -776,6 +783,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ksplit = EPI == EPI_F32 ? epi.ksplit : 1;
     const int kb_per = (num_kb + ksplit - 1) / ksplit;
     const int num_units = num_tiles * ksplit;
+    // it-th work unit of this CTA's slot (-1: none left).  With a schedule table the units of one round (`slots` consecutive
+    // units) are dealt so that every slot accumulates the same MMA time although the last N tile is narrower.
+    auto unit_at = [&](int it) -> int {
+        if (epi.sched) return it < epi.sched_rounds ? __ldg(epi.sched + (size_t)unit0 * epi.sched_rounds + it) : -1;
+        const int u = unit0 + it * unit_stride;
+        return u < num_units ? u : -1;
+    };
 
     if (warp == 0) {
         if (elect_one()) {
@@ -810,7 +824,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int unit = unit0; unit < num_units; unit += unit_stride) {
+            int unit = unit_at(0);
+            for (int it = 0; unit >= 0; ++it) {
+                const int unit_next = unit_at(it + 1);      // the table read of the next unit overlaps this one's K loop
                 const int tile = unit % num_tiles, kb0 = (unit / num_tiles) * kb_per;
                 const int kb1 = kb0 + kb_per < num_kb ? kb0 + kb_per : num_kb;
                 const int m0 = (unit_mg(tile) * CLN + (int)cta_rank) * BM;
@@ -872,6 +888,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                unit = unit_next;
             }
         }
     } else if (warp == 1) {
@@ -879,8 +896,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if ((!P2 || cta_rank == 0) && elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
-            for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
+            int unit = unit_at(0);
+            for (int it = 0; unit >= 0; ++it) {
+                const int unit_next = unit_at(it + 1);
                 const int tile = unit % num_tiles, kb0 = (unit / num_tiles) * kb_per;
                 const int kb1 = kb0 + kb_per < num_kb ? kb0 + kb_per : num_kb;
                 const int acc = it & 1;
@@ -914,16 +932,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 if constexpr (P2) umma_commit_pair(&tfull_bar[acc], kMask);     // both CTAs' epilogues read their half
                 else umma_commit(&tfull_bar[acc]);
+                unit = unit_next;
             }
         }
     } else {
         // ------------------------------------------------------------- epilogue (warps 2..9)
         const int q = warp & 3;            // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;  // which of the two warps of that quarter: owns chunks c with (c & 1) == half
-        int it = 0;
         uint32_t sidx = 0;                 // TMA store tiles of this warp alternate (specialised epilogues)
-        for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
-            const int tile = unit % num_tiles;
+        int unit = unit_at(0);
+        for (int it = 0; unit >= 0; ++it) {
+            const int unit_cur = unit;
+            unit = unit_at(it + 1);
+            const int tile = unit_cur % num_tiles;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int m0 = (unit_mg(tile) * CLN + (int)cta_rank) * BM;
@@ -1031,17 +1052,131 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
-// split-K factor of a weight gradient: the split whose unit count fills whole waves of `slots` best, keeping >= 16 K blocks
-// per part (see launch_gemm)
-static int pick_ksplit(int units, int slots, int num_kb) {
-    static const int ks_max = [] { const char* e = getenv("MICO_GEMM_SPLITK_MAX"); return e ? atoi(e) : 4; }();
-    auto fill = [&](int u) { return (double)u / ((double)ceil_div(u, slots) * slots); };
+// ---------------------------------------------------------------------------------------------------------------------------
+// Work-unit plan of one launch: the split-K factor (weight gradients) and a balanced unit schedule.
+//
+// The persistent kernel used to deal units to its slots (CTAs / CTA pairs) with a fixed stride.  With N = 1408 on 256-wide tiles
+// the sixth N tile issues a half-width MMA, and a stride of 74 slots over 6 N tiles leaves every slot on n tiles of ONE parity:
+// odd slots only ever saw n = 1, 3, 5 -- 5/6 of the even slots' MMA time -- so the launch ran 62.5 full-tile times where 57.3
+// were needed, and the faster half of the grid drifted ahead of the A panels the others were still reading (fc2 forward at
+// 197 376 rows: 8.4 GB of DRAM reads for 3.5 GB of operands).  The plan keeps the round structure (round r = the r-th group of
+// `slots` consecutive units: concurrent CTAs share A panels through L2, and the K parts of a split weight gradient stay in lock
+// step) but deals each round's units longest-first to the least-loaded slots, so every slot's accumulated MMA time stays
+// within half a tile of every other's.  Unit cost = MMA columns x K blocks (+ a fixed per-unit drain).  The split-K factor of a
+// weight gradient is the one with the smallest planned makespan.  MICO_GEMM_SCHED=0 restores the strided schedule.
+struct GemmPlan {
     int ks = 1;
-    for (int cand = 2; cand <= ks_max; cand *= 2) {
-        if (num_kb / cand < 16) break;
-        if (fill(units * cand) > fill(units * ks) * 1.08) ks = cand;
+    int rounds = 0;
+    double makespan = 0;            // planned time of the slowest slot, in (MMA column x K block) units
+    bool uniform = true;            // every unit costs the same: the strided default is already balanced
+    std::vector<int> table;         // [slots x rounds], -1 padded
+    const int* dev = nullptr;       // device copy, uploaded on first use
+};
+
+static constexpr int kUnitDrainKb = 4;      // per-unit fixed cost (pipeline fill + accumulator hand-over), in K blocks
+
+static void plan_units(GemmPlan& p, int num_tiles, int num_n, int bn, int n_last, int num_kb, int ks, int slots) {
+    const int kb_per = ceil_div(num_kb, ks);
+    const int num_units = num_tiles * ks;
+    auto cost = [&](int u) {
+        const int tile = u % num_tiles, part = u / num_tiles;
+        const int w = (tile % num_n == num_n - 1) ? n_last : bn;
+        int kbc = num_kb - part * kb_per;
+        if (kbc > kb_per) kbc = kb_per;
+        if (kbc < 0) kbc = 0;
+        return (double)w * (kbc + kUnitDrainKb);
+    };
+    p.ks = ks;
+    p.rounds = ceil_div(num_units, slots);
+    p.uniform = true;
+    const double c0 = cost(0);
+    for (int u = 1; u < num_units && p.uniform; ++u) p.uniform = cost(u) == c0;
+    std::vector<double> load(slots, 0.0);
+    std::vector<int> count(slots, 0), order(slots), units;
+    p.table.assign((size_t)slots * p.rounds, -1);
+    for (int r = 0; r < p.rounds; ++r) {
+        const int u0 = r * slots, u1 = u0 + slots < num_units ? u0 + slots : num_units;
+        units.resize(u1 - u0);
+        for (int u = u0; u < u1; ++u) units[u - u0] = u;
+        if (!p.uniform) {
+            std::stable_sort(units.begin(), units.end(), [&](int a, int b) { return cost(a) > cost(b); });
+            for (int s = 0; s < slots; ++s) order[s] = s;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return load[a] < load[b]; });
+        }
+        for (int i = 0; i < (int)units.size(); ++i) {
+            const int s = p.uniform ? i : order[i];
+            p.table[(size_t)s * p.rounds + count[s]++] = units[i];
+            load[s] += cost(units[i]);
+        }
     }
-    return ks;
+    p.makespan = *std::max_element(load.begin(), load.end());
+}
+
+static bool sched_enabled() {
+    static const bool on = [] { const char* e = getenv("MICO_GEMM_SCHED"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+// cached per (shape, device); returned reference stays valid (node-based map)
+static GemmPlan& get_plan(int num_tiles, int num_n, int bn, int n_last, int num_kb, int slots, bool allow_split) {
+    static std::mutex mu;
+    static std::map<std::array<int, 8>, GemmPlan> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const std::array<int, 8> key = {num_tiles, num_n, bn, n_last, num_kb, slots, allow_split ? 1 : 0, dev};
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    static const int ks_max = [] { const char* e = getenv("MICO_GEMM_SPLITK_MAX"); return e ? atoi(e) : 4; }();
+    GemmPlan best;
+    plan_units(best, num_tiles, num_n, bn, n_last, num_kb, 1, slots);
+    if (allow_split) {
+        // keep >= 16 K blocks per part; a finer split has to win by 4 % (it zeroes the output first and adds partial tiles:
+        // two parts add commutatively (bit-reproducible), more than two arrive in any order -- last-bit run-to-run
+        // differences like cuBLAS split-K; MICO_GEMM_SPLITK_MAX=2 / =1 restricts)
+        for (int cand = 2; cand <= ks_max; cand *= 2) {
+            if (num_kb / cand < 16) break;
+            GemmPlan p;
+            plan_units(p, num_tiles, num_n, bn, n_last, num_kb, cand, slots);
+            if (p.makespan < best.makespan * 0.96) best = std::move(p);
+        }
+    }
+    if (!sched_enabled()) {          // strided schedule: its makespan is what the estimate should see
+        const int ks = best.ks, num_units = num_tiles * ks, kb_per = ceil_div(num_kb, ks);
+        std::vector<double> load(slots, 0.0);
+        for (int u = 0; u < num_units; ++u) {
+            const int tile = u % num_tiles, part = u / num_tiles;
+            int kbc = num_kb - part * kb_per;
+            kbc = kbc > kb_per ? kb_per : (kbc < 0 ? 0 : kbc);
+            load[u % slots] += (double)((tile % num_n == num_n - 1) ? n_last : bn) * (kbc + kUnitDrainKb);
+        }
+        best.makespan = *std::max_element(load.begin(), load.end());
+        best.uniform = true;
+    }
+    return cache.emplace(key, std::move(best)).first->second;
+}
+
+// device copy of a plan's schedule table (null when the strided default is as good)
+static int plan_device_table(GemmPlan& p, const int** out) {
+    *out = nullptr;
+    if (p.uniform || p.table.empty()) return MICO_OK;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!p.dev) {
+        int* d = nullptr;
+        MICO_CHECK_CUDA(cudaMalloc(&d, p.table.size() * sizeof(int)));
+        MICO_CHECK_CUDA(cudaMemcpy(d, p.table.data(), p.table.size() * sizeof(int), cudaMemcpyHostToDevice));
+        p.dev = d;
+    }
+    *out = p.dev;
+    return MICO_OK;
+}
+
+// MMA columns of the last N tile (the narrower MMA the issuer picks, see the kernel)
+static int last_tile_cols(int N, int bn, bool p2) {
+    const int n_left = N - (ceil_div(N, bn) - 1) * bn;
+    const int g = p2 ? 32 : 16;
+    return n_left >= bn ? bn : ((n_left + g - 1) / g) * g;
 }
 
 template <int BN, bool A_MN, bool B_MN, int STAGES, int CL, int EPI>
@@ -1091,20 +1226,25 @@ int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi_in, cudaStream_t strea
         MICO_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    int units = ceil_div(ceil_div(g.M, BM), CLN) * ceil_div(g.N, BN);
+    const int num_n = ceil_div(g.N, BN);
+    int units = ceil_div(ceil_div(g.M, BM), CLN) * num_n;
     const int max_clusters = num_sms() / CLN;
     GemmEpi epi = epi_in;
     epi.ksplit = 1;
-    if constexpr (EPI == EPI_F32) {
-        // Split-K for weight gradients with fewer output tiles than SM (pair) slots: pick the split whose unit count fills
-        // whole waves best, keeping >= 16 K blocks per part.  Two parts add commutatively (bit-reproducible); more than two
-        // arrive in any order (last-bit run-to-run differences, like cuBLAS split-K) -- MICO_GEMM_SPLITK_MAX=2 / =1 restricts.
-        const int ks = pick_ksplit(units, max_clusters, ceil_div(g.K, BK));
-        if (ks > 1) {
+    epi.sched = nullptr;
+    epi.sched_rounds = 0;
+    {
+        // Split-K for weight gradients (EPI_F32) with fewer output tiles than SM (pair) slots, and the balanced unit schedule
+        // (GemmPlan above).
+        GemmPlan& plan = get_plan(units, num_n, BN, last_tile_cols(g.N, BN, CL == 3), ceil_div(g.K, BK), max_clusters,
+                                  EPI == EPI_F32);
+        if (plan.ks > 1) {
             MICO_CHECK_CUDA(cudaMemset2DAsync(epi.out, (size_t)epi.ldo * 4, 0, (size_t)g.N * 4, (size_t)g.M, stream));
-            epi.ksplit = ks;
-            units *= ks;
+            epi.ksplit = plan.ks;
+            units *= plan.ks;
         }
+        if ((rc = plan_device_table(plan, &epi.sched))) return rc;
+        epi.sched_rounds = plan.rounds;
     }
     const int grid = (units < max_clusters ? units : max_clusters) * CLN;
     cudaLaunchConfig_t cfg{};
@@ -1193,9 +1333,8 @@ int dispatch_bn(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) 
         if (splitk_aware && m_tiles >= 2 && g.N % 128 == 0 && g_pair_mma && g_pair_mma_wgrad && g_pair_mma_128 && !g_force_single_cta) {
             const int slots = num_sms() / 2, num_kb = ceil_div(g.K, BK);
             auto est_w = [&](int bn, double eff) {
-                const int ug = ceil_div(m_tiles, 2) * ceil_div(g.N, bn);
-                const int ks = pick_ksplit(ug, slots, num_kb);
-                return (double)ceil_div(ug * ks, slots) * bn / ks / eff;
+                const int nn = ceil_div(g.N, bn);
+                return get_plan(ceil_div(m_tiles, 2) * nn, nn, bn, last_tile_cols(g.N, bn, true), num_kb, slots, true).makespan / eff;
             };
             best = est_w(256, 1.0) <= est_w(128, 0.85) ? 256 : 128;
         }
@@ -1232,6 +1371,22 @@ int dispatch_bn(const MicoGemmArgs& g, const GemmEpi& epi, cudaStream_t stream) 
 
 }  // namespace
 }  // namespace mico
+
+extern "C" int mico_gemm_plan(int num_tiles, int num_n, int bn, int n_last, int num_kb, int slots, int allow_split, int* ks,
+                              int* rounds, double* makespan, int* table, int table_cap) {
+    using namespace mico;
+    MICO_CHECK_ARG(num_tiles > 0 && num_n > 0 && num_tiles % num_n == 0 && bn > 0 && n_last > 0 && n_last <= bn);
+    MICO_CHECK_ARG(num_kb > 0 && slots > 0);
+    GemmPlan& p = get_plan(num_tiles, num_n, bn, n_last, num_kb, slots, allow_split != 0);
+    if (ks) *ks = p.ks;
+    if (rounds) *rounds = p.rounds;
+    if (makespan) *makespan = p.makespan;
+    if (table) {
+        MICO_CHECK_ARG(table_cap >= (int)p.table.size());
+        for (size_t i = 0; i < p.table.size(); ++i) table[i] = p.table[i];
+    }
+    return MICO_OK;
+}
 
 extern "C" int mico_gemm_bf16(const MicoGemmArgs* args, void* stream_) {
     using namespace mico;

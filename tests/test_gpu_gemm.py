@@ -210,3 +210,35 @@ def test_wgrad_split_k(M, N, K):
     acc = torch.zeros((M, N), device="cuda")
     ops.gemm(dy, x, a_mn=True, b_mn=True, out=acc, accumulate=True)      # generic epilogue, never split
     assert rel_l2(out, acc) < 2e-5       # different fp32 partial-sum grouping over K
+
+
+@pytest.mark.parametrize("M,N,K,wgrad", [(37000, 1408, 192, False),     # 145 pair groups x (5 full + 1 half tile): 12 rounds of the balanced schedule
+                                         (37000, 1408, 192, "dgrad"),   # MN-major B
+                                         (4224, 1408, 8192, True),      # qkv weight gradient: split K, last M group half empty
+                                         (6144, 1408, 4096, True)])     # fc1 weight gradient
+def test_balanced_unit_schedule_exact(M, N, K, wgrad):
+    """The balanced work-unit schedule (gemm.cu:GemmPlan: each round's units dealt longest-first to the least-loaded CTA pairs,
+    split-K chosen by planned makespan) must cover every (tile, K part) exactly once: small-integer operands make every
+    partial sum exact in fp32, so the result equals the fp32 product bit for bit whatever the unit order."""
+    from mico_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    if wgrad is True:
+        dy = torch.randint(-4, 4, (K, M), generator=g).to(torch.bfloat16).cuda()
+        x = torch.randint(-4, 4, (K, N), generator=g).to(torch.bfloat16).cuda()
+        out = torch.full((M, N), 3.0, device="cuda")
+        ops.gemm(dy, x, a_mn=True, b_mn=True, out=out)
+        assert torch.equal(out, dy.float().t() @ x.float())
+        return
+    a = torch.randint(-8, 8, (M, K), generator=g).to(torch.bfloat16).cuda()
+    if wgrad == "dgrad":
+        w = torch.randint(-4, 4, (K, N), generator=g).to(torch.bfloat16).cuda()
+        ref = a.float() @ w.float()
+        out = ops.gemm(a, w, b_mn=True, out_dtype=torch.float32)
+    else:
+        w = torch.randint(-4, 4, (N, K), generator=g).to(torch.bfloat16).cuda()
+        ref = a.float() @ w.float().t()
+        out = ops.gemm(a, w, out_dtype=torch.float32)
+    assert torch.equal(out, ref)
+    res = torch.randint(-64, 64, (M, N), generator=g).float().cuda()
+    out2 = ops.gemm(a, w, b_mn=wgrad == "dgrad", residual=res, out_dtype=torch.float32)        # fp32 residual epilogue
+    assert torch.equal(out2, ref + res)
