@@ -86,8 +86,10 @@ struct DqSmem {
 };
 constexpr uint32_t kDqS = 0, kDqDP = 160, kDqDS = 320, kDqAcc = 400;
 
-// kPlain: no additive mask and no dropout (every ViT tower): the per-element mask / dropout code is compiled out
-template <int HD_PAD, bool kPlain>
+// kMode 1 (plain): no additive mask and no dropout (every ViT tower): the per-element mask / dropout code is compiled out.
+// kMode 2: dropout without a mask (fusion-encoder cross-attention): no mask code, full chunks take a branch-free path.
+// kMode 0: mask and dropout decided at run time.
+template <int HD_PAD, int kMode>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -252,10 +254,11 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const bool row_ok = qi < p.Sq;
             const float nlse2 = -lse_n * kLog2e;
             const float ndlt = -dlt_n * p.scale;     // dS = p * (dP*scale - delta*scale)
-            const float* mrow = (!kPlain && p.mask) ? (p.mask + (int64_t)(p.mask_bmod ? b % p.mask_bmod : b) * p.mask_bs + (int64_t)h * p.mask_hs) + (int64_t)(row_ok ? qi : 0) * p.mask_qs : nullptr;
-            const bool dropping = !kPlain && p.drop.p > 0.f;
+            const float* mrow = (kMode == 0 && p.mask) ? (p.mask + (int64_t)(p.mask_bmod ? b % p.mask_bmod : b) * p.mask_bs + (int64_t)h * p.mask_hs) + (int64_t)(row_ok ? qi : 0) * p.mask_qs : nullptr;
+            const bool dropping = kMode == 2 || (kMode == 0 && p.drop.p > 0.f);
             const uint32_t drop_key = dropping ? drop_row_key(p.drop, (uint64_t)(b * p.H + h) * p.Sq + (row_ok ? qi : 0)) : 0u;
             const uint32_t drop_thr = drop_thresh16(p.drop);
+            const float inv_keep = p.drop.inv_keep, scale = p.scale;
             for (int j = 0; j < nkv; ++j, ++tcount) {
                 const int valid = n_valid(kt, j);
                 const int nch = (valid + 31) >> 5;
@@ -275,6 +278,17 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
                             ds[i] = ex2_fast(fmaf(__uint_as_float(sv[i]), sc2, nlse2)) * fmaf(__uint_as_float(dv[i]), p.scale, ndlt);
+                    } else if (!mrow && lim >= 32) {       // dropout only, full chunk: no per-element predicates
+                        const uint32_t pair0 = (uint32_t)(j * kTile + c * 32) >> 1;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const uint32_t bits = drop_pair_bits(drop_key, pair0 + (i >> 1));
+                            // dP flows only through the kept probabilities
+                            const float m0 = (bits & 0xFFFFu) >= drop_thr ? inv_keep : 0.0f;
+                            const float m1 = (bits >> 16) >= drop_thr ? inv_keep : 0.0f;
+                            ds[i] = ex2_fast(fmaf(__uint_as_float(sv[i]), sc2, nlse2)) * fmaf(__uint_as_float(dv[i]) * m0, scale, ndlt);
+                            ds[i + 1] = ex2_fast(fmaf(__uint_as_float(sv[i + 1]), sc2, nlse2)) * fmaf(__uint_as_float(dv[i + 1]) * m1, scale, ndlt);
+                        }
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; i += 2) {
@@ -338,7 +352,7 @@ constexpr uint32_t kKvST = 0, kKvDPT = 144, kKvDV = 288, kKvDK = 384;
 
 __device__ __forceinline__ int split_a(int n16) { return ((n16 / 16 + 1) / 2) * 16; }   // columns owned by half 0
 
-template <int HD_PAD, bool kPlain>
+template <int HD_PAD, int kMode>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -482,8 +496,9 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         bool first_tile = true;
         // -lse*log2(e) and -delta*scale of query t (= threadIdx.x < 160) of q tile i of work item w; queries past the
         // tile's valid count get lse = +huge -> p = 0, dS = 0 with no per-element predicate
-        const bool dropping = !kPlain && p.drop.p > 0.f;
+        const bool dropping = kMode == 2 || (kMode == 0 && p.drop.p > 0.f);
         const uint32_t drop_thr = drop_thresh16(p.drop);
+        const float inv_keep = p.drop.inv_keep, scale = p.scale;
         auto load_stats = [&](int qb_, int h_, int i_, float& l, float& d, uint32_t& key) {
             l = 1e30f;       // raw values: the scaling is applied where they are stored, long after the loads were issued
             d = 0.f;
@@ -541,7 +556,11 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 mbar_wait(st_full, qcount & 1);
                 tc_fence_after();
                 const int c_begin = half == 0 ? 0 : hA, c_end = half == 0 ? hA : n16;
-                const bool masked = !kPlain && p.mask != nullptr;
+                const bool masked = kMode == 0 && p.mask != nullptr;
+                // dropout without a mask: this thread's key column enters the pair hash as a constant
+                const uint32_t kj_d = (uint32_t)min(kj, p.Sk - 1);
+                const uint32_t kjc = (kj_d >> 1) * 0x9E3779B1u;
+                const bool kodd = kj_d & 1u;
                 for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                     uint32_t sv[32], dv[32];
                     float pt[32], dst[32];
@@ -557,6 +576,25 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         for (int q = 0; q < 16; ++q) { sv[q] = a16[q]; dv[q] = b16[q]; sv[16 + q] = 0; dv[16 + q] = 0; }
                     }
                     tmem_ld_wait();
+                    if (!masked && dropping) {       // no per-element predicates; the row keys of four queries per shared load
+#pragma unroll
+                        for (int q4 = 0; q4 < 8; ++q4) {
+                            const uint4 lu = lds128(s_stats + (c0 + q4 * 4) * 4);
+                            const uint4 du = lds128(s_stats + (256 + c0 + q4 * 4) * 4);
+                            const uint4 ku = lds128(s_stats + (512 + c0 + q4 * 4) * 4);
+                            const uint32_t ls[4] = {lu.x, lu.y, lu.z, lu.w}, dl[4] = {du.x, du.y, du.z, du.w}, ks[4] = {ku.x, ku.y, ku.z, ku.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int q = q4 * 4 + e;
+                                uint32_t x = (ks[e] ^ kjc) * 0x85EBCA6Bu;
+                                x ^= x >> 15;
+                                const float m = (kodd ? x >> 16 : x & 0xFFFFu) >= drop_thr ? inv_keep : 0.0f;
+                                const float pu = ex2_fast(fmaf(__uint_as_float(sv[q]), sc2, __uint_as_float(ls[e])));
+                                pt[q] = pu * m;                                          // dV uses the dropped probabilities
+                                dst[q] = pu * fmaf(__uint_as_float(dv[q]) * m, scale, __uint_as_float(dl[e]));
+                            }
+                        }
+                    } else
 #pragma unroll
                     for (int q4 = 0; q4 < 8; ++q4) {
                         const uint4 lu = lds128(s_stats + (c0 + q4 * 4) * 4);                          // c0 + 32 <= 160
@@ -724,11 +762,13 @@ extern "C" int mico_attention_bwd(const MicoAttnArgs* a, void* stream_) {
         return rc_tail;
     };
     const bool plain = a->mask == nullptr && a->dropout_p == 0.0f;
+    const bool drop_only = a->mask == nullptr && a->dropout_p > 0.0f && drop_only_enabled();
     switch (hd_pad) {
         case 32: return plain ? launch(attn_dq_kernel<32, true>, attn_dkv_kernel<32, true>)
                               : launch(attn_dq_kernel<32, false>, attn_dkv_kernel<32, false>);
-        case 64: return plain ? launch(attn_dq_kernel<64, true>, attn_dkv_kernel<64, true>)
-                              : launch(attn_dq_kernel<64, false>, attn_dkv_kernel<64, false>);
+        case 64: return plain ? launch(attn_dq_kernel<64, 1>, attn_dkv_kernel<64, 1>)
+                     : drop_only ? launch(attn_dq_kernel<64, 2>, attn_dkv_kernel<64, 2>)
+                                 : launch(attn_dq_kernel<64, 0>, attn_dkv_kernel<64, 0>);
         case 96: return plain ? launch(attn_dq_kernel<96, true>, attn_dkv_kernel<96, true>)
                               : launch(attn_dq_kernel<96, false>, attn_dkv_kernel<96, false>);
         default:

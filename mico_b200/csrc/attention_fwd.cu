@@ -59,8 +59,10 @@ constexpr float kRescaleLog2 = 8.0f; // the running max is only raised when it g
 //   * with P and O out of registers / shared memory a CTA needs <= 104 KB of shared memory, 256 TMEM columns and ~100
 //     registers per thread: TWO CTAs run per SM.  While one CTA's softmax warps work, the other CTA's MMAs and TMA loads
 //     proceed, and the SM sub-partitions have two softmax warps each to issue from.
-// kPlain: no additive mask and no dropout (every ViT tower): that code is compiled out
-template <int HD_PAD, bool kPlain>
+// kMode 1 (plain): no additive mask and no dropout (every ViT tower): that code is compiled out.  kMode 2: dropout without a
+// mask (the fusion encoder's cross-attention over the visual tokens): the mask code is compiled out and full 32-key chunks
+// take a branch-free path.  kMode 0: everything decided at run time.
+template <int HD_PAD, int kMode>
 __global__ void __launch_bounds__(kAttThreads, HD_PAD <= 96 ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKx,
@@ -188,11 +190,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const int h = bh % p.H, b = bh / p.H;
             const int qi = qt * kTile + r;
             const bool row_ok = qi < p.Sq;
-            const float* mrow = (!kPlain && p.mask) ? (p.mask + (int64_t)(p.mask_bmod ? b % p.mask_bmod : b) * p.mask_bs + (int64_t)h * p.mask_hs) + (int64_t)(row_ok ? qi : 0) * p.mask_qs : nullptr;
+            const float* mrow = (kMode == 0 && p.mask) ? (p.mask + (int64_t)(p.mask_bmod ? b % p.mask_bmod : b) * p.mask_bs + (int64_t)h * p.mask_hs) + (int64_t)(row_ok ? qi : 0) * p.mask_qs : nullptr;
             float m = -INFINITY, l = 0.f;
-            const bool dropping = !kPlain && p.drop.p > 0.f;
+            const bool dropping = kMode == 2 || (kMode == 0 && p.drop.p > 0.f);
             const uint32_t drop_key = dropping ? drop_row_key(p.drop, (uint64_t)(b * p.H + h) * p.Sq + (row_ok ? qi : 0)) : 0u;
             const uint32_t drop_thr = drop_thresh16(p.drop);
+            const float inv_keep = p.drop.inv_keep;
 
             for (int j = 0; j < nkv; ++j, ++scount) {
                 const int valid = n_valid(kt, j);
@@ -269,6 +272,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         for (int i = 0; i < 32; ++i) {
                             pv[i] = ex2_fast(fmaf(__uint_as_float(v[i]), sc2, -m));
                             sum += pv[i];
+                        }
+                    } else if (!mrow && lim >= 32) {       // dropout only, full chunk: no per-element predicates
+                        const uint32_t pair0 = (uint32_t)(j * kTile + c * 32) >> 1;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const uint32_t bits = drop_pair_bits(drop_key, pair0 + (i >> 1));
+                            const float p0 = ex2_fast(fmaf(__uint_as_float(v[i]), sc2, -m));
+                            const float p1 = ex2_fast(fmaf(__uint_as_float(v[i + 1]), sc2, -m));
+                            sum += p0;                            // the softmax denominator is taken before dropout
+                            sum += p1;
+                            pv[i] = (bits & 0xFFFFu) >= drop_thr ? p0 * inv_keep : 0.0f;
+                            pv[i + 1] = (bits >> 16) >= drop_thr ? p1 * inv_keep : 0.0f;
                         }
                     } else {
 #pragma unroll
@@ -400,9 +415,11 @@ extern "C" int mico_attention_fwd(const MicoAttnArgs* a, void* stream_) {
         return MICO_OK;
     };
     const bool plain = a->mask == nullptr && a->dropout_p == 0.0f;
+    const bool drop_only = a->mask == nullptr && a->dropout_p > 0.0f && drop_only_enabled();
     switch (hd_pad) {
         case 32: return plain ? launch(attn_fwd_kernel<32, true>, AttnSmem<32>::TOTAL, 2) : launch(attn_fwd_kernel<32, false>, AttnSmem<32>::TOTAL, 2);
-        case 64: return plain ? launch(attn_fwd_kernel<64, true>, AttnSmem<64>::TOTAL, 2) : launch(attn_fwd_kernel<64, false>, AttnSmem<64>::TOTAL, 2);
+        case 64: return plain ? launch(attn_fwd_kernel<64, 1>, AttnSmem<64>::TOTAL, 2)
+                     : drop_only ? launch(attn_fwd_kernel<64, 2>, AttnSmem<64>::TOTAL, 2) : launch(attn_fwd_kernel<64, 0>, AttnSmem<64>::TOTAL, 2);
         case 96: return plain ? launch(attn_fwd_kernel<96, true>, AttnSmem<96>::TOTAL, 2) : launch(attn_fwd_kernel<96, false>, AttnSmem<96>::TOTAL, 2);
         case 128: return plain ? launch(attn_fwd_kernel<128, true>, AttnSmem<128>::TOTAL, 1) : launch(attn_fwd_kernel<128, false>, AttnSmem<128>::TOTAL, 1);
         default:

@@ -1,6 +1,7 @@
 // mico_b200 -- shared pieces of the attention forward/backward kernels.
 #pragma once
 #include "common.cuh"
+#include <stdlib.h>
 #include "host_utils.h"
 
 namespace mico {
@@ -132,6 +133,12 @@ __device__ __forceinline__ void tmem_store_bf16x32(uint32_t taddr, const float (
 #pragma unroll
     for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
     tmem_st_x16(taddr, w);
+}
+
+// MICO_ATTN_DROP_ONLY=0: calls with dropout and no mask go through the general (kMode 0) kernels (A/B switch for measurements)
+inline bool drop_only_enabled() {
+    static const bool on = [] { const char* e = getenv("MICO_ATTN_DROP_ONLY"); return !(e && e[0] == '0'); }();
+    return on;
 }
 
 }  // namespace mico

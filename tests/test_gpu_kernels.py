@@ -217,8 +217,9 @@ def test_colsum_two_ranges_single_pass():
         assert rel_l2(ops.colsum(y), y.float().sum(0)) < 1e-5
 
 
-@pytest.mark.parametrize("Sq,Sk,p_drop", [(128, 771, 0.0), (40, 257, 0.25), (130, 200, 0.1)])
-def test_attention_shared_kv_entries(Sq, Sk, p_drop):
+@pytest.mark.parametrize("Sq,Sk,p_drop,masked", [(128, 771, 0.0, True), (40, 257, 0.25, True), (130, 200, 0.1, True),
+                                                 (128, 771, 0.1, False), (72, 300, 0.25, False)])     # dropout-only kernels (kMode 2)
+def test_attention_shared_kv_entries(Sq, Sk, p_drop, masked):
     """kv_index: several query batch entries read ONE K/V entry (fusion encoder: ITM + caption sequences of a sample).
     Forward equals attention against the expanded K/V; dK / dV are the sums over the readers (fp32 reference with the same
     dropout mask)."""
@@ -232,9 +233,12 @@ def test_attention_shared_kv_entries(Sq, Sk, p_drop):
     mask = torch.zeros(B, Sk)
     mask[:, Sk - 5:] = -10000.0          # per-query-entry key padding
     mask[3, :7] = -10000.0
+    if not masked:       # the fusion encoder's cross-attention over visual tokens: no mask, dropout on
+        mask.zero_()
     drop = (p_drop, 99) if p_drop > 0 else None
-    o, lse = ops.attention_fwd(q, k, v, D ** -0.5, mask=mask.cuda(), dropout=drop, kv_index=idx.cuda())
-    dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, do, D ** -0.5, mask=mask.cuda(), dropout=drop, kv_index=idx.cuda())
+    mk = mask.cuda() if masked else None
+    o, lse = ops.attention_fwd(q, k, v, D ** -0.5, mask=mk, dropout=drop, kv_index=idx.cuda())
+    dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, do, D ** -0.5, mask=mk, dropout=drop, kv_index=idx.cuda())
     assert dk.shape == k.shape and dv.shape == v.shape
     qf = q.float().cpu().requires_grad_(True)
     kf, vf = (t.float().cpu().requires_grad_(True) for t in (k, v))
