@@ -91,6 +91,14 @@ typedef struct MicoGemmArgs {
      * eva_vit_model.py:613-619): out_row = (m / remap_gin) * remap_gout + m % remap_gin + remap_off.
      * residual_bcast != 0: the residual row is (m % remap_gin) + remap_off (pos_embed broadcast over batch). */
     int32_t remap_gin, remap_gout, remap_off, residual_bcast;
+    /* Weight gradients (a_mn_major = b_mn_major = 1, fp32 out, no bias / residual / accumulate): asum_out (fp32 [M]) also
+     * receives sum_k A(m,k) -- with A = dY^T the layer's BIAS gradient (the column sum of dY over tokens, what
+     * eva_vit_model.py:191,310's nn.Linear bias receives in autograd) -- from the same pass over dY: the last N tile issues 32
+     * more MMA columns against a tile of ones.  `ones`: bf16 [>= K rows][64] of 1.0, row pitch 64 elements.  Supported when
+     * the last 256-wide N tile has room (N % 256 in (96, 160], M >= 256: the ViT-g tower's N = 1408); otherwise the call
+     * returns MICO_ERR_UNSUPPORTED and the caller sums the columns of dY with mico_colsum_bf16. */
+    float* asum_out;
+    const void* ones;
 } MicoGemmArgs;
 
 int mico_gemm_bf16(const MicoGemmArgs* args, void* stream);

@@ -34,6 +34,7 @@ class GemmArgs(C.Structure):
         ("alpha", C.c_float),
         ("remap_gin", C.c_int32), ("remap_gout", C.c_int32), ("remap_off", C.c_int32),
         ("residual_bcast", C.c_int32),
+        ("asum_out", C.c_void_p), ("ones", C.c_void_p),
     ]
 
 

@@ -60,6 +60,8 @@ struct GemmEpi {
     int vec_ok;   // all pitches / bases allow 16-byte vector access
     int ksplit;   // > 1: the K loop of every output tile is split over `ksplit` work units whose fp32 partial tiles are
                   // ADDED into the (zeroed) output by TMA reduce (EPI_F32 only: weight gradients with few output tiles)
+    float* asum_out;    // weight gradients: asum_out[m] += sum_k A(m,k) (the layer's bias gradient) from 32 extra MMA columns of
+                        // the last N tile, whose B operand is a tile of ones (tmAux); null = off
     const int* sched;   // balanced unit schedule (plan_schedule below): slot s runs sched[s * sched_rounds + it], -1 ends its
     int sched_rounds;   // list; null = the strided default (slot s runs units s, s + slots, ...)
 };
@@ -840,7 +842,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
                         if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
                         const int n_left = N - n0;
-                        const int n_eff = n_left >= BN ? BN : ((n_left + 31) & ~31);
+                        // asum_out: the last (narrow) N tile carries 32 more MMA columns; the peer CTA's second 64-column box
+                        // (tile columns n_eff/2 + 64 ..., all past N) is loaded from the ones tensor instead of B
+                        const bool ones_tile = B_MN && epi.asum_out != nullptr && n_left < BN;
+                        const int n_eff = n_left >= BN ? BN : ((n_left + 31) & ~31) + (ones_tile ? 32 : 0);
                         const int nb = n0 + (int)cta_rank * (n_eff / 2);        // this CTA's half of the (possibly narrow) tile
                         if constexpr (!A_MN) {
                             tma_load_2d_pair(sa, &tmA, fb, kb * BK, m0);
@@ -852,7 +857,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             tma_load_2d_pair(sb, &tmB, fb, kb * BK, nb);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < Cfg::B_CHUNKS / 2; ++j) tma_load_2d_pair(sb + j * 8192, &tmB, fb, nb + 64 * j, kb * BK);
+                            for (int j = 0; j < Cfg::B_CHUNKS / 2; ++j) {
+                                if (ones_tile && cta_rank == 1 && j == 1) tma_load_2d_pair(sb + j * 8192, &tmAux, fb, 0, kb * BK);
+                                else tma_load_2d_pair(sb + j * 8192, &tmB, fb, nb + 64 * j, kb * BK);
+                            }
                         }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         continue;
@@ -906,7 +914,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 // the last N tile issues a narrower MMA: no tensor-pipe time is spent on the columns past N (the smem rows
                 // behind them are zero-filled by TMA), which lets N = 1408 run on 256-wide tiles as 5 full tiles + 1 half
                 const int n_left = N - unit_nt(tile) * BN;
-                const uint32_t idesc = P2 ? umma_idesc_bf16(n_left >= BN ? BN : ((n_left + 31) & ~31), A_MN, B_MN, 256)
+                const bool ones_tile = P2 && B_MN && epi.asum_out != nullptr && n_left < BN;
+                const uint32_t idesc = P2 ? umma_idesc_bf16(n_left >= BN ? BN : ((n_left + 31) & ~31) + (ones_tile ? 32 : 0), A_MN, B_MN, 256)
                                           : umma_idesc_bf16(n_left >= BN ? BN : ((n_left + 15) & ~15), A_MN, B_MN);
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -988,6 +997,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     fast_chunk32<EPI>(epi, &tmOut, &tmAux, st, sidx, pre, sbias + c * 32, v, row0, n0 + c * 32, M, rs);
                 }
                 if (!waited) { mbar_wait(&tfull_bar[acc], acc_phase); tc_fence_after(); }
+                if constexpr (EPI == EPI_F32 && P2 && B_MN) {
+                    // asum_out: the ones columns of the last N tile start at tile column n_eff/2 + 64 (see the producer);
+                    // every row adds its sum over this unit's K range
+                    if (epi.asum_out != nullptr && N - n0 < BN && half == 0) {
+                        const int n_eff = ((N - n0 + 31) & ~31) + 32;
+                        uint32_t v[16];
+                        tmem_ld_x16(t0 + n_eff / 2 + 64, v);
+                        tmem_ld_wait();
+                        if (row < M) atomicAdd(epi.asum_out + row, __uint_as_float(v[0]));
+                    }
+                }
                 if constexpr (BN % 32 != 0) {
                     constexpr int c0 = (BN / 32) * 32;
                     if (half == ((BN / 32) & 1) && n0 + c0 < N) {
@@ -1219,6 +1239,20 @@ int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi_in, cudaStream_t strea
         if (epi_in.aux_out)
         if ((rc = make_tmap_tile64(&tmAux, epi_in.aux_out, false, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)epi_in.ld_aux_out * 2))) return rc;
     }
+    int asum_cols = 0;      // extra MMA columns of the last N tile (asum_out)
+    if (epi_in.asum_out) {
+        if constexpr (EPI == EPI_F32 && CL == 3 && A_MN && B_MN && BN == 256) {
+            const uint64_t dims[2] = {64, (uint64_t)g.K};
+            const uint64_t strides[2] = {2, 128};
+            const uint32_t box[2] = {64, BK};
+            if ((rc = make_tmap_bf16(&tmAux, g.ones, 2, dims, strides, box))) return rc;
+            MICO_CHECK_CUDA(cudaMemsetAsync(epi_in.asum_out, 0, (size_t)g.M * sizeof(float), stream));
+            asum_cols = 32;
+        } else {
+            set_last_error(__FILE__, __LINE__, "asum_out: unsupported kernel variant");
+            return MICO_ERR_UNSUPPORTED;
+        }
+    }
 
     auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES, CL, EPI>;
     static bool attr_set = false;   // benign race: idempotent
@@ -1236,7 +1270,7 @@ int launch_gemm(const MicoGemmArgs& g, const GemmEpi& epi_in, cudaStream_t strea
     {
         // Split-K for weight gradients (EPI_F32) with fewer output tiles than SM (pair) slots, and the balanced unit schedule
         // (GemmPlan above).
-        GemmPlan& plan = get_plan(units, num_n, BN, last_tile_cols(g.N, BN, CL == 3), ceil_div(g.K, BK), max_clusters,
+        GemmPlan& plan = get_plan(units, num_n, BN, last_tile_cols(g.N, BN, CL == 3) + asum_cols, ceil_div(g.K, BK), max_clusters,
                                   EPI == EPI_F32);
         if (plan.ks > 1) {
             MICO_CHECK_CUDA(cudaMemset2DAsync(epi.out, (size_t)epi.ldo * 4, 0, (size_t)g.N * 4, (size_t)g.M, stream));
@@ -1426,6 +1460,9 @@ extern "C" int mico_gemm_bf16(const MicoGemmArgs* args, void* stream_) {
     e.remap_gin = g.remap_gin; e.remap_gout = g.remap_gout; e.remap_off = g.remap_off;
     e.residual_bcast = g.residual_bcast;
     e.ksplit = 1;
+    e.asum_out = g.asum_out;
+    e.sched = nullptr;
+    e.sched_rounds = 0;
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const int oel = g.out_fp32 ? 4 : 8;   // elements per 16 bytes
     bool vec = al16(g.out) && (g.ldo % oel == 0);
@@ -1435,6 +1472,21 @@ extern "C" int mico_gemm_bf16(const MicoGemmArgs* args, void* stream_) {
     if (g.aux_in) vec = vec && al16(g.aux_in) && (g.ld_aux_in % 8 == 0);
     e.vec_ok = vec ? 1 : 0;
     ProfScope prof(kProfGemm, 2.0 * g.M * (double)g.N * g.K, stream);
+
+    if (g.asum_out) {
+        // bias gradient from the weight-gradient pass: only the cta_group::2 256-wide wgrad kernel carries the ones columns
+        MICO_CHECK_ARG(g.ones != nullptr && (reinterpret_cast<uintptr_t>(g.ones) & 127) == 0);
+        MICO_CHECK_ARG(g.a_mn_major && g.b_mn_major && g.out_fp32 && !g.bias && !g.residual && !g.row_scale && !g.accumulate);
+        MICO_CHECK_ARG(g.act == MICO_ACT_NONE && g.alpha == 1.0f && g.remap_gin == 0 && !g.aux_out);
+        const int n_last = g.N % 256;
+        const bool ok = e.vec_ok && g.M >= 256 && n_last > 96 && n_last <= 160 && n_last % 32 == 0 && g.N % 128 == 0 &&
+                        g_pair_mma && g_pair_mma_wgrad && !g_force_single_cta && !g_force_generic;
+        if (!ok) {
+            set_last_error(__FILE__, __LINE__, "asum_out: shape / configuration not supported by the fused bias-gradient columns");
+            return MICO_ERR_UNSUPPORTED;
+        }
+        return launch_gemm<256, true, true, 6, 3, EPI_F32>(g, e, stream);
+    }
 
     if (!g.a_mn_major && !g.b_mn_major) return dispatch_bn<false, false>(g, e, stream);
     if (!g.a_mn_major && g.b_mn_major) return dispatch_bn<false, true>(g, e, stream);

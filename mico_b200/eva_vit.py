@@ -555,8 +555,11 @@ class EVAVisionTransformer(nn.Module):
                 ops.colsum(dxb, out=pgrad(base + _F2B))
             dpre = ops.gemm(dxb, c.get(params[base + _F2W], ("fc2", i)), b_mn=True, act=self._act_bwd, aux_in=pre)
             del a, pre
-            ops.gemm(dpre, h2, a_mn=True, b_mn=True, out=pgrad(base + _F1W))         # dW1
-            ops.colsum(dpre, out=pgrad(base + _F1B))
+            if ops.gemm_fuses_asum(dpre.shape[1], D):      # dW1 and db1 = column sums of dpre from one pass over dpre
+                ops.gemm(dpre, h2, a_mn=True, b_mn=True, out=pgrad(base + _F1W), asum_out=pgrad(base + _F1B))
+            else:
+                ops.gemm(dpre, h2, a_mn=True, b_mn=True, out=pgrad(base + _F1W))         # dW1
+                ops.colsum(dpre, out=pgrad(base + _F1B))
             dh2 = ops.gemm(dpre, c.get(params[base + _F1W], ("fc1", i)), b_mn=True)
             del dpre, h2
             dx1, dx1b = ops.layernorm_bwd(dh2, x1, mean2, rstd2, p[_N2W], pgrad(base + _N2W), pgrad(base + _N2B),
@@ -574,11 +577,20 @@ class EVAVisionTransformer(nn.Module):
             ops.attention_bwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], o, lse, do.view(B, T, H, d), scale,
                               dq=g5[:, :, 0], dk=g5[:, :, 1], dv=g5[:, :, 2])
             del do, o, lse, qkv
-            ops.gemm(dqkv, h, a_mn=True, b_mn=True, out=pgrad(base + _QKVW))
-            if self._full_qkv_bias:
-                ops.colsum(dqkv, out=pgrad(base + _QB))
+            if ops.gemm_fuses_asum(3 * D, D):              # dWqkv and the q / v bias gradients from one pass over dqkv
+                if self._full_qkv_bias:
+                    ops.gemm(dqkv, h, a_mn=True, b_mn=True, out=pgrad(base + _QKVW), asum_out=pgrad(base + _QB))
+                else:
+                    bsum = torch.empty(3 * D, device=dev, dtype=F32)
+                    ops.gemm(dqkv, h, a_mn=True, b_mn=True, out=pgrad(base + _QKVW), asum_out=bsum)
+                    pgrad(base + _QB).copy_(bsum[:D])
+                    pgrad(base + _VB).copy_(bsum[2 * D:])                          # k has no bias (eva_vit_model.py:307)
             else:
-                ops.colsum2(dqkv, D, D, D, pgrad(base + _QB), pgrad(base + _VB))   # k has no bias (eva_vit_model.py:307)
+                ops.gemm(dqkv, h, a_mn=True, b_mn=True, out=pgrad(base + _QKVW))
+                if self._full_qkv_bias:
+                    ops.colsum(dqkv, out=pgrad(base + _QB))
+                else:
+                    ops.colsum2(dqkv, D, D, D, pgrad(base + _QB), pgrad(base + _VB))   # k has no bias (eva_vit_model.py:307)
             dh = ops.gemm(dqkv, c.get(params[base + _QKVW], ("qkv", i)), b_mn=True)
             del dqkv, h
             dx, dxb = ops.layernorm_bwd(dh, xr, mean1, rstd1, p[_N1W], pgrad(base + _N1W), pgrad(base + _N1B),

@@ -39,11 +39,12 @@ def _req(t, dtype, name):
 
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, residual=None,
          row_scale=None, rows_per_group=0, act=ACT_NONE, aux_out=None, aux_in=None,
-         accumulate=False, alpha=1.0, remap=None, residual_bcast=False, out_rows=None):
+         accumulate=False, alpha=1.0, remap=None, residual_bcast=False, out_rows=None, asum_out=None):
     """out[M,N] = epilogue(alpha * A . B^T); see MicoGemmArgs in include/mico_b200.h.
 
     a: bf16 2-D. K-major [M,K] (a_mn=False) or MN-major [K,M] (a_mn=True).
     b: bf16 2-D. K-major [N,K] (b_mn=False) or MN-major [K,N] (b_mn=True).
+    asum_out (fp32 [M], weight gradients only, see gemm_fuses_asum): also receives sum_k A(m,k) = the bias gradient.
     """
     _req(a, BF16, "a")
     _req(b, BF16, "b")
@@ -90,8 +91,33 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, r
     if remap is not None:
         g.remap_gin, g.remap_gout, g.remap_off = remap
         g.residual_bcast = int(residual_bcast)
+    if asum_out is not None:
+        _req(asum_out, F32, "asum_out")
+        if asum_out.numel() != M or not asum_out.is_contiguous():
+            raise MicoError("gemm: asum_out must be a contiguous fp32 [M] tensor")
+        g.asum_out, g.ones = asum_out.data_ptr(), _ones_rows(K, a.device).data_ptr()
     check(lib.mico_gemm_bf16(C.byref(g), _stream()), "mico_gemm_bf16")
     return out
+
+
+_ONES = {}
+
+
+def _ones_rows(K, device):
+    """bf16 [>= K][64] of ones: the B tile behind the bias-gradient columns of a weight-gradient GEMM (MicoGemmArgs::ones)"""
+    t = _ONES.get(device)
+    if t is None or t.shape[0] < K:
+        t = torch.ones((max(K, 4096), 64), device=device, dtype=BF16)
+        _ONES[device] = t
+    return t
+
+
+def gemm_fuses_asum(M, N):
+    """True when the weight gradient dW[M, N] = dY^T X can also return the bias gradient (asum_out) from the same pass: the
+    last 256-wide N tile has room for the 32 ones columns (gemm.cu).  MICO_GEMM_ASUM=0 switches the fusion off (A/B)."""
+    if os.environ.get("MICO_GEMM_ASUM", "1") == "0":
+        return False
+    return M >= 256 and N % 128 == 0 and 96 < N % 256 <= 160 and (N % 256) % 32 == 0
 
 
 # ----------------------------------------------------------------------------- attention

@@ -242,3 +242,25 @@ def test_balanced_unit_schedule_exact(M, N, K, wgrad):
     res = torch.randint(-64, 64, (M, N), generator=g).float().cuda()
     out2 = ops.gemm(a, w, b_mn=wgrad == "dgrad", residual=res, out_dtype=torch.float32)        # fp32 residual epilogue
     assert torch.equal(out2, ref + res)
+
+
+@pytest.mark.parametrize("M,N,K", [(6144, 1408, 4096), (4224, 1408, 8192 + 72), (1408, 1408, 1000), (512, 384, 333)])
+def test_wgrad_returns_bias_gradient(M, N, K):
+    """asum_out: the weight-gradient GEMM dW = dY^T X also returns the bias gradient sum_t dY[t, :] from 32 extra MMA columns
+    of its last N tile (B operand = a tile of ones), so the tower backward no longer re-reads dY for a column sum.  Small
+    integers: both results are exact in fp32 whatever the split-K order."""
+    from mico_b200 import ops
+    assert ops.gemm_fuses_asum(M, N)
+    g = torch.Generator().manual_seed(M + K)
+    dy = torch.randint(-4, 4, (K, M), generator=g).to(torch.bfloat16).cuda()
+    x = torch.randint(-4, 4, (K, N), generator=g).to(torch.bfloat16).cuda()
+    out = torch.full((M, N), 3.0, device="cuda")
+    bsum = torch.full((M,), 5.0, device="cuda")
+    ops.gemm(dy, x, a_mn=True, b_mn=True, out=out, asum_out=bsum)
+    assert torch.equal(out, dy.float().t() @ x.float())
+    assert torch.equal(bsum, dy.float().sum(0))
+    # real-valued operands against the separate column-sum kernel
+    dy = (torch.randn(K, M, generator=g) * 0.3).to(torch.bfloat16).cuda()
+    ops.gemm(dy, x, a_mn=True, b_mn=True, out=out, asum_out=bsum)
+    assert rel_l2(bsum, ops.colsum(dy)) < 1e-5
+    assert not ops.gemm_fuses_asum(768, 768) and not ops.gemm_fuses_asum(128, 1408)
