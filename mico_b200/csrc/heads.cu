@@ -290,6 +290,33 @@ __global__ void dropout_kernel(const TIn* __restrict__ x, const float* __restric
     if (out_bf16) out_bf16[i] = __float2bfloat16(v);
 }
 
+// four elements per thread, 128-bit (bf16: 64-bit) accesses: the scalar kernel above moved 2.4 TB/s in the omni step
+// (54 GB of hidden-dropout traffic in 22 ms); same mask (one splitmix64 per element counter)
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+dropout_vec4_kernel(const TIn* __restrict__ x, const float* __restrict__ res, float* __restrict__ out_f32,
+                    __nv_bfloat16* __restrict__ out_bf16, int64_t n4, DropCfg d, uint64_t site_offset) {
+    const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 >= n4) return;
+    const int64_t i = i4 * 4;
+    float v[4];
+    if constexpr (sizeof(TIn) == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(x) + i4);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+        const uint2 t = __ldg(reinterpret_cast<const uint2*>(x) + i4);
+        v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xFFFF0000u);
+        v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xFFFF0000u);
+    }
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (res) r = __ldg(reinterpret_cast<const float4*>(res) + i4);
+    const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = v[e] * drop_mult(d, site_offset + (uint64_t)(i + e)) + rr[e];
+    if (out_f32) reinterpret_cast<float4*>(out_f32)[i4] = make_float4(v[0], v[1], v[2], v[3]);
+    if (out_bf16) reinterpret_cast<uint2*>(out_bf16)[i4] = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+}
+
 // out[0] (+)= alpha * sum_i a[i] * b[i]   (single block, deterministic)
 __global__ void __launch_bounds__(256)
 dot_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, float alpha, float* __restrict__ out,
@@ -470,6 +497,20 @@ extern "C" int mico_dropout(const void* x, int x_is_bf16, const float* res, floa
     ProfScope prof(kProfOther, (double)n * ((x_is_bf16 ? 2 : 4) + (res ? 4 : 0) + (out_f32 ? 4 : 0) + (out_bf16 ? 2 : 0)), stream);
     DropCfg d;
     d.p = p; d.inv_keep = 1.0f / (1.0f - p); d.seed = seed;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (n % 4 == 0 && al16(x) && al16(res) && al16(out_f32) && al16(out_bf16)) {
+        const int64_t n4 = n / 4;
+        const int grid4 = (int)((n4 + 255) / 256);
+        if (x_is_bf16)
+            dropout_vec4_kernel<__nv_bfloat16><<<grid4, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), res, out_f32,
+                                                                         reinterpret_cast<__nv_bfloat16*>(out_bf16), n4, d, site_offset);
+        else
+            dropout_vec4_kernel<float><<<grid4, 256, 0, stream>>>(reinterpret_cast<const float*>(x), res, out_f32,
+                                                                 reinterpret_cast<__nv_bfloat16*>(out_bf16), n4, d, site_offset);
+        MICO_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+        return MICO_OK;
+    }
     const int grid = (int)((n + 255) / 256);
     if (x_is_bf16)
         dropout_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), res, out_f32,
