@@ -669,7 +669,8 @@ def run_product_omni(args):
         traffic, traffic_src = tj["avg_dram_bytes_per_launch"], tj["source"]
         traffic_note = ("average over the four representative TOWER launches of the capture (" + tj.get("note", "") + "); their "
                         "algorithmic operand + output bytes average 4.62 GB (5.43 / 5.43 / 2.98 / 4.65): the two GEMMs with a K = 6144 "
-                        "or 197 376-row contraction re-read their streamed operand 2.4x from DRAM (DESIGN.md 4a); `achieved` "
+                        "or 197 376-row contraction still re-read part of their streamed operand (fc2 fwd 5.1 GB read for 3.5, fc2 wgrad 5.6 for 3.0; "
+                        "8.4 / 7.4 GB before the balanced unit schedule, DESIGN.md 4a); `achieved` "
                         "averages all of the family's launches, including the small text-encoder GEMMs")
     is_tf = lambda k: "attention" in k or k == "gemm"
     roofline = dict(bound="tensor", kernel="gemm_bf16_kernel (tcgen05 GEMM: every linear layer fwd / dgrad / wgrad of the tower and "

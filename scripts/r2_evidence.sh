@@ -5,6 +5,7 @@
 # kept: gpurun_out/ is capped at 64 MiB.
 T=${1:-r2i}
 O=gpurun_out
+python __graft_entry__.py --smoke > $O/${T}_smoke.txt 2>&1; tail -2 $O/${T}_smoke.txt
 timeout 900 python bench.py --steps 5 --warmup 3 --gpu-eager > $O/${T}_bench_omni.json 2> $O/${T}_bench_omni.err
 # launch list: two plain steps, the second one captured (cudaProfilerStart / Stop around it)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file /tmp/${T}_launches.csv \
