@@ -6,7 +6,7 @@ set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 CS=/usr/local/cuda/bin/compute-sanitizer
-summary=gpurun_out/r2_sanitizer_summary.txt
+summary=gpurun_out/${SANITIZE_SUMMARY:-r2_sanitizer_summary.txt}
 : > "$summary"
 run() {   # tool, family
   local out=gpurun_out/r2_sanitizer_$1_$2.txt
@@ -16,6 +16,6 @@ run() {   # tool, family
 }
 FAMS=${SANITIZE_FAMILIES:-"gemm attention rowwise heads"}      # e.g. SANITIZE_FAMILIES="attention heads" for a partial re-run
 for fam in $FAMS; do run memcheck "$fam"; done
-for fam in $FAMS; do case $fam in gemm|attention|rowwise) run racecheck "$fam";; esac; done
-for fam in $FAMS; do case $fam in gemm|attention) run synccheck "$fam";; esac; done
+for fam in $FAMS; do case $fam in gemm|gemm_r2n|attention|rowwise) run racecheck "$fam";; esac; done
+for fam in $FAMS; do case $fam in gemm|gemm_r2n|attention) run synccheck "$fam";; esac; done
 cat "$summary"

@@ -29,6 +29,28 @@ def gemms():
     torch.cuda.synchronize()
 
 
+def gemms_r2n():
+    """End of round 2: the balanced unit schedule over several rounds (84 units on 74 CTA pairs, narrow last N tile), split-K
+    weight gradients dealt by the plan, the bias gradient from the weight-gradient GEMM's ones columns (asum_out), and the
+    dropout-only attention kernels (head_dim 64, no mask)."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    r = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    a, b = r(3400, 64).to(BF16), r(1408, 64).to(BF16)
+    ops.gemm(a, b, bias=r(1408))                                                # 14 pair groups x 6 N tiles: two rounds
+    ops.gemm(a, b, out_dtype=F32, bias=r(1408), residual=r(3400, 1408))
+    ops.gemm(a, r(64, 1408).to(BF16), b_mn=True)
+    for (M, N, K) in [(512, 384, 333), (1408, 1408, 2048), (4224, 1408, 1100)]:
+        dy, x = r(K, M).to(BF16), r(K, N).to(BF16)
+        out, bsum = torch.empty(M, N, device="cuda"), torch.empty(M, device="cuda")
+        ops.gemm(dy, x, a_mn=True, b_mn=True, out=out)                           # planned split-K
+        ops.gemm(dy, x, a_mn=True, b_mn=True, out=out, asum_out=bsum)            # + bias gradient
+    q, do = r(3, 128, 2, 64).to(BF16), r(3, 128, 2, 64).to(BF16)
+    k, v = r(3, 300, 2, 64).to(BF16), r(3, 300, 2, 64).to(BF16)
+    o, lse = ops.attention_fwd(q, k, v, 0.125, dropout=(0.1, 4))
+    ops.attention_bwd(q, k, v, o, lse, do, 0.125, dropout=(0.1, 4))
+    torch.cuda.synchronize()
+
+
 def attention():
     g = torch.Generator(device="cuda").manual_seed(1)
     r = lambda *s: torch.randn(*s, device="cuda", generator=g).to(BF16)
@@ -125,5 +147,5 @@ def heads_and_io():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "attention", "rowwise", "heads"]
     for w in which:
-        dict(gemm=gemms, attention=attention, rowwise=rowwise, heads=heads_and_io)[w]()
+        dict(gemm=gemms, gemm_r2n=gemms_r2n, attention=attention, rowwise=rowwise, heads=heads_and_io)[w]()
         print(f"[sanitize_sweep] {w}: done", flush=True)
