@@ -107,7 +107,7 @@ def _ones_rows(K, device):
     """bf16 [>= K][64] of ones: the B tile behind the bias-gradient columns of a weight-gradient GEMM (MicoGemmArgs::ones)"""
     t = _ONES.get(device)
     if t is None or t.shape[0] < K:
-        t = torch.ones((max(K, 4096), 64), device=device, dtype=BF16)
+        t = torch.ones((max(K, 1 << 18), 64), device=device, dtype=BF16)     # 32 MB: never regrown at the MiCo shapes
         _ONES[device] = t
     return t
 
