@@ -182,6 +182,19 @@ int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, const void*
                        const float* row_scale, int rows_per_group, float* dgamma, float* dbeta,
                        int accumulate_param_grads, float* dxb_colsum, int M, int D, void* workspace, size_t ws_bytes,
                        void* stream);
+/* Same, for a LayerNorm whose input was dropout(dense(x)) + residual (post-LN BERT, bert.py:293-296, 370-373): the bf16 copy
+ * of dx (and dxb_colsum) is additionally multiplied by the hidden-dropout mask of the forward pass -- element (row, col) by
+ * the multiplier mico_dropout gives flat index drop_site + row * D + col under (drop_p, drop_seed) -- i.e. it is the gradient
+ * w.r.t. the dense layer's output and dxb_colsum its bias gradient; the fp32 dx (residual gradient) stays unmasked.  One pass
+ * instead of LayerNorm backward + mico_dropout + mico_colsum_bf16.  fp32 dy, 512 <= D <= 1536, aligned rows, dx_bf16 required;
+ * otherwise MICO_ERR_UNSUPPORTED. */
+int mico_layernorm_bwd_dropout(const void* dy, int dy_is_bf16, int64_t lddy, const void* dy2_bf16, int64_t lddy2,
+                               const float* x, int64_t ldx,
+                               const float* mean, const float* rstd, const float* gamma, const float* dres,
+                               int64_t lddres, float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb,
+                               const float* row_scale, int rows_per_group, float* dgamma, float* dbeta,
+                               int accumulate_param_grads, float* dxb_colsum, int M, int D, void* workspace, size_t ws_bytes,
+                               float drop_p, uint64_t drop_seed, uint64_t drop_site, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * HBM-bound helpers on the path (all vectorised 128-bit, grid sized in multiples of the SM count).

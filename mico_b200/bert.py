@@ -408,6 +408,18 @@ class BertModel(nn.Module):
             """gradient entering a dense layer whose output was dropped out: the same mask again"""
             return ops.dropout(gb, ph, seed, self._site(li, k), out_f32=False, out_bf16=True)[1] if ph > 0 else gb
 
+        def ln_bwd_dense(g32_, g16_, y, st, i_w, i_b, i_bias, li, k):
+            """Backward of LN(dropout(dense(x)) + residual): (fp32 residual gradient, bf16 gradient of the dense output) and
+            the dense layer's bias gradient -> pg(i_bias).  One launch when the LayerNorm kernel can carry the dropout mask and
+            the column sums; else LayerNorm backward, then the mask, then the column sums."""
+            if ops.layernorm_bwd_fuses_dropout(Dh, g32_):
+                return ops.layernorm_bwd(g32_, y, *st, det(i_w), pg(i_w), pg(i_b), want_bf16=True, dy2=g16_,
+                                         colsum_out=pg(i_bias), dropout=(ph, seed, self._site(li, k)) if ph > 0 else None)
+            d32, d16 = ops.layernorm_bwd(g32_, y, *st, det(i_w), pg(i_w), pg(i_b), want_bf16=True, dy2=g16_)
+            d16 = dmask(d16, li, k)
+            ops.colsum(d16, out=pg(i_bias))
+            return d32, d16
+
         def adrop(li, cross):
             return (pa, seed + 2 * li + (2 if cross else 1)) if pa > 0 else None
         for li in range(c.num_hidden_layers - 1, -1, -1):
@@ -416,11 +428,8 @@ class BertModel(nn.Module):
             P = lambda k: params[base + k]
             hb_in = rec["h2b"] if has_enc else rec["h1b"]
             # ---- FFN: h3 = LN(a Wo^T + bo + h_in)
-            dy3, dy3b = ops.layernorm_bwd(g32, rec["y3"], *rec["st3"], det(base + 24), pg(base + 24), pg(base + 25),
-                                          want_bf16=True, dy2=g16)
-            dy3b = dmask(dy3b, li, 3)
+            dy3, dy3b = ln_bwd_dense(g32, g16, rec["y3"], rec["st3"], base + 24, base + 25, base + 23, li, 3)
             ops.gemm(dy3b, rec["a"], a_mn=True, b_mn=True, out=pg(base + 22))
-            ops.colsum(dy3b, out=pg(base + 23))
             dpre = ops.gemm(dy3b, cache.cat_w(("o", li), [P(22)]), b_mn=True, act=ACT_MUL_AUX, aux_in=rec["pre"])
             ops.gemm(dpre, hb_in, a_mn=True, b_mn=True, out=pg(base + 20))
             ops.colsum(dpre, out=pg(base + 21))
@@ -428,11 +437,8 @@ class BertModel(nn.Module):
             g32 = dy3
             # ---- cross attention: h2 = LN(ctx2 Wo^T + bo + h1)
             if has_enc:
-                dy2_, dy2b = ops.layernorm_bwd(g32, rec["y2"], *rec["st2"], det(base + 18), pg(base + 18), pg(base + 19),
-                                               want_bf16=True, dy2=g16)
-                dy2b = dmask(dy2b, li, 2)
+                dy2_, dy2b = ln_bwd_dense(g32, g16, rec["y2"], rec["st2"], base + 18, base + 19, base + 17, li, 2)
                 ops.gemm(dy2b, rec["ctx2"].view(M, Dh), a_mn=True, b_mn=True, out=pg(base + 16))
-                ops.colsum(dy2b, out=pg(base + 17))
                 dctx = ops.gemm(dy2b, cache.cat_w(("co", li), [P(16)]), b_mn=True)
                 kv5 = rec["kv"].view(E, Sk, 2, H, d)
                 dqc = torch.empty_like(rec["qc"])
@@ -453,11 +459,8 @@ class BertModel(nn.Module):
                 ops.gemm(dkv, cache.cat_w(("ckv", li), [P(12), P(14)]), b_mn=True, out=denc, accumulate=True)
                 g32 = dy2_
             # ---- self attention: h1 = LN(ctx Wo^T + bo + h)
-            dy1, dy1b = ops.layernorm_bwd(g32, rec["y1"], *rec["st1"], det(base + 8), pg(base + 8), pg(base + 9),
-                                          want_bf16=True, dy2=g16)
-            dy1b = dmask(dy1b, li, 1)
+            dy1, dy1b = ln_bwd_dense(g32, g16, rec["y1"], rec["st1"], base + 8, base + 9, base + 7, li, 1)
             ops.gemm(dy1b, rec["ctx"].view(M, Dh), a_mn=True, b_mn=True, out=pg(base + 6))
-            ops.colsum(dy1b, out=pg(base + 7))
             dctx = ops.gemm(dy1b, cache.cat_w(("so", li), [P(6)]), b_mn=True)
             q5 = rec["qkv"].view(b, S, 3, H, d)
             dqkv = torch.empty_like(rec["qkv"])

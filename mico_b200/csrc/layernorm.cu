@@ -293,14 +293,18 @@ ln_bwd_kernel(const TDy* __restrict__ dy, int64_t lddy, const __nv_bfloat16* __r
 // upstream linear layer: nn.Linear bias backward fused here instead of re-reading the tensor) stay in registers and go
 // straight to the per-block partials -- no cross-warp reduction.
 constexpr int kV2 = 3;
-template <typename TDy, bool kColsum>
+// kDrop: the bf16 copy (and its column sums) is the gradient w.r.t. the INPUT of a hidden-state dropout that sat between the
+// upstream dense layer and this LayerNorm's residual add (post-LN BERT, bert.py:293-296): element (row, col) is multiplied by
+// the same counter-based mask the forward pass used (drop_mult(seed, site_offset + row * D + col)); the fp32 dx (the residual
+// gradient) is not masked.  Replaces a separate pass over the bf16 gradient plus a column-sum pass.
+template <typename TDy, bool kColsum, bool kDrop = false>
 __global__ void __launch_bounds__(kLnThreads, 5)
 ln_bwd_row_kernel(const TDy* __restrict__ dy, int64_t lddy, const __nv_bfloat16* __restrict__ dy2, int64_t lddy2,
                   const float* __restrict__ x, int64_t ldx, const float* __restrict__ mean,
                   const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
                   int64_t lddres, float* __restrict__ dx, int64_t lddx, __nv_bfloat16* __restrict__ dx_bf16,
                   int64_t lddxb, const float* __restrict__ row_scale, int rows_per_group, float* __restrict__ partials,
-                  int M, int D) {
+                  int M, int D, DropCfg drop = DropCfg{}, uint64_t drop_site = 0) {
     __shared__ float red[2][kLnWarps][2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nvec = D >> 2;
@@ -368,7 +372,12 @@ ln_bwd_row_kernel(const TDy* __restrict__ dy, int64_t lddy, const __nv_bfloat16*
                 o.z = rs * (d[j].z - m1 - xh[j].z * m2) + r[j].z;
                 o.w = rs * (d[j].w - m1 - xh[j].w * m2) + r[j].w;
                 if (dx) st4(dx + (int64_t)row * lddx + 4 * i, o);
-                const float4 os = make_float4(o.x * sc, o.y * sc, o.z * sc, o.w * sc);
+                float4 os = make_float4(o.x * sc, o.y * sc, o.z * sc, o.w * sc);
+                if constexpr (kDrop) {
+                    const uint64_t ctr = drop_site + (uint64_t)row * (uint64_t)D + (uint64_t)(4 * i);
+                    os.x *= drop_mult(drop, ctr); os.y *= drop_mult(drop, ctr + 1);
+                    os.z *= drop_mult(drop, ctr + 2); os.w *= drop_mult(drop, ctr + 3);
+                }
                 if (dx_bf16) st4(dx_bf16 + (int64_t)row * lddxb + 4 * i, os);
                 if constexpr (kColsum) { ac[j].x += os.x; ac[j].y += os.y; ac[j].z += os.z; ac[j].w += os.w; }
             }
@@ -573,16 +582,25 @@ extern "C" size_t mico_layernorm_bwd_workspace(int M, int D) {
     return (size_t)ln_bwd_grid(M) * 2 * (size_t)D * sizeof(float);
 }
 
-extern "C" int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, const void* dy2_bf16, int64_t lddy2,
-                                  const float* x, int64_t ldx,
-                                  const float* mean, const float* rstd, const float* gamma, const float* dres,
-                                  int64_t lddres, float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb,
-                                  const float* row_scale, int rows_per_group, float* dgamma, float* dbeta,
-                                  int accumulate_param_grads, float* dxb_colsum, int M, int D, void* workspace,
-                                  size_t ws_bytes, void* stream_) {
+static int layernorm_bwd_impl(const void* dy, int dy_is_bf16, int64_t lddy, const void* dy2_bf16, int64_t lddy2,
+                              const float* x, int64_t ldx,
+                              const float* mean, const float* rstd, const float* gamma, const float* dres,
+                              int64_t lddres, float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb,
+                              const float* row_scale, int rows_per_group, float* dgamma, float* dbeta,
+                              int accumulate_param_grads, float* dxb_colsum, int M, int D, void* workspace,
+                              size_t ws_bytes, void* stream_, float drop_p, uint64_t drop_seed, uint64_t drop_site) {
     using namespace mico;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     MICO_CHECK_ARG(dy && x && mean && rstd && gamma && dgamma && dbeta && workspace);
+    MICO_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f);
+    const bool dropping = drop_p > 0.0f;
+    if (dropping && (!dx_bf16 || !ln_bwd_use_rows(D) || ln_needs_generic(D, lddy, ldx, lddx, lddxb, lddres, lddy2))) {
+        set_last_error(__FILE__, __LINE__, "layernorm_bwd: the fused dropout mask needs the block-per-row kernel (512 <= D <= 1536, "
+                                           "aligned rows) and a bf16 output");
+        return MICO_ERR_UNSUPPORTED;
+    }
+    DropCfg dcfg;
+    dcfg.p = drop_p; dcfg.inv_keep = 1.0f / (1.0f - drop_p); dcfg.seed = drop_seed;
     MICO_CHECK_ARG(dx || dx_bf16);
     MICO_CHECK_ARG(M > 0 && D > 0);
     const __nv_bfloat16* dy2 = reinterpret_cast<const __nv_bfloat16*>(dy2_bf16);
@@ -618,9 +636,13 @@ extern "C" int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, 
         grid = ln_bwd_row_grid(M);
         auto go = [&](auto k, auto dyp) {
             k<<<grid, kLnThreads, 0, stream>>>(dyp, lddy, dy2, lddy2, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dxb,
-                                               lddxb, row_scale, rows_per_group, partials, M, D);
+                                               lddxb, row_scale, rows_per_group, partials, M, D, dcfg, drop_site);
         };
-        if (dy_is_bf16) {
+        if (dropping) {      // post-LN BERT sub-layers: fp32 upstream gradient, masked bf16 copy, optional column sums
+            MICO_CHECK_ARG(!dy_is_bf16);
+            const float* p = reinterpret_cast<const float*>(dy);
+            if (dxb_colsum) go(ln_bwd_row_kernel<float, true, true>, p); else go(ln_bwd_row_kernel<float, false, true>, p);
+        } else if (dy_is_bf16) {
             const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(dy);
             if (dxb_colsum) go(ln_bwd_row_kernel<__nv_bfloat16, true>, p); else go(ln_bwd_row_kernel<__nv_bfloat16, false>, p);
         } else {
@@ -651,3 +673,29 @@ extern "C" int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, 
     count_launch(2);
     return MICO_OK;
 }
+
+extern "C" int mico_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t lddy, const void* dy2_bf16, int64_t lddy2,
+                                  const float* x, int64_t ldx,
+                                  const float* mean, const float* rstd, const float* gamma, const float* dres,
+                                  int64_t lddres, float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb,
+                                  const float* row_scale, int rows_per_group, float* dgamma, float* dbeta,
+                                  int accumulate_param_grads, float* dxb_colsum, int M, int D, void* workspace,
+                                  size_t ws_bytes, void* stream_) {
+    return layernorm_bwd_impl(dy, dy_is_bf16, lddy, dy2_bf16, lddy2, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dx_bf16,
+                              lddxb, row_scale, rows_per_group, dgamma, dbeta, accumulate_param_grads, dxb_colsum, M, D,
+                              workspace, ws_bytes, stream_, 0.0f, 0, 0);
+}
+
+extern "C" int mico_layernorm_bwd_dropout(const void* dy, int dy_is_bf16, int64_t lddy, const void* dy2_bf16, int64_t lddy2,
+                                          const float* x, int64_t ldx,
+                                          const float* mean, const float* rstd, const float* gamma, const float* dres,
+                                          int64_t lddres, float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb,
+                                          const float* row_scale, int rows_per_group, float* dgamma, float* dbeta,
+                                          int accumulate_param_grads, float* dxb_colsum, int M, int D, void* workspace,
+                                          size_t ws_bytes, float drop_p, uint64_t drop_seed, uint64_t drop_site,
+                                          void* stream_) {
+    return layernorm_bwd_impl(dy, dy_is_bf16, lddy, dy2_bf16, lddy2, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dx_bf16,
+                              lddxb, row_scale, rows_per_group, dgamma, dbeta, accumulate_param_grads, dxb_colsum, M, D,
+                              workspace, ws_bytes, stream_, drop_p, drop_seed, drop_site);
+}
+

@@ -257,10 +257,18 @@ def layernorm_bwd_fuses_colsum(D):
     return 512 <= D <= 1536 and D % 4 == 0
 
 
+def layernorm_bwd_fuses_dropout(D, dy):
+    """True when mico_layernorm_bwd can mask its bf16 output with the forward pass's hidden-dropout mask and sum its columns
+    (block-per-row kernel, fp32 upstream gradient).  MICO_LN_BWD_DROPOUT=0 switches the fusion off (A/B)."""
+    return layernorm_bwd_fuses_colsum(D) and dy.dtype == F32 and os.environ.get("MICO_LN_BWD_DROPOUT", "1") != "0"
+
+
 def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, dres=None, want_f32=True, want_bf16=False,
-                  row_scale=None, rows_per_group=0, accumulate=False, dy2=None, colsum_out=None):
+                  row_scale=None, rows_per_group=0, accumulate=False, dy2=None, colsum_out=None, dropout=None):
     """Returns (dx_f32|None, dx_bf16|None); writes dgamma/dbeta (fp32 [D]).  colsum_out (fp32 [D]): also receives the
-    column sums of the scaled output (the upstream linear layer's bias gradient)."""
+    column sums of the scaled output (the upstream linear layer's bias gradient).  dropout = (p, seed, site_offset): the
+    bf16 output and colsum_out carry the hidden-dropout mask of the forward pass (mico_layernorm_bwd_dropout; see
+    layernorm_bwd_fuses_dropout)."""
     M, D = x.shape
     _req(x, F32, "x")
     dx = torch.empty((M, D), device=x.device, dtype=F32) if want_f32 else None
@@ -269,6 +277,17 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, dres=None, want_f3
     ws = workspace(nws, x.device)
     if dy2 is not None:
         _req(dy2, BF16, "dy2")
+    if dropout is not None and dropout[0] > 0:
+        p_, seed, site = dropout
+        check(lib.mico_layernorm_bwd_dropout(
+            _ptr(dy), int(dy.dtype == BF16), C.c_int64(dy.stride(0)), _ptr(dy2),
+            C.c_int64(dy2.stride(0) if dy2 is not None else 0), _ptr(x), C.c_int64(x.stride(0)),
+            _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres),
+            C.c_int64(dres.stride(0) if dres is not None else 0), _ptr(dx), C.c_int64(D), _ptr(dxb),
+            C.c_int64(D), _ptr(row_scale), int(rows_per_group), _ptr(dgamma), _ptr(dbeta),
+            int(accumulate), _ptr(colsum_out), M, D, _ptr(ws), C.c_size_t(ws.numel()), C.c_float(p_),
+            C.c_uint64(int(seed) & (2 ** 64 - 1)), C.c_uint64(int(site)), _stream()), "mico_layernorm_bwd_dropout")
+        return dx, dxb
     check(lib.mico_layernorm_bwd(_ptr(dy), int(dy.dtype == BF16), C.c_int64(dy.stride(0)), _ptr(dy2),
                                  C.c_int64(dy2.stride(0) if dy2 is not None else 0), _ptr(x), C.c_int64(x.stride(0)),
                                  _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres),

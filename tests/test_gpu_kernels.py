@@ -277,3 +277,29 @@ def test_layernorm_any_width(M, D):
     dx, dxb = ops.layernorm_bwd(dy.cuda(), x.cuda(), mean, rstd, gam.cuda(), dg, db, dres=dres.cuda(), want_bf16=True)
     assert rel_l2(dx.cpu(), xr.grad + dres) < 1e-5 and rel_l2(dxb.float().cpu(), xr.grad + dres) < 4e-3
     assert rel_l2(dg.cpu(), gr.grad) < 1e-5 and rel_l2(db.cpu(), br.grad) < 1e-5
+
+
+@pytest.mark.parametrize("M,D", [(300, 768), (130, 1408)])
+def test_layernorm_bwd_with_fused_dropout_mask(M, D):
+    """mico_layernorm_bwd_dropout: the bf16 output and its column sums carry the forward pass's hidden-dropout mask (post-LN
+    BERT: the gradient of the dense output and its bias gradient) -- against LayerNorm backward + mico_dropout + column sums."""
+    from mico_b200 import ops
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn(M, D, generator=g).cuda()
+    dy = torch.randn(M, D, generator=g).cuda()
+    dy2 = torch.randn(M, D, generator=g).to(torch.bfloat16).cuda()
+    gamma = (torch.rand(D, generator=g) + 0.5).cuda()
+    _, _, mean, rstd = ops.layernorm_fwd(x, gamma, torch.zeros(D, device="cuda"), 1e-12)
+    p_, seed, site = 0.1, 424242, 7 << 40
+    assert ops.layernorm_bwd_fuses_dropout(D, dy)
+    dg0, db0, dg1, db1 = (torch.empty(D, device="cuda") for _ in range(4))
+    cs = torch.empty(D, device="cuda")
+    d32, d16 = ops.layernorm_bwd(dy, x, mean, rstd, gamma, dg1, db1, want_bf16=True, dy2=dy2, colsum_out=cs, dropout=(p_, seed, site))
+    r32, r16 = ops.layernorm_bwd(dy, x, mean, rstd, gamma, dg0, db0, want_bf16=True, dy2=dy2)
+    assert torch.equal(d32, r32) and torch.equal(dg0, dg1) and torch.equal(db0, db1)        # the fp32 side is untouched
+    mult = ops.dropout(torch.ones(M, D, device="cuda"), p_, seed, site)[0]                  # the mask itself: 0 or 1 / (1 - p)
+    ref = r32 * mult
+    assert rel_l2(d16, ref) < 4e-3
+    assert ((d16 == 0) == (mult == 0)).float().mean().item() > 0.999                        # same elements dropped
+    assert 0.05 < (mult == 0).float().mean().item() < 0.15
+    assert rel_l2(cs, ref.sum(0)) < 2e-3
