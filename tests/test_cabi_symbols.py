@@ -54,6 +54,31 @@ def test_new_entry_points_validate_before_touching_cuda():
     assert L.mico_layernorm_bwd_workspace(16448, 1408) >= 148 * 2 * 1408 * 4
 
 
+def test_round2_late_entry_points_validate_before_touching_cuda():
+    """asum_out (bias gradient from the weight-gradient GEMM) and the fused-dropout LayerNorm backward refuse what their kernels
+    cannot do with MICO_ERR_UNSUPPORTED (-3) / MICO_ERR_INVALID_ARG (-1) and a message -- callers then take the separate passes."""
+    from mico_b200 import _lib
+    L = _lib.lib
+    g = _lib.GemmArgs()
+    g.a, g.b, g.out = 256, 256, 256
+    g.M, g.N, g.K, g.lda, g.ldb, g.ldo = 512, 768, 64, 512, 768, 768          # N % 256 == 0: no room for the ones columns
+    g.a_mn_major = g.b_mn_major = 1
+    g.out_fp32, g.alpha = 1, 1.0
+    g.asum_out, g.ones = 256, 256
+    assert L.mico_gemm_bf16(C.byref(g), None) == -3 and b"asum_out" in L.mico_last_error()
+    g.ones = 0
+    assert L.mico_gemm_bf16(C.byref(g), None) == -1 and b"ones" in L.mico_last_error()
+    p = C.c_void_p(256)
+    z = C.c_int64(0)
+    # D = 2048 is outside the block-per-row kernel: the dropout mask cannot be fused
+    rc = L.mico_layernorm_bwd_dropout(p, 0, C.c_int64(2048), None, z, p, C.c_int64(2048), p, p, p, None, z, p, C.c_int64(2048), p,
+                                      C.c_int64(2048), None, 0, p, p, 0, None, 8, 2048, p, C.c_size_t(1 << 30), C.c_float(0.1),
+                                      C.c_uint64(1), C.c_uint64(0), None)
+    assert rc == -3 and b"dropout" in L.mico_last_error()
+    ks, rounds, ms = C.c_int(0), C.c_int(0), C.c_double(0)
+    assert L.mico_gemm_plan(12, 5, 256, 128, 8, 74, 0, C.byref(ks), C.byref(rounds), C.byref(ms), None, 0) == -1   # 12 % 5 != 0
+
+
 def test_product_never_imports_oracle():
     """The oracle is test infrastructure: nothing under mico_b200/ may reference it."""
     pkg = os.path.join(REPO, "mico_b200")
