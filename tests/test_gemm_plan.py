@@ -77,3 +77,22 @@ def test_weight_gradient_split_is_chosen_by_makespan():
 def test_ragged_k_parts_and_small_launches():
     for args in [(3 * 2, 2, 128, 32, 70, 148, 1), (5, 1, 256, 256, 33, 74, 1), (7 * 3, 3, 176, 176, 12, 148, 0), (1, 1, 64, 16, 1, 148, 0)]:
         _check(*args)
+
+
+def test_plan_properties_over_random_launch_shapes():
+    """Property test (hypothesis): for any launch geometry the plan is a partition of the units into compact per-slot lists with
+    one unit per round, its makespan is what the table says, never worse than the strided schedule's, and within one unit of the
+    mean load when a round-robin deal could be balanced at all."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None, derandomize=True, database=None)
+    @given(st.integers(1, 40), st.integers(1, 7), st.sampled_from([64, 128, 176, 256]), st.integers(1, 16),
+           st.integers(1, 300), st.sampled_from([74, 148, 70, 3]), st.booleans())
+    def prop(mg, nn, bn, last16, num_kb, slots, split):
+        n_last = min(bn, 16 * last16)
+        ks, load, strided, cost = _check(mg * nn, nn, bn, n_last, num_kb, slots, int(split))
+        assert ks in (1, 2, 4) and (split or ks == 1)
+        assert load.max() <= strided + 1e-9
+        assert load.max() <= cost.sum() / slots + 2 * cost.max() + 1e-9 or len(cost) < slots
+
+    prop()
