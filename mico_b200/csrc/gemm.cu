@@ -16,6 +16,9 @@
 //                             run-time epilogue (two warps per TMEM lane quarter, alternating 32-column chunks)
 // Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.  The last N tile of
 // a row issues a narrower MMA, so N = 1408 runs on 256-wide tiles (5 full + 1 half).
+// Work units are dealt to the CTA pairs by a balanced schedule table (GemmPlan below: per round, longest-first to the least
+// loaded pair; split-K of a weight gradient by planned makespan); a weight gradient can also return its layer's bias gradient
+// from 32 ones columns behind the last N tile (asum_out).
 // Either operand may be "MN-major" (the contraction index is the slow dimension in HBM); that is how
 // wgrad (dW = dY^T X) and dgrad (dX = dY W) run on the same kernel with no transposes in HBM.
 //
