@@ -44,6 +44,12 @@ def gemms_r2n():
         out, bsum = torch.empty(M, N, device="cuda"), torch.empty(M, device="cuda")
         ops.gemm(dy, x, a_mn=True, b_mn=True, out=out)                           # planned split-K
         ops.gemm(dy, x, a_mn=True, b_mn=True, out=out, asum_out=bsum)            # + bias gradient
+    # LayerNorm backward carrying the hidden-dropout mask + bias column sums (post-LN BERT)
+    x, dy = r(130, 768), r(130, 768)
+    gam = r(768).abs() + 0.5
+    _, _, mean, rstd = ops.layernorm_fwd(x, gam, torch.zeros(768, device="cuda"), 1e-12)
+    ops.layernorm_bwd(dy, x, mean, rstd, gam, torch.empty(768, device="cuda"), torch.empty(768, device="cuda"), want_bf16=True,
+                      dy2=r(130, 768).to(BF16), colsum_out=torch.empty(768, device="cuda"), dropout=(0.1, 5, 3 << 40))
     q, do = r(3, 128, 2, 64).to(BF16), r(3, 128, 2, 64).to(BF16)
     k, v = r(3, 300, 2, 64).to(BF16), r(3, 300, 2, 64).to(BF16)
     o, lse = ops.attention_fwd(q, k, v, 0.125, dropout=(0.1, 4))
